@@ -98,7 +98,7 @@ def conv_pool_tokens_taps(x, thw, weight, stride, has_cls, ln_w, ln_b):
     To, Ho, Wo = pooled_size(T, kt, st), pooled_size(H, kh, sh), pooled_size(W, kw, sw)
     vol = tok.reshape(B, nh, T, H, W, C)
     pad = F.pad(vol, (0, 0, kw // 2, kw // 2, kh // 2, kh // 2, kt // 2, kt // 2))
-    out = torch.zeros(B, nh, To, Ho, Wo, C, dtype=x.dtype)
+    out = torch.zeros(B, nh, To, Ho, Wo, C, dtype=x.dtype, device=x.device)
     for a in range(kt):
         for b in range(kh):
             for c in range(kw):
@@ -166,12 +166,12 @@ def rel_pos_bias_terms(
     r_q = q[:, :, s:].reshape(B, nh, qt, qh, qw, C)
     bh = bw = bt = None
     if rel_h is not None:
-        Rh = interp_rel_table(rel_h, 2 * max(qh, kh) - 1)[rel_index(qh, kh)]  # [qh, kh, C]
-        Rw = interp_rel_table(rel_w, 2 * max(qw, kw) - 1)[rel_index(qw, kw)]  # [qw, kw, C]
+        Rh = interp_rel_table(rel_h, 2 * max(qh, kh) - 1)[rel_index(qh, kh).to(q.device)]  # [qh, kh, C]
+        Rw = interp_rel_table(rel_w, 2 * max(qw, kw) - 1)[rel_index(qw, kw).to(q.device)]  # [qw, kw, C]
         bh = torch.einsum("bnthwc,hkc->bnthwk", r_q, Rh).reshape(B, nh, -1, kh)
         bw = torch.einsum("bnthwc,wkc->bnthwk", r_q, Rw).reshape(B, nh, -1, kw)
     if rel_t is not None:
-        Rt = interp_rel_table(rel_t, 2 * max(qt, kt) - 1)[rel_index(qt, kt)]  # [qt, kt, C]
+        Rt = interp_rel_table(rel_t, 2 * max(qt, kt) - 1)[rel_index(qt, kt).to(q.device)]  # [qt, kt, C]
         bt = torch.einsum("bnthwc,tkc->bnthwk", r_q, Rt).reshape(B, nh, -1, kt)
     return bh, bw, bt
 
@@ -183,7 +183,7 @@ def add_rel_pos_bias(attn, q, has_cls, q_shape, k_shape, rel_h, rel_w, rel_t):
     B, nh, Nq, Nk = attn.shape
     bh, bw, bt = rel_pos_bias_terms(q, has_cls, q_shape, k_shape, rel_h, rel_w, rel_t)
     Lq = Nq - s
-    bias = torch.zeros(B, nh, Lq, kt, kh, kw, dtype=attn.dtype)
+    bias = torch.zeros(B, nh, Lq, kt, kh, kw, dtype=attn.dtype, device=attn.device)
     if bh is not None:
         bias = bias + bh[:, :, :, None, :, None] + bw[:, :, :, None, None, :]
     if bt is not None:

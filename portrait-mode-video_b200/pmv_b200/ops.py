@@ -1,0 +1,161 @@
+"""Thin tensor-level wrappers over the C ABI (no autograd here — see functional.py).
+
+Every function allocates its outputs with torch (device memory + current stream are the only things
+torch provides) and launches the hand-written kernels through ctypes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+LN_EPS = 1e-6
+
+
+def _tc_default(dtype) -> int:
+    return 1 if dtype == torch.bfloat16 else 0
+
+
+# ----------------------------------------------------------------------------- LayerNorm
+def layernorm_fwd(x: torch.Tensor, gamma, beta, out_dtype, save_stats=True, eps=LN_EPS):
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    Cdim = x.shape[-1]
+    rows = x.numel() // Cdim
+    y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    mean = rstd = None
+    if save_stats:
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    L.check(L.lib().pmv_layernorm_fwd(L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(y), L.dt(out_dtype), L.ptr(mean),
+                                      L.ptr(rstd), rows, Cdim, eps, L.stream()), "pmv_layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx_accum: Optional[torch.Tensor] = None):
+    """Returns (dx fp32, dgamma, dbeta).  If dx_accum is given the input gradient is added into it in place."""
+    Cdim = x.shape[-1]
+    rows = x.numel() // Cdim
+    dy = dy.contiguous()
+    dx = dx_accum if dx_accum is not None else torch.empty_like(x)
+    dgb = torch.zeros(2, Cdim, dtype=torch.float32, device=x.device)
+    L.check(L.lib().pmv_layernorm_bwd(L.ptr(dy), L.dt(dy), L.ptr(x), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), L.ptr(dx),
+                                      1 if dx_accum is not None else 0, L.ptr(dgb[0]), L.ptr(dgb[1]), rows, Cdim,
+                                      L.stream()), "pmv_layernorm_bwd")
+    return dx, dgb[0], dgb[1]
+
+
+# ----------------------------------------------------------------------------- GEMM
+def gemm(layout: int, A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, out: torch.Tensor, *, bias=None, act=L.ACT_NONE,
+         aux_in=None, aux_out=None, row_scale=None, rows_per_scale=1, residual=None, accumulate=False,
+         out_group=0, out_skip=0, tc: Optional[bool] = None, split_k: int = 1, ldo: Optional[int] = None):
+    """C = op(A) op(B) with the fused epilogue of pmv_gemm.  A/B/out are 2-D row-major (last stride 1)."""
+    assert A.stride(-1) == 1 and B.stride(-1) == 1 and out.stride(-1) == 1
+    assert A.dtype == B.dtype
+    lda, ldb = A.stride(0), B.stride(0)
+    ldo = out.stride(0) if ldo is None else ldo
+    use_tc = _tc_default(A.dtype) if tc is None else int(tc)
+    need_epi = any(v is not None for v in (bias, aux_in, aux_out, row_scale, residual)) or act or accumulate or out_group
+    epi = None
+    if need_epi:
+        aux = aux_in if aux_in is not None else aux_out
+        epi = L.Epilogue(L.ptr(bias), act, L.ptr(aux_in), L.ptr(aux_out), aux.stride(0) if aux is not None else 0,
+                         L.ptr(row_scale), rows_per_scale, L.ptr(residual),
+                         residual.stride(0) if residual is not None else 0, int(accumulate), out_group, out_skip)
+    L.check(L.lib().pmv_gemm(layout, L.ptr(A), lda, L.ptr(B), ldb, L.ptr(out), ldo, M, N, K, L.dt(A), L.dt(out),
+                             C.byref(epi) if epi is not None else None, use_tc, split_k, L.stream()), "pmv_gemm")
+    return out
+
+
+def linear_fwd(x2d, weight, bias, out_dtype, **kw):
+    """y[M,N] = x[M,K] @ weight[N,K]^T (+ epilogue)."""
+    M, K = x2d.shape
+    N = weight.shape[0]
+    out = kw.pop("out", None)
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype, device=x2d.device)
+    return gemm(L.GEMM_TN, x2d, weight, M, N, K, out, bias=bias, **kw)
+
+
+def linear_dgrad(dy2d, weight, out_dtype, **kw):
+    """dx[M,K] = dy[M,N] @ weight[N,K]."""
+    M, N = dy2d.shape
+    K = weight.shape[1]
+    out = kw.pop("out", None)
+    if out is None:
+        out = torch.empty(M, K, dtype=out_dtype, device=dy2d.device)
+    return gemm(L.GEMM_NN, dy2d, weight, M, K, N, out, **kw)
+
+
+def _pick_split(rows: int, n1: int, n2: int) -> int:
+    tiles = ((n1 + 127) // 128) * ((n2 + 95) // 96)
+    want = max(1, (148 * 2) // max(tiles, 1))
+    return max(1, min(want, rows // 512 if rows >= 512 else 1))
+
+
+def linear_wgrad(dy2d, x2d, tc=None):
+    """dW[N,K] = dy[M,N]^T @ x[M,K] in fp32 (split over the token rows, fp32 atomics)."""
+    M, N = dy2d.shape
+    K = x2d.shape[1]
+    split = _pick_split(M, N, K)
+    out = torch.zeros(N, K, dtype=torch.float32, device=dy2d.device) if split > 1 else \
+        torch.empty(N, K, dtype=torch.float32, device=dy2d.device)
+    return gemm(L.GEMM_NT_REDUCE_M, dy2d, x2d, M, N, K, out, split_k=split, tc=tc)
+
+
+def colsum_cast(x2d, cast_dtype=None, row_scale=None, rows_per_scale=1, want_sum=True):
+    rows, cols = x2d.shape
+    s = torch.zeros(cols, dtype=torch.float32, device=x2d.device) if want_sum else None
+    c = torch.empty(rows, cols, dtype=cast_dtype, device=x2d.device) if cast_dtype is not None else None
+    L.check(L.lib().pmv_colsum_cast(L.ptr(x2d), L.dt(x2d), x2d.stride(0), rows, cols, L.ptr(row_scale), rows_per_scale,
+                                    L.ptr(s), L.ptr(c), L.dt(cast_dtype) if cast_dtype is not None else 0,
+                                    c.stride(0) if c is not None else 0, L.stream()), "pmv_colsum_cast")
+    return s, c
+
+
+# ----------------------------------------------------------------------------- pooling
+def pooled_hw(n: int, s: int) -> int:
+    return (n - 1) // s + 1
+
+
+def pool_ln_fwd(qkv: torch.Tensor, which: int, heads: int, thw: Sequence[int], stride_hw: int, w, gamma, beta,
+                out: torch.Tensor, eps=LN_EPS):
+    """qkv: [B, N, 3, heads, 96] contiguous; writes out [B, heads, 1+L', ld] columns [0,96)."""
+    B, N = qkv.shape[0], qkv.shape[1]
+    T, H, W = thw
+    view = qkv[:, :, which]
+    L.check(L.lib().pmv_pool_ln_fwd(view.data_ptr(), qkv.stride(0), qkv.stride(1), qkv.stride(3), L.ptr(w), L.ptr(gamma),
+                                    L.ptr(beta), L.ptr(out), out.stride(2), B, heads, T, H, W, stride_hw, eps, L.dt(qkv),
+                                    L.stream()), "pmv_pool_ln_fwd")
+    return out
+
+
+def pool_ln_bwd(qkv, which, heads, thw, stride_hw, w, gamma, dout, dqkv, dw, dgamma, dbeta, eps=LN_EPS):
+    B = qkv.shape[0]
+    T, H, W = thw
+    Lo = T * pooled_hw(H, stride_hw) * pooled_hw(W, stride_hw)
+    ws = torch.empty(B * heads * Lo * 96, dtype=torch.float32, device=qkv.device)
+    L.check(L.lib().pmv_pool_ln_bwd(qkv[:, :, which].data_ptr(), qkv.stride(0), qkv.stride(1), qkv.stride(3), L.ptr(w),
+                                    L.ptr(gamma), L.ptr(dout), dout.stride(2), dqkv[:, :, which].data_ptr(), L.ptr(dw),
+                                    L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), B, heads, T, H, W, stride_hw, eps, L.dt(qkv),
+                                    L.stream()), "pmv_pool_ln_bwd")
+
+
+def maxpool_skip_fwd(x, thw):
+    B, N, Cdim = x.shape
+    T, H, W = thw
+    Lo = T * pooled_hw(H, 2) * pooled_hw(W, 2)
+    y = torch.empty(B, 1 + Lo, Cdim, dtype=torch.float32, device=x.device)
+    L.check(L.lib().pmv_maxpool_skip_fwd(L.ptr(x), L.ptr(y), B, T, H, W, Cdim, L.stream()), "pmv_maxpool_skip_fwd")
+    return y
+
+
+def maxpool_skip_bwd(x, dy, thw, dx_accum=None):
+    B, N, Cdim = x.shape
+    T, H, W = thw
+    dx = dx_accum if dx_accum is not None else torch.zeros_like(x)
+    L.check(L.lib().pmv_maxpool_skip_bwd(L.ptr(x), L.ptr(dy.contiguous()), L.ptr(dx), B, T, H, W, Cdim, L.stream()),
+            "pmv_maxpool_skip_bwd")
+    return dx

@@ -1,0 +1,170 @@
+"""Kernel-level parity on the GPU: every C-ABI kernel against the oracle / a plain fp32 torch statement of
+the same op, on seeded inputs.  Tolerances: fp32 mode 1e-4, bf16 mode 1e-2 (normalised max error
+max|a-b| / max|b|, the metric BASELINE.json's north star states)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-4, torch.bfloat16: 1e-2}
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+def nerr(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def randn(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("rows,C", [(1000, 96), (777, 768), (33, 384)])
+def test_layernorm_fwd_bwd(dtype, rows, C):
+    from oracle import mvit_oracle as orc
+    from pmv_b200 import ops
+    x = randn(rows, C, seed=1) * 2 + 0.3
+    g, b = randn(C, seed=2) * 0.1 + 1, randn(C, seed=3) * 0.1
+    y, mean, rstd = ops.layernorm_fwd(x, g, b, dtype)
+    xr = x.clone().requires_grad_(True)
+    gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = orc.layer_norm(xr, gr, br)
+    assert nerr(y.float(), yr.detach()) < TOL[dtype]
+    dy = randn(rows, C, seed=4).to(dtype)
+    yr.backward(dy.float())
+    dx, dg, db = ops.layernorm_bwd(dy, x, g, mean, rstd)
+    assert nerr(dx, xr.grad) < TOL[dtype]
+    assert nerr(dg, gr.grad) < TOL[dtype]
+    assert nerr(db, br.grad) < TOL[dtype]
+    acc = torch.ones_like(x)
+    ops.layernorm_bwd(dy, x, g, mean, rstd, dx_accum=acc)
+    assert nerr(acc, xr.grad + 1) < TOL[dtype]
+
+
+POOL_CASES = [  # B, heads, thw, stride
+    (2, 1, (2, 8, 8), 8), (2, 2, (2, 8, 8), 2), (1, 2, (2, 7, 5), 2), (1, 4, (8, 14, 14), 1), (2, 2, (3, 12, 10), 4),
+]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("B,heads,thw,s", POOL_CASES)
+def test_pool_ln_fwd_bwd(dtype, B, heads, thw, s):
+    from oracle import mvit_oracle as orc
+    from pmv_b200 import ops
+    T, H, W = thw
+    N = 1 + T * H * W
+    qkv = randn(B, N, 3, heads, 96, seed=5).to(dtype)
+    w = randn(96, 1, 3, 3, 3, seed=6) * 0.2
+    g, b = randn(96, seed=7) * 0.1 + 1, randn(96, seed=8) * 0.1
+    Lo = T * ops.pooled_hw(H, s) * ops.pooled_hw(W, s)
+    for which in range(3):
+        ld = 128 if which == 0 else 96
+        out = torch.zeros(B, heads, 1 + Lo, ld, dtype=dtype, device="cuda")
+        ops.pool_ln_fwd(qkv, which, heads, thw, s, w, g, b, out)
+        xin = qkv[:, :, which].permute(0, 2, 1, 3).float().clone().requires_grad_(True)
+        wr, gr, br = (t.clone().requires_grad_(True) for t in (w, g, b))
+        ref, thw_o = orc.conv_pool_tokens(xin, thw, wr, (1, s, s), True, gr, br)
+        assert ref.shape[2] == 1 + Lo
+        assert nerr(out[..., :96].float(), ref.detach()) < TOL[dtype], which
+        assert float(out[..., 96:].abs().max()) == 0.0 if ld > 96 else True
+        dout = torch.zeros(B, heads, 1 + Lo, ld, dtype=dtype, device="cuda")
+        dout[..., :96] = randn(B, heads, 1 + Lo, 96, seed=9 + which).to(dtype)
+        ref.backward(dout[..., :96].float())
+        dqkv = torch.full_like(qkv, float("nan"))
+        dwg = torch.zeros(96 * 27 + 192, device="cuda")
+        ops.pool_ln_bwd(qkv, which, heads, thw, s, w, g, dout, dqkv, dwg[:2592], dwg[2592:2688], dwg[2688:])
+        got_dx = dqkv[:, :, which].permute(0, 2, 1, 3).float()
+        assert nerr(got_dx, xin.grad) < TOL[dtype], which
+        assert nerr(dwg[:2592].view(96, 27), wr.grad.view(96, 27)) < TOL[dtype]
+        assert nerr(dwg[2592:2688], gr.grad) < TOL[dtype]
+        assert nerr(dwg[2688:], br.grad) < TOL[dtype]
+
+
+@pytest.mark.parametrize("B,thw,C", [(2, (2, 8, 8), 192), (1, (2, 7, 5), 96), (2, (8, 14, 14), 768)])
+def test_maxpool_skip(B, thw, C):
+    from oracle import mvit_oracle as orc
+    from pmv_b200 import ops
+    T, H, W = thw
+    x = randn(B, 1 + T * H * W, C, seed=11)
+    y = ops.maxpool_skip_fwd(x, thw)
+    xr = x.clone().requires_grad_(True)
+    yr, _ = orc.max_pool_tokens(xr, thw, (1, 3, 3), (1, 2, 2), True)
+    assert torch.equal(y, yr.detach())
+    dy = randn(*y.shape, seed=12)
+    yr.backward(dy)
+    dx = ops.maxpool_skip_bwd(x, dy, thw)
+    assert nerr(dx, xr.grad) < 1e-6
+
+
+GEMM_SHAPES = [(300, 288, 96), (1000, 96, 384), (129, 1152, 384), (513, 768, 3072), (64, 400, 768)]
+
+
+@pytest.mark.parametrize("tc", [0, 1])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_layouts(tc, M, N, K):
+    """TN / NN / reduce-over-rows against torch fp32 matmul (bf16 operands on both sides)."""
+    from pmv_b200 import _lib as L, ops
+    dtype = torch.bfloat16 if tc else torch.float32
+    x = randn(M, K, seed=20).to(dtype)
+    w = (randn(N, K, seed=21) * 0.05).to(dtype)
+    dy = randn(M, N, seed=22).to(dtype)
+    tol = TOL[dtype]
+    y = ops.linear_fwd(x, w, None, dtype, tc=tc)
+    assert nerr(y.float(), x.float() @ w.float().t()) < tol
+    dx = ops.linear_dgrad(dy, w, torch.float32, tc=tc)
+    assert nerr(dx, dy.float() @ w.float()) < tol
+    dw = ops.linear_wgrad(dy, x, tc=tc)
+    assert nerr(dw, dy.float().t() @ x.float()) < tol
+
+
+@pytest.mark.parametrize("tc", [0, 1])
+def test_gemm_epilogues(tc):
+    from pmv_b200 import _lib as L, ops
+    dtype = torch.bfloat16 if tc else torch.float32
+    tol = TOL[dtype]
+    B, Nq, K, N = 3, 101, 192, 384
+    M = B * Nq
+    x = randn(M, K, seed=30).to(dtype)
+    w = (randn(N, K, seed=31) * 0.05).to(dtype)
+    bias = randn(N, seed=32) * 0.1
+    res = randn(M, N, seed=33)
+    scale = torch.tensor([0.0, 1.25, 1.25], device="cuda")
+    ref_lin = x.float() @ w.float().t() + bias
+    # bias + DropPath scale + residual -> fp32
+    y = ops.linear_fwd(x, w, bias, torch.float32, residual=res, row_scale=scale, rows_per_scale=Nq, tc=tc)
+    assert nerr(y, res + ref_lin * scale.repeat_interleave(Nq)[:, None]) < tol
+    # GELU + saved pre-activation
+    u = torch.empty(M, N, dtype=dtype, device="cuda")
+    h = ops.linear_fwd(x, w, bias, dtype, act=L.ACT_GELU, aux_out=u, tc=tc)
+    assert nerr(u.float(), ref_lin) < tol
+    assert nerr(h.float(), torch.nn.functional.gelu(ref_lin)) < tol
+    # GELU backward in the dgrad epilogue: du = (dh @ W2) * gelu'(u)
+    w2 = (randn(K, N, seed=34) * 0.05).to(dtype)  # fc2 weight [out=K, in=N]
+    dyo = randn(M, K, seed=35).to(dtype)
+    du = ops.linear_dgrad(dyo, w2, dtype, act=L.ACT_GELU_BWD, aux_in=u, tc=tc)
+    uu = u.float().requires_grad_(True)
+    torch.nn.functional.gelu(uu).backward(dyo.float() @ w2.float())
+    assert nerr(du.float(), uu.grad) < tol
+    # accumulate + row remap (PatchEmbed tokens written behind the cls slot)
+    out = torch.zeros(B * (Nq + 1), N, device="cuda")
+    ops.linear_fwd(x, w, bias, torch.float32, out=out, out_group=Nq, out_skip=1, tc=tc)
+    o3 = out.view(B, Nq + 1, N)
+    assert float(o3[:, 0].abs().max()) == 0.0
+    assert nerr(o3[:, 1:].reshape(M, N), ref_lin) < tol
+    acc = torch.ones(M, N, device="cuda")
+    ops.linear_fwd(x, w, None, torch.float32, out=acc, accumulate=True, tc=tc)
+    assert nerr(acc, ref_lin - bias + 1) < tol
+
+
+def test_colsum_cast():
+    from pmv_b200 import ops
+    x = randn(1234, 384, seed=40)
+    scale = torch.tensor([1.0, 0.0], device="cuda")
+    s, c = ops.colsum_cast(x, torch.bfloat16, row_scale=scale, rows_per_scale=617)
+    ref = x * scale.repeat_interleave(617)[:, None]
+    assert nerr(s, ref.sum(0)) < 1e-5
+    assert nerr(c.float(), ref) < 1e-2
