@@ -149,7 +149,7 @@ int pmv_maxpool_skip_bwd(const float* x, const float* dy, float* dx, int B, int 
  * float-ratio / .long() index arithmetic (attention.py:80-99,132-139), computed on the host. */
 int pmv_relpos_augment_q(void* q_aug, int64_t ld, const float* rel_h, const float* rel_w, const float* rel_t,
                          const int32_t* idx_h, const int32_t* idx_w, const int32_t* idx_t,
-                         int BH, int heads_unused, int qt, int qh, int qw, int kt, int kh, int kw,
+                         int BH, int qt, int qh, int qw, int kt, int kh, int kw,
                          float inv_scale, int dtype, void* stream);
 int pmv_relpos_augment_k(void* k_aug, int64_t ld, int BH, int kt, int kh, int kw, int dtype, void* stream);
 /* Backward of augment_q: given dQ' (same layout), accumulates (fp32, atomics) d rel_h/w/t and adds the

@@ -63,13 +63,14 @@ def lib() -> C.CDLL:
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python portrait-mode-video_b200/build.py` "
                 "(there is no CPU / eager fallback on the product path)")
-        _lib = C.CDLL(LIB_PATH)
-        _lib.pmv_last_error.restype = C.c_char_p
-        _lib.pmv_last_error.argtypes = []
+        handle = C.CDLL(LIB_PATH)
+        handle.pmv_last_error.restype = C.c_char_p
+        handle.pmv_last_error.argtypes = []
         for name, (res, args) in _SIGS.items():
-            fn = getattr(_lib, name)
+            fn = getattr(handle, name)  # AttributeError here = stale build: rebuild the library
             fn.restype = res
             fn.argtypes = args
+        _lib = handle
     return _lib
 
 

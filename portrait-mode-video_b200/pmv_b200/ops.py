@@ -159,3 +159,98 @@ def maxpool_skip_bwd(x, dy, thw, dx_accum=None):
     L.check(L.lib().pmv_maxpool_skip_bwd(L.ptr(x), L.ptr(dy.contiguous()), L.ptr(dx), B, T, H, W, Cdim, L.stream()),
             "pmv_maxpool_skip_bwd")
     return dx
+
+
+# ----------------------------------------------------------------------------- rel-pos augmentation + attention
+_IDX_CACHE = {}
+
+
+def rel_index_table(q_n: int, k_n: int, device) -> torch.Tensor:
+    """int32 [q_n*k_n] rows of the rel-pos table for every (query, key) coordinate pair on one axis.
+    Same float32 arithmetic and truncation as the reference (attention.py:80-86,98)."""
+    key = (q_n, k_n, str(device))
+    t = _IDX_CACHE.get(key)
+    if t is None:
+        q_ratio = max(k_n / q_n, 1.0)
+        k_ratio = max(q_n / k_n, 1.0)
+        dist = torch.arange(q_n)[:, None] * q_ratio - torch.arange(k_n)[None, :] * k_ratio
+        dist = dist + (k_n - 1) * k_ratio
+        t = dist.long().to(torch.int32).reshape(-1).contiguous().to(device)
+        _IDX_CACHE[key] = t
+    return t
+
+
+def aug_ld(k_shape) -> int:
+    """Row width of Q'/K': 96 channels + the one-hot key-coordinate columns, padded to a multiple of 32."""
+    rk = k_shape[0] + k_shape[1] + k_shape[2]
+    return 96 + ((rk + 31) // 32) * 32
+
+
+def relpos_augment_q(q_aug, q_shape, k_shape, rel_h, rel_w, rel_t, inv_scale):
+    BH, Nq, ld = q_aug.shape
+    dev = q_aug.device
+    ih, iw, it = (rel_index_table(q_shape[1], k_shape[1], dev), rel_index_table(q_shape[2], k_shape[2], dev),
+                  rel_index_table(q_shape[0], k_shape[0], dev))
+    L.check(L.lib().pmv_relpos_augment_q(L.ptr(q_aug), ld, L.ptr(rel_h), L.ptr(rel_w), L.ptr(rel_t), L.ptr(ih), L.ptr(iw),
+                                         L.ptr(it), BH, *q_shape, *k_shape, inv_scale, L.dt(q_aug), L.stream()),
+            "pmv_relpos_augment_q")
+
+
+def relpos_augment_k(k_aug, k_shape):
+    BH, Nk, ld = k_aug.shape
+    L.check(L.lib().pmv_relpos_augment_k(L.ptr(k_aug), ld, BH, *k_shape, L.dt(k_aug), L.stream()), "pmv_relpos_augment_k")
+
+
+def relpos_augment_q_bwd(dq_aug, q_aug, q_shape, k_shape, rel_h, rel_w, rel_t, inv_scale):
+    """In place: dq_aug[:, :, :96] += bias-path gradient.  Returns fp32 (d_rel_h, d_rel_w, d_rel_t)."""
+    BH, Nq, ld = q_aug.shape
+    dev = q_aug.device
+    ih, iw, it = (rel_index_table(q_shape[1], k_shape[1], dev), rel_index_table(q_shape[2], k_shape[2], dev),
+                  rel_index_table(q_shape[0], k_shape[0], dev))
+    dh, dw, dt_ = torch.zeros_like(rel_h), torch.zeros_like(rel_w), torch.zeros_like(rel_t)
+    L.check(L.lib().pmv_relpos_augment_q_bwd(L.ptr(dq_aug), L.ptr(q_aug), ld, L.ptr(rel_h), L.ptr(rel_w), L.ptr(rel_t),
+                                             L.ptr(ih), L.ptr(iw), L.ptr(it), L.ptr(dh), L.ptr(dw), L.ptr(dt_), BH,
+                                             *q_shape, *k_shape, inv_scale, L.dt(q_aug), L.stream()),
+            "pmv_relpos_augment_q_bwd")
+    return dh, dw, dt_
+
+
+def attention_fwd(q_aug, k_aug, v, B, heads, kd, scale, residual=True, want_lse=True, tc=None):
+    BH, Nq, ld = q_aug.shape
+    Nk = k_aug.shape[1]
+    out = torch.empty(B, Nq, heads * 96, dtype=q_aug.dtype, device=q_aug.device)
+    lse = torch.empty(BH, Nq, dtype=torch.float32, device=q_aug.device) if want_lse else None
+    use_tc = _tc_default(q_aug.dtype) if tc is None else int(tc)
+    L.check(L.lib().pmv_attention_fwd(L.ptr(q_aug), L.ptr(k_aug), ld, kd, L.ptr(v), v.stride(1), L.ptr(out), L.ptr(lse),
+                                      B, heads, Nq, Nk, scale, int(residual), L.dt(q_aug), use_tc, L.stream()),
+            "pmv_attention_fwd")
+    return out, lse
+
+
+def attention_bwd(q_aug, k_aug, v, out, dout, lse, B, heads, kd, scale, residual=True):
+    BH, Nq, ld = q_aug.shape
+    Nk = k_aug.shape[1]
+    dq_aug = torch.empty_like(q_aug)
+    dk = torch.empty(BH, Nk, 96, dtype=q_aug.dtype, device=q_aug.device)
+    dv = torch.empty(BH, Nk, 96, dtype=q_aug.dtype, device=q_aug.device)
+    ws = torch.empty(L.lib().pmv_attention_bwd_workspace_bytes(B, heads, Nq, Nk) // 4, dtype=torch.float32,
+                     device=q_aug.device)
+    L.check(L.lib().pmv_attention_bwd(L.ptr(q_aug), L.ptr(k_aug), ld, kd, L.ptr(v), v.stride(1), L.ptr(out),
+                                      L.ptr(dout.contiguous()), L.ptr(lse), L.ptr(dq_aug), L.ptr(dk), 96, L.ptr(dv), 96,
+                                      L.ptr(ws), B, heads, Nq, Nk, scale, int(residual), L.dt(q_aug), L.stream()),
+            "pmv_attention_bwd")
+    return dq_aug, dk, dv
+
+
+# ----------------------------------------------------------------------------- PatchEmbed
+def patch_im2col(clip, kernel, stride, padding, dtype):
+    B, Cin, T, H, W = clip.shape
+    To = (T + 2 * padding[0] - kernel[0]) // stride[0] + 1
+    Ho = (H + 2 * padding[1] - kernel[1]) // stride[1] + 1
+    Wo = (W + 2 * padding[2] - kernel[2]) // stride[2] + 1
+    K = Cin * kernel[0] * kernel[1] * kernel[2]
+    ld = (K + 63) // 64 * 64
+    col = torch.empty(B * To * Ho * Wo, ld, dtype=dtype, device=clip.device)
+    L.check(L.lib().pmv_patch_im2col(L.ptr(clip), L.ptr(col), ld, B, Cin, T, H, W, *kernel, *stride, *padding, L.dt(dtype),
+                                     L.stream()), "pmv_patch_im2col")
+    return col, (To, Ho, Wo), K

@@ -11,6 +11,10 @@ for p in (ROOT, PKG):
 
 
 def pytest_configure(config):
+    import torch
+    # the comparison side must be true fp32 (cuDNN / cuBLAS default to TF32 for convolutions)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 

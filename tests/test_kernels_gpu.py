@@ -168,3 +168,74 @@ def test_colsum_cast():
     ref = x * scale.repeat_interleave(617)[:, None]
     assert nerr(s, ref.sum(0)) < 1e-5
     assert nerr(c.float(), ref) < 1e-2
+
+
+ATTN_CASES = [  # B, heads, q_shape, k_shape
+    (2, 2, (2, 4, 4), (2, 2, 2)), (1, 1, (8, 14, 14), (8, 7, 7)), (2, 2, (2, 3, 2), (2, 6, 4)), (1, 2, (2, 7, 5), (2, 4, 3)),
+    (1, 2, (8, 7, 7), (8, 14, 14)),
+]
+
+
+def _attn_reference(q, k, v, q_shape, k_shape, rh, rw, rt, scale):
+    from oracle import mvit_oracle as orc
+    attn = (q * scale) @ k.transpose(-2, -1)
+    attn = orc.add_rel_pos_bias(attn, q, True, q_shape, k_shape, rh, rw, rt).softmax(dim=-1)
+    o = attn @ v
+    o = torch.cat([o[:, :, :1], o[:, :, 1:] + q[:, :, 1:]], dim=2)
+    B, nh, Nq, C = q.shape
+    return o.transpose(1, 2).reshape(B, Nq, nh * C)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("B,heads,q_shape,k_shape", ATTN_CASES)
+def test_relpos_attention_fwd_bwd(dtype, B, heads, q_shape, k_shape):
+    """rel-pos augmentation + attention (CUDA-core kernels) against the oracle's materialised-score formulation."""
+    from pmv_b200 import ops
+    tol = TOL[dtype]
+    Nq, Nk = 1 + math.prod(q_shape), 1 + math.prod(k_shape)
+    q = randn(B, heads, Nq, 96, seed=50).to(dtype)
+    k = randn(B, heads, Nk, 96, seed=51).to(dtype)
+    v = randn(B, heads, Nk, 96, seed=52).to(dtype)
+    rh = randn(2 * max(q_shape[1], k_shape[1]) - 1, 96, seed=53) * 0.3
+    rw = randn(2 * max(q_shape[2], k_shape[2]) - 1, 96, seed=54) * 0.3
+    rt = randn(2 * max(q_shape[0], k_shape[0]) - 1, 96, seed=55) * 0.3
+    scale = 96 ** -0.5
+    ld = ops.aug_ld(k_shape)
+    q_aug = torch.zeros(B * heads, Nq, ld, dtype=dtype, device="cuda")
+    k_aug = torch.zeros(B * heads, Nk, ld, dtype=dtype, device="cuda")
+    q_aug[..., :96] = q.reshape(B * heads, Nq, 96)
+    k_aug[..., :96] = k.reshape(B * heads, Nk, 96)
+    ops.relpos_augment_q(q_aug, q_shape, k_shape, rh, rw, rt, 1.0 / scale)
+    ops.relpos_augment_k(k_aug, k_shape)
+    vv = v.reshape(B * heads, Nk, 96).contiguous()
+    out, lse = ops.attention_fwd(q_aug, k_aug, vv, B, heads, ld, scale, residual=True, tc=0)
+    leaves = [t.float().clone().requires_grad_(True) for t in (q, k, v, rh, rw, rt)]
+    ref = _attn_reference(*leaves[:3], q_shape, k_shape, *leaves[3:], scale)
+    assert nerr(out.float(), ref.detach()) < tol
+    dout = randn(*ref.shape, seed=56).to(dtype)
+    ref.backward(dout.float())
+    dq_aug, dk, dv = ops.attention_bwd(q_aug, k_aug, vv, out, dout, lse, B, heads, ld, scale, residual=True)
+    drh, drw, drt = ops.relpos_augment_q_bwd(dq_aug, q_aug, q_shape, k_shape, rh, rw, rt, 1.0 / scale)
+    assert nerr(dq_aug[..., :96].float().reshape(B, heads, Nq, 96), leaves[0].grad) < tol
+    assert nerr(dk.float().reshape(B, heads, Nk, 96), leaves[1].grad) < tol
+    assert nerr(dv.float().reshape(B, heads, Nk, 96), leaves[2].grad) < tol
+    assert nerr(drh, leaves[3].grad) < tol
+    assert nerr(drw, leaves[4].grad) < tol
+    assert nerr(drt, leaves[5].grad) < tol
+
+
+def test_patch_embed_im2col_gemm():
+    from pmv_b200 import ops
+    clip = randn(2, 3, 4, 32, 24, seed=60)
+    w = randn(96, 3, 3, 7, 7, seed=61) * 0.05
+    b = randn(96, seed=62) * 0.1
+    ref = torch.nn.functional.conv3d(clip, w, b, stride=(2, 4, 4), padding=(1, 3, 3))
+    ref = ref.flatten(2).transpose(1, 2)
+    for dtype in DTYPES:
+        col, thw, K = ops.patch_im2col(clip, (3, 7, 7), (2, 4, 4), (1, 3, 3), dtype)
+        wp = torch.zeros(96, col.shape[1], dtype=dtype, device="cuda")
+        wp[:, :K] = w.reshape(96, K).to(dtype)
+        L_ = thw[0] * thw[1] * thw[2]
+        out = torch.zeros(2 * (L_ + 1), 96, device="cuda")
+        ops.linear_fwd(col, wp, b, torch.float32, out=out, out_group=L_, out_skip=1)
+        assert nerr(out.view(2, L_ + 1, 96)[:, 1:], ref) < TOL[dtype]
