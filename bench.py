@@ -1,0 +1,297 @@
+"""Benchmark of the MViTv2 pooling-attention hot path (BASELINE.json metric: MViTv2-S 16x4 clips/s).
+
+    python bench.py --gpus N --steps K --warmup W [--mode train|infer] [--batch B] [--impl reference]
+
+A step = one pass of the full MViTv2-S 16x4 model over one batch of synthetic 3x16x224x224 clips per GPU:
+  train (default): forward + backward through the hand-written kernels, bucketed NCCL gradient all-reduce
+                   overlapped with backward (N > 1), fused AdamW step.  Per-GPU batch 8 (BASELINE config 4).
+  infer          : bf16 forward, batch-partitioned (BASELINE config 3).
+`value` is timed with inputs resident in HBM; `e2e` repeats the run through the public module API with the
+clips in pinned host memory (H2D copy and a D2H read of the loss / logits inside the timed region).
+One JSON line is printed by rank 0.  --impl reference times the CPU oracle port of the reference path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "portrait-mode-video_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+FWD_GFLOP_PER_CLIP = 128.45  # SURVEY.md Appendix A.1 (2 x 64.22 GMAC, matches the published 64 G)
+CLIP_SHAPE = (3, 16, 224, 224)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, f"/tmp/pmv_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.proc.wait()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            c = [t.strip() for t in line.split(",")]
+            if len(c) < 8:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def summarize_kernels(rec, peaks):
+    """Per-family CUDA-event time from ops.record_kernels(); roofline of the dominant family."""
+    fam = {}
+    for name, meta, e0, e1 in rec:
+        ms = e0.elapsed_time(e1)
+        key = name.replace("pmv_", "")
+        if name == "pmv_gemm":
+            key = "gemm_tcgen05" if meta.get("tc") else "gemm_ffma"
+        if name == "pmv_attention_fwd":
+            key = "attention_fwd_tcgen05" if meta.get("tc") else "attention_fwd_cuda_core"
+        f = fam.setdefault(key, dict(ms=0.0, launches=0, flops=0.0, bytes=0.0))
+        f["ms"] += ms; f["launches"] += 1
+        f["flops"] += meta.get("flops", 0.0); f["bytes"] += meta.get("bytes", 0.0)
+    total = sum(f["ms"] for f in fam.values()) or 1.0
+    shares = {k: round(f["ms"] / total, 4) for k, f in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+    dom = max(fam, key=lambda k: fam[k]["ms"])
+    d = fam[dom]
+    if d["flops"] > 0:
+        ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
+        roof = dict(bound="tensor", kernel=dom, achieved=round(ach, 2), peak=peaks["bf16_sustained"], unit="TFLOP/s",
+                    frac=round(ach / peaks["bf16_sustained"], 4), traffic=None,
+                    peak_source=f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
+                    avg_launch_us=round(d["ms"] * 1e3 / d["launches"], 2), launches_per_pass=d["launches"])
+    else:
+        ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+        roof = dict(bound="hbm", kernel=dom, achieved=round(ach, 1), peak=peaks["hbm_gbs"], unit="GB/s",
+                    frac=round(ach / peaks["hbm_gbs"], 4), traffic=None, peak_source=f"MEASURED_PEAKS.json hbm_gbs ({peaks['source']})",
+                    avg_launch_us=round(d["ms"] * 1e3 / d["launches"], 2), launches_per_pass=d["launches"])
+    detail = {}
+    for k, f in fam.items():
+        e = dict(ms=round(f["ms"], 3), launches=f["launches"])
+        if f["flops"]:
+            e["tflops"] = round(f["flops"] / (f["ms"] * 1e-3) / 1e12, 2)
+        elif f["bytes"]:
+            e["gbs"] = round(f["bytes"] / (f["ms"] * 1e-3) / 1e9, 1)
+        detail[k] = e
+    return roof, shares, detail
+
+
+# ---------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference(mode: str, steps: int, warmup: int, threads: int):
+    """The oracle port of the reference path (same ATen CPU ops as the reference's eager path) on the host cores."""
+    from oracle import detgen, mvit_oracle as orc
+    torch.set_num_threads(threads)
+    params = detgen.det_params(orc.param_shapes(orc.MVITV2_S), 4321)
+    clip = detgen.det_normal((1,) + CLIP_SHAPE, 4321, "clip")
+    label = torch.tensor([7])
+    if mode == "train":
+        params = {k: v.requires_grad_(True) for k, v in params.items()}
+        opt = torch.optim.AdamW(list(params.values()), lr=1e-4, weight_decay=0.05)
+
+    def step():
+        if mode == "train":
+            opt.zero_grad(set_to_none=True)
+            loss = torch.nn.functional.cross_entropy(orc.mvit_forward(clip, params, orc.MVITV2_S), label)
+            loss.backward()
+            opt.step()
+            return float(loss)
+        with torch.no_grad():
+            return float(orc.mvit_forward(clip, params, orc.MVITV2_S)[0, 0])
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return 1.0 / dt, dt * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="train", choices=["train", "infer"])
+    ap.add_argument("--batch", type=int, default=8, help="clips per GPU per step")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    threads = os.cpu_count() or 1
+    workload = (f"MViTv2-S 16x4 {'training step (fwd+bwd+grad all-reduce+AdamW)' if args.mode == 'train' else 'inference forward'}, "
+                f"400 classes, random init, {args.batch} synthetic 3x16x224x224 clips per GPU")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+        v, ms = cpu_reference(args.mode, steps, warm, threads)
+        sample = f"oracle port of the reference MViT ({args.mode}), 1 clip per step, fp32, {steps} steps after {warm} warm-up"
+        print(json.dumps({"impl": "reference", "metric": f"MViTv2-S 16x4 {args.mode} clips/sec", "value": round(v, 4), "unit": "clips/s",
+                          "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": round(ms, 2), "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": workload, "device": "cpu"},
+                          "cpu_baseline": {"value": round(v, 4), "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample},
+                          "e2e": {"value": round(v, 4), "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    assert torch.cuda.is_available(), "bench.py (impl ours) needs a CUDA device: there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from pmv_b200 import mvit, ops
+    from pmv_b200.ddp import GradAllReducer
+
+    peaks = load_peaks()
+    T = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    torch.manual_seed(1234)
+    model = mvit.MViT(mvit.MVITV2_S, compute_dtype=T).to(dev)
+    B = args.batch
+    g = torch.Generator(device="cpu").manual_seed(100 + rank)
+    host_clips = torch.randn((B,) + CLIP_SHAPE, generator=g).pin_memory()
+    host_labels = torch.randint(0, 400, (B,), generator=g).pin_memory()
+    clips, labels = host_clips.to(dev), host_labels.to(dev)
+    train = args.mode == "train"
+    if train:
+        model.train()
+        reducer = GradAllReducer(model, bucket_mb=25.0)
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.05, fused=True)
+    else:
+        model.eval()
+        model.head.act = None
+
+    def step(c, l):
+        if train:
+            reducer.zero_grad()
+            loss = torch.nn.functional.cross_entropy(model([c]), l)
+            loss.backward()
+            reducer.finish()
+            opt.step()
+            return loss
+        with torch.no_grad():
+            return model([c])
+
+    def e2e_step():
+        c = host_clips.to(dev, non_blocking=True)
+        l = host_labels.to(dev, non_blocking=True)
+        out = step(c, l)
+        return out.float().cpu()  # D2H read of the loss (train) / logits (infer)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / n
+
+    for _ in range(max(args.warmup, 3)):
+        step(clips, labels)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ops.LAUNCHES
+    ms_dev = timed(lambda: step(clips, labels), args.steps)
+    launches = (ops.LAUNCHES - l0) // args.steps
+    ms_e2e = timed(e2e_step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # per-kernel CUDA-event times over two more passes of the same step (events on the launching stream)
+    with ops.record_kernels() as rec:
+        for _ in range(2):
+            step(clips, labels)
+        torch.cuda.synchronize()
+        roof, shares, detail = summarize_kernels(rec, peaks)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    total_clips = B * world
+    value = total_clips / (ms_dev * 1e-3)
+    e2e_v = total_clips / (ms_e2e * 1e-3)
+    flop_per_clip = FWD_GFLOP_PER_CLIP * (3 if train else 1)
+    line = {
+        "metric": f"MViTv2-S 16x4 {'train' if train else 'infer'} clips/sec", "value": round(value, 2), "unit": "clips/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_dev, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": workload, "per_gpu_batch": B, "global_batch": total_clips, "mode": args.mode,
+                   "parallelism": f"dp{world} (batch-sharded; {'bucketed NCCL grad all-reduce overlapped with backward' if train else 'no collective'})",
+                   "l2": "no explicit flush: per-step activations (>2 GB) exceed the 126 MB L2",
+                   "model_tflops_per_gpu": round(flop_per_clip * B / (ms_dev * 1e-3) / 1e3, 1)},
+        "e2e": {"value": round(e2e_v, 2), "unit": "clips/s", "h2d_bytes_per_step": host_clips.numel() * 4 + host_labels.numel() * 8,
+                "d2h_bytes_per_step": 4 if train else B * 400 * 4, "ms_per_step": round(ms_e2e, 3)},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernel_time_share": shares, "kernels": detail,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        v, ms = cpu_reference(args.mode, 2 if train else 3, 1, threads)
+        line["cpu_baseline"] = {"value": round(v, 4), "unit": "clips/s", "cores": threads, "kind": "port",
+                                "sample": f"oracle port of the reference MViT ({args.mode}), 1 clip per step, fp32, "
+                                          f"{2 if train else 3} steps after 1 warm-up ({ms:.0f} ms/step)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,113 @@
+"""Batch-sharded data parallelism: bucketed gradient all-reduce overlapped with backward.
+
+Mirrors what the reference gets from ``torch.nn.parallel.DistributedDataParallel`` in
+models/build.py:71-79 (bucketed all-reduce launched as gradients become ready, mean over ranks,
+find_unused_parameters=False) and the optional fp16-compressed hook of build.py:80-83 (here: bf16).
+
+Design: parameters are packed, in reverse registration order (the order backward produces gradients),
+into flat fp32 buckets; each parameter's ``.grad`` is a view into its bucket, so no gather copy is needed.
+A post-accumulate-grad hook counts down the bucket; when the last gradient of a bucket has been written,
+the bucket is all-reduced on a dedicated communication stream (NCCL over NVLink / NVSwitch) while backward
+keeps running on the compute stream.  ``finish()`` makes the compute stream wait for the reductions.
+Inference needs no collective (pure batch partitioning, tools/test_net.py:131-132 gathers logits only).
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+import torch.distributed as dist
+
+
+class _Bucket:
+    def __init__(self, params, device, compress_dtype):
+        self.params = params
+        n = sum(p.numel() for p in params)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=device)
+        off = 0
+        for p in params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.pending = len(params)
+        self.work = None
+        self.event = torch.cuda.Event() if device.type == "cuda" else None
+        self.compressed = torch.empty(n, dtype=compress_dtype, device=device) if compress_dtype is not None else None
+
+
+class GradAllReducer:
+    def __init__(self, module: torch.nn.Module, bucket_mb: float = 25.0, compress_dtype=None, process_group=None):
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        params = [p for p in module.parameters() if p.requires_grad]
+        assert params, "no trainable parameters"
+        self.device = params[0].device
+        self.stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self.buckets: List[_Bucket] = []
+        cur, cur_bytes, limit = [], 0, int(bucket_mb * 2 ** 20)
+        for p in reversed(params):
+            cur.append(p)
+            cur_bytes += p.numel() * 4
+            if cur_bytes >= limit:
+                self.buckets.append(_Bucket(cur, self.device, compress_dtype))
+                cur, cur_bytes = [], 0
+        if cur:
+            self.buckets.append(_Bucket(cur, self.device, compress_dtype))
+        self._owner = {}
+        for b in self.buckets:
+            for p in b.params:
+                self._owner[p] = b
+                p.register_post_accumulate_grad_hook(self._hook)
+
+    @property
+    def num_buckets(self):
+        return len(self.buckets)
+
+    def zero_grad(self):
+        for b in self.buckets:
+            b.flat.zero_()
+            b.pending = len(b.params)
+            b.work = None
+
+    def _hook(self, p):
+        b = self._owner[p]
+        b.pending -= 1
+        if b.pending == 0 and self.world > 1:
+            self._launch(b)
+
+    def _launch(self, b: _Bucket):
+        if self.stream is not None:
+            b.event.record(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.stream):
+                self.stream.wait_event(b.event)
+                self._reduce(b)
+        else:
+            self._reduce(b)
+
+    def _reduce(self, b: _Bucket):
+        buf = b.flat
+        if b.compressed is not None:
+            b.compressed.copy_(b.flat)
+            buf = b.compressed
+        avg = dist.ReduceOp.AVG if self.device.type == "cuda" else dist.ReduceOp.SUM
+        b.work = dist.all_reduce(buf, op=avg, group=self.group, async_op=True)
+        b.avg_done = self.device.type == "cuda"
+
+    def finish(self):
+        """Call after backward(): waits for every bucket reduction; gradients are then the mean over ranks."""
+        if self.world == 1:
+            return
+        for b in self.buckets:
+            assert b.pending == 0, "a parameter received no gradient (find_unused_parameters=False semantics)"
+            if self.stream is not None:
+                with torch.cuda.stream(self.stream):
+                    b.work.wait()
+                    if b.compressed is not None:
+                        b.flat.copy_(b.compressed)
+            else:
+                b.work.wait()
+                if b.compressed is not None:
+                    b.flat.copy_(b.compressed)
+                if not b.avg_done:
+                    b.flat.div_(self.world)
+        if self.stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)

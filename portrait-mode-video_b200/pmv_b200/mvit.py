@@ -1,0 +1,140 @@
+"""MViTv2 backbone harness: re-states video_model_builder.MViT (video_model_builder.py:1726-2171) for the v2
+configurations (cls token, no abs-pos, rel-pos spatial+temporal, residual pooling, dim_mul_in_att) on top of
+the pmv_b200 MultiScaleBlock.  The reference MViT itself is kept unchanged by the drop-in;
+this class exists so the repository can run and benchmark the full model without the reference's fvcore /
+detectron2 / pytorchvideo dependencies.  Parameter names match the reference state_dict one to one."""
+from __future__ import annotations
+
+from functools import partial
+
+import torch
+import torch.nn as nn
+from torch.nn.init import trunc_normal_
+
+from . import functional as Fn
+from .attention import MultiScaleBlock, set_compute_dtype
+from .common import compute_dtype_of
+from .stem import PatchEmbed
+
+MVITV2_S = dict(  # MViT/configs/Kinetics/MVITv2_S_16x4.yaml:8-44
+    name="MViTv2-S 16x4", num_frames=16, crop=(224, 224), depth=16, embed_dim=96, num_heads=1, mlp_ratio=4.0,
+    patch_kernel=(3, 7, 7), patch_stride=(2, 4, 4), patch_padding=(1, 3, 3),
+    dim_mul={1: 2.0, 3: 2.0, 14: 2.0}, head_mul={1: 2.0, 3: 2.0, 14: 2.0},
+    pool_q_stride={1: (1, 2, 2), 3: (1, 2, 2), 14: (1, 2, 2)}, kv_stride_adaptive=(1, 8, 8),
+    num_classes=400, drop_path_rate=0.2, head_dropout=0.5,
+)
+MVITV2_B = dict(  # MViT/configs/Kinetics/MVITv2_B_32x3.yaml:8-44
+    name="MViTv2-B 32x3", num_frames=32, crop=(224, 224), depth=24, embed_dim=96, num_heads=1, mlp_ratio=4.0,
+    patch_kernel=(3, 7, 7), patch_stride=(2, 4, 4), patch_padding=(1, 3, 3),
+    dim_mul={2: 2.0, 5: 2.0, 21: 2.0}, head_mul={2: 2.0, 5: 2.0, 21: 2.0},
+    pool_q_stride={2: (1, 2, 2), 5: (1, 2, 2), 21: (1, 2, 2)}, kv_stride_adaptive=(1, 8, 8),
+    num_classes=400, drop_path_rate=0.3, head_dropout=0.5,
+)
+
+
+def round_width(width, multiplier, min_width=1, divisor=1):
+    """models/utils.py:15-31."""
+    if not multiplier:
+        return width
+    width *= multiplier
+    min_width = min_width or divisor
+    out = max(min_width, int(width + divisor / 2) // divisor * divisor)
+    if out < 0.9 * width:
+        out += divisor
+    return int(out)
+
+
+def block_schedule(cfg):
+    """(dim, dim_out, heads, thw, stride_q, stride_kv) per block — video_model_builder.py:1862-1967."""
+    depth = cfg["depth"]
+    dim_mul = [cfg["dim_mul"].get(i, 1.0) for i in range(depth + 1)]
+    head_mul = [cfg["head_mul"].get(i, 1.0) for i in range(depth + 1)]
+    thw = [cfg["num_frames"] // cfg["patch_stride"][0], cfg["crop"][0] // cfg["patch_stride"][1],
+           cfg["crop"][1] // cfg["patch_stride"][2]]
+    skv = list(cfg["kv_stride_adaptive"])
+    embed, heads = cfg["embed_dim"], cfg["num_heads"]
+    out = []
+    for i in range(depth):
+        sq = list(cfg["pool_q_stride"].get(i, (1, 1, 1)))
+        skv = [max(skv[d] // sq[d], 1) for d in range(3)]
+        heads = round_width(heads, head_mul[i])
+        dim_out = round_width(embed, dim_mul[i], divisor=round_width(heads, head_mul[i]))
+        out.append(dict(dim=embed, dim_out=dim_out, num_heads=heads, thw=list(thw), stride_q=sq, stride_kv=list(skv)))
+        thw = [n // s for n, s in zip(thw, sq)]
+        embed = dim_out
+    return out
+
+
+class _Head(nn.Module):
+    """TransformerBasicHead (head_helper.py:502-577): dropout (train) -> Linear -> softmax (eval).  Left in
+    PyTorch: a [B,768] x [768,400] product is not on the hot path."""
+
+    def __init__(self, dim_in, num_classes, dropout_rate=0.0, act="softmax"):
+        super().__init__()
+        if dropout_rate > 0.0:
+            self.dropout = nn.Dropout(dropout_rate)
+        self.projection = nn.Linear(dim_in, num_classes, bias=True)
+        self.act = nn.Softmax(dim=1) if act == "softmax" else None
+
+    def forward(self, x):
+        if hasattr(self, "dropout"):
+            x = self.dropout(x)
+        x = self.projection(x)
+        if not self.training and self.act is not None:
+            x = self.act(x)
+        return x.view(x.shape[0], -1)
+
+
+class MViT(nn.Module):
+    compute_dtype = torch.bfloat16
+
+    def __init__(self, cfg=MVITV2_S, compute_dtype=torch.bfloat16):
+        super().__init__()
+        self.cfg = cfg
+        norm_layer = partial(nn.LayerNorm, eps=1e-6)
+        embed = cfg["embed_dim"]
+        self.patch_embed = PatchEmbed(3, embed, cfg["patch_kernel"], cfg["patch_stride"], cfg["patch_padding"])
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed))
+        dpr = [x.item() for x in torch.linspace(0, cfg["drop_path_rate"], cfg["depth"])]
+        self.blocks = nn.ModuleList()
+        sched = block_schedule(cfg)
+        self.T, self.H, self.W = sched[0]["thw"]
+        for i, b in enumerate(sched):
+            self.blocks.append(MultiScaleBlock(
+                dim=b["dim"], dim_out=b["dim_out"], num_heads=b["num_heads"], input_size=b["thw"],
+                mlp_ratio=cfg["mlp_ratio"], qkv_bias=True, drop_rate=0.0, drop_path=dpr[i], norm_layer=norm_layer,
+                kernel_q=[3, 3, 3], kernel_kv=[3, 3, 3], stride_q=b["stride_q"], stride_kv=b["stride_kv"], mode="conv",
+                has_cls_embed=True, pool_first=False, rel_pos_spatial=True, rel_pos_temporal=True,
+                rel_pos_zero_init=False, residual_pooling=True, dim_mul_in_att=True, separate_qkv=False,
+                hw_switch_auto=cfg.get("hw_switch_auto", False)))
+        last = sched[-1]["dim_out"]
+        self.norm = norm_layer(last)
+        self.head = _Head(last, cfg["num_classes"], cfg.get("head_dropout", 0.0))
+        trunc_normal_(self.cls_token, std=0.02)
+        self.apply(self._init_weights)
+        set_compute_dtype(self, compute_dtype)
+
+    @staticmethod
+    def _init_weights(m):  # video_model_builder.py:2018-2025
+        if isinstance(m, (nn.Linear, nn.Conv2d, nn.Conv3d)):
+            nn.init.trunc_normal_(m.weight, std=0.02)
+            if isinstance(m, nn.Linear) and m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    def forward_features(self, clip):
+        x, thw = self.patch_embed.forward_tokens(clip, self.cls_token)        # :2100-2121
+        assert tuple(thw) == (self.T, self.H, self.W), thw                    # :2106
+        for blk in self.blocks:                                               # :2144-2146
+            x, thw = blk(x, thw)
+        x = Fn.layer_norm(x, self.norm.weight, self.norm.bias, torch.float32, self.norm.eps)  # :2163
+        return x[:, 0]                                                        # :2165
+
+    def forward(self, x, pm=None):
+        clip = x[0] if isinstance(x, (list, tuple)) else x                    # :2099 takes a list
+        if pm is not None:
+            raise NotImplementedError("portrait/landscape batch routing (video_model_builder.py:2075-2096) "
+                                      "is row f1 of SURVEY.md section 8 (next)")
+        return self.head(self.forward_features(clip))

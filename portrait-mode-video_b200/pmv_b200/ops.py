@@ -19,6 +19,38 @@ def _tc_default(dtype) -> int:
     return 1 if dtype == torch.bfloat16 else 0
 
 
+# ----------------------------------------------------------------------------- launch accounting
+LAUNCHES = 0       # kernels of libpmv_b200.so launched so far (bench.py reports the delta as gpu_launches)
+_RECORDER = None   # optional list of (kind, meta, start_event, end_event) for per-kernel CUDA-event timing
+
+
+class record_kernels:
+    """Context manager: time every C-ABI launch with CUDA events on the launching stream (bench.py roofline)."""
+
+    def __enter__(self):
+        global _RECORDER
+        _RECORDER = []
+        return _RECORDER
+
+    def __exit__(self, *exc):
+        global _RECORDER
+        _RECORDER = None
+
+
+def _run(name: str, nkernels: int, meta, *args):
+    global LAUNCHES
+    LAUNCHES += nkernels
+    fn = getattr(L.lib(), name)
+    if _RECORDER is None:
+        L.check(fn(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    L.check(fn(*args), name)
+    e1.record()
+    _RECORDER.append((name, meta, e0, e1))
+
+
 # ----------------------------------------------------------------------------- LayerNorm
 def layernorm_fwd(x: torch.Tensor, gamma, beta, out_dtype, save_stats=True, eps=LN_EPS):
     assert x.dtype == torch.float32 and x.is_contiguous()
@@ -29,8 +61,8 @@ def layernorm_fwd(x: torch.Tensor, gamma, beta, out_dtype, save_stats=True, eps=
     if save_stats:
         mean = torch.empty(rows, dtype=torch.float32, device=x.device)
         rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
-    L.check(L.lib().pmv_layernorm_fwd(L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(y), L.dt(out_dtype), L.ptr(mean),
-                                      L.ptr(rstd), rows, Cdim, eps, L.stream()), "pmv_layernorm_fwd")
+    _run("pmv_layernorm_fwd", 1, dict(bytes=rows * Cdim * (4 + y.element_size())), L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(y), L.dt(out_dtype), L.ptr(mean),
+                                      L.ptr(rstd), rows, Cdim, eps, L.stream())
     return y, mean, rstd
 
 
@@ -41,9 +73,9 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dx_accum: Optional[torch.Tensor] = N
     dy = dy.contiguous()
     dx = dx_accum if dx_accum is not None else torch.empty_like(x)
     dgb = torch.zeros(2, Cdim, dtype=torch.float32, device=x.device)
-    L.check(L.lib().pmv_layernorm_bwd(L.ptr(dy), L.dt(dy), L.ptr(x), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), L.ptr(dx),
+    _run("pmv_layernorm_bwd", 1, dict(bytes=rows * Cdim * (8 + dy.element_size() + (4 if dx_accum is not None else 0))), L.ptr(dy), L.dt(dy), L.ptr(x), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), L.ptr(dx),
                                       1 if dx_accum is not None else 0, L.ptr(dgb[0]), L.ptr(dgb[1]), rows, Cdim,
-                                      L.stream()), "pmv_layernorm_bwd")
+                                      L.stream())
     return dx, dgb[0], dgb[1]
 
 
@@ -64,8 +96,8 @@ def gemm(layout: int, A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, 
         epi = L.Epilogue(L.ptr(bias), act, L.ptr(aux_in), L.ptr(aux_out), aux.stride(0) if aux is not None else 0,
                          L.ptr(row_scale), rows_per_scale, L.ptr(residual),
                          residual.stride(0) if residual is not None else 0, int(accumulate), out_group, out_skip)
-    L.check(L.lib().pmv_gemm(layout, L.ptr(A), lda, L.ptr(B), ldb, L.ptr(out), ldo, M, N, K, L.dt(A), L.dt(out),
-                             C.byref(epi) if epi is not None else None, use_tc, split_k, L.stream()), "pmv_gemm")
+    _run("pmv_gemm", 1, dict(flops=2 * M * N * K, layout=layout, tc=use_tc, shape=(M, N, K)), layout, L.ptr(A), lda, L.ptr(B), ldb, L.ptr(out), ldo, M, N, K, L.dt(A), L.dt(out),
+                             C.byref(epi) if epi is not None else None, use_tc, split_k, L.stream())
     return out
 
 
@@ -109,9 +141,9 @@ def colsum_cast(x2d, cast_dtype=None, row_scale=None, rows_per_scale=1, want_sum
     rows, cols = x2d.shape
     s = torch.zeros(cols, dtype=torch.float32, device=x2d.device) if want_sum else None
     c = torch.empty(rows, cols, dtype=cast_dtype, device=x2d.device) if cast_dtype is not None else None
-    L.check(L.lib().pmv_colsum_cast(L.ptr(x2d), L.dt(x2d), x2d.stride(0), rows, cols, L.ptr(row_scale), rows_per_scale,
+    _run("pmv_colsum_cast", 1, dict(bytes=rows * cols * (x2d.element_size() + (c.element_size() if c is not None else 0))), L.ptr(x2d), L.dt(x2d), x2d.stride(0), rows, cols, L.ptr(row_scale), rows_per_scale,
                                     L.ptr(s), L.ptr(c), L.dt(cast_dtype) if cast_dtype is not None else 0,
-                                    c.stride(0) if c is not None else 0, L.stream()), "pmv_colsum_cast")
+                                    c.stride(0) if c is not None else 0, L.stream())
     return s, c
 
 
@@ -126,9 +158,9 @@ def pool_ln_fwd(qkv: torch.Tensor, which: int, heads: int, thw: Sequence[int], s
     B, N = qkv.shape[0], qkv.shape[1]
     T, H, W = thw
     view = qkv[:, :, which]
-    L.check(L.lib().pmv_pool_ln_fwd(view.data_ptr(), qkv.stride(0), qkv.stride(1), qkv.stride(3), L.ptr(w), L.ptr(gamma),
+    _run("pmv_pool_ln_fwd", 1, dict(bytes=(B * N * heads * 96 + out.shape[0] * out.shape[1] * out.shape[2] * 96) * qkv.element_size()), view.data_ptr(), qkv.stride(0), qkv.stride(1), qkv.stride(3), L.ptr(w), L.ptr(gamma),
                                     L.ptr(beta), L.ptr(out), out.stride(2), B, heads, T, H, W, stride_hw, eps, L.dt(qkv),
-                                    L.stream()), "pmv_pool_ln_fwd")
+                                    L.stream())
     return out
 
 
@@ -137,10 +169,10 @@ def pool_ln_bwd(qkv, which, heads, thw, stride_hw, w, gamma, dout, dqkv, dw, dga
     T, H, W = thw
     Lo = T * pooled_hw(H, stride_hw) * pooled_hw(W, stride_hw)
     ws = torch.empty(B * heads * Lo * 96, dtype=torch.float32, device=qkv.device)
-    L.check(L.lib().pmv_pool_ln_bwd(qkv[:, :, which].data_ptr(), qkv.stride(0), qkv.stride(1), qkv.stride(3), L.ptr(w),
+    _run("pmv_pool_ln_bwd", 2, dict(bytes=(2 * B * qkv.shape[1] * heads * 96 + dout.shape[0] * dout.shape[1] * dout.shape[2] * 96) * qkv.element_size()), qkv[:, :, which].data_ptr(), qkv.stride(0), qkv.stride(1), qkv.stride(3), L.ptr(w),
                                     L.ptr(gamma), L.ptr(dout), dout.stride(2), dqkv[:, :, which].data_ptr(), L.ptr(dw),
                                     L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), B, heads, T, H, W, stride_hw, eps, L.dt(qkv),
-                                    L.stream()), "pmv_pool_ln_bwd")
+                                    L.stream())
 
 
 def maxpool_skip_fwd(x, thw):
@@ -148,7 +180,7 @@ def maxpool_skip_fwd(x, thw):
     T, H, W = thw
     Lo = T * pooled_hw(H, 2) * pooled_hw(W, 2)
     y = torch.empty(B, 1 + Lo, Cdim, dtype=torch.float32, device=x.device)
-    L.check(L.lib().pmv_maxpool_skip_fwd(L.ptr(x), L.ptr(y), B, T, H, W, Cdim, L.stream()), "pmv_maxpool_skip_fwd")
+    _run("pmv_maxpool_skip_fwd", 1, dict(bytes=(x.numel() + y.numel()) * 4), L.ptr(x), L.ptr(y), B, T, H, W, Cdim, L.stream())
     return y
 
 
@@ -156,8 +188,7 @@ def maxpool_skip_bwd(x, dy, thw, dx_accum=None):
     B, N, Cdim = x.shape
     T, H, W = thw
     dx = dx_accum if dx_accum is not None else torch.zeros_like(x)
-    L.check(L.lib().pmv_maxpool_skip_bwd(L.ptr(x), L.ptr(dy.contiguous()), L.ptr(dx), B, T, H, W, Cdim, L.stream()),
-            "pmv_maxpool_skip_bwd")
+    _run("pmv_maxpool_skip_bwd", 1, dict(bytes=(2 * x.numel() + dy.numel()) * 4), L.ptr(x), L.ptr(dy.contiguous()), L.ptr(dx), B, T, H, W, Cdim, L.stream())
     return dx
 
 
@@ -191,14 +222,13 @@ def relpos_augment_q(q_aug, q_shape, k_shape, rel_h, rel_w, rel_t, inv_scale):
     dev = q_aug.device
     ih, iw, it = (rel_index_table(q_shape[1], k_shape[1], dev), rel_index_table(q_shape[2], k_shape[2], dev),
                   rel_index_table(q_shape[0], k_shape[0], dev))
-    L.check(L.lib().pmv_relpos_augment_q(L.ptr(q_aug), ld, L.ptr(rel_h), L.ptr(rel_w), L.ptr(rel_t), L.ptr(ih), L.ptr(iw),
-                                         L.ptr(it), BH, *q_shape, *k_shape, inv_scale, L.dt(q_aug), L.stream()),
-            "pmv_relpos_augment_q")
+    _run("pmv_relpos_augment_q", 1, dict(bytes=BH * Nq * ld * q_aug.element_size()), L.ptr(q_aug), ld, L.ptr(rel_h), L.ptr(rel_w), L.ptr(rel_t), L.ptr(ih), L.ptr(iw),
+                                         L.ptr(it), BH, *q_shape, *k_shape, inv_scale, L.dt(q_aug), L.stream())
 
 
 def relpos_augment_k(k_aug, k_shape):
     BH, Nk, ld = k_aug.shape
-    L.check(L.lib().pmv_relpos_augment_k(L.ptr(k_aug), ld, BH, *k_shape, L.dt(k_aug), L.stream()), "pmv_relpos_augment_k")
+    _run("pmv_relpos_augment_k", 1, dict(bytes=BH * Nk * (ld - 96) * k_aug.element_size()), L.ptr(k_aug), ld, BH, *k_shape, L.dt(k_aug), L.stream())
 
 
 def relpos_augment_q_bwd(dq_aug, q_aug, q_shape, k_shape, rel_h, rel_w, rel_t, inv_scale):
@@ -208,10 +238,9 @@ def relpos_augment_q_bwd(dq_aug, q_aug, q_shape, k_shape, rel_h, rel_w, rel_t, i
     ih, iw, it = (rel_index_table(q_shape[1], k_shape[1], dev), rel_index_table(q_shape[2], k_shape[2], dev),
                   rel_index_table(q_shape[0], k_shape[0], dev))
     dh, dw, dt_ = torch.zeros_like(rel_h), torch.zeros_like(rel_w), torch.zeros_like(rel_t)
-    L.check(L.lib().pmv_relpos_augment_q_bwd(L.ptr(dq_aug), L.ptr(q_aug), ld, L.ptr(rel_h), L.ptr(rel_w), L.ptr(rel_t),
+    _run("pmv_relpos_augment_q_bwd", 1, dict(bytes=2 * BH * Nq * ld * q_aug.element_size()), L.ptr(dq_aug), L.ptr(q_aug), ld, L.ptr(rel_h), L.ptr(rel_w), L.ptr(rel_t),
                                              L.ptr(ih), L.ptr(iw), L.ptr(it), L.ptr(dh), L.ptr(dw), L.ptr(dt_), BH,
-                                             *q_shape, *k_shape, inv_scale, L.dt(q_aug), L.stream()),
-            "pmv_relpos_augment_q_bwd")
+                                             *q_shape, *k_shape, inv_scale, L.dt(q_aug), L.stream())
     return dh, dw, dt_
 
 
@@ -221,9 +250,8 @@ def attention_fwd(q_aug, k_aug, v, B, heads, kd, scale, residual=True, want_lse=
     out = torch.empty(B, Nq, heads * 96, dtype=q_aug.dtype, device=q_aug.device)
     lse = torch.empty(BH, Nq, dtype=torch.float32, device=q_aug.device) if want_lse else None
     use_tc = _tc_default(q_aug.dtype) if tc is None else int(tc)
-    L.check(L.lib().pmv_attention_fwd(L.ptr(q_aug), L.ptr(k_aug), ld, kd, L.ptr(v), v.stride(1), L.ptr(out), L.ptr(lse),
-                                      B, heads, Nq, Nk, scale, int(residual), L.dt(q_aug), use_tc, L.stream()),
-            "pmv_attention_fwd")
+    _run("pmv_attention_fwd", 1, dict(flops=4 * BH * Nq * Nk * 96, tc=use_tc, shape=(BH, Nq, Nk, kd)), L.ptr(q_aug), L.ptr(k_aug), ld, kd, L.ptr(v), v.stride(1), L.ptr(out), L.ptr(lse),
+                                      B, heads, Nq, Nk, scale, int(residual), L.dt(q_aug), use_tc, L.stream())
     return out, lse
 
 
@@ -235,10 +263,9 @@ def attention_bwd(q_aug, k_aug, v, out, dout, lse, B, heads, kd, scale, residual
     dv = torch.empty(BH, Nk, 96, dtype=q_aug.dtype, device=q_aug.device)
     ws = torch.empty(L.lib().pmv_attention_bwd_workspace_bytes(B, heads, Nq, Nk) // 4, dtype=torch.float32,
                      device=q_aug.device)
-    L.check(L.lib().pmv_attention_bwd(L.ptr(q_aug), L.ptr(k_aug), ld, kd, L.ptr(v), v.stride(1), L.ptr(out),
+    _run("pmv_attention_bwd", 3, dict(flops=10 * BH * Nq * Nk * 96, shape=(BH, Nq, Nk, kd)), L.ptr(q_aug), L.ptr(k_aug), ld, kd, L.ptr(v), v.stride(1), L.ptr(out),
                                       L.ptr(dout.contiguous()), L.ptr(lse), L.ptr(dq_aug), L.ptr(dk), 96, L.ptr(dv), 96,
-                                      L.ptr(ws), B, heads, Nq, Nk, scale, int(residual), L.dt(q_aug), L.stream()),
-            "pmv_attention_bwd")
+                                      L.ptr(ws), B, heads, Nq, Nk, scale, int(residual), L.dt(q_aug), L.stream())
     return dq_aug, dk, dv
 
 
@@ -251,6 +278,6 @@ def patch_im2col(clip, kernel, stride, padding, dtype):
     K = Cin * kernel[0] * kernel[1] * kernel[2]
     ld = (K + 63) // 64 * 64
     col = torch.empty(B * To * Ho * Wo, ld, dtype=dtype, device=clip.device)
-    L.check(L.lib().pmv_patch_im2col(L.ptr(clip), L.ptr(col), ld, B, Cin, T, H, W, *kernel, *stride, *padding, L.dt(dtype),
-                                     L.stream()), "pmv_patch_im2col")
+    _run("pmv_patch_im2col", 1, dict(bytes=clip.numel() * 4 + col.numel() * col.element_size()), L.ptr(clip), L.ptr(col), ld, B, Cin, T, H, W, *kernel, *stride, *padding, L.dt(dtype),
+                                     L.stream())
     return col, (To, Ho, Wo), K

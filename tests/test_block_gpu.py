@@ -1,0 +1,157 @@
+"""Block- and model-level parity of the CUDA path, called through the reference-shaped modules
+(pmv_b200.attention.MultiScaleBlock / MultiScaleAttention, pmv_b200.mvit.MViT):
+  * against the golden fixtures the UNMODIFIED reference produced (tests/golden/),
+  * against the oracle on the real MViTv2-S stage shapes, forward + backward.
+Tolerances (normalised max error): fp32 mode 1e-4, bf16 mode 1e-2 on outputs (north star); bf16 gradients
+3e-2 (one extra bf16 rounding per backward operand)."""
+import glob
+import json
+import os
+from functools import partial
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+BLOCK_FILES = sorted(glob.glob(os.path.join(GOLDEN, "blk_*.npz")))
+OUT_TOL = {torch.float32: 1e-4, torch.bfloat16: 1e-2}
+GRAD_TOL = {torch.float32: 1e-4, torch.bfloat16: 3e-2}
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+def nerr(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def make_block(cfg, dtype):
+    from pmv_b200.attention import MultiScaleBlock, set_compute_dtype
+    blk = MultiScaleBlock(
+        dim=cfg["dim"], dim_out=cfg["dim_out"], num_heads=cfg["num_heads"], input_size=cfg["thw"], mlp_ratio=4.0,
+        qkv_bias=True, drop_rate=0.0, drop_path=0.0, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6),
+        kernel_q=[3, 3, 3], kernel_kv=[3, 3, 3], stride_q=cfg["stride_q"], stride_kv=cfg["stride_kv"], mode="conv",
+        has_cls_embed=True, pool_first=False, rel_pos_spatial=True, rel_pos_temporal=True, rel_pos_zero_init=False,
+        residual_pooling=True, dim_mul_in_att=True, separate_qkv=False, hw_switch_auto=cfg.get("hw_switch_auto", False))
+    return set_compute_dtype(blk, dtype).cuda()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("path", BLOCK_FILES, ids=[os.path.basename(p)[:-4] for p in BLOCK_FILES])
+def test_block_matches_reference_fixture(path, dtype):
+    from oracle import detgen, mvit_oracle as orc
+    z = np.load(path)
+    cfg = json.loads(str(z["cfg"]))
+    name = os.path.basename(path)[:-4]
+    shapes = orc.block_param_shapes("", cfg["dim"], cfg["dim_out"], cfg["num_heads"], cfg["thw"], cfg["stride_q"], cfg["stride_kv"])
+    params = detgen.det_params(shapes, cfg["seed"])
+    blk = make_block(cfg, dtype)
+    blk.load_state_dict(params, strict=True)  # the reference's own state_dict keys
+    N = 1 + int(np.prod(cfg["thw"]))
+    x = detgen.det_normal((cfg["B"], N, cfg["dim"]), cfg["seed"], name + ".x").cuda().requires_grad_(True)
+    y, thw = blk(x, cfg["thw"])
+    assert list(thw) == cfg["thw_out"]
+    assert nerr(y.detach(), z["y"]) < OUT_TOL[dtype]
+    dy = detgen.det_normal(tuple(y.shape), cfg["seed"], name + ".dy").cuda()
+    y.backward(dy)
+    gt = GRAD_TOL[dtype]
+    assert nerr(x.grad, z["dx"]) < gt
+    for k, p in blk.named_parameters():
+        g = p.grad.reshape(-1).double().cpu()
+        if f"g::{k}::full" in z.files:
+            ref = torch.from_numpy(z[f"g::{k}::full"]).double()
+            if k.endswith("norm_k.bias"):  # analytically zero
+                assert float(g.abs().max()) < (1e-4 if dtype == torch.float32 else 0.5), k
+            else:
+                assert nerr(g, ref) < gt, k
+        else:
+            idx = torch.from_numpy(z[f"g::{k}::idx"])
+            rms = float(np.sqrt(z[f"g::{k}::sumsq"] / g.numel()))
+            gmax = float(g.abs().max())
+            assert float((g[idx] - torch.from_numpy(z[f"g::{k}::val"]).double()).abs().max()) < gt * max(gmax, rms), k
+            assert abs(float((g * g).sum()) - float(z[f"g::{k}::sumsq"])) < 4 * gt * float(z[f"g::{k}::sumsq"]), k
+
+
+STAGES = [  # dim, dim_out, heads, thw, stride_q, stride_kv  (the 7 distinct MViTv2-S rows)
+    (96, 96, 1, [8, 56, 56], 1, 8), (96, 192, 2, [8, 56, 56], 2, 4), (192, 192, 2, [8, 28, 28], 1, 4),
+    (192, 384, 4, [8, 28, 28], 2, 2), (384, 384, 4, [8, 14, 14], 1, 2), (384, 768, 8, [8, 14, 14], 2, 1),
+    (768, 768, 8, [8, 7, 7], 1, 1),
+]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("stage", range(len(STAGES)))
+def test_stage_shapes_fwd_bwd_vs_oracle(stage, dtype):
+    """BASELINE config 2: one MultiScaleBlock at every MViTv2-S stage shape, fwd + bwd, B = 1, against the
+    oracle evaluated on the GPU in fp32."""
+    from oracle import detgen, mvit_oracle as orc
+    dim, dim_out, heads, thw, sq, skv = STAGES[stage]
+    cfg = dict(dim=dim, dim_out=dim_out, num_heads=heads, thw=thw, stride_q=[1, sq, sq], stride_kv=[1, skv, skv], seed=100 + stage)
+    shapes = orc.block_param_shapes("", dim, dim_out, heads, thw, cfg["stride_q"], cfg["stride_kv"])
+    params = {k: v.cuda() for k, v in detgen.det_params(shapes, cfg["seed"]).items()}
+    blk = make_block(cfg, dtype)
+    blk.load_state_dict(params, strict=True)
+    N = 1 + int(np.prod(thw))
+    x = detgen.det_normal((1, N, dim), cfg["seed"], "x").cuda().requires_grad_(True)
+    y, thw_new = blk(x, thw)
+    po = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    xo = x.detach().clone().requires_grad_(True)
+    yo, thw_o = orc.multiscale_block(xo, thw, po, "", heads, cfg["stride_q"], cfg["stride_kv"])
+    assert list(thw_new) == list(thw_o)
+    assert nerr(y.detach(), yo.detach()) < OUT_TOL[dtype]
+    dy = detgen.det_normal(tuple(y.shape), cfg["seed"], "dy").cuda()
+    y.backward(dy)
+    yo.backward(dy)
+    gt = GRAD_TOL[dtype]
+    assert nerr(x.grad, xo.grad) < gt
+    for k, p in blk.named_parameters():
+        if k.endswith("norm_k.bias"):
+            continue
+        assert nerr(p.grad, po[k].grad) < gt, k
+
+
+def test_droppath_training_mode_matches_oracle():
+    """DropPath is folded into the GEMM epilogues; with the same torch RNG state the per-sample mask must
+    match the reference's drop_path (common.py:46-59)."""
+    from oracle import detgen, mvit_oracle as orc
+    cfg = dict(dim=96, dim_out=192, num_heads=2, thw=[2, 8, 8], stride_q=[1, 2, 2], stride_kv=[1, 4, 4], seed=7)
+    from pmv_b200.attention import MultiScaleBlock, set_compute_dtype
+    blk = MultiScaleBlock(dim=96, dim_out=192, num_heads=2, input_size=cfg["thw"], qkv_bias=True, drop_path=0.5,
+                          norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), kernel_q=[3, 3, 3], kernel_kv=[3, 3, 3],
+                          stride_q=cfg["stride_q"], stride_kv=cfg["stride_kv"], rel_pos_spatial=True, rel_pos_temporal=True,
+                          residual_pooling=True, dim_mul_in_att=True)
+    set_compute_dtype(blk, torch.float32).cuda().train()
+    shapes = orc.block_param_shapes("", 96, 192, 2, cfg["thw"], cfg["stride_q"], cfg["stride_kv"])
+    params = {k: v.cuda() for k, v in detgen.det_params(shapes, 7).items()}
+    blk.load_state_dict(params, strict=True)
+    B = 6
+    x = detgen.det_normal((B, 129, 96), 7, "x").cuda()
+    torch.manual_seed(123)
+    y, _ = blk(x, cfg["thw"])
+    torch.manual_seed(123)
+    keep = 0.5
+    s1 = (keep + torch.rand((B,), device="cuda")).floor_() / keep
+    s2 = (keep + torch.rand((B,), device="cuda")).floor_() / keep
+    yo, _ = orc.multiscale_block(x, cfg["thw"], params, "", 2, cfg["stride_q"], cfg["stride_kv"], drop_scale=torch.stack([s1, s2]))
+    assert nerr(y.detach(), yo) < 1e-4
+    assert 0 < int((s1 == 0).sum() + (s2 == 0).sum()) < 2 * B  # the mask actually dropped something
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_full_model_logits_match_reference_fixture(dtype):
+    """BASELINE config 1/3: MViTv2-S 16x4, one deterministic clip, logits vs the reference MViT's own output."""
+    from oracle import detgen, mvit_oracle as orc
+    from pmv_b200 import mvit
+    z = np.load(os.path.join(GOLDEN, "mvitv2_s_logits.npz"))
+    model = mvit.MViT(mvit.MVITV2_S, compute_dtype=dtype)
+    params = detgen.det_params(orc.param_shapes(orc.MVITV2_S), int(z["seed"]))
+    model.load_state_dict(params, strict=True)
+    model.cuda().eval()
+    model.head.act = None
+    clip = detgen.det_normal((1, 3, 16, 224, 224), int(z["seed"]), "clip").cuda()
+    with torch.no_grad():
+        logits = model([clip])
+    assert nerr(logits, z["logits"]) < OUT_TOL[dtype]
+    assert int(logits.argmax()) == int(np.argmax(z["logits"]))  # top-1 agrees

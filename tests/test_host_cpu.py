@@ -1,0 +1,65 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/pmv_b200.h declares (no compute
+calls without a GPU), the reference-shaped modules keep the reference state_dict, host index logic."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    from pmv_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "pmv_b200.h")).read()
+    declared = set(re.findall(r"\b(pmv_[a-z0-9_]+)\s*\(", hdr))
+    assert "pmv_gemm" in declared and "pmv_pool_ln_fwd" in declared and "pmv_attention_fwd" in declared
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(handle, s)]
+    assert not missing, missing
+    assert declared - {"pmv_last_error"} == set(_lib.exported_symbols())  # ctypes table covers the whole header
+    lib = _lib.lib()
+    assert lib.pmv_version() >= 100
+    assert lib.pmv_has_tcgen05() in (0, 1)
+
+
+def test_product_path_fails_loudly_without_gpu_tensors():
+    from pmv_b200 import ops
+    x = torch.randn(4, 96)
+    with pytest.raises((AssertionError, RuntimeError)):
+        ops.layernorm_fwd(x, torch.ones(96), torch.zeros(96), torch.float32)
+
+
+def test_state_dict_matches_reference_keys():
+    from oracle import mvit_oracle as orc
+    from pmv_b200 import mvit
+    m = mvit.MViT(mvit.MVITV2_S)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == orc.param_shapes(orc.MVITV2_S)
+    assert sum(p.numel() for p in m.parameters()) == 34537744
+    assert mvit.block_schedule(mvit.MVITV2_B) == orc.block_schedule(orc.MVITV2_B)
+
+
+def test_unsupported_configurations_raise():
+    from pmv_b200.attention import MultiScaleAttention
+    kw = dict(dim=96, dim_out=96, input_size=[2, 8, 8], num_heads=1, kernel_q=[3, 3, 3], kernel_kv=[3, 3, 3],
+              stride_q=[1, 1, 1], stride_kv=[1, 2, 2])
+    MultiScaleAttention(**kw)
+    for bad in (dict(pool_first=True), dict(mode="avg"), dict(separate_qkv=True), dict(num_heads=2), dict(mode="bogus")):
+        with pytest.raises(NotImplementedError):
+            MultiScaleAttention(**{**kw, **bad})
+
+
+@pytest.mark.parametrize("q,k", [(56, 7), (7, 14), (4, 7), (3, 6), (14, 14), (5, 3)])
+def test_rel_index_table_matches_oracle(q, k):
+    from oracle import mvit_oracle as orc
+    from pmv_b200 import ops
+    got = ops.rel_index_table(q, k, "cpu").view(q, k)
+    assert torch.equal(got.long(), orc.rel_index(q, k))
+    assert int(got.min()) >= 0 and int(got.max()) <= 2 * max(q, k) - 2
+
+
+def test_aug_ld():
+    from pmv_b200 import ops
+    assert ops.aug_ld((8, 7, 7)) == 128 and ops.aug_ld((8, 14, 14)) == 160 and ops.aug_ld((16, 7, 7)) == 128

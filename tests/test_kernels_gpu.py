@@ -196,9 +196,9 @@ def test_relpos_attention_fwd_bwd(dtype, B, heads, q_shape, k_shape):
     q = randn(B, heads, Nq, 96, seed=50).to(dtype)
     k = randn(B, heads, Nk, 96, seed=51).to(dtype)
     v = randn(B, heads, Nk, 96, seed=52).to(dtype)
-    rh = randn(2 * max(q_shape[1], k_shape[1]) - 1, 96, seed=53) * 0.3
-    rw = randn(2 * max(q_shape[2], k_shape[2]) - 1, 96, seed=54) * 0.3
-    rt = randn(2 * max(q_shape[0], k_shape[0]) - 1, 96, seed=55) * 0.3
+    rh = randn(2 * max(q_shape[1], k_shape[1]) - 1, 96, seed=53) * 0.05
+    rw = randn(2 * max(q_shape[2], k_shape[2]) - 1, 96, seed=54) * 0.05
+    rt = randn(2 * max(q_shape[0], k_shape[0]) - 1, 96, seed=55) * 0.05
     scale = 96 ** -0.5
     ld = ops.aug_ld(k_shape)
     q_aug = torch.zeros(B * heads, Nq, ld, dtype=dtype, device="cuda")
