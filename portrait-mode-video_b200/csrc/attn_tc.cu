@@ -1,6 +1,320 @@
-// placeholder until the tcgen05 attention kernel lands
-#include "common.cuh"
-int attn_tc_fwd(const void*, const void*, int64_t, int, const void*, int64_t, void*, float*, int, int, int, int, float, int, cudaStream_t) {
-  pmv_set_error("attention: tcgen05 kernel not built yet");
-  return PMV_ERR_UNSUPPORTED;
+// tcgen05 / TMEM / TMA pooling attention, forward (bf16 operands, fp32 softmax and accumulation):
+//     O = softmax(scale * Q' K'^T) V  (+ q for rows >= 1: residual pooling), head-merged store.
+// The decomposed relative-position bias rides in the augmented columns of Q'/K' (relpos.cu), so the score
+// tile that leaves the tensor core is already biased; the [Nq, Nk] score matrix of the reference
+// (attention.py:412-446) lives only in tensor memory, 128 x 128 at a time.
+//
+// One CTA = 128 query rows of one (batch, head).  256 threads:
+//   warp 0      TMA producer : Q' once, then K'/V tiles of 128 keys through a 2-stage mbarrier ring
+//   warp 1      MMA issuer   : S_j = Q' K'_j^T  (SS, K-major, 128 x 128 x kd)  into TMEM buffer j&1,
+//                              O += P_j V_j     (TS: P read from TMEM, V MN-major from smem, 128 x 96 x 128)
+//   warp 2      TMEM allocator
+//   warps 4..7  softmax      : one thread per query row; tcgen05.ld S -> online softmax with lazy rescaling
+//                              (O is touched only when the running max grows by > 2^8) -> bf16 P written back
+//                              over S with tcgen05.st -> epilogue (O / l, residual, lse)
+// S_{j+1} is issued before the MMA warp waits for P_j, so the tensor core computes the next score tile while
+// the softmax warps work on the current one.
+//
+// Shared-memory operand layouts (pinned by tests/test_tcgen05_probe.py):
+//   Q', K' : K-major; columns [0,128) as two 64-wide 128B-swizzle blocks, columns [128,160) (kd = 160 only) as
+//            one 32-wide 64B-swizzle block.
+//   V      : MN-major (channel axis contiguous), three 32-channel 64B-swizzle groups of [128 keys x 64 B].
+//   P      : tensor memory, bf16 pairs packed in 32-bit columns (column c = keys 2c, 2c+1).
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int HD = PMV_HEAD_DIM;
+constexpr int BQ = 128, BKV = 128;
+constexpr int THREADS = 256;
+constexpr int V_BYTES = 3 * BKV * 64;  // 24576
+
+struct TcAttnGeom {
+  int B, heads, Nq, Nk;
+  float scale;
+  int residual;
+};
+
+template <int KD> struct ACfg {
+  static constexpr int QK_BYTES = BQ * KD * 2;  // 32768 (kd 128) / 40960 (kd 160)
+  static constexpr int STAGE_BYTES = QK_BYTES + V_BYTES;
+  static constexpr int SMEM_BYTES = QK_BYTES + 2 * STAGE_BYTES + 1024 + 256;
+};
+
+template <int KD>
+__global__ void __launch_bounds__(THREADS, 1)
+attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQ2,
+                   const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmK2,
+                   const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ out, float* __restrict__ lse, TcAttnGeom g) {
+  using Cfg = ACfg<KD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sStage = smem + Cfg::QK_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::QK_BYTES + 2 * Cfg::STAGE_BYTES);
+  uint64_t* q_full = bars;         // [1]
+  uint64_t* kv_full = bars + 1;    // [2]
+  uint64_t* kv_empty = bars + 3;   // [2]
+  uint64_t* s_full = bars + 5;     // [2]
+  uint64_t* p_full = bars + 7;     // [2]
+  uint64_t* o_done = bars + 9;     // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int q0 = blockIdx.x * BQ;
+  const int ntiles = (g.Nk + BKV - 1) / BKV;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmQ);
+    tc::tma_prefetch_desc(&tmK);
+    tc::tma_prefetch_desc(&tmV);
+    tc::mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&kv_full[i], 1);
+      tc::mbar_init(&kv_empty[i], 1);
+      tc::mbar_init(&s_full[i], 1);
+      tc::mbar_init(&p_full[i], 4);
+    }
+    tc::mbar_init(o_done, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) {
+    tc::tmem_alloc(tmem_slot, 512);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tc::mbar_expect_tx(q_full, Cfg::QK_BYTES);
+      tc::tma_load_3d(sQ, &tmQ, 0, q0, bh, q_full);
+      tc::tma_load_3d(sQ + 16384, &tmQ, 64, q0, bh, q_full);
+      if (KD == 160) tc::tma_load_3d(sQ + 32768, &tmQ2, 128, q0, bh, q_full);
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j & 1;
+        tc::mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        uint8_t* sK = sStage + st * Cfg::STAGE_BYTES;
+        uint8_t* sV = sK + Cfg::QK_BYTES;
+        tc::mbar_expect_tx(&kv_full[st], Cfg::STAGE_BYTES);
+        tc::tma_load_3d(sK, &tmK, 0, j * BKV, bh, &kv_full[st]);
+        tc::tma_load_3d(sK + 16384, &tmK, 64, j * BKV, bh, &kv_full[st]);
+        if (KD == 160) tc::tma_load_3d(sK + 32768, &tmK2, 128, j * BKV, bh, &kv_full[st]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) tc::tma_load_3d(sV + c * 8192, &tmV, c * 32, j * BKV, bh, &kv_full[st]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t sq_addr = tc::smem_u32(sQ);
+      auto issue_s = [&](int j) {
+        const int st = j & 1;
+        tc::mbar_wait(&kv_full[st], (j >> 1) & 1);
+        tc::tc_fence_after();
+        const int nvalid = min(BKV, g.Nk - j * BKV);
+        const uint32_t idesc = tc::make_idesc_bf16(BQ, (nvalid + 15) & ~15, false, false);
+        const uint32_t sk_addr = tc::smem_u32(sStage + st * Cfg::STAGE_BYTES);
+        const uint32_t tmem_s = tmem_base + (uint32_t)(j & 1) * 128;
+#pragma unroll
+        for (int ks = 0; ks < KD / 16; ++ks) {
+          uint64_t da, db;
+          if (ks < 8) {
+            const uint32_t off = (uint32_t)(ks >> 2) * 16384 + (uint32_t)(ks & 3) * 32;
+            da = tc::make_smem_desc(sq_addr + off, 16, 1024, tc::SWIZZLE_128B);
+            db = tc::make_smem_desc(sk_addr + off, 16, 1024, tc::SWIZZLE_128B);
+          } else {
+            const uint32_t off = 32768 + (uint32_t)(ks - 8) * 32;
+            da = tc::make_smem_desc(sq_addr + off, 16, 512, tc::SWIZZLE_64B);
+            db = tc::make_smem_desc(sk_addr + off, 16, 512, tc::SWIZZLE_64B);
+          }
+          tc::umma_ss(tmem_s, da, db, idesc, ks > 0);
+        }
+        tc::umma_commit(&s_full[j & 1]);
+      };
+      tc::mbar_wait(q_full, 0);
+      tc::tc_fence_after();
+      issue_s(0);
+      const uint32_t idesc_pv = tc::make_idesc_bf16(BQ, HD, false, true);
+      for (int j = 0; j < ntiles; ++j) {
+        if (j + 1 < ntiles) issue_s(j + 1);
+        tc::mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        tc::tc_fence_after();
+        const int nvalid = min(BKV, g.Nk - j * BKV);
+        const int nks = (nvalid + 15) >> 4;
+        const uint32_t sv_addr = tc::smem_u32(sStage + (j & 1) * Cfg::STAGE_BYTES + Cfg::QK_BYTES);
+        const uint32_t tmem_p = tmem_base + (uint32_t)(j & 1) * 128;
+        for (int ks = 0; ks < nks; ++ks) {
+          const uint64_t db = tc::make_smem_desc(sv_addr + ks * 1024, 8192, 512, tc::SWIZZLE_64B);
+          tc::umma_ts(tmem_o, tmem_p + ks * 8, db, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
+        }
+        tc::umma_commit(&kv_empty[j & 1]);
+        tc::umma_commit(o_done);
+      }
+    }
+  } else if (warp >= 4) {
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    const float c = g.scale * 1.4426950408889634f;  // scores are exponentiated in base 2
+    float m_used = 0.f, l_run = 0.f;
+    for (int j = 0; j < ntiles; ++j) {
+      const int b = j & 1;
+      tc::mbar_wait(&s_full[b], (j >> 1) & 1);
+      tc::tc_fence_after();
+      const int nvalid = min(BKV, g.Nk - j * BKV);
+      const int nchunks = (nvalid + 31) >> 5;
+      const uint32_t tmem_s = tmem_base + lane_addr + (uint32_t)b * 128;
+      uint32_t s[4][32];
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+        if (ch < nchunks) tc::tmem_ld32(tmem_s + ch * 32, s[ch]);
+      tc::tmem_ld_wait();
+      float mx = -INFINITY;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        if (ch < nchunks) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float v = __uint_as_float(s[ch][i]);
+            if (ch * 32 + i >= nvalid) v = -INFINITY;
+            s[ch][i] = __float_as_uint(v);
+            mx = fmaxf(mx, v);
+          }
+        }
+      }
+      if (j == 0) {
+        m_used = mx;
+      } else {
+        const bool grow = (mx - m_used) * c > 8.0f;  // lazy rescale: keep the old reference max while exp2 stays <= 2^8
+        if (__any_sync(0xffffffffu, grow)) {
+          tc::mbar_wait(o_done, (j - 1) & 1);  // P_{j-1} V_{j-1} has landed in O
+          tc::tc_fence_after();
+          const float alpha = grow ? exp2f((m_used - mx) * c) : 1.0f;
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            uint32_t o[32];
+            tc::tmem_ld32(tmem_o + lane_addr + ch * 32, o);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tc::tmem_st32(tmem_o + lane_addr + ch * 32, o);
+          }
+          tc::tmem_st_wait();
+          l_run *= alpha;
+          if (grow) m_used = mx;
+        }
+      }
+      const float mc = m_used * c;
+      float sum = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        if (ch < nchunks) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = exp2f(fmaf(__uint_as_float(s[ch][2 * i]), c, -mc));
+            const float p1 = exp2f(fmaf(__uint_as_float(s[ch][2 * i + 1]), c, -mc));
+            sum += p0 + p1;
+            __nv_bfloat162 pp = __floats2bfloat162_rn(p0, p1);
+            pk[i] = *reinterpret_cast<uint32_t*>(&pp);
+          }
+          tc::tmem_st16(tmem_s + ch * 16, pk);
+        }
+      }
+      l_run += sum;
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&p_full[b]);
+    }
+    // ---------------- epilogue: O / l (+ residual q), head-merged bf16 store, log-sum-exp
+    tc::mbar_wait(o_done, (ntiles - 1) & 1);
+    tc::tc_fence_after();
+    tc::mbar_wait(q_full, 0);
+    const int n = q0 + row;
+    const float inv = 1.0f / l_run;
+    const int bidx = bh / g.heads, head = bh - bidx * g.heads;
+    bf16* op = out + ((int64_t)bidx * g.Nq + n) * (g.heads * HD) + head * HD;
+    const bool add_q = g.residual && n >= 1;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      uint32_t o[32];
+      tc::tmem_ld32(tmem_o + lane_addr + ch * 32, o);
+      tc::tmem_ld_wait();
+      if (n < g.Nq) {
+#pragma unroll
+        for (int v8 = 0; v8 < 4; ++v8) {  // 8 channels = one 16-byte chunk of the swizzled Q' row
+          const int col = ch * 32 + v8 * 8;
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[v8 * 8 + i]) * inv;
+          if (add_q) {
+            const int blk = col >> 6, cc = (col & 63) >> 3;
+            const uint4 qv = *reinterpret_cast<const uint4*>(sQ + blk * 16384 + row * 128 + ((cc ^ (row & 7)) << 4));
+            const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&qv);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              f[2 * i] += __low2float(q2[i]);
+              f[2 * i + 1] += __high2float(q2[i]);
+            }
+          }
+          uint4 pk;
+          __nv_bfloat162 t0 = __floats2bfloat162_rn(f[0], f[1]), t1 = __floats2bfloat162_rn(f[2], f[3]);
+          __nv_bfloat162 t2 = __floats2bfloat162_rn(f[4], f[5]), t3 = __floats2bfloat162_rn(f[6], f[7]);
+          pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+          pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+          *reinterpret_cast<uint4*>(op + col) = pk;
+        }
+      }
+    }
+    if (lse != nullptr && n < g.Nq) lse[(int64_t)bh * g.Nq + n] = m_used * g.scale + logf(l_run);
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int KD>
+int launch(const void* q_aug, const void* k_aug, int64_t ld_qk, const void* v, int64_t ld_v, void* out, float* lse,
+           const TcAttnGeom& g, cudaStream_t stream) {
+  using Cfg = ACfg<KD>;
+  const uint64_t BH = (uint64_t)g.B * g.heads;
+  CUtensorMap tmQ, tmQ2, tmK, tmK2, tmV;
+  int rc;
+  if ((rc = pmv_make_tensor_map_3d(&tmQ, q_aug, 2, KD, g.Nq, BH, ld_qk, (uint64_t)g.Nq * ld_qk, 64, BQ, 1, 128))) return rc;
+  if ((rc = pmv_make_tensor_map_3d(&tmK, k_aug, 2, KD, g.Nk, BH, ld_qk, (uint64_t)g.Nk * ld_qk, 64, BKV, 1, 128))) return rc;
+  if ((rc = pmv_make_tensor_map_3d(&tmQ2, q_aug, 2, KD, g.Nq, BH, ld_qk, (uint64_t)g.Nq * ld_qk, 32, BQ, 1, 64))) return rc;
+  if ((rc = pmv_make_tensor_map_3d(&tmK2, k_aug, 2, KD, g.Nk, BH, ld_qk, (uint64_t)g.Nk * ld_qk, 32, BKV, 1, 64))) return rc;
+  if ((rc = pmv_make_tensor_map_3d(&tmV, v, 2, HD, g.Nk, BH, ld_v, (uint64_t)g.Nk * ld_v, 32, BKV, 1, 64))) return rc;
+  auto kern = attn_tc_fwd_kernel<KD>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PMV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((g.Nq + BQ - 1) / BQ), (unsigned)BH);
+  kern<<<grid, THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmQ2, tmK, tmK2, tmV, (bf16*)out, lse, g);
+  PMV_CHECK_LAUNCH();
+  return PMV_OK;
+}
+
+}  // namespace
+
+int attn_tc_fwd(const void* q_aug, const void* k_aug, int64_t ld_qk, int kd, const void* v, int64_t ld_v, void* out,
+                float* lse, int B, int heads, int Nq, int Nk, float scale, int residual, cudaStream_t stream) {
+  PMV_CHECK_ARG(kd == 128 || kd == 160, "attention(tc): kd must be 128 or 160 (got %d)", kd);
+  PMV_CHECK_ARG(ld_qk % 8 == 0 && ld_v % 8 == 0, "attention(tc): row strides must be multiples of 8 elements");
+  PMV_CHECK_ARG(((uintptr_t)q_aug & 15) == 0 && ((uintptr_t)k_aug & 15) == 0 && ((uintptr_t)v & 15) == 0 && ((uintptr_t)out & 15) == 0,
+                "attention(tc): operands must be 16-byte aligned");
+  TcAttnGeom g{B, heads, Nq, Nk, scale, residual};
+  if (kd == 128) return launch<128>(q_aug, k_aug, ld_qk, v, ld_v, out, lse, g, stream);
+  return launch<160>(q_aug, k_aug, ld_qk, v, ld_v, out, lse, g, stream);
 }

@@ -26,7 +26,7 @@ class LayerNormFn(Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, out_dtype, eps):
         x = x.contiguous()
-        need = torch.is_grad_enabled() and any(t.requires_grad for t in (x, gamma, beta))
+        need = any(ctx.needs_input_grad)
         y, mean, rstd = ops.layernorm_fwd(x, gamma, beta, out_dtype, save_stats=need, eps=eps)
         if need:
             ctx.save_for_backward(x, gamma, mean, rstd)
@@ -62,7 +62,8 @@ class LinearFn(Function):
         res2 = residual.reshape(-1, N) if residual is not None else None
         y = ops.linear_fwd(x2, w, bias, torch.float32 if fp32_out else T, residual=res2, row_scale=row_scale,
                            rows_per_scale=rows_per_scale)
-        ctx.save_for_backward(x2, w, row_scale)
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(x2, w, row_scale)
         ctx.meta = (x.shape, rows_per_scale, bias is not None, residual is not None, T)
         return y.view(*x.shape[:-1], N)
 
@@ -100,7 +101,7 @@ class MlpFn(Function):
         if not x2.is_contiguous():
             x2 = x2.contiguous()
         w1c, w2c = _cast(w1, T), _cast(w2, T)
-        need = torch.is_grad_enabled()
+        need = any(ctx.needs_input_grad)
         M, Hd, N = x2.shape[0], w1.shape[0], w2.shape[0]
         u = torch.empty(M, Hd, dtype=T, device=x.device) if need else None
         h = ops.linear_fwd(x2, w1c, b1, T, act=L.ACT_GELU, aux_out=u)
@@ -143,7 +144,8 @@ class MaxPoolSkipFn(Function):
     def forward(ctx, x, thw):
         x = x.contiguous()
         y = ops.maxpool_skip_fwd(x, thw)
-        ctx.save_for_backward(x)
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(x)
         ctx.thw = tuple(thw)
         return y
 
@@ -186,7 +188,7 @@ class PoolAttentionFn(Function):
         if has_rel:
             ops.relpos_augment_q(q_aug, q_shape, k_shape, rel_h, rel_w, rel_t, 1.0 / scale)
             ops.relpos_augment_k(k_aug, k_shape)
-        need = torch.is_grad_enabled()
+        need = any(ctx.needs_input_grad)
         out, lse = ops.attention_fwd(q_aug, k_aug, v, B, heads, ld, scale, residual=residual, want_lse=need,
                                      tc=(1 if (use_tc_attn and T == torch.bfloat16) else 0))
         if need:
@@ -237,7 +239,8 @@ class PatchEmbedFn(Function):
         x = torch.empty(B, Ltok + 1, Cout, dtype=torch.float32, device=clip.device)
         x[:, 0] = cls_token.reshape(1, Cout)
         ops.linear_fwd(col, wp, bias, torch.float32, out=x.view(B * (Ltok + 1), Cout), out_group=Ltok, out_skip=1)
-        ctx.save_for_backward(col)
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(col)
         ctx.meta = (K, weight.shape, thw, T)
         ctx.thw = thw
         return x

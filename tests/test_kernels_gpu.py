@@ -239,3 +239,44 @@ def test_patch_embed_im2col_gemm():
         out = torch.zeros(2 * (L_ + 1), 96, device="cuda")
         ops.linear_fwd(col, wp, b, torch.float32, out=out, out_group=L_, out_skip=1)
         assert nerr(out.view(2, L_ + 1, 96)[:, 1:], ref) < TOL[dtype]
+
+
+TC_ATTN_CASES = [  # B, heads, q_shape, k_shape — incl. ragged tails and both kd = 128 / 160
+    (2, 2, (2, 4, 4), (2, 2, 2)), (1, 2, (8, 14, 14), (8, 7, 7)), (1, 2, (8, 7, 7), (8, 14, 14)),
+    (1, 1, (8, 28, 28), (8, 14, 14)), (2, 1, (8, 56, 56), (8, 7, 7)), (1, 2, (2, 7, 5), (2, 4, 3)),
+]
+
+
+@pytest.mark.parametrize("B,heads,q_shape,k_shape", TC_ATTN_CASES)
+def test_attention_tcgen05_fwd(B, heads, q_shape, k_shape):
+    """tcgen05/TMEM/TMA attention forward (bf16) against the oracle's materialised-score formulation and
+    against the CUDA-core kernel (same inputs, same Q'/K' buffers)."""
+    from pmv_b200 import ops
+    dtype = torch.bfloat16
+    Nq, Nk = 1 + math.prod(q_shape), 1 + math.prod(k_shape)
+    q = randn(B, heads, Nq, 96, seed=70).to(dtype)
+    k = randn(B, heads, Nk, 96, seed=71).to(dtype)
+    v = randn(B, heads, Nk, 96, seed=72).to(dtype)
+    rh = randn(2 * max(q_shape[1], k_shape[1]) - 1, 96, seed=73) * 0.05
+    rw = randn(2 * max(q_shape[2], k_shape[2]) - 1, 96, seed=74) * 0.05
+    rt = randn(2 * max(q_shape[0], k_shape[0]) - 1, 96, seed=75) * 0.05
+    scale = 96 ** -0.5
+    ld = ops.aug_ld(k_shape)
+    q_aug = torch.zeros(B * heads, Nq, ld, dtype=dtype, device="cuda")
+    k_aug = torch.zeros(B * heads, Nk, ld, dtype=dtype, device="cuda")
+    q_aug[..., :96] = q.reshape(B * heads, Nq, 96)
+    k_aug[..., :96] = k.reshape(B * heads, Nk, 96)
+    ops.relpos_augment_q(q_aug, q_shape, k_shape, rh, rw, rt, 1.0 / scale)
+    ops.relpos_augment_k(k_aug, k_shape)
+    vv = v.reshape(B * heads, Nk, 96).contiguous()
+    out_tc, lse_tc = ops.attention_fwd(q_aug, k_aug, vv, B, heads, ld, scale, residual=True, tc=1)
+    out_cc, lse_cc = ops.attention_fwd(q_aug, k_aug, vv, B, heads, ld, scale, residual=True, tc=0)
+    torch.cuda.synchronize()
+    ref = _attn_reference(q.float(), k.float(), v.float(), q_shape, k_shape, rh, rw, rt, scale)
+    assert nerr(out_cc.float(), ref) < 1e-2
+    assert nerr(out_tc.float(), ref) < 1e-2
+    assert nerr(lse_tc, lse_cc) < 1e-2
+    # no residual, no lse
+    out2, _ = ops.attention_fwd(q_aug, k_aug, vv, B, heads, ld, scale, residual=False, want_lse=False, tc=1)
+    out3, _ = ops.attention_fwd(q_aug, k_aug, vv, B, heads, ld, scale, residual=False, want_lse=False, tc=0)
+    assert nerr(out2.float(), out3.float()) < 1e-2
