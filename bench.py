@@ -95,6 +95,19 @@ def summarize_kernels(rec, peaks):
         f = fam.setdefault(key, dict(ms=0.0, launches=0, flops=0.0, bytes=0.0))
         f["ms"] += ms; f["launches"] += 1
         f["flops"] += meta.get("flops", 0.0); f["bytes"] += meta.get("bytes", 0.0)
+    dump = os.environ.get("PMV_BENCH_DUMP")
+    if dump:
+        agg = {}
+        for name, meta, e0, e1 in rec:
+            k = name + ":" + json.dumps({a: b for a, b in meta.items() if a in ("layout", "tc", "shape")}, sort_keys=True)
+            a = agg.setdefault(k, dict(ms=0.0, n=0, flops=0.0, bytes=0.0))
+            a["ms"] += e0.elapsed_time(e1); a["n"] += 1
+            a["flops"] += meta.get("flops", 0.0); a["bytes"] += meta.get("bytes", 0.0)
+        rows = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])
+        with open(dump, "w") as f:
+            for k, a in rows:
+                rate = (a["flops"] / a["ms"] / 1e9) if a["flops"] else (a["bytes"] / a["ms"] / 1e6)
+                f.write(f"{a['ms']:9.3f} ms  n={a['n']:3d}  {rate:9.1f} {'TFLOP/s' if a['flops'] else 'GB/s'}  {k}\n")
     total = sum(f["ms"] for f in fam.values()) or 1.0
     shares = {k: round(f["ms"] / total, 4) for k, f in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
     dom = max(fam, key=lambda k: fam[k]["ms"])

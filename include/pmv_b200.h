@@ -165,12 +165,14 @@ int pmv_relpos_augment_q_bwd(void* dq_aug, const void* q_aug, int64_t ld, const 
  * (attention.py:456).  Q' [B*heads, Nq, ld_qk], K' [B*heads, Nk, ld_qk], V [B*heads, Nk, 96]
  * (row stride ld_v), out [B, Nq, heads*96], lse [B*heads, Nq] (natural-log sum-exp of the scaled
  * scores, saved for backward; may be NULL).  residual != 0 adds Q'[:, :96] to rows >= 1
- * (un-scaled post-LN q, cls row excluded, attention.py:450-452).
+ * (un-scaled post-LN q, cls row excluded, attention.py:450-452).  out_pre (may be NULL) additionally receives the
+ * output BEFORE that add: the backward pass needs it at its own precision (recovering it as out - q from a
+ * bf16-rounded sum loses most of its bits).
  * tc != 0 selects the tcgen05/TMEM/TMA kernel (bf16 only). */
 int pmv_attention_fwd(const void* q_aug, const void* k_aug, int64_t ld_qk, int kd,
-                      const void* v, int64_t ld_v, void* out, float* lse,
+                      const void* v, int64_t ld_v, void* out, void* out_pre, float* lse,
                       int B, int heads, int Nq, int Nk, float scale, int residual, int dtype, int tc, void* stream);
-/* Backward: dout [B, Nq, heads*96].  Writes dQ' [B*heads, Nq, ld_qk] (columns [0,kd): the first 96 are dq
+/* Backward: dout [B, Nq, heads*96]; `out` is the PRE-residual output (out_pre of the forward call).  Writes dQ' [B*heads, Nq, ld_qk] (columns [0,kd): the first 96 are dq
  * incl. the residual-pooling path (dout added to rows >= 1), the rest d(rq/scale)), dk [B*heads, Nk, ld_dk]
  * (96 columns; the one-hot columns of K' carry no gradient) and dv [B*heads, Nk, ld_dv].
  * ws: fp32 workspace of pmv_attention_bwd_workspace_bytes() bytes (row deltas + dk/dv accumulators). */

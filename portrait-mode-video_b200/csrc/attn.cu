@@ -2,12 +2,12 @@
 #include "common.cuh"
 
 int attn_simt_fwd(const void* q_aug, const void* k_aug, int64_t ld_qk, int kd, const void* v, int64_t ld_v, void* out,
-                  float* lse, int B, int heads, int Nq, int Nk, float scale, int residual, int dtype, cudaStream_t stream);
+                  void* out_pre, float* lse, int B, int heads, int Nq, int Nk, float scale, int residual, int dtype, cudaStream_t stream);
 int attn_tc_fwd(const void* q_aug, const void* k_aug, int64_t ld_qk, int kd, const void* v, int64_t ld_v, void* out,
-                float* lse, int B, int heads, int Nq, int Nk, float scale, int residual, cudaStream_t stream);
+                void* out_pre, float* lse, int B, int heads, int Nq, int Nk, float scale, int residual, cudaStream_t stream);
 
 extern "C" int pmv_attention_fwd(const void* q_aug, const void* k_aug, int64_t ld_qk, int kd,
-                                 const void* v, int64_t ld_v, void* out, float* lse,
+                                 const void* v, int64_t ld_v, void* out, void* out_pre, float* lse,
                                  int B, int heads, int Nq, int Nk, float scale, int residual, int dtype, int tc, void* stream) {
   PMV_CHECK_ARG(kd % 16 == 0 && kd >= PMV_HEAD_DIM && kd <= 160, "attention: kd=%d must be a multiple of 16 in [96,160]", kd);
   PMV_CHECK_ARG(ld_qk >= kd && ld_qk % 4 == 0 && ld_v % 4 == 0, "attention: bad row strides");
@@ -18,7 +18,7 @@ extern "C" int pmv_attention_fwd(const void* q_aug, const void* k_aug, int64_t l
       pmv_set_error("attention: tcgen05 kernel requested on a device that is not sm_100");
       return PMV_ERR_UNSUPPORTED;
     }
-    return attn_tc_fwd(q_aug, k_aug, ld_qk, kd, v, ld_v, out, lse, B, heads, Nq, Nk, scale, residual, (cudaStream_t)stream);
+    return attn_tc_fwd(q_aug, k_aug, ld_qk, kd, v, ld_v, out, out_pre, lse, B, heads, Nq, Nk, scale, residual, (cudaStream_t)stream);
   }
-  return attn_simt_fwd(q_aug, k_aug, ld_qk, kd, v, ld_v, out, lse, B, heads, Nq, Nk, scale, residual, dtype, (cudaStream_t)stream);
+  return attn_simt_fwd(q_aug, k_aug, ld_qk, kd, v, ld_v, out, out_pre, lse, B, heads, Nq, Nk, scale, residual, dtype, (cudaStream_t)stream);
 }

@@ -40,7 +40,7 @@ __device__ __forceinline__ void load_rows(const T* __restrict__ src, int64_t ld,
 template <typename T>
 __global__ void __launch_bounds__(THREADS) attn_fwd_kernel(const T* __restrict__ q_aug, const T* __restrict__ k_aug,
                                                            const T* __restrict__ v, T* __restrict__ out,
-                                                           float* __restrict__ lse, AttnGeom g) {
+                                                           T* __restrict__ out_pre, float* __restrict__ lse, AttnGeom g) {
   extern __shared__ float sm[];
   const int KP = g.kd + 1;
   float* Qs = sm;                 // [64][KP]
@@ -146,13 +146,14 @@ __global__ void __launch_bounds__(THREADS) attn_fwd_kernel(const T* __restrict__
     const int n = q0 + r;
     if (n >= g.Nq) continue;
     const float inv = 1.0f / l_s[r];
-    T* op = out + ((int64_t)b * g.Nq + n) * (g.heads * HD) + head * HD;
+    const int64_t ooff = ((int64_t)b * g.Nq + n) * (g.heads * HD) + head * HD;
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
       const int c = tx + 16 * j;
       float val = o[i][j] * inv;
+      if (out_pre != nullptr) out_pre[ooff + c] = from_f32<T>(val);  // pre-residual output, kept for backward
       if (g.residual && n >= 1) val += Qs[r * KP + c];  // residual pooling with the un-scaled q, cls row excluded
-      op[c] = from_f32<T>(val);
+      out[ooff + c] = from_f32<T>(val);
     }
   }
 }
@@ -188,15 +189,13 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_kernel(const T* __restrict__
   load_rows(qb, g.ld_qk, q0, g.Nq, g.kd, Qs, KP);
   load_rows(dob, ld_o, q0, g.Nq, HD, dOs, VP);
   __syncthreads();
-  {  // delta[r] = sum_c dO[r][c] * O_attn[r][c], O_attn = out - q (rows >= 1) when residual pooling is on
+  {  // delta[r] = sum_c dO[r][c] * O_attn[r][c]  (O_attn = attention output BEFORE the residual-pooling add)
     const int r = threadIdx.x >> 2, part = threadIdx.x & 3;
     const int n = q0 + r;
     float d = 0.f;
     if (n < g.Nq) {
       for (int c = part * 24; c < part * 24 + 24; ++c) {
-        float ov = to_f32(ob[(int64_t)n * ld_o + c]);
-        if (g.residual && n >= 1) ov -= Qs[r * KP + c];
-        d = fmaf(dOs[r * VP + c], ov, d);
+        d = fmaf(dOs[r * VP + c], to_f32(ob[(int64_t)n * ld_o + c]), d);
       }
     }
     d += __shfl_xor_sync(0xffffffffu, d, 1);
@@ -339,13 +338,13 @@ __global__ void __launch_bounds__(256) cast_rows_kernel(const float* __restrict_
 }  // namespace
 
 int attn_simt_fwd(const void* q_aug, const void* k_aug, int64_t ld_qk, int kd, const void* v, int64_t ld_v, void* out,
-                  float* lse, int B, int heads, int Nq, int Nk, float scale, int residual, int dtype, cudaStream_t stream) {
+                  void* out_pre, float* lse, int B, int heads, int Nq, int Nk, float scale, int residual, int dtype, cudaStream_t stream) {
   AttnGeom g{B, heads, Nq, Nk, kd, ld_qk, ld_v, scale, residual};
   const size_t smem = ((size_t)(BQ + BKV) * (kd + 1) + (size_t)BKV * VP + (size_t)BQ * SP + 2 * BQ) * sizeof(float);
   dim3 grid((unsigned)ceil_div64(Nq, BQ), (unsigned)(B * heads));
   PMV_DISPATCH_DTYPE(dtype, T, {
     PMV_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attn_fwd_kernel<T><<<grid, THREADS, smem, stream>>>((const T*)q_aug, (const T*)k_aug, (const T*)v, (T*)out, lse, g);
+    attn_fwd_kernel<T><<<grid, THREADS, smem, stream>>>((const T*)q_aug, (const T*)k_aug, (const T*)v, (T*)out, (T*)out_pre, lse, g);
   });
   PMV_CHECK_LAUNCH();
   return PMV_OK;

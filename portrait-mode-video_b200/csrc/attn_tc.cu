@@ -45,7 +45,8 @@ template <int KD>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQ2,
                    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmK2,
-                   const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ out, float* __restrict__ lse, TcAttnGeom g) {
+                   const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ out, bf16* __restrict__ out_pre,
+                   float* __restrict__ lse, TcAttnGeom g) {
   using Cfg = ACfg<KD>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -57,8 +58,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* kv_empty = bars + 3;   // [2]
   uint64_t* s_full = bars + 5;     // [2]
   uint64_t* p_full = bars + 7;     // [2]
-  uint64_t* o_done = bars + 9;     // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* o_done = bars + 9;     // [1]  arrives after every P_j V_j
+  uint64_t* o_final = bars + 10;   // [1]  arrives once, after the last P V (unambiguous phase for the epilogue)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
@@ -77,6 +79,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc::mbar_init(&p_full[i], 4);
     }
     tc::mbar_init(o_done, 1);
+    tc::mbar_init(o_final, 1);
     tc::fence_barrier_init();
   }
   if (warp == 2) {
@@ -153,6 +156,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         tc::umma_commit(&kv_empty[j & 1]);
         tc::umma_commit(o_done);
+        if (j == ntiles - 1) tc::umma_commit(o_final);
       }
     }
   } else if (warp >= 4) {
@@ -232,13 +236,14 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (lane == 0) tc::mbar_arrive(&p_full[b]);
     }
     // ---------------- epilogue: O / l (+ residual q), head-merged bf16 store, log-sum-exp
-    tc::mbar_wait(o_done, (ntiles - 1) & 1);
+    tc::mbar_wait(o_final, 0);
     tc::tc_fence_after();
     tc::mbar_wait(q_full, 0);
     const int n = q0 + row;
     const float inv = 1.0f / l_run;
     const int bidx = bh / g.heads, head = bh - bidx * g.heads;
-    bf16* op = out + ((int64_t)bidx * g.Nq + n) * (g.heads * HD) + head * HD;
+    const int64_t ooff = ((int64_t)bidx * g.Nq + n) * (g.heads * HD) + head * HD;
+    bf16* op = out + ooff;
     const bool add_q = g.residual && n >= 1;
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
@@ -252,6 +257,14 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           float f[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[v8 * 8 + i]) * inv;
+          if (out_pre != nullptr) {  // pre-residual output, kept for backward (delta = rowsum(dO * O_attn))
+            uint4 pk;
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(f[0], f[1]), t1 = __floats2bfloat162_rn(f[2], f[3]);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(f[4], f[5]), t3 = __floats2bfloat162_rn(f[6], f[7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+            pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+            *reinterpret_cast<uint4*>(out_pre + ooff + col) = pk;
+          }
           if (add_q) {
             const int blk = col >> 6, cc = (col & 63) >> 3;
             const uint4 qv = *reinterpret_cast<const uint4*>(sQ + blk * 16384 + row * 128 + ((cc ^ (row & 7)) << 4));
@@ -283,7 +296,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 template <int KD>
-int launch(const void* q_aug, const void* k_aug, int64_t ld_qk, const void* v, int64_t ld_v, void* out, float* lse,
+int launch(const void* q_aug, const void* k_aug, int64_t ld_qk, const void* v, int64_t ld_v, void* out, void* out_pre, float* lse,
            const TcAttnGeom& g, cudaStream_t stream) {
   using Cfg = ACfg<KD>;
   const uint64_t BH = (uint64_t)g.B * g.heads;
@@ -301,7 +314,7 @@ int launch(const void* q_aug, const void* k_aug, int64_t ld_qk, const void* v, i
     attr_set = true;
   }
   dim3 grid((unsigned)((g.Nq + BQ - 1) / BQ), (unsigned)BH);
-  kern<<<grid, THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmQ2, tmK, tmK2, tmV, (bf16*)out, lse, g);
+  kern<<<grid, THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmQ2, tmK, tmK2, tmV, (bf16*)out, (bf16*)out_pre, lse, g);
   PMV_CHECK_LAUNCH();
   return PMV_OK;
 }
@@ -309,12 +322,12 @@ int launch(const void* q_aug, const void* k_aug, int64_t ld_qk, const void* v, i
 }  // namespace
 
 int attn_tc_fwd(const void* q_aug, const void* k_aug, int64_t ld_qk, int kd, const void* v, int64_t ld_v, void* out,
-                float* lse, int B, int heads, int Nq, int Nk, float scale, int residual, cudaStream_t stream) {
+                void* out_pre, float* lse, int B, int heads, int Nq, int Nk, float scale, int residual, cudaStream_t stream) {
   PMV_CHECK_ARG(kd == 128 || kd == 160, "attention(tc): kd must be 128 or 160 (got %d)", kd);
   PMV_CHECK_ARG(ld_qk % 8 == 0 && ld_v % 8 == 0, "attention(tc): row strides must be multiples of 8 elements");
   PMV_CHECK_ARG(((uintptr_t)q_aug & 15) == 0 && ((uintptr_t)k_aug & 15) == 0 && ((uintptr_t)v & 15) == 0 && ((uintptr_t)out & 15) == 0,
                 "attention(tc): operands must be 16-byte aligned");
   TcAttnGeom g{B, heads, Nq, Nk, scale, residual};
-  if (kd == 128) return launch<128>(q_aug, k_aug, ld_qk, v, ld_v, out, lse, g, stream);
-  return launch<160>(q_aug, k_aug, ld_qk, v, ld_v, out, lse, g, stream);
+  if (kd == 128) return launch<128>(q_aug, k_aug, ld_qk, v, ld_v, out, out_pre, lse, g, stream);
+  return launch<160>(q_aug, k_aug, ld_qk, v, ld_v, out, out_pre, lse, g, stream);
 }

@@ -39,7 +39,8 @@ template <int BN> struct TileCfg {
   static constexpr int B_BYTES = B_BYTES_MN;                  // reserve the larger of the two
   static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
   static constexpr int ACC_COLS = BN <= 128 ? 128 : 256;      // TMEM columns per accumulator stage
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_BYTES = 4 * 32 * 33 * 4;           // per-epilogue-warp transpose buffer (padded rows)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
 };
 
 template <int BN, bool A_MN, bool B_MN, typename TOut>
@@ -54,6 +55,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* acc_full = bars + 2 * STAGES;    // [2]       MMA -> epilogue
   uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2]    epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* epi_buf = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -155,11 +157,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ------------------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4)
     const int q = warp & 3;
+    float* stage_buf = epi_buf + q * (32 * 33);
     int64_t it = 0;
     for (int64_t wi = blockIdx.x; wi < num_work; wi += gridDim.x, ++it) {
       const int tn = (int)(wi % p.tiles_n);
       const int tm = (int)((wi / p.tiles_n) % p.tiles_m);
-      const int64_t row = (int64_t)tm * BM + q * 32 + lane;
+      const int64_t row0 = (int64_t)tm * BM + q * 32;
       const int64_t n0 = (int64_t)tn * BN;
       const int as = (int)(it & 1);
       const uint32_t aphase = (uint32_t)((it >> 1) & 1);
@@ -171,16 +174,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t r[32];
         tc::tmem_ld32(taddr + c, r);
         tc::tmem_ld_wait();
-        if (row < p.M) {
+        // transpose through shared memory so that 8 consecutive lanes cover one 32-column row segment:
+        // every global access of the epilogue (out, residual, aux) is then a full 64/128-byte run per row
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const int64_t col = n0 + c + j;
-            if (col < p.N) {
-              float v[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])};
-              epi_store4<bf16, TOut>(p.e, row, col, v);
-            }
-          }
+        for (int j = 0; j < 32; ++j) stage_buf[lane * 33 + j] = __uint_as_float(r[j]);
+        __syncwarp();
+        const int64_t col = n0 + c + (lane & 7) * 4;
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr) {
+          const int rr = itr * 4 + (lane >> 3);
+          const int64_t row = row0 + rr;
+          float v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = stage_buf[rr * 33 + (lane & 7) * 4 + j];
+          if (row < p.M && col < p.N) epi_store4<bf16, TOut>(p.e, row, col, v);
         }
+        __syncwarp();
       }
       tc::tc_fence_before();
       __syncwarp();

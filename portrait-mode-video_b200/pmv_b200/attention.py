@@ -10,6 +10,8 @@ silently diverging.
 """
 from __future__ import annotations
 
+import os
+
 import numpy
 import torch
 import torch.nn as nn
@@ -19,7 +21,7 @@ from torch.nn.init import trunc_normal_
 from . import functional as Fn
 from .common import DropPath, Mlp, compute_dtype_of, drop_path_scale
 
-USE_TC_ATTENTION = False  # flipped on once the tcgen05 attention kernel is validated on the GPU
+USE_TC_ATTENTION = os.environ.get("PMV_TC_ATTENTION", "1") == "1"  # tcgen05 attention forward in bf16 mode
 
 
 def _as_list(v):

@@ -189,10 +189,10 @@ class PoolAttentionFn(Function):
             ops.relpos_augment_q(q_aug, q_shape, k_shape, rel_h, rel_w, rel_t, 1.0 / scale)
             ops.relpos_augment_k(k_aug, k_shape)
         need = any(ctx.needs_input_grad)
-        out, lse = ops.attention_fwd(q_aug, k_aug, v, B, heads, ld, scale, residual=residual, want_lse=need,
+        out, out_pre, lse = ops.attention_fwd(q_aug, k_aug, v, B, heads, ld, scale, residual=residual, want_lse=need,
                                      tc=(1 if (use_tc_attn and T == torch.bfloat16) else 0))
         if need:
-            ctx.save_for_backward(qkv5, q_aug, k_aug, v, out, lse, wq, wk, wv, gq, gk, gv, rel_h, rel_w, rel_t)
+            ctx.save_for_backward(qkv5, q_aug, k_aug, v, out_pre, lse, wq, wk, wv, gq, gk, gv, rel_h, rel_w, rel_t)
         ctx.meta = (heads, tuple(thw), stride_q, stride_kv, q_shape, k_shape, scale, residual, ld, has_rel, eps)
         return out
 

@@ -245,14 +245,17 @@ def relpos_augment_q_bwd(dq_aug, q_aug, q_shape, k_shape, rel_h, rel_w, rel_t, i
 
 
 def attention_fwd(q_aug, k_aug, v, B, heads, kd, scale, residual=True, want_lse=True, tc=None):
+    """Returns (out, out_pre, lse): out_pre is the pre-residual output kept for backward (None in inference;
+    aliases out when there is no residual pooling)."""
     BH, Nq, ld = q_aug.shape
     Nk = k_aug.shape[1]
     out = torch.empty(B, Nq, heads * 96, dtype=q_aug.dtype, device=q_aug.device)
+    out_pre = torch.empty_like(out) if (want_lse and residual) else None
     lse = torch.empty(BH, Nq, dtype=torch.float32, device=q_aug.device) if want_lse else None
     use_tc = _tc_default(q_aug.dtype) if tc is None else int(tc)
-    _run("pmv_attention_fwd", 1, dict(flops=4 * BH * Nq * Nk * 96, tc=use_tc, shape=(BH, Nq, Nk, kd)), L.ptr(q_aug), L.ptr(k_aug), ld, kd, L.ptr(v), v.stride(1), L.ptr(out), L.ptr(lse),
+    _run("pmv_attention_fwd", 1, dict(flops=4 * BH * Nq * Nk * 96, tc=use_tc, shape=(BH, Nq, Nk, kd)), L.ptr(q_aug), L.ptr(k_aug), ld, kd, L.ptr(v), v.stride(1), L.ptr(out), L.ptr(out_pre), L.ptr(lse),
                                       B, heads, Nq, Nk, scale, int(residual), L.dt(q_aug), use_tc, L.stream())
-    return out, lse
+    return out, (out_pre if out_pre is not None else (out if want_lse else None)), lse
 
 
 def attention_bwd(q_aug, k_aug, v, out, dout, lse, B, heads, kd, scale, residual=True):
