@@ -6,7 +6,7 @@
 // Persistent, warp-specialised kernel, one CTA per SM:
 //   warp 0      TMA producer   (cp.async.bulk.tensor 2-D, 128-byte swizzle, 4-stage mbarrier ring)
 //   warp 1      MMA issuer     (one elected lane issues tcgen05.mma 128 x BN x 16; accumulators double-buffered in TMEM)
-//   warps 2..5  epilogue       (tcgen05.ld 32x32b -> bias / GELU / DropPath scale / residual -> global)
+//   warps 2..9  epilogue       (tcgen05.ld 32x32b -> smem transpose -> bias / GELU / DropPath scale / residual -> global)
 //
 // Operand staging.  A "K-major" operand (reduction axis contiguous in global memory) is one TMA box of
 // [rows x 64 elements] -> rows of 128 B, 8-row swizzle atoms of 1024 B (SBO = 1024).  An "MN-major" operand
@@ -22,7 +22,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int STAGES = 4;
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;                        // two warps per TMEM lane quarter, alternating 32-column chunks
+constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;
 
 struct TcParams {
   int64_t M, N, K;          // logical output rows / cols and reduction length
@@ -39,7 +40,7 @@ template <int BN> struct TileCfg {
   static constexpr int B_BYTES = B_BYTES_MN;                  // reserve the larger of the two
   static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
   static constexpr int ACC_COLS = BN <= 128 ? 128 : 256;      // TMEM columns per accumulator stage
-  static constexpr int EPI_BYTES = 4 * 32 * 33 * 4;           // per-epilogue-warp transpose buffer (padded rows)
+  static constexpr int EPI_BYTES = EPI_WARPS * 32 * 33 * 4;           // per-epilogue-warp transpose buffer (padded rows)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
 };
 
@@ -69,7 +70,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&acc_full[i], 1);
-      tc::mbar_init(&acc_empty[i], 4);
+      tc::mbar_init(&acc_empty[i], EPI_WARPS);
     }
     tc::fence_barrier_init();
   }
@@ -157,7 +158,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ------------------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4)
     const int q = warp & 3;
-    float* stage_buf = epi_buf + q * (32 * 33);
+    const int half = (warp - 2) >> 2;  // which of the two warps of this lane quarter
+    float* stage_buf = epi_buf + (warp - 2) * (32 * 33);
     int64_t it = 0;
     for (int64_t wi = blockIdx.x; wi < num_work; wi += gridDim.x, ++it) {
       const int tn = (int)(wi % p.tiles_n);
@@ -170,7 +172,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * Cfg::ACC_COLS;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = half * 32; c < BN; c += 64) {
         uint32_t r[32];
         tc::tmem_ld32(taddr + c, r);
         tc::tmem_ld_wait();
