@@ -92,6 +92,8 @@ def summarize_kernels(rec, peaks):
             key = "gemm_tcgen05" if meta.get("tc") else "gemm_ffma"
         if name == "pmv_attention_fwd":
             key = "attention_fwd_tcgen05" if meta.get("tc") else "attention_fwd_cuda_core"
+        if name == "pmv_attention_bwd":
+            key = "attention_bwd_tcgen05" if meta.get("tc") else "attention_bwd_cuda_core"
         f = fam.setdefault(key, dict(ms=0.0, launches=0, flops=0.0, bytes=0.0))
         f["ms"] += ms; f["launches"] += 1
         f["flops"] += meta.get("flops", 0.0); f["bytes"] += meta.get("bytes", 0.0)

@@ -180,7 +180,7 @@ int64_t pmv_attention_bwd_workspace_bytes(int B, int heads, int Nq, int Nk);
 int pmv_attention_bwd(const void* q_aug, const void* k_aug, int64_t ld_qk, int kd, const void* v, int64_t ld_v,
                       const void* out, const void* dout, const float* lse,
                       void* dq_aug, void* dk, int64_t ld_dk, void* dv, int64_t ld_dv, float* ws,
-                      int B, int heads, int Nq, int Nk, float scale, int residual, int dtype, void* stream);
+                      int B, int heads, int Nq, int Nk, float scale, int residual, int dtype, int tc, void* stream);
 
 /* ---------------------------------------------------------------- PatchEmbed ---------
  * Conv3d(3 -> 96, k (3,7,7), s (2,4,4), p (1,3,3)) as an implicit GEMM: stem_helper.py:293-325.

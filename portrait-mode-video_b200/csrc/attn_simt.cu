@@ -350,23 +350,16 @@ int attn_simt_fwd(const void* q_aug, const void* k_aug, int64_t ld_qk, int kd, c
   return PMV_OK;
 }
 
-extern "C" int64_t pmv_attention_bwd_workspace_bytes(int B, int heads, int Nq, int Nk) {
-  (void)Nq;
-  return (int64_t)2 * B * heads * Nk * HD * (int64_t)sizeof(float);
-}
-
-extern "C" int pmv_attention_bwd(const void* q_aug, const void* k_aug, int64_t ld_qk, int kd, const void* v, int64_t ld_v,
-                                 const void* out, const void* dout, const float* lse,
-                                 void* dq_aug, void* dk, int64_t ld_dk, void* dv, int64_t ld_dv, float* ws,
-                                 int B, int heads, int Nq, int Nk, float scale, int residual, int dtype, void* stream) {
-  PMV_CHECK_ARG(kd % 16 == 0 && kd >= HD && kd <= 160, "attention: kd=%d must be a multiple of 16 in [96,160]", kd);
-  PMV_CHECK_ARG(ld_qk % 4 == 0 && ld_v % 4 == 0 && ld_dk % 4 == 0 && ld_dv % 4 == 0, "attention: row strides must be multiples of 4");
+int attn_simt_bwd(const void* q_aug, const void* k_aug, int64_t ld_qk, int kd, const void* v, int64_t ld_v,
+                  const void* out, const void* dout, const float* lse,
+                  void* dq_aug, void* dk, int64_t ld_dk, void* dv, int64_t ld_dv, float* ws,
+                  int B, int heads, int Nq, int Nk, float scale, int residual, int dtype, void* stream) {
   AttnGeom g{B, heads, Nq, Nk, kd, ld_qk, ld_v, scale, residual};
   const int64_t rows = (int64_t)B * heads * Nk;
   float* dk_ws = ws;
   float* dv_ws = ws + rows * HD;
   cudaStream_t st = (cudaStream_t)stream;
-  PMV_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)pmv_attention_bwd_workspace_bytes(B, heads, Nq, Nk), st));
+  PMV_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)(2 * rows * HD) * sizeof(float), st));
   const size_t smem = ((size_t)(BQ + BKV) * (kd + 1) + (size_t)(BKV + BQ) * VP + (size_t)2 * BQ * SP + 2 * BQ) * sizeof(float);
   dim3 grid((unsigned)ceil_div64(Nq, BQ), (unsigned)(B * heads));
   int64_t cblocks = ceil_div64(rows * (HD / 4), 256);

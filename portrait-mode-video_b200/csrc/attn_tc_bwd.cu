@@ -1,0 +1,503 @@
+// tcgen05 / TMEM / TMA pooling attention, backward (bf16 operands, fp32 accumulation).
+//
+// Two kernels, both structured like the forward kernel (attn_tc.cu) and both free of the [Nq, Nk] score
+// matrix; the scores and probabilities are recomputed per 128 x 128 tile from the saved log-sum-exp:
+//
+//   dQ kernel  (CTA = 128 query rows, walks the key tiles)            lanes = queries
+//       S  = Q' K'^T            SS MMA      P  = exp2(S c - lse2)          softmax warps, fp32
+//       dP = dO V^T             SS MMA      dS = P (dP - delta) scale  ->  bf16 into TMEM (over S)
+//       dQ' += dS K'            TS MMA (A = dS from TMEM, B = K' read MN-major from the same smem tile)
+//     also produces delta[q] = sum_c dO[q,c] O_pre[q,c] for the second kernel and folds the residual-pooling
+//     path (dQ'[:, :96] += dO for rows >= 1) into its epilogue.
+//
+//   dK/dV kernel (CTA = 128 keys x a chunk of query tiles)             lanes = keys  (everything transposed)
+//       S^T  = K' Q'^T          SS MMA      P^T  = exp2(S^T c - lse2[q])
+//       dP^T = V dO^T           SS MMA      dS^T = P^T (dP^T - delta[q]) scale -> bf16 into TMEM
+//       dV += P^T dO            TS MMA (B = dO read MN-major)          dK += dS^T Q'[:, :96]   TS MMA
+//     partial sums of the query chunks are added into fp32 workspaces with red.global.add.
+//
+// Recomputing S / dP in both kernels costs 1.4x the tensor work of a fused kernel but needs no shared-memory
+// round trip for P / dS and no per-tile atomics.  Operand tiles are staged as 64-column 128B-swizzle blocks
+// (+ one 32-column 64B-swizzle block for the bias columns when kd = 160); a tile is read K-major or MN-major
+// through the matrix descriptor only (layouts pinned by tests/test_tcgen05_probe.py).
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int HD = PMV_HEAD_DIM;
+constexpr int BT = 128;  // tile edge (queries and keys)
+constexpr int THREADS = 256;
+constexpr int X96_BYTES = 2 * BT * 128;  // a [128 x 96] operand staged as two 64-column blocks (second half-used)
+
+struct BwdGeom {
+  int B, heads, Nq, Nk;
+  float scale;
+  int residual;
+  int64_t ld_qk;
+  int q_tiles_per_chunk;
+};
+
+template <int KD> struct BCfg {
+  static constexpr int QK_BYTES = BT * KD * 2;
+  static constexpr int STAGE_BYTES = QK_BYTES + X96_BYTES;
+  static constexpr int SMEM_BYTES = 3 * STAGE_BYTES + 1024 /*align*/ + 2048 /*lse, delta*/ + 256;
+};
+
+// K-major descriptor of k-step ks (16 columns) inside a [rows x KD] tile
+template <int KD> __device__ __forceinline__ uint64_t kmajor_desc(uint32_t base, int ks) {
+  if (ks < 8) return tc::make_smem_desc(base + (uint32_t)(ks >> 2) * 16384 + (uint32_t)(ks & 3) * 32, 16, 1024, tc::SWIZZLE_128B);
+  return tc::make_smem_desc(base + 32768 + (uint32_t)(ks - 8) * 32, 16, 512, tc::SWIZZLE_64B);
+}
+
+__device__ __forceinline__ void load_tile_qk(uint8_t* dst, const CUtensorMap* m128, const CUtensorMap* m64, int kd, int row0,
+                                             int bh, uint64_t* bar) {
+  tc::tma_load_3d(dst, m128, 0, row0, bh, bar);
+  tc::tma_load_3d(dst + 16384, m128, 64, row0, bh, bar);
+  if (kd == 160) tc::tma_load_3d(dst + 32768, m64, 128, row0, bh, bar);
+}
+
+// ================================================================================================ dQ kernel
+template <int KD>
+__global__ void __launch_bounds__(THREADS, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQ2,
+                   const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmK2,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                   const bf16* __restrict__ o_pre, const bf16* __restrict__ dout, const float* __restrict__ lse,
+                   float* __restrict__ delta_out, bf16* __restrict__ dq_aug, BwdGeom g) {
+  using Cfg = BCfg<KD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;                    // Q' tile, then dO tile
+  uint8_t* sdO = smem + Cfg::QK_BYTES;
+  uint8_t* sStage = smem + Cfg::STAGE_BYTES;  // 2 x (K' tile, V tile)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * Cfg::STAGE_BYTES + 2048);
+  uint64_t* q_full = bars;        // [1]
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* sdp_full = bars + 5;  // [1]  S and dP of the current tile are in TMEM
+  uint64_t* ds_full = bars + 6;   // [1]  dS written (4 warps)
+  uint64_t* dq_final = bars + 7;  // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int bidx = bh / g.heads, head = bh - bidx * g.heads;
+  const int q0 = blockIdx.x * BT;
+  const int ntiles = (g.Nk + BT - 1) / BT;
+
+  if (warp == 0 && lane == 0) {
+    tc::mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&kv_full[i], 1); tc::mbar_init(&kv_empty[i], 1); }
+    tc::mbar_init(sdp_full, 1);
+    tc::mbar_init(ds_full, 4);
+    tc::mbar_init(dq_final, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) { tc::tmem_alloc(tmem_slot, 512); tc::tmem_relinquish(); }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dq = tmem_base + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tc::mbar_expect_tx(q_full, Cfg::STAGE_BYTES);
+      load_tile_qk(sQ, &tmQ, &tmQ2, KD, q0, bh, q_full);
+      tc::tma_load_3d(sdO, &tmdO, head * HD, q0, bidx, q_full);
+      tc::tma_load_3d(sdO + 16384, &tmdO, head * HD + 64, q0, bidx, q_full);
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j & 1;
+        tc::mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        uint8_t* sK = sStage + st * Cfg::STAGE_BYTES;
+        uint8_t* sV = sK + Cfg::QK_BYTES;
+        tc::mbar_expect_tx(&kv_full[st], Cfg::STAGE_BYTES);
+        load_tile_qk(sK, &tmK, &tmK2, KD, j * BT, bh, &kv_full[st]);
+        tc::tma_load_3d(sV, &tmV, 0, j * BT, bh, &kv_full[st]);
+        tc::tma_load_3d(sV + 16384, &tmV, 64, j * BT, bh, &kv_full[st]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t sq_addr = tc::smem_u32(sQ), sdo_addr = tc::smem_u32(sdO);
+      tc::mbar_wait(q_full, 0);
+      tc::tc_fence_after();
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j & 1;
+        tc::mbar_wait(&kv_full[st], (j >> 1) & 1);
+        tc::tc_fence_after();
+        const int nvalid = min(BT, g.Nk - j * BT);
+        const int n16 = (nvalid + 15) & ~15;
+        const uint32_t sk_addr = tc::smem_u32(sStage + st * Cfg::STAGE_BYTES);
+        const uint32_t sv_addr = sk_addr + Cfg::QK_BYTES;
+        const uint32_t idesc_s = tc::make_idesc_bf16(BT, n16, false, false);
+#pragma unroll
+        for (int ks = 0; ks < KD / 16; ++ks)  // S = Q' K'^T
+          tc::umma_ss(tmem_s, kmajor_desc<KD>(sq_addr, ks), kmajor_desc<KD>(sk_addr, ks), idesc_s, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)  // dP = dO V^T
+          tc::umma_ss(tmem_dp, kmajor_desc<128>(sdo_addr, ks), kmajor_desc<128>(sv_addr, ks), idesc_s, ks > 0);
+        tc::umma_commit(sdp_full);
+        tc::mbar_wait(ds_full, j & 1);
+        tc::tc_fence_after();
+        // dQ' += dS K' : A = dS (TMEM, packed bf16 over the S columns), B = K' tile read MN-major
+        const int nks = n16 >> 4;
+        const uint32_t idesc_128 = tc::make_idesc_bf16(BT, 128, false, true);
+        const uint32_t idesc_32 = tc::make_idesc_bf16(BT, 32, false, true);
+        for (int ks = 0; ks < nks; ++ks) {
+          const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
+          tc::umma_ts(tmem_dq, tmem_s + ks * 8, tc::make_smem_desc(sk_addr + ks * 2048, 16384, 1024, tc::SWIZZLE_128B), idesc_128, acc);
+          if (KD == 160)
+            tc::umma_ts(tmem_dq + 128, tmem_s + ks * 8, tc::make_smem_desc(sk_addr + 32768 + ks * 1024, 8192, 512, tc::SWIZZLE_64B), idesc_32, acc);
+        }
+        tc::umma_commit(&kv_empty[st]);
+      }
+      tc::umma_commit(dq_final);
+    }
+  } else if (warp >= 4) {
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const int n = q0 + row;
+    const bool rvalid = n < g.Nq;
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    const float c = g.scale * 1.4426950408889634f;
+    const int64_t ld_o = (int64_t)g.heads * HD;
+    const int64_t ooff = ((int64_t)bidx * g.Nq + n) * ld_o + head * HD;
+    // delta = rowsum(dO * O_pre), straight from global memory (192 contiguous bytes per row and tensor)
+    float delta = 0.f, lse2 = 0.f;
+    if (rvalid) {
+#pragma unroll
+      for (int v8 = 0; v8 < HD / 8; ++v8) {
+        const uint4 a = *reinterpret_cast<const uint4*>(dout + ooff + v8 * 8);
+        const uint4 b = *reinterpret_cast<const uint4*>(o_pre + ooff + v8 * 8);
+        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+        const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          delta = fmaf(__low2float(a2[i]), __low2float(b2[i]), delta);
+          delta = fmaf(__high2float(a2[i]), __high2float(b2[i]), delta);
+        }
+      }
+      delta_out[(int64_t)bh * g.Nq + n] = delta;
+      lse2 = lse[(int64_t)bh * g.Nq + n] * 1.4426950408889634f;
+    }
+    for (int j = 0; j < ntiles; ++j) {
+      tc::mbar_wait(sdp_full, j & 1);
+      tc::tc_fence_after();
+      const int nvalid = min(BT, g.Nk - j * BT);
+      const int nchunks = (nvalid + 31) >> 5;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        uint32_t s[32], dp[32], pk[16];
+        tc::tmem_ld32(tmem_s + lane_addr + ch * 32, s);
+        tc::tmem_ld32(tmem_dp + lane_addr + ch * 32, dp);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float d[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int col = ch * 32 + 2 * i + h;
+            const float p = (rvalid && col < nvalid) ? exp2f(fmaf(__uint_as_float(s[2 * i + h]), c, -lse2)) : 0.f;
+            d[h] = p * (__uint_as_float(dp[2 * i + h]) - delta) * g.scale;
+          }
+          __nv_bfloat162 pp = __floats2bfloat162_rn(d[0], d[1]);
+          pk[i] = *reinterpret_cast<uint32_t*>(&pp);
+        }
+        tc::tmem_st16(tmem_s + lane_addr + ch * 16, pk);
+      }
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(ds_full);
+    }
+    // epilogue: dQ' (+ dO on the first 96 columns for rows >= 1: residual pooling) -> bf16
+    tc::mbar_wait(dq_final, 0);
+    tc::tc_fence_after();
+    bf16* dqp = dq_aug + ((int64_t)bh * g.Nq + n) * g.ld_qk;
+    const bool add_do = g.residual && n >= 1;
+#pragma unroll 1
+    for (int ch = 0; ch < KD / 32; ++ch) {
+      uint32_t o[32];
+      tc::tmem_ld32(tmem_dq + lane_addr + ch * 32, o);
+      tc::tmem_ld_wait();
+      if (rvalid) {
+#pragma unroll
+        for (int v8 = 0; v8 < 4; ++v8) {
+          const int col = ch * 32 + v8 * 8;
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[v8 * 8 + i]);
+          if (add_do && col < HD) {
+            const uint4 a = *reinterpret_cast<const uint4*>(dout + ooff + col);
+            const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { f[2 * i] += __low2float(a2[i]); f[2 * i + 1] += __high2float(a2[i]); }
+          }
+          uint4 pk;
+          __nv_bfloat162 t0 = __floats2bfloat162_rn(f[0], f[1]), t1 = __floats2bfloat162_rn(f[2], f[3]);
+          __nv_bfloat162 t2 = __floats2bfloat162_rn(f[4], f[5]), t3 = __floats2bfloat162_rn(f[6], f[7]);
+          pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+          pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+          *reinterpret_cast<uint4*>(dqp + col) = pk;
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 512); }
+}
+
+// ================================================================================================ dK / dV kernel
+template <int KD>
+__global__ void __launch_bounds__(THREADS, 1)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQ2,
+                    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmK2,
+                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                    const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dk_ws,
+                    float* __restrict__ dv_ws, BwdGeom g) {
+  using Cfg = BCfg<KD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sK = smem;  // K' tile then V tile (loaded once)
+  uint8_t* sV = smem + Cfg::QK_BYTES;
+  uint8_t* sStage = smem + Cfg::STAGE_BYTES;  // 2 x (Q' tile, dO tile)
+  float* s_lse = reinterpret_cast<float*>(smem + 3 * Cfg::STAGE_BYTES);  // [2][128] lse * log2e
+  float* s_delta = s_lse + 256;                                           // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * Cfg::STAGE_BYTES + 2048);
+  uint64_t* k_full = bars;       // [1]
+  uint64_t* q_full = bars + 1;   // [2]
+  uint64_t* q_empty = bars + 3;  // [2]
+  uint64_t* sdp_full = bars + 5;
+  uint64_t* pds_full = bars + 6;  // P^T and dS^T written (4 warps)
+  uint64_t* final_bar = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int bidx = bh / g.heads, head = bh - bidx * g.heads;
+  const int k0 = blockIdx.x * BT;
+  const int total_qt = (g.Nq + BT - 1) / BT;
+  const int qt_begin = blockIdx.z * g.q_tiles_per_chunk;
+  const int qt_end = min(total_qt, qt_begin + g.q_tiles_per_chunk);
+  const int nq_tiles = qt_end - qt_begin;  // >= 1 by construction of the grid
+
+  if (warp == 0 && lane == 0) {
+    tc::mbar_init(k_full, 1);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&q_full[i], 1); tc::mbar_init(&q_empty[i], 1); }
+    tc::mbar_init(sdp_full, 1);
+    tc::mbar_init(pds_full, 4);
+    tc::mbar_init(final_bar, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) { tc::tmem_alloc(tmem_slot, 512); tc::tmem_relinquish(); }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_st = tmem_base, tmem_dpt = tmem_base + 128, tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 384;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tc::mbar_expect_tx(k_full, Cfg::STAGE_BYTES);
+      load_tile_qk(sK, &tmK, &tmK2, KD, k0, bh, k_full);
+      tc::tma_load_3d(sV, &tmV, 0, k0, bh, k_full);
+      tc::tma_load_3d(sV + 16384, &tmV, 64, k0, bh, k_full);
+      for (int i = 0; i < nq_tiles; ++i) {
+        const int st = i & 1;
+        const int q0 = (qt_begin + i) * BT;
+        tc::mbar_wait(&q_empty[st], ((i >> 1) & 1) ^ 1);
+        uint8_t* sQ = sStage + st * Cfg::STAGE_BYTES;
+        uint8_t* sdO = sQ + Cfg::QK_BYTES;
+        tc::mbar_expect_tx(&q_full[st], Cfg::STAGE_BYTES);
+        load_tile_qk(sQ, &tmQ, &tmQ2, KD, q0, bh, &q_full[st]);
+        tc::tma_load_3d(sdO, &tmdO, head * HD, q0, bidx, &q_full[st]);
+        tc::tma_load_3d(sdO + 16384, &tmdO, head * HD + 64, q0, bidx, &q_full[st]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t sk_addr = tc::smem_u32(sK), sv_addr = tc::smem_u32(sV);
+      tc::mbar_wait(k_full, 0);
+      tc::tc_fence_after();
+      const uint32_t idesc_o = tc::make_idesc_bf16(BT, HD, false, true);  // N = 96 channels, B read MN-major
+      for (int i = 0; i < nq_tiles; ++i) {
+        const int st = i & 1;
+        const int q0 = (qt_begin + i) * BT;
+        tc::mbar_wait(&q_full[st], (i >> 1) & 1);
+        tc::tc_fence_after();
+        const int nqv = min(BT, g.Nq - q0);
+        const int n16 = (nqv + 15) & ~15;
+        const uint32_t sq_addr = tc::smem_u32(sStage + st * Cfg::STAGE_BYTES);
+        const uint32_t sdo_addr = sq_addr + Cfg::QK_BYTES;
+        const uint32_t idesc_s = tc::make_idesc_bf16(BT, n16, false, false);
+#pragma unroll
+        for (int ks = 0; ks < KD / 16; ++ks)  // S^T = K' Q'^T
+          tc::umma_ss(tmem_st, kmajor_desc<KD>(sk_addr, ks), kmajor_desc<KD>(sq_addr, ks), idesc_s, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)  // dP^T = V dO^T
+          tc::umma_ss(tmem_dpt, kmajor_desc<128>(sv_addr, ks), kmajor_desc<128>(sdo_addr, ks), idesc_s, ks > 0);
+        tc::umma_commit(sdp_full);
+        tc::mbar_wait(pds_full, i & 1);
+        tc::tc_fence_after();
+        const int nks = n16 >> 4;
+        for (int ks = 0; ks < nks; ++ks) {
+          const uint32_t acc = (i > 0 || ks > 0) ? 1u : 0u;
+          // dV += P^T dO ; dK += dS^T Q'[:, :96]   (B tiles read MN-major: 64-column groups 16384 B apart)
+          tc::umma_ts(tmem_dv, tmem_st + ks * 8, tc::make_smem_desc(sdo_addr + ks * 2048, 16384, 1024, tc::SWIZZLE_128B), idesc_o, acc);
+          tc::umma_ts(tmem_dk, tmem_dpt + ks * 8, tc::make_smem_desc(sq_addr + ks * 2048, 16384, 1024, tc::SWIZZLE_128B), idesc_o, acc);
+        }
+        tc::umma_commit(&q_empty[st]);
+      }
+      tc::umma_commit(final_bar);
+    }
+  } else if (warp >= 4) {
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;  // key row of this thread
+    const int tid128 = threadIdx.x - 128;
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    const float c = g.scale * 1.4426950408889634f;
+    for (int i = 0; i < nq_tiles; ++i) {
+      const int q0 = (qt_begin + i) * BT;
+      const int nqv = min(BT, g.Nq - q0);
+      float* lse_t = s_lse + (i & 1) * 128;
+      float* del_t = s_delta + (i & 1) * 128;
+      {
+        const int n = q0 + tid128;
+        const bool ok = n < g.Nq;
+        lse_t[tid128] = ok ? lse[(int64_t)bh * g.Nq + n] * 1.4426950408889634f : 0.f;
+        del_t[tid128] = ok ? delta[(int64_t)bh * g.Nq + n] : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four softmax warps only
+      tc::mbar_wait(sdp_full, i & 1);
+      tc::tc_fence_after();
+      const int nchunks = (nqv + 31) >> 5;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        uint32_t s[32], dp[32], pk[16], dk[16];
+        tc::tmem_ld32(tmem_st + lane_addr + ch * 32, s);
+        tc::tmem_ld32(tmem_dpt + lane_addr + ch * 32, dp);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          float p[2], d[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int col = ch * 32 + 2 * e + h;  // query inside the tile
+            p[h] = col < nqv ? exp2f(fmaf(__uint_as_float(s[2 * e + h]), c, -lse_t[col])) : 0.f;
+            d[h] = p[h] * (__uint_as_float(dp[2 * e + h]) - del_t[col]) * g.scale;
+          }
+          __nv_bfloat162 pp = __floats2bfloat162_rn(p[0], p[1]);
+          __nv_bfloat162 dd = __floats2bfloat162_rn(d[0], d[1]);
+          pk[e] = *reinterpret_cast<uint32_t*>(&pp);
+          dk[e] = *reinterpret_cast<uint32_t*>(&dd);
+        }
+        tc::tmem_st16(tmem_st + lane_addr + ch * 16, pk);
+        tc::tmem_st16(tmem_dpt + lane_addr + ch * 16, dk);
+      }
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(pds_full);
+    }
+    tc::mbar_wait(final_bar, 0);
+    tc::tc_fence_after();
+    const int key = k0 + row;
+    float* dkp = dk_ws + ((int64_t)bh * g.Nk + key) * HD;
+    float* dvp = dv_ws + ((int64_t)bh * g.Nk + key) * HD;
+#pragma unroll 1
+    for (int ch = 0; ch < 3; ++ch) {
+      uint32_t a[32], b[32];
+      tc::tmem_ld32(tmem_dv + lane_addr + ch * 32, a);
+      tc::tmem_ld32(tmem_dk + lane_addr + ch * 32, b);
+      tc::tmem_ld_wait();
+      if (key < g.Nk) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          atomicAdd(dvp + ch * 32 + e, __uint_as_float(a[e]));
+          atomicAdd(dkp + ch * 32 + e, __uint_as_float(b[e]));
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 512); }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) cast_rows96_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t rows, int64_t ld) {
+  const int64_t total = rows * (HD / 4);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / (HD / 4);
+    const int c4 = (int)(i - r * (HD / 4));
+    float v[4];
+    load4(src + r * HD + c4 * 4, v);
+    store4(dst + r * ld + c4 * 4, v);
+  }
+}
+
+template <int KD>
+int launch_bwd(const void* q_aug, const void* k_aug, int64_t ld_qk, const void* v, int64_t ld_v, const void* o_pre,
+               const void* dout, const float* lse, void* dq_aug, void* dk, int64_t ld_dk, void* dv, int64_t ld_dv, float* ws,
+               BwdGeom g, cudaStream_t stream) {
+  using Cfg = BCfg<KD>;
+  const uint64_t BH = (uint64_t)g.B * g.heads;
+  CUtensorMap tmQ, tmQ2, tmK, tmK2, tmV, tmdO;
+  int rc;
+  if ((rc = pmv_make_tensor_map_3d(&tmQ, q_aug, 2, KD, g.Nq, BH, ld_qk, (uint64_t)g.Nq * ld_qk, 64, BT, 1, 128))) return rc;
+  if ((rc = pmv_make_tensor_map_3d(&tmK, k_aug, 2, KD, g.Nk, BH, ld_qk, (uint64_t)g.Nk * ld_qk, 64, BT, 1, 128))) return rc;
+  if ((rc = pmv_make_tensor_map_3d(&tmQ2, q_aug, 2, KD, g.Nq, BH, ld_qk, (uint64_t)g.Nq * ld_qk, 32, BT, 1, 64))) return rc;
+  if ((rc = pmv_make_tensor_map_3d(&tmK2, k_aug, 2, KD, g.Nk, BH, ld_qk, (uint64_t)g.Nk * ld_qk, 32, BT, 1, 64))) return rc;
+  if ((rc = pmv_make_tensor_map_3d(&tmV, v, 2, HD, g.Nk, BH, ld_v, (uint64_t)g.Nk * ld_v, 64, BT, 1, 128))) return rc;
+  const uint64_t ld_o = (uint64_t)g.heads * HD;
+  if ((rc = pmv_make_tensor_map_3d(&tmdO, dout, 2, ld_o, g.Nq, (uint64_t)g.B, ld_o, (uint64_t)g.Nq * ld_o, 64, BT, 1, 128))) return rc;
+
+  const int64_t krows = (int64_t)BH * g.Nk;
+  float* dk_ws = ws;
+  float* dv_ws = ws + krows * HD;
+  float* delta = ws + 2 * krows * HD;
+  PMV_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)(2 * krows * HD) * sizeof(float), stream));
+
+  auto kq = attn_bwd_dq_kernel<KD>;
+  auto kkv = attn_bwd_dkv_kernel<KD>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PMV_CHECK_CUDA(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    PMV_CHECK_CUDA(cudaFuncSetAttribute(kkv, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int q_tiles = (g.Nq + BT - 1) / BT, k_tiles = (g.Nk + BT - 1) / BT;
+  g.ld_qk = ld_qk;
+  kq<<<dim3((unsigned)q_tiles, (unsigned)BH), THREADS, Cfg::SMEM_BYTES, stream>>>(
+      tmQ, tmQ2, tmK, tmK2, tmV, tmdO, (const bf16*)o_pre, (const bf16*)dout, lse, delta, (bf16*)dq_aug, g);
+  // split the query tiles so that about 3 CTAs per SM exist
+  int chunks = (int)((148 * 3 + (int64_t)k_tiles * BH - 1) / ((int64_t)k_tiles * BH));
+  if (chunks < 1) chunks = 1;
+  if (chunks > q_tiles) chunks = q_tiles;
+  g.q_tiles_per_chunk = (q_tiles + chunks - 1) / chunks;
+  chunks = (q_tiles + g.q_tiles_per_chunk - 1) / g.q_tiles_per_chunk;
+  kkv<<<dim3((unsigned)k_tiles, (unsigned)BH, (unsigned)chunks), THREADS, Cfg::SMEM_BYTES, stream>>>(
+      tmQ, tmQ2, tmK, tmK2, tmV, tmdO, lse, delta, dk_ws, dv_ws, g);
+  int64_t cblocks = ceil_div64(krows * (HD / 4), 256);
+  if (cblocks > 148 * 8) cblocks = 148 * 8;
+  cast_rows96_kernel<bf16><<<(unsigned)cblocks, 256, 0, stream>>>(dk_ws, (bf16*)dk, krows, ld_dk);
+  cast_rows96_kernel<bf16><<<(unsigned)cblocks, 256, 0, stream>>>(dv_ws, (bf16*)dv, krows, ld_dv);
+  PMV_CHECK_LAUNCH();
+  return PMV_OK;
+}
+
+}  // namespace
+
+int64_t attn_tc_bwd_workspace_floats(int B, int heads, int Nq, int Nk) {
+  return (int64_t)2 * B * heads * Nk * HD + (int64_t)B * heads * Nq;
+}
+
+int attn_tc_bwd(const void* q_aug, const void* k_aug, int64_t ld_qk, int kd, const void* v, int64_t ld_v, const void* o_pre,
+                const void* dout, const float* lse, void* dq_aug, void* dk, int64_t ld_dk, void* dv, int64_t ld_dv, float* ws,
+                int B, int heads, int Nq, int Nk, float scale, int residual, cudaStream_t stream) {
+  PMV_CHECK_ARG(kd == 128 || kd == 160, "attention bwd(tc): kd must be 128 or 160 (got %d)", kd);
+  PMV_CHECK_ARG(ld_qk % 8 == 0 && ld_v % 8 == 0 && ld_dk % 4 == 0 && ld_dv % 4 == 0, "attention bwd(tc): bad row strides");
+  BwdGeom g{B, heads, Nq, Nk, scale, residual, ld_qk, 1};
+  if (kd == 128) return launch_bwd<128>(q_aug, k_aug, ld_qk, v, ld_v, o_pre, dout, lse, dq_aug, dk, ld_dk, dv, ld_dv, ws, g, stream);
+  return launch_bwd<160>(q_aug, k_aug, ld_qk, v, ld_v, o_pre, dout, lse, dq_aug, dk, ld_dk, dv, ld_dv, ws, g, stream);
+}

@@ -43,7 +43,7 @@ _SIGS = {
     "pmv_relpos_augment_q_bwd": (_i, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
     "pmv_attention_fwd": (_i, [_p, _p, _i64, _i, _p, _i64, _p, _p, _p, _i, _i, _i, _i, _f, _i, _i, _i, _p]),
     "pmv_attention_bwd_workspace_bytes": (_i64, [_i, _i, _i, _i]),
-    "pmv_attention_bwd": (_i, [_p, _p, _i64, _i, _p, _i64, _p, _p, _p, _p, _p, _i64, _p, _i64, _p, _i, _i, _i, _i, _f, _i, _i, _p]),
+    "pmv_attention_bwd": (_i, [_p, _p, _i64, _i, _p, _i64, _p, _p, _p, _p, _p, _i64, _p, _i64, _p, _i, _i, _i, _i, _f, _i, _i, _i, _p]),
     "pmv_patch_im2col": (_i, [_p, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "pmv_probe_umma": (_i, [_p, _i, _u64, _u64, _u32, _u32, _u32, _i, _u32, _u32, _i, _p, _i, _p, _i, _p]),
     "pmv_probe_tma": (_i, [_p, _i, _u64, _u64, _u64, _u32, _u32, _i, _i, _i, _p, _i, _p]),

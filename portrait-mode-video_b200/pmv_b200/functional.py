@@ -5,6 +5,7 @@ The residual stream stays fp32; activations between kernels are in the compute d
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -193,16 +194,18 @@ class PoolAttentionFn(Function):
                                      tc=(1 if (use_tc_attn and T == torch.bfloat16) else 0))
         if need:
             ctx.save_for_backward(qkv5, q_aug, k_aug, v, out_pre, lse, wq, wk, wv, gq, gk, gv, rel_h, rel_w, rel_t)
-        ctx.meta = (heads, tuple(thw), stride_q, stride_kv, q_shape, k_shape, scale, residual, ld, has_rel, eps)
+        ctx.meta = (heads, tuple(thw), stride_q, stride_kv, q_shape, k_shape, scale, residual, ld, has_rel, eps,
+                    bool(use_tc_attn and T == torch.bfloat16 and ld in (128, 160)))
         return out
 
     @staticmethod
     def backward(ctx, dout):
         qkv5, q_aug, k_aug, v, out, lse, wq, wk, wv, gq, gk, gv, rel_h, rel_w, rel_t = ctx.saved_tensors
-        heads, thw, sq, skv, q_shape, k_shape, scale, residual, ld, has_rel, eps = ctx.meta
+        heads, thw, sq, skv, q_shape, k_shape, scale, residual, ld, has_rel, eps, tc_bwd = ctx.meta
         B, N = qkv5.shape[0], qkv5.shape[1]
         Nq, Nk = q_aug.shape[1], k_aug.shape[1]
-        dq_aug, dk, dv = ops.attention_bwd(q_aug, k_aug, v, out, dout, lse, B, heads, ld, scale, residual=residual)
+        dq_aug, dk, dv = ops.attention_bwd(q_aug, k_aug, v, out, dout, lse, B, heads, ld, scale, residual=residual,
+                                           tc=int(tc_bwd and os.environ.get("PMV_TC_ATTENTION_BWD", "1") == "1"))
         drh = drw = drt = None
         if has_rel:
             drh, drw, drt = ops.relpos_augment_q_bwd(dq_aug, q_aug, q_shape, k_shape, rel_h, rel_w, rel_t, 1.0 / scale)

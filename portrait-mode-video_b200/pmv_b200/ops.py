@@ -258,17 +258,18 @@ def attention_fwd(q_aug, k_aug, v, B, heads, kd, scale, residual=True, want_lse=
     return out, (out_pre if out_pre is not None else (out if want_lse else None)), lse
 
 
-def attention_bwd(q_aug, k_aug, v, out, dout, lse, B, heads, kd, scale, residual=True):
+def attention_bwd(q_aug, k_aug, v, out, dout, lse, B, heads, kd, scale, residual=True, tc=None):
     BH, Nq, ld = q_aug.shape
     Nk = k_aug.shape[1]
+    use_tc = _tc_default(q_aug.dtype) if tc is None else int(tc)
     dq_aug = torch.empty_like(q_aug)
     dk = torch.empty(BH, Nk, 96, dtype=q_aug.dtype, device=q_aug.device)
     dv = torch.empty(BH, Nk, 96, dtype=q_aug.dtype, device=q_aug.device)
     ws = torch.empty(L.lib().pmv_attention_bwd_workspace_bytes(B, heads, Nq, Nk) // 4, dtype=torch.float32,
                      device=q_aug.device)
-    _run("pmv_attention_bwd", 3, dict(flops=10 * BH * Nq * Nk * 96, shape=(BH, Nq, Nk, kd)), L.ptr(q_aug), L.ptr(k_aug), ld, kd, L.ptr(v), v.stride(1), L.ptr(out),
+    _run("pmv_attention_bwd", 4 if use_tc else 3, dict(flops=10 * BH * Nq * Nk * 96, tc=use_tc, shape=(BH, Nq, Nk, kd)), L.ptr(q_aug), L.ptr(k_aug), ld, kd, L.ptr(v), v.stride(1), L.ptr(out),
                                       L.ptr(dout.contiguous()), L.ptr(lse), L.ptr(dq_aug), L.ptr(dk), 96, L.ptr(dv), 96,
-                                      L.ptr(ws), B, heads, Nq, Nk, scale, int(residual), L.dt(q_aug), L.stream())
+                                      L.ptr(ws), B, heads, Nq, Nk, scale, int(residual), L.dt(q_aug), use_tc, L.stream())
     return dq_aug, dk, dv
 
 

@@ -278,6 +278,14 @@ def test_attention_tcgen05_fwd(B, heads, q_shape, k_shape):
     assert nerr(out_tc.float(), ref) < 1e-2
     assert nerr(lse_tc, lse_cc) < 1e-2
     assert nerr(pre_tc.float(), pre_cc.float()) < 1e-2
+    # backward: tensor-core kernels against the CUDA-core kernels on the same saved tensors
+    dout = randn(*out_tc.shape, seed=76).to(dtype)
+    dq_t, dk_t, dv_t = ops.attention_bwd(q_aug, k_aug, vv, pre_cc, dout, lse_cc, B, heads, ld, scale, residual=True, tc=1)
+    dq_c, dk_c, dv_c = ops.attention_bwd(q_aug, k_aug, vv, pre_cc, dout, lse_cc, B, heads, ld, scale, residual=True, tc=0)
+    torch.cuda.synchronize()
+    assert nerr(dq_t.float(), dq_c.float()) < 2e-2
+    assert nerr(dk_t.float(), dk_c.float()) < 2e-2
+    assert nerr(dv_t.float(), dv_c.float()) < 2e-2
     # no residual, no lse
     out2, _, _ = ops.attention_fwd(q_aug, k_aug, vv, B, heads, ld, scale, residual=False, want_lse=False, tc=1)
     out3, _, _ = ops.attention_fwd(q_aug, k_aug, vv, B, heads, ld, scale, residual=False, want_lse=False, tc=0)
