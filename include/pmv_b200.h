@@ -62,11 +62,13 @@ int pmv_has_tcgen05(void);
  * (may be NULL in inference). */
 int pmv_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_dtype,
                       float* mean, float* rstd, int64_t rows, int C, float eps, void* stream);
-/* dx (fp32) = LN'(dy) [+ dx if accumulate]; dgamma/dbeta (fp32 [C]) are ATOMICALLY added to
- * (caller zero-initialises). */
+/* dx (fp32) = LN'(dy) [+ dx if accumulate]; dgamma_dbeta (fp32 [2][C]: dgamma then dbeta) is added to.
+ * ws: fp32 workspace of pmv_layernorm_bwd_workspace_bytes() bytes (one partial vector per CTA, folded by a
+ * second small kernel: same-address global atomics from hundreds of CTAs serialise in L2). */
+int64_t pmv_layernorm_bwd_workspace_bytes(int64_t rows, int C);
 int pmv_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma,
                       const float* mean, const float* rstd, float* dx, int accumulate,
-                      float* dgamma, float* dbeta, int64_t rows, int C, void* stream);
+                      float* dgamma_dbeta, float* ws, int64_t rows, int C, void* stream);
 
 /* ---------------------------------------------------------------- GEMM family --------
  * qkv / proj / skip-proj / fc1 / fc2 Linear layers and their autograd:
@@ -104,11 +106,13 @@ int pmv_gemm(int layout, const void* A, int64_t lda, const void* B, int64_t ldb,
              int64_t M, int64_t N, int64_t K, int io_dtype, int out_dtype, const pmv_epilogue* epi,
              int tc, int split_k, void* stream);
 
-/* column sums: out[c] (+)= sum_r in[r, c] * (row_scale ? row_scale[r / rows_per_scale] : 1); also
+/* column sums: out_sum[c] += sum_r in[r, c] * (row_scale ? row_scale[r / rows_per_scale] : 1); also
  * optionally writes the scaled copy cast to cast_dtype (bias gradients + operand cast of the fp32
- * residual-stream gradient in one pass). out_sum may be NULL. */
+ * residual-stream gradient in one pass). out_sum may be NULL; otherwise ws must hold
+ * pmv_colsum_workspace_bytes() bytes. */
+int64_t pmv_colsum_workspace_bytes(int64_t rows, int64_t cols);
 int pmv_colsum_cast(const void* in, int in_dtype, int64_t ld_in, int64_t rows, int64_t cols,
-                    const float* row_scale, int64_t rows_per_scale, float* out_sum,
+                    const float* row_scale, int64_t rows_per_scale, float* out_sum, float* ws,
                     void* cast_out, int cast_dtype, int64_t ld_cast, void* stream);
 
 /* ---------------------------------------------------------------- pooling ------------
@@ -122,12 +126,14 @@ int pmv_colsum_cast(const void* in, int in_dtype, int64_t ld_in, int64_t rows, i
 int pmv_pool_ln_fwd(const void* in, int64_t in_batch_stride, int64_t in_token_stride, int64_t in_head_stride,
                     const float* w, const float* gamma, const float* beta, void* out, int64_t out_ld,
                     int B, int heads, int T, int H, int W, int stride_hw, float eps, int dtype, void* stream);
-/* Backward.  dconv_ws: fp32 workspace [B*heads*T*Ho*Wo*96].  din is written (not accumulated) with
- * the same strides as `in` (so q/k/v gradients land interleaved in the dQKV buffer); dw [96*27],
- * dgamma/dbeta [96] fp32 are atomically added to. */
+/* Backward.  din is written (not accumulated) with the same strides as `in` (so q/k/v gradients land
+ * interleaved in the dQKV buffer); dw_dgamma_dbeta is fp32 [96*27 + 96 + 96] (Conv3d weight gradient in the
+ * reference layout, then the LayerNorm weight and bias gradients) and is added to.
+ * ws: fp32 workspace of pmv_pool_ln_bwd_workspace_bytes() bytes (pre-LN gradient + per-CTA partial sums). */
+int64_t pmv_pool_ln_bwd_workspace_bytes(int B, int heads, int T, int H, int W, int stride_hw);
 int pmv_pool_ln_bwd(const void* in, int64_t in_batch_stride, int64_t in_token_stride, int64_t in_head_stride,
                     const float* w, const float* gamma, const void* dout, int64_t dout_ld,
-                    void* din, float* dw, float* dgamma, float* dbeta, float* dconv_ws,
+                    void* din, float* dw_dgamma_dbeta, float* ws,
                     int B, int heads, int T, int H, int W, int stride_hw, float eps, int dtype, void* stream);
 
 /* Skip-path MaxPool3d k (1,3,3) s (1,2,2) p (0,1,1) on [B, 1+T*H*W, C] fp32 tokens (cls copied):
@@ -152,11 +158,14 @@ int pmv_relpos_augment_q(void* q_aug, int64_t ld, const float* rel_h, const floa
                          int BH, int qt, int qh, int qw, int kt, int kh, int kw,
                          float inv_scale, int dtype, void* stream);
 int pmv_relpos_augment_k(void* k_aug, int64_t ld, int BH, int kt, int kh, int kw, int dtype, void* stream);
-/* Backward of augment_q: given dQ' (same layout), accumulates (fp32, atomics) d rel_h/w/t and adds the
- * bias path's contribution to dq in place (columns [0,96) of dq_aug, non-cls rows). */
+/* Backward of augment_q: given dQ' (same layout), adds the table gradients into d_rel (fp32
+ * [rows_h + rows_w + rows_t][96]: the three tables stacked in that order) and adds the bias path's
+ * contribution to dq in place (columns [0,96) of dq_aug, non-cls rows).
+ * ws: fp32 workspace of pmv_relpos_bwd_workspace_bytes() bytes. */
+int64_t pmv_relpos_bwd_workspace_bytes(int BH, int qt, int qh, int qw, int kt, int kh, int kw);
 int pmv_relpos_augment_q_bwd(void* dq_aug, const void* q_aug, int64_t ld, const float* rel_h, const float* rel_w,
                              const float* rel_t, const int32_t* idx_h, const int32_t* idx_w, const int32_t* idx_t,
-                             float* d_rel_h, float* d_rel_w, float* d_rel_t,
+                             float* d_rel, float* ws,
                              int BH, int qt, int qh, int qw, int kt, int kh, int kw,
                              float inv_scale, int dtype, void* stream);
 

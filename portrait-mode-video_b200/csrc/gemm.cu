@@ -1,5 +1,6 @@
 // pmv_gemm dispatcher (fp32 FFMA kernel vs tcgen05 kernel) and the column-sum / cast helper.
 #include "gemm.h"
+#include "reduce.cuh"
 
 extern "C" int pmv_gemm(int layout, const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldo,
                         int64_t M, int64_t N, int64_t K, int io_dtype, int out_dtype, const pmv_epilogue* epi,
@@ -58,36 +59,49 @@ __global__ void __launch_bounds__(256) colsum_cast_kernel(const TIn* __restrict_
 #pragma unroll
     for (int j = 0; j < 4; ++j) s[j] += v[j];
   }
-  if (out_sum) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) atomicAdd(out_sum + c4 + j, s[j]);
-  }
+  if (out_sum) store4(out_sum + (int64_t)blockIdx.y * cols + c4, s);  // one partial row per row slice
 }
 }  // namespace
 
+static void colsum_grid(int64_t rows, int64_t cols, unsigned* bx, int64_t* rpb, unsigned* by) {
+  const int64_t col_threads = cols / 4;
+  *bx = (unsigned)ceil_div64(col_threads, 256);
+  int64_t slices = ceil_div64(148 * 4, *bx);  // enough row slices to fill the machine
+  if (slices > ceil_div64(rows, 16)) slices = ceil_div64(rows, 16);
+  if (slices < 1) slices = 1;
+  *rpb = ceil_div64(rows, slices);
+  *by = (unsigned)ceil_div64(rows, *rpb);
+}
+
+extern "C" int64_t pmv_colsum_workspace_bytes(int64_t rows, int64_t cols) {
+  unsigned bx, by;
+  int64_t rpb;
+  colsum_grid(rows, cols, &bx, &rpb, &by);
+  return (int64_t)by * cols * (int64_t)sizeof(float);
+}
+
 extern "C" int pmv_colsum_cast(const void* in, int in_dtype, int64_t ld_in, int64_t rows, int64_t cols,
-                               const float* row_scale, int64_t rows_per_scale, float* out_sum,
+                               const float* row_scale, int64_t rows_per_scale, float* out_sum, float* ws,
                                void* cast_out, int cast_dtype, int64_t ld_cast, void* stream) {
   PMV_CHECK_ARG(cols % 4 == 0 && ld_in % 4 == 0 && (cast_out == nullptr || ld_cast % 4 == 0), "colsum: cols / ld must be multiples of 4");
   if (rows == 0) return PMV_OK;
   if (rows_per_scale <= 0) rows_per_scale = 1;
   const int64_t col_threads = cols / 4;
-  const unsigned bx = (unsigned)ceil_div64(col_threads, 256);
-  // enough row slices to fill the machine: ~148*8 blocks
-  int64_t slices = ceil_div64(148 * 8, bx);
-  if (slices > ceil_div64(rows, 16)) slices = ceil_div64(rows, 16);
-  if (slices < 1) slices = 1;
-  const int64_t rpb = ceil_div64(rows, slices);
-  dim3 grid(bx, (unsigned)ceil_div64(rows, rpb));
+  unsigned bx, by;
+  int64_t rpb;
+  colsum_grid(rows, cols, &bx, &rpb, &by);
+  dim3 grid(bx, by);
+  PMV_CHECK_ARG(out_sum == nullptr || ws != nullptr, "colsum: workspace required when out_sum is given");
   const int threads = col_threads < 256 ? (int)((col_threads + 31) / 32 * 32) : 256;
 #define LAUNCH(TI, TC) colsum_cast_kernel<TI, TC><<<grid, threads, 0, (cudaStream_t)stream>>>( \
-      (const TI*)in, ld_in, rows, cols, row_scale, rows_per_scale, out_sum, (TC*)cast_out, ld_cast, rpb)
+      (const TI*)in, ld_in, rows, cols, row_scale, rows_per_scale, out_sum ? ws : nullptr, (TC*)cast_out, ld_cast, rpb)
   if (in_dtype == PMV_F32 && cast_dtype == PMV_F32) LAUNCH(float, float);
   else if (in_dtype == PMV_F32 && cast_dtype == PMV_BF16) LAUNCH(float, bf16);
   else if (in_dtype == PMV_BF16 && cast_dtype == PMV_BF16) LAUNCH(bf16, bf16);
   else if (in_dtype == PMV_BF16 && cast_dtype == PMV_F32) LAUNCH(bf16, float);
   else { pmv_set_error("colsum: bad dtype"); return PMV_ERR_INVALID_ARGUMENT; }
 #undef LAUNCH
+  if (out_sum) launch_reduce_partials(ws, (int)by, (int)cols, out_sum, (cudaStream_t)stream);
   PMV_CHECK_LAUNCH();
   return PMV_OK;
 }

@@ -2,6 +2,7 @@
 // Replaces native_layer_norm at attention.py:567,578 and video_model_builder.py:2163.
 // Memory-bound: one warp per row, 16-byte loads, two-pass (mean, then centred variance) in fp32.
 #include "common.cuh"
+#include "reduce.cuh"
 
 namespace {
 
@@ -59,12 +60,12 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_fwd_kernel(
 // Backward.  Per row:  xhat = (x-mu)*rstd, g = dy*gamma,
 //   dx = rstd * (g - mean(g) - xhat*mean(g*xhat));  dgamma += dy*xhat; dbeta += dy.
 // dgamma/dbeta: per-thread partials over the rows this warp visits -> smem reduce over warps ->
-// one atomicAdd per column per block.
+// one partial vector per block (folded by reduce_partials_kernel; dgamma and dbeta must be adjacent: [2][C]).
 template <typename TDy>
 __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(
     const TDy* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
     const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dx, int accumulate,
-    float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int C) {
+    float* __restrict__ partials, int64_t rows, int C) {
   extern __shared__ float red[];  // [2][C]
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -136,10 +137,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    atomicAdd(&dgamma[i], red[i]);
-    atomicAdd(&dbeta[i], red[C + i]);
-  }
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) partials[(int64_t)blockIdx.x * 2 * C + i] = red[i];
 }
 
 }  // namespace
@@ -157,17 +155,24 @@ extern "C" int pmv_layernorm_fwd(const float* x, const float* gamma, const float
   return PMV_OK;
 }
 
+static int64_t ln_bwd_blocks(int64_t rows) {
+  int64_t blocks = ceil_div64(rows, LN_WARPS * 4);
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  return blocks < 1 ? 1 : blocks;
+}
+
+extern "C" int64_t pmv_layernorm_bwd_workspace_bytes(int64_t rows, int C) { return ln_bwd_blocks(rows) * 2 * C * (int64_t)sizeof(float); }
+
 extern "C" int pmv_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma,
                                  const float* mean, const float* rstd, float* dx, int accumulate,
-                                 float* dgamma, float* dbeta, int64_t rows, int C, void* stream) {
+                                 float* dgamma_dbeta, float* ws, int64_t rows, int C, void* stream) {
   PMV_CHECK_ARG(C % 4 == 0 && C <= 1024 && C > 0, "layernorm: C=%d must be a multiple of 4 and <= 1024", C);
   if (rows == 0) return PMV_OK;
-  int64_t blocks = ceil_div64(rows, LN_WARPS * 4);
-  if (blocks > 148 * 4) blocks = 148 * 4;
-  if (blocks < 1) blocks = 1;
+  const int64_t blocks = ln_bwd_blocks(rows);
   size_t smem = 2 * (size_t)C * sizeof(float);
   PMV_DISPATCH_DTYPE(dy_dtype, T, (layernorm_bwd_kernel<T><<<(unsigned)blocks, LN_WARPS * 32, smem, (cudaStream_t)stream>>>(
-                                      (const T*)dy, x, gamma, mean, rstd, dx, accumulate, dgamma, dbeta, rows, C)));
+                                      (const T*)dy, x, gamma, mean, rstd, dx, accumulate, ws, rows, C)));
+  launch_reduce_partials(ws, (int)blocks, 2 * C, dgamma_dbeta, (cudaStream_t)stream);
   PMV_CHECK_LAUNCH();
   return PMV_OK;
 }

@@ -12,6 +12,7 @@
 // (24 B of bf16 / 48 B of fp32 -> 8- or 16-byte vector loads); a warp handles 4 tokens that are
 // neighbours along w, so the 3-wide window overlap is served by L1.
 #include "common.cuh"
+#include "reduce.cuh"
 
 namespace {
 
@@ -132,8 +133,8 @@ constexpr int BWD_WARPS = 8;
 template <typename T>
 __global__ void __launch_bounds__(BWD_WARPS * 32) pool_ln_bwd_tokens_kernel(
     const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ gamma,
-    const T* __restrict__ dout, int64_t dout_ld, T* __restrict__ din, float* __restrict__ dw,
-    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dconv, PoolGeom g, float eps) {
+    const T* __restrict__ dout, int64_t dout_ld, T* __restrict__ din, float* __restrict__ partials,
+    float* __restrict__ dconv, PoolGeom g, float eps) {
   __shared__ float sw[TAPS * HD];
   __shared__ float sred[(TAPS + 2) * HD];
   stage_weights(w, sw);
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) pool_ln_bwd_tokens_kernel(
       }
     }
   }
-  // block reduction through shared memory, then one global atomic per (tap, channel) per block
+  // block reduction through shared memory
 #pragma unroll
   for (int k = 0; k < TAPS; ++k)
 #pragma unroll
@@ -252,14 +253,13 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) pool_ln_bwd_tokens_kernel(
     atomicAdd(&sred[(TAPS + 1) * HD + lane + 32 * j], adb[j]);
   }
   __syncthreads();
+  // one partial vector per block, already in the destination order: dw in the reference layout [96][27], dgamma, dbeta
+  float* pb = partials + (int64_t)blockIdx.x * ((TAPS + 2) * HD);
   for (int i = threadIdx.x; i < TAPS * HD; i += blockDim.x) {
     const int tap = i / HD, c = i - tap * HD;
-    atomicAdd(&dw[c * TAPS + tap], sred[i]);  // back to the reference layout [96][27]
+    pb[c * TAPS + tap] = sred[i];
   }
-  for (int i = threadIdx.x; i < HD; i += blockDim.x) {
-    atomicAdd(&dgamma[i], sred[TAPS * HD + i]);
-    atomicAdd(&dbeta[i], sred[(TAPS + 1) * HD + i]);
-  }
+  for (int i = threadIdx.x; i < 2 * HD; i += blockDim.x) pb[TAPS * HD + i] = sred[TAPS * HD + i];
 }
 
 // backward, pass 2: gather form of the transposed stencil — one 8-lane group per INPUT token,
@@ -436,22 +436,32 @@ extern "C" int pmv_pool_ln_fwd(const void* in, int64_t in_batch_stride, int64_t 
   return PMV_OK;
 }
 
+extern "C" int64_t pmv_pool_ln_bwd_workspace_bytes(int B, int heads, int T, int H, int W, int stride_hw) {
+  const int Ho = (H - 1) / stride_hw + 1, Wo = (W - 1) / stride_hw + 1;
+  const int64_t ntok_out = (int64_t)B * heads * (1 + (int64_t)T * Ho * Wo);
+  const int64_t dconv = (int64_t)B * heads * T * Ho * Wo * HD;
+  return (dconv + (int64_t)grid_for(ntok_out, BWD_WARPS * 8, 148 * 2) * (TAPS + 2) * HD) * (int64_t)sizeof(float);
+}
+
 extern "C" int pmv_pool_ln_bwd(const void* in, int64_t in_batch_stride, int64_t in_token_stride, int64_t in_head_stride,
                                const float* w, const float* gamma, const void* dout, int64_t dout_ld,
-                               void* din, float* dw, float* dgamma, float* dbeta, float* dconv_ws,
+                               void* din, float* dw_dgamma_dbeta, float* ws,
                                int B, int heads, int T, int H, int W, int stride_hw, float eps, int dtype, void* stream) {
   int rc = check_geom(B, heads, T, H, W, stride_hw, in_token_stride, in_head_stride, dout_ld, dtype);
   if (rc) return rc;
   PoolGeom g = make_geom(B, heads, T, H, W, stride_hw, in_batch_stride, in_token_stride, in_head_stride, dout_ld);
   const int64_t ntok_out = (int64_t)B * heads * (1 + (int64_t)T * g.Ho * g.Wo);
   const int64_t ntok_in = (int64_t)B * heads * T * H * W;
-  unsigned grid1 = grid_for(ntok_out, BWD_WARPS * 8, 148 * 4);
+  unsigned grid1 = grid_for(ntok_out, BWD_WARPS * 8, 148 * 2);
   unsigned grid2 = grid_for(ntok_in, TOK_PER_BLOCK, 148 * 32);
+  float* dconv_ws = ws;
+  float* partials = ws + (int64_t)B * heads * T * g.Ho * g.Wo * HD;
   PMV_DISPATCH_DTYPE(dtype, TT, {
     pool_ln_bwd_tokens_kernel<TT><<<grid1, BWD_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        (const TT*)in, w, gamma, (const TT*)dout, dout_ld, (TT*)din, dw, dgamma, dbeta, dconv_ws, g, eps);
+        (const TT*)in, w, gamma, (const TT*)dout, dout_ld, (TT*)din, partials, dconv_ws, g, eps);
     pool_ln_bwd_input_kernel<TT><<<grid2, POOL_THREADS, 0, (cudaStream_t)stream>>>(w, dconv_ws, (TT*)din, g);
   });
+  launch_reduce_partials(partials, (int)grid1, (TAPS + 2) * HD, dw_dgamma_dbeta, (cudaStream_t)stream);
   PMV_CHECK_LAUNCH();
   return PMV_OK;
 }

@@ -10,6 +10,7 @@
 // coordinates (zeros for the cls key).  R_j(q) are rows of rel_pos_h/w/t selected by the reference's index
 // arithmetic (attention.py:80-99,132-139), passed in as small int32 tables.
 #include "common.cuh"
+#include "reduce.cuh"
 
 namespace {
 
@@ -101,13 +102,13 @@ __global__ void __launch_bounds__(256) relpos_augment_k_kernel(T* __restrict__ k
 }
 
 // backward of augment_q.  One warp per query, lane owns channels {lane, lane+32, lane+64}.
-// dynamic smem: fp32 gradient tables [(rows)][96] accumulated with shared atomics, flushed once per block.
+// dynamic smem: fp32 gradient tables [(rows)][96] accumulated with shared atomics, written out once per block.
 template <typename T>
 __global__ void __launch_bounds__(AUG_WARPS * 32) relpos_augment_q_bwd_kernel(
     T* __restrict__ dq_aug, const T* __restrict__ q_aug, int64_t ld, const float* __restrict__ rel_h,
     const float* __restrict__ rel_w, const float* __restrict__ rel_t, const int32_t* __restrict__ idx_h,
-    const int32_t* __restrict__ idx_w, const int32_t* __restrict__ idx_t, float* __restrict__ d_rel_h,
-    float* __restrict__ d_rel_w, float* __restrict__ d_rel_t, int64_t BH, RelGeom g, float inv_scale) {
+    const int32_t* __restrict__ idx_w, const int32_t* __restrict__ idx_t, float* __restrict__ partials,
+    int64_t BH, RelGeom g, float inv_scale) {
   extern __shared__ float dtab[];
   const int rows = g.rows_h + g.rows_w + g.rows_t;
   for (int i = threadIdx.x; i < rows * HD; i += blockDim.x) dtab[i] = 0.f;
@@ -146,14 +147,8 @@ __global__ void __launch_bounds__(AUG_WARPS * 32) relpos_augment_q_bwd_kernel(
     for (int j = 0; j < 3; ++j) dqp[lane + 32 * j] = from_f32<T>(acc[j]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < rows * HD; i += blockDim.x) {
-    const int r = i / HD, c = i - r * HD;
-    const float v = dtab[i];
-    if (v == 0.f) continue;
-    if (r < g.rows_h) atomicAdd(&d_rel_h[r * HD + c], v);
-    else if (r < g.rows_h + g.rows_w) atomicAdd(&d_rel_w[(r - g.rows_h) * HD + c], v);
-    else atomicAdd(&d_rel_t[(r - g.rows_h - g.rows_w) * HD + c], v);
-  }
+  // one partial table per block ([rows_h + rows_w + rows_t][96], folded by reduce_partials_kernel)
+  for (int i = threadIdx.x; i < rows * HD; i += blockDim.x) partials[(int64_t)blockIdx.x * rows * HD + i] = dtab[i];
 }
 
 RelGeom make_rel(int qt, int qh, int qw, int kt, int kh, int kw) {
@@ -198,22 +193,34 @@ extern "C" int pmv_relpos_augment_k(void* k_aug, int64_t ld, int BH, int kt, int
   return PMV_OK;
 }
 
+static int64_t relpos_bwd_blocks(int64_t total_rows) {
+  int64_t blocks = ceil_div64(total_rows, AUG_WARPS * 8);
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  return blocks < 1 ? 1 : blocks;
+}
+
+extern "C" int64_t pmv_relpos_bwd_workspace_bytes(int BH, int qt, int qh, int qw, int kt, int kh, int kw) {
+  RelGeom g = make_rel(qt, qh, qw, kt, kh, kw);
+  return relpos_bwd_blocks((int64_t)BH * (qt * qh * qw + 1)) * (g.rows_h + g.rows_w + g.rows_t) * HD * (int64_t)sizeof(float);
+}
+
+/* d_rel: [rows_h + rows_w + rows_t][96] fp32 (the three tables stacked), added to. */
 extern "C" int pmv_relpos_augment_q_bwd(void* dq_aug, const void* q_aug, int64_t ld, const float* rel_h, const float* rel_w,
                                         const float* rel_t, const int32_t* idx_h, const int32_t* idx_w, const int32_t* idx_t,
-                                        float* d_rel_h, float* d_rel_w, float* d_rel_t,
+                                        float* d_rel, float* ws,
                                         int BH, int qt, int qh, int qw, int kt, int kh, int kw,
                                         float inv_scale, int dtype, void* stream) {
   RelGeom g = make_rel(qt, qh, qw, kt, kh, kw);
   const size_t smem = (size_t)(g.rows_h + g.rows_w + g.rows_t) * HD * sizeof(float);
   PMV_CHECK_ARG(smem <= 200 * 1024, "relpos: tables too large for shared memory");
   const int64_t total = (int64_t)BH * (qt * qh * qw + 1);
-  int64_t blocks = ceil_div64(total, AUG_WARPS * 8);
-  if (blocks > 148 * 2) blocks = 148 * 2;
+  const int64_t blocks = relpos_bwd_blocks(total);
   PMV_DISPATCH_DTYPE(dtype, T, {
     PMV_CHECK_CUDA(cudaFuncSetAttribute(relpos_augment_q_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     relpos_augment_q_bwd_kernel<T><<<(unsigned)blocks, AUG_WARPS * 32, smem, (cudaStream_t)stream>>>(
-        (T*)dq_aug, (const T*)q_aug, ld, rel_h, rel_w, rel_t, idx_h, idx_w, idx_t, d_rel_h, d_rel_w, d_rel_t, BH, g, inv_scale);
+        (T*)dq_aug, (const T*)q_aug, ld, rel_h, rel_w, rel_t, idx_h, idx_w, idx_t, ws, BH, g, inv_scale);
   });
+  launch_reduce_partials(ws, (int)blocks, (g.rows_h + g.rows_w + g.rows_t) * HD, d_rel, (cudaStream_t)stream);
   PMV_CHECK_LAUNCH();
   return PMV_OK;
 }

@@ -31,16 +31,20 @@ _SIGS = {
     "pmv_version": (_i, []),
     "pmv_has_tcgen05": (_i, []),
     "pmv_layernorm_fwd": (_i, [_p, _p, _p, _p, _i, _p, _p, _i64, _i, _f, _p]),
+    "pmv_layernorm_bwd_workspace_bytes": (_i64, [_i64, _i]),
     "pmv_layernorm_bwd": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _p, _p, _i64, _i, _p]),
     "pmv_gemm": (_i, [_i, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _i, _i, C.POINTER(Epilogue), _i, _i, _p]),
-    "pmv_colsum_cast": (_i, [_p, _i, _i64, _i64, _i64, _p, _i64, _p, _p, _i, _i64, _p]),
+    "pmv_colsum_workspace_bytes": (_i64, [_i64, _i64]),
+    "pmv_colsum_cast": (_i, [_p, _i, _i64, _i64, _i64, _p, _i64, _p, _p, _p, _i, _i64, _p]),
     "pmv_pool_ln_fwd": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
-    "pmv_pool_ln_bwd": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
+    "pmv_pool_ln_bwd_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, _i]),
+    "pmv_pool_ln_bwd": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _i64, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
     "pmv_maxpool_skip_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "pmv_maxpool_skip_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "pmv_relpos_augment_q": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
     "pmv_relpos_augment_k": (_i, [_p, _i64, _i, _i, _i, _i, _i, _p]),
-    "pmv_relpos_augment_q_bwd": (_i, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
+    "pmv_relpos_bwd_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, _i, _i]),
+    "pmv_relpos_augment_q_bwd": (_i, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
     "pmv_attention_fwd": (_i, [_p, _p, _i64, _i, _p, _i64, _p, _p, _p, _i, _i, _i, _i, _f, _i, _i, _i, _p]),
     "pmv_attention_bwd_workspace_bytes": (_i64, [_i, _i, _i, _i]),
     "pmv_attention_bwd": (_i, [_p, _p, _i64, _i, _p, _i64, _p, _p, _p, _p, _p, _i64, _p, _i64, _p, _i, _i, _i, _i, _f, _i, _i, _i, _p]),

@@ -211,9 +211,9 @@ class PoolAttentionFn(Function):
             drh, drw, drt = ops.relpos_augment_q_bwd(dq_aug, q_aug, q_shape, k_shape, rel_h, rel_w, rel_t, 1.0 / scale)
         dqkv = torch.empty_like(qkv5)
         g = torch.zeros(3, 96 * 27 + 192, dtype=torch.float32, device=qkv5.device)
-        ops.pool_ln_bwd(qkv5, 0, heads, thw, sq, wq, gq, dq_aug.view(B, heads, Nq, ld), dqkv, g[0, :2592], g[0, 2592:2688], g[0, 2688:], eps)
-        ops.pool_ln_bwd(qkv5, 1, heads, thw, skv, wk, gk, dk.view(B, heads, Nk, 96), dqkv, g[1, :2592], g[1, 2592:2688], g[1, 2688:], eps)
-        ops.pool_ln_bwd(qkv5, 2, heads, thw, skv, wv, gv, dv.view(B, heads, Nk, 96), dqkv, g[2, :2592], g[2, 2592:2688], g[2, 2688:], eps)
+        ops.pool_ln_bwd(qkv5, 0, heads, thw, sq, wq, gq, dq_aug.view(B, heads, Nq, ld), dqkv, g[0], eps)
+        ops.pool_ln_bwd(qkv5, 1, heads, thw, skv, wk, gk, dk.view(B, heads, Nk, 96), dqkv, g[1], eps)
+        ops.pool_ln_bwd(qkv5, 2, heads, thw, skv, wv, gv, dv.view(B, heads, Nk, 96), dqkv, g[2], eps)
         dw = [g[i, :2592].view(96, 1, 3, 3, 3) for i in range(3)]
         dg = [g[i, 2592:2688] for i in range(3)]
         db = [g[i, 2688:] for i in range(3)]

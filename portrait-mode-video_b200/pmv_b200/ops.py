@@ -37,6 +37,11 @@ class record_kernels:
         _RECORDER = None
 
 
+def _ws(nbytes: int, device) -> torch.Tensor:
+    """fp32 scratch for the block-partial reductions (stream-ordered: torch's caching allocator recycles it)."""
+    return torch.empty(max(int(nbytes) // 4, 1), dtype=torch.float32, device=device)
+
+
 def _run(name: str, nkernels: int, meta, *args):
     global LAUNCHES
     LAUNCHES += nkernels
@@ -73,8 +78,9 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dx_accum: Optional[torch.Tensor] = N
     dy = dy.contiguous()
     dx = dx_accum if dx_accum is not None else torch.empty_like(x)
     dgb = torch.zeros(2, Cdim, dtype=torch.float32, device=x.device)
-    _run("pmv_layernorm_bwd", 1, dict(bytes=rows * Cdim * (8 + dy.element_size() + (4 if dx_accum is not None else 0))), L.ptr(dy), L.dt(dy), L.ptr(x), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), L.ptr(dx),
-                                      1 if dx_accum is not None else 0, L.ptr(dgb[0]), L.ptr(dgb[1]), rows, Cdim,
+    ws = _ws(L.lib().pmv_layernorm_bwd_workspace_bytes(rows, Cdim), x.device)
+    _run("pmv_layernorm_bwd", 2, dict(bytes=rows * Cdim * (8 + dy.element_size() + (4 if dx_accum is not None else 0))), L.ptr(dy), L.dt(dy), L.ptr(x), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), L.ptr(dx),
+                                      1 if dx_accum is not None else 0, L.ptr(dgb), L.ptr(ws), rows, Cdim,
                                       L.stream())
     return dx, dgb[0], dgb[1]
 
@@ -141,8 +147,9 @@ def colsum_cast(x2d, cast_dtype=None, row_scale=None, rows_per_scale=1, want_sum
     rows, cols = x2d.shape
     s = torch.zeros(cols, dtype=torch.float32, device=x2d.device) if want_sum else None
     c = torch.empty(rows, cols, dtype=cast_dtype, device=x2d.device) if cast_dtype is not None else None
-    _run("pmv_colsum_cast", 1, dict(bytes=rows * cols * (x2d.element_size() + (c.element_size() if c is not None else 0))), L.ptr(x2d), L.dt(x2d), x2d.stride(0), rows, cols, L.ptr(row_scale), rows_per_scale,
-                                    L.ptr(s), L.ptr(c), L.dt(cast_dtype) if cast_dtype is not None else 0,
+    ws = _ws(L.lib().pmv_colsum_workspace_bytes(rows, cols), x2d.device) if want_sum else None
+    _run("pmv_colsum_cast", 2 if want_sum else 1, dict(bytes=rows * cols * (x2d.element_size() + (c.element_size() if c is not None else 0))), L.ptr(x2d), L.dt(x2d), x2d.stride(0), rows, cols, L.ptr(row_scale), rows_per_scale,
+                                    L.ptr(s), L.ptr(ws), L.ptr(c), L.dt(cast_dtype) if cast_dtype is not None else 0,
                                     c.stride(0) if c is not None else 0, L.stream())
     return s, c
 
@@ -164,15 +171,15 @@ def pool_ln_fwd(qkv: torch.Tensor, which: int, heads: int, thw: Sequence[int], s
     return out
 
 
-def pool_ln_bwd(qkv, which, heads, thw, stride_hw, w, gamma, dout, dqkv, dw, dgamma, dbeta, eps=LN_EPS):
+def pool_ln_bwd(qkv, which, heads, thw, stride_hw, w, gamma, dout, dqkv, grads, eps=LN_EPS):
+    """grads: fp32 [96*27 + 96 + 96] (Conv3d weight gradient, LayerNorm weight gradient, bias gradient), added to."""
     B = qkv.shape[0]
     T, H, W = thw
-    Lo = T * pooled_hw(H, stride_hw) * pooled_hw(W, stride_hw)
-    ws = torch.empty(B * heads * Lo * 96, dtype=torch.float32, device=qkv.device)
-    _run("pmv_pool_ln_bwd", 2, dict(bytes=(2 * B * qkv.shape[1] * heads * 96 + dout.shape[0] * dout.shape[1] * dout.shape[2] * 96) * qkv.element_size()), qkv[:, :, which].data_ptr(), qkv.stride(0), qkv.stride(1), qkv.stride(3), L.ptr(w),
-                                    L.ptr(gamma), L.ptr(dout), dout.stride(2), dqkv[:, :, which].data_ptr(), L.ptr(dw),
-                                    L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), B, heads, T, H, W, stride_hw, eps, L.dt(qkv),
-                                    L.stream())
+    ws = _ws(L.lib().pmv_pool_ln_bwd_workspace_bytes(B, heads, T, H, W, stride_hw), qkv.device)
+    _run("pmv_pool_ln_bwd", 3, dict(bytes=(2 * B * qkv.shape[1] * heads * 96 + dout.shape[0] * dout.shape[1] * dout.shape[2] * 96) * qkv.element_size()),
+         qkv[:, :, which].data_ptr(), qkv.stride(0), qkv.stride(1), qkv.stride(3), L.ptr(w), L.ptr(gamma), L.ptr(dout),
+         dout.stride(2), dqkv[:, :, which].data_ptr(), L.ptr(grads), L.ptr(ws), B, heads, T, H, W, stride_hw, eps,
+         L.dt(qkv), L.stream())
 
 
 def maxpool_skip_fwd(x, thw):
@@ -237,11 +244,13 @@ def relpos_augment_q_bwd(dq_aug, q_aug, q_shape, k_shape, rel_h, rel_w, rel_t, i
     dev = q_aug.device
     ih, iw, it = (rel_index_table(q_shape[1], k_shape[1], dev), rel_index_table(q_shape[2], k_shape[2], dev),
                   rel_index_table(q_shape[0], k_shape[0], dev))
-    dh, dw, dt_ = torch.zeros_like(rel_h), torch.zeros_like(rel_w), torch.zeros_like(rel_t)
-    _run("pmv_relpos_augment_q_bwd", 1, dict(bytes=2 * BH * Nq * ld * q_aug.element_size()), L.ptr(dq_aug), L.ptr(q_aug), ld, L.ptr(rel_h), L.ptr(rel_w), L.ptr(rel_t),
-                                             L.ptr(ih), L.ptr(iw), L.ptr(it), L.ptr(dh), L.ptr(dw), L.ptr(dt_), BH,
-                                             *q_shape, *k_shape, inv_scale, L.dt(q_aug), L.stream())
-    return dh, dw, dt_
+    nh, nw, nt = rel_h.shape[0], rel_w.shape[0], rel_t.shape[0]
+    d_rel = torch.zeros(nh + nw + nt, 96, dtype=torch.float32, device=dev)
+    ws = _ws(L.lib().pmv_relpos_bwd_workspace_bytes(BH, *q_shape, *k_shape), dev)
+    _run("pmv_relpos_augment_q_bwd", 2, dict(bytes=2 * BH * Nq * ld * q_aug.element_size()), L.ptr(dq_aug), L.ptr(q_aug), ld,
+         L.ptr(rel_h), L.ptr(rel_w), L.ptr(rel_t), L.ptr(ih), L.ptr(iw), L.ptr(it), L.ptr(d_rel), L.ptr(ws), BH,
+         *q_shape, *k_shape, inv_scale, L.dt(q_aug), L.stream())
+    return d_rel[:nh], d_rel[nh:nh + nw], d_rel[nh + nw:]
 
 
 def attention_fwd(q_aug, k_aug, v, B, heads, kd, scale, residual=True, want_lse=True, tc=None):

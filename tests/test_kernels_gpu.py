@@ -76,7 +76,7 @@ def test_pool_ln_fwd_bwd(dtype, B, heads, thw, s):
         ref.backward(dout[..., :96].float())
         dqkv = torch.full_like(qkv, float("nan"))
         dwg = torch.zeros(96 * 27 + 192, device="cuda")
-        ops.pool_ln_bwd(qkv, which, heads, thw, s, w, g, dout, dqkv, dwg[:2592], dwg[2592:2688], dwg[2688:])
+        ops.pool_ln_bwd(qkv, which, heads, thw, s, w, g, dout, dqkv, dwg)
         got_dx = dqkv[:, :, which].permute(0, 2, 1, 3).float()
         assert nerr(got_dx, xin.grad) < TOL[dtype], which
         assert nerr(dwg[:2592].view(96, 27), wr.grad.view(96, 27)) < TOL[dtype]
