@@ -136,6 +136,30 @@ int pmv_pool_ln_bwd(const void* in, int64_t in_batch_stride, int64_t in_token_st
                     void* din, float* dw_dgamma_dbeta, float* ws,
                     int B, int heads, int T, int H, int W, int stride_hw, float eps, int dtype, void* stream);
 
+/* q, k and v pooled in ONE launch (the three jobs share the QKV buffer and the launch overhead).  Job i reads the
+ * tensor that starts `which * which_stride` elements into `qkv` ([B, N, 3, heads, 96]: which_stride = heads*96).
+ * Forward fills out / out_ld; backward reads dout / dout_ld, adds into grads (fp32 [96*27 + 96 + 96]) and writes
+ * the input gradient into `dqkv` at the same offset.  ws: pmv_pool_ln_qkv_bwd_workspace_bytes() bytes. */
+typedef struct {
+  const float* w;      /* Conv3d weight [96,1,3,3,3] */
+  const float* gamma;  /* LayerNorm weight [96] */
+  const float* beta;   /* LayerNorm bias [96] (forward only) */
+  void* out;           /* forward: [B, heads, 1+T*Ho*Wo, out_ld] */
+  int64_t out_ld;
+  const void* dout;    /* backward: gradient of out */
+  int64_t dout_ld;
+  float* grads;        /* backward */
+  int stride_hw;
+  int which;           /* 0 = q, 1 = k, 2 = v */
+} pmv_pool_job;
+int pmv_pool_ln_qkv_fwd(const void* qkv, int64_t batch_stride, int64_t token_stride, int64_t which_stride, int64_t head_stride,
+                        const pmv_pool_job* jobs, int njobs, int B, int heads, int T, int H, int W, float eps, int dtype,
+                        void* stream);
+int64_t pmv_pool_ln_qkv_bwd_workspace_bytes(int B, int heads, int T, int H, int W, const int* strides_hw, int njobs);
+int pmv_pool_ln_qkv_bwd(const void* qkv, int64_t batch_stride, int64_t token_stride, int64_t which_stride, int64_t head_stride,
+                        const pmv_pool_job* jobs, int njobs, void* dqkv, float* ws, int B, int heads, int T, int H, int W,
+                        float eps, int dtype, void* stream);
+
 /* Skip-path MaxPool3d k (1,3,3) s (1,2,2) p (0,1,1) on [B, 1+T*H*W, C] fp32 tokens (cls copied):
  * attention.py:500-502,558-564,571-573.  Backward recomputes the arg-max (first maximum in window
  * scan order, like ATen) and ATOMICALLY accumulates into dx (caller zero-initialises; dx may alias

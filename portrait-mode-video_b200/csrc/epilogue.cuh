@@ -47,7 +47,7 @@ __device__ __forceinline__ void epi_store(const EpiDev& e, int64_t row, int64_t 
 }
 
 // 4 consecutive columns (col % 4 == 0, all leading dimensions % 4 == 0)
-template <typename TIO, typename TOut>
+template <typename TIO, typename TOut, bool FAST = false>
 __device__ __forceinline__ void epi_store4(const EpiDev& e, int64_t row, int64_t col, const float (&acc)[4]) {
   float v[4] = {acc[0], acc[1], acc[2], acc[3]};
   if (e.atomic) {
@@ -65,12 +65,12 @@ __device__ __forceinline__ void epi_store4(const EpiDev& e, int64_t row, int64_t
   if (e.aux_out) store4(reinterpret_cast<TIO*>(e.aux_out) + row * e.ld_aux + col, v);
   if (e.act == PMV_ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = gelu_erf(v[j]);
+    for (int j = 0; j < 4; ++j) v[j] = FAST ? gelu_fast(v[j]) : gelu_erf(v[j]);
   } else if (e.act == PMV_ACT_GELU_BWD) {
     float u[4];
     load4(reinterpret_cast<const TIO*>(e.aux_in) + row * e.ld_aux + col, u);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] *= gelu_erf_grad(u[j]);
+    for (int j = 0; j < 4; ++j) v[j] *= FAST ? gelu_fast_grad(u[j]) : gelu_erf_grad(u[j]);
   }
   if (e.row_scale) {
     const float s = e.row_scale[row / e.rows_per_scale];

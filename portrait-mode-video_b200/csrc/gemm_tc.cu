@@ -189,7 +189,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float v[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) v[j] = stage_buf[rr * 33 + (lane & 7) * 4 + j];
-          if (row < p.M && col < p.N) epi_store4<bf16, TOut>(p.e, row, col, v);
+          if (row < p.M && col < p.N) epi_store4<bf16, TOut, true>(p.e, row, col, v);
         }
         __syncwarp();
       }
@@ -238,14 +238,18 @@ int launch_bn(int layout, int out_dtype, const CUtensorMap& tmA, const CUtensorM
   return launch_cfg<BN, true, true, float>(tmA, tmB, p, s);
 }
 
-int pick_bn(int64_t N) {
-  // smallest padded width first, then the widest tile (better operand reuse)
+int pick_bn(int64_t M, int64_t N, int splits) {
+  // wave-quantisation model: cost = waves over 148 SMs x (tile width + fixed per-tile overhead in columns);
+  // ties go to the wider tile (better operand reuse per byte staged)
   const int cands[4] = {256, 192, 128, 96};
   int best = 96;
-  int64_t best_pad = -1;
+  double best_cost = -1.0;
+  const int64_t tiles_m = ceil_div64(M, BM);
   for (int i = 0; i < 4; ++i) {
-    int64_t pad = ceil_div64(N, cands[i]) * cands[i];
-    if (best_pad < 0 || pad < best_pad) { best_pad = pad; best = cands[i]; }
+    const int64_t tiles = tiles_m * ceil_div64(N, cands[i]) * splits;
+    const int64_t waves = ceil_div64(tiles, 148);
+    const double cost = (double)waves * (cands[i] + 48);
+    if (best_cost < 0 || cost < best_cost - 1e-9) { best_cost = cost; best = cands[i]; }
   }
   return best;
 }
@@ -261,7 +265,8 @@ int gemm_tc_launch(int layout, const void* A, int64_t lda, const void* B, int64_
   PMV_CHECK_ARG(NN % 4 == 0 && e.ldo % 4 == 0, "gemm(tc): N and ldo must be multiples of 4");
   PMV_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "gemm(tc): operands must be 16-byte aligned");
   PMV_CHECK_ARG(layout != PMV_GEMM_NT_REDUCE_M || out_dtype == PMV_F32, "gemm(tc): wgrad output must be fp32");
-  const int BN = pick_bn(NN);
+  if (split_k < 1) split_k = 1;
+  const int BN = pick_bn(MM, NN, split_k);
   CUtensorMap tmA, tmB;
   int rc;
   if (layout == PMV_GEMM_TN) {

@@ -111,7 +111,14 @@ __global__ void __launch_bounds__(AUG_WARPS * 32) relpos_augment_q_bwd_kernel(
     int64_t BH, RelGeom g, float inv_scale) {
   extern __shared__ float dtab[];
   const int rows = g.rows_h + g.rows_w + g.rows_t;
-  for (int i = threadIdx.x; i < rows * HD; i += blockDim.x) dtab[i] = 0.f;
+  float* tab = dtab + rows * HD;  // the three tables stacked, staged once per block
+  for (int i = threadIdx.x; i < rows * HD; i += blockDim.x) {
+    dtab[i] = 0.f;
+    const int r = i / HD, c = i - r * HD;
+    tab[i] = r < g.rows_h ? rel_h[r * HD + c]
+             : r < g.rows_h + g.rows_w ? rel_w[(r - g.rows_h) * HD + c]
+                                       : rel_t[(r - g.rows_h - g.rows_w) * HD + c];
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Lq = g.qt * g.qh * g.qw;
@@ -130,13 +137,26 @@ __global__ void __launch_bounds__(AUG_WARPS * 32) relpos_augment_q_bwd_kernel(
     float qv[3], acc[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) { qv[j] = to_f32(qp[lane + 32 * j]); acc[j] = to_f32(dqp[lane + 32 * j]); }
+    // the d rq values of this query: one coalesced load, broadcast by shuffle inside the loop
+    const float d_lo = lane < RK ? to_f32(dqp[HD + lane]) * inv_scale : 0.f;
+    const float d_hi = lane + 32 < RK ? to_f32(dqp[HD + 32 + lane]) * inv_scale : 0.f;
+    // table row of column (j0 + lane): resolved once per query by the lanes, broadcast by shuffle
+    int my_row_lo = 0, my_row_hi = 0;
+    {
+      const int j = lane;
+      if (j < RK) my_row_lo = j < g.kh ? idx_h[ih * g.kh + j]
+                              : j < g.kh + g.kw ? g.rows_h + idx_w[iw * g.kw + (j - g.kh)]
+                                                : g.rows_h + g.rows_w + idx_t[it * g.kt + (j - g.kh - g.kw)];
+      const int j2 = lane + 32;
+      if (j2 < RK) my_row_hi = j2 < g.kh ? idx_h[ih * g.kh + j2]
+                               : j2 < g.kh + g.kw ? g.rows_h + idx_w[iw * g.kw + (j2 - g.kh)]
+                                                  : g.rows_h + g.rows_w + idx_t[it * g.kt + (j2 - g.kh - g.kw)];
+    }
+#pragma unroll 4
     for (int j = 0; j < RK; ++j) {
-      const float d = to_f32(dqp[HD + j]) * inv_scale;  // d rq[j]
-      int trow;
-      const float* src;
-      if (j < g.kh) { trow = idx_h[ih * g.kh + j]; src = rel_h + trow * HD; }
-      else if (j < g.kh + g.kw) { trow = idx_w[iw * g.kw + (j - g.kh)]; src = rel_w + trow * HD; trow += g.rows_h; }
-      else { trow = idx_t[it * g.kt + (j - g.kh - g.kw)]; src = rel_t + trow * HD; trow += g.rows_h + g.rows_w; }
+      const float d = __shfl_sync(0xffffffffu, j < 32 ? d_lo : d_hi, j & 31);
+      const int trow = __shfl_sync(0xffffffffu, j < 32 ? my_row_lo : my_row_hi, j & 31);
+      const float* src = tab + trow * HD;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         acc[c] = fmaf(d, src[lane + 32 * c], acc[c]);
@@ -211,8 +231,9 @@ extern "C" int pmv_relpos_augment_q_bwd(void* dq_aug, const void* q_aug, int64_t
                                         int BH, int qt, int qh, int qw, int kt, int kh, int kw,
                                         float inv_scale, int dtype, void* stream) {
   RelGeom g = make_rel(qt, qh, qw, kt, kh, kw);
-  const size_t smem = (size_t)(g.rows_h + g.rows_w + g.rows_t) * HD * sizeof(float);
+  const size_t smem = (size_t)2 * (g.rows_h + g.rows_w + g.rows_t) * HD * sizeof(float);
   PMV_CHECK_ARG(smem <= 200 * 1024, "relpos: tables too large for shared memory");
+  PMV_CHECK_ARG(kh + kw + kt <= 64, "relpos: at most 64 bias columns");
   const int64_t total = (int64_t)BH * (qt * qh * qw + 1);
   const int64_t blocks = relpos_bwd_blocks(total);
   PMV_DISPATCH_DTYPE(dtype, T, {

@@ -27,6 +27,11 @@ class Epilogue(C.Structure):
                 ("out_group", _i64), ("out_skip", _i64)]
 
 
+class PoolJob(C.Structure):
+    _fields_ = [("w", _p), ("gamma", _p), ("beta", _p), ("out", _p), ("out_ld", _i64), ("dout", _p), ("dout_ld", _i64),
+                ("grads", _p), ("stride_hw", _i), ("which", _i)]
+
+
 _SIGS = {
     "pmv_version": (_i, []),
     "pmv_has_tcgen05": (_i, []),
@@ -39,6 +44,9 @@ _SIGS = {
     "pmv_pool_ln_fwd": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
     "pmv_pool_ln_bwd_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, _i]),
     "pmv_pool_ln_bwd": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _i64, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
+    "pmv_pool_ln_qkv_fwd": (_i, [_p, _i64, _i64, _i64, _i64, C.POINTER(PoolJob), _i, _i, _i, _i, _i, _i, _f, _i, _p]),
+    "pmv_pool_ln_qkv_bwd_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, C.POINTER(_i), _i]),
+    "pmv_pool_ln_qkv_bwd": (_i, [_p, _i64, _i64, _i64, _i64, C.POINTER(PoolJob), _i, _p, _p, _i, _i, _i, _i, _i, _f, _i, _p]),
     "pmv_maxpool_skip_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "pmv_maxpool_skip_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "pmv_relpos_augment_q": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p]),

@@ -183,9 +183,9 @@ class PoolAttentionFn(Function):
         q_aug = torch.empty(B * heads, Nq, ld, dtype=T, device=dev)
         k_aug = torch.empty(B * heads, Nk, ld, dtype=T, device=dev)
         v = torch.empty(B * heads, Nk, 96, dtype=T, device=dev)
-        ops.pool_ln_fwd(qkv5, 0, heads, thw, stride_q, wq, gq, bq, q_aug.view(B, heads, Nq, ld), eps)
-        ops.pool_ln_fwd(qkv5, 1, heads, thw, stride_kv, wk, gk, bk, k_aug.view(B, heads, Nk, ld), eps)
-        ops.pool_ln_fwd(qkv5, 2, heads, thw, stride_kv, wv, gv, bv, v.view(B, heads, Nk, 96), eps)
+        ops.pool_ln_qkv_fwd(qkv5, heads, thw, [(0, stride_q, wq, gq, bq, q_aug.view(B, heads, Nq, ld)),
+                                               (1, stride_kv, wk, gk, bk, k_aug.view(B, heads, Nk, ld)),
+                                               (2, stride_kv, wv, gv, bv, v.view(B, heads, Nk, 96))], eps)
         if has_rel:
             ops.relpos_augment_q(q_aug, q_shape, k_shape, rel_h, rel_w, rel_t, 1.0 / scale)
             ops.relpos_augment_k(k_aug, k_shape)
@@ -211,9 +211,9 @@ class PoolAttentionFn(Function):
             drh, drw, drt = ops.relpos_augment_q_bwd(dq_aug, q_aug, q_shape, k_shape, rel_h, rel_w, rel_t, 1.0 / scale)
         dqkv = torch.empty_like(qkv5)
         g = torch.zeros(3, 96 * 27 + 192, dtype=torch.float32, device=qkv5.device)
-        ops.pool_ln_bwd(qkv5, 0, heads, thw, sq, wq, gq, dq_aug.view(B, heads, Nq, ld), dqkv, g[0], eps)
-        ops.pool_ln_bwd(qkv5, 1, heads, thw, skv, wk, gk, dk.view(B, heads, Nk, 96), dqkv, g[1], eps)
-        ops.pool_ln_bwd(qkv5, 2, heads, thw, skv, wv, gv, dv.view(B, heads, Nk, 96), dqkv, g[2], eps)
+        ops.pool_ln_qkv_bwd(qkv5, heads, thw, [(0, sq, wq, gq, dq_aug.view(B, heads, Nq, ld), g[0]),
+                                               (1, skv, wk, gk, dk.view(B, heads, Nk, 96), g[1]),
+                                               (2, skv, wv, gv, dv.view(B, heads, Nk, 96), g[2])], dqkv, eps)
         dw = [g[i, :2592].view(96, 1, 3, 3, 3) for i in range(3)]
         dg = [g[i, 2592:2688] for i in range(3)]
         db = [g[i, 2688:] for i in range(3)]

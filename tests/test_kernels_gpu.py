@@ -290,3 +290,40 @@ def test_attention_tcgen05_fwd(B, heads, q_shape, k_shape):
     out2, _, _ = ops.attention_fwd(q_aug, k_aug, vv, B, heads, ld, scale, residual=False, want_lse=False, tc=1)
     out3, _, _ = ops.attention_fwd(q_aug, k_aug, vv, B, heads, ld, scale, residual=False, want_lse=False, tc=0)
     assert nerr(out2.float(), out3.float()) < 1e-2
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_pool_ln_qkv_fused_launch(dtype):
+    """q / k / v pooled by ONE launch each way (different strides per job) against the oracle."""
+    from oracle import mvit_oracle as orc
+    from pmv_b200 import ops
+    B, heads, thw, sq, skv = 2, 2, (3, 12, 10), 2, 4
+    T, H, W = thw
+    N = 1 + T * H * W
+    qkv = randn(B, N, 3, heads, 96, seed=80).to(dtype)
+    ws = [randn(96, 1, 3, 3, 3, seed=81 + i) * 0.2 for i in range(3)]
+    gs = [randn(96, seed=84 + i) * 0.1 + 1 for i in range(3)]
+    bs = [randn(96, seed=87 + i) * 0.1 for i in range(3)]
+    strides = [sq, skv, skv]
+    Ls = [1 + T * ops.pooled_hw(H, s) * ops.pooled_hw(W, s) for s in strides]
+    lds = [128, 128, 96]
+    outs = [torch.zeros(B, heads, Ls[i], lds[i], dtype=dtype, device="cuda") for i in range(3)]
+    ops.pool_ln_qkv_fwd(qkv, heads, thw, [(i, strides[i], ws[i], gs[i], bs[i], outs[i]) for i in range(3)])
+    douts = [torch.zeros_like(o) for o in outs]
+    grads = torch.zeros(3, 96 * 27 + 192, device="cuda")
+    dqkv = torch.full_like(qkv, float("nan"))
+    refs = []
+    for i in range(3):
+        xin = qkv[:, :, i].permute(0, 2, 1, 3).float().clone().requires_grad_(True)
+        wr, gr, br = (t.clone().requires_grad_(True) for t in (ws[i], gs[i], bs[i]))
+        ref, _ = orc.conv_pool_tokens(xin, thw, wr, (1, strides[i], strides[i]), True, gr, br)
+        assert nerr(outs[i][..., :96].float(), ref.detach()) < TOL[dtype], i
+        douts[i][..., :96] = randn(B, heads, Ls[i], 96, seed=90 + i).to(dtype)
+        ref.backward(douts[i][..., :96].float())
+        refs.append((xin, wr, gr, br))
+    ops.pool_ln_qkv_bwd(qkv, heads, thw, [(i, strides[i], ws[i], gs[i], douts[i], grads[i]) for i in range(3)], dqkv)
+    for i, (xin, wr, gr, br) in enumerate(refs):
+        assert nerr(dqkv[:, :, i].permute(0, 2, 1, 3).float(), xin.grad) < TOL[dtype], i
+        assert nerr(grads[i, :2592].view(96, 27), wr.grad.view(96, 27)) < TOL[dtype], i
+        assert nerr(grads[i, 2592:2688], gr.grad) < TOL[dtype], i
+        assert nerr(grads[i, 2688:], br.grad) < TOL[dtype], i
