@@ -331,14 +331,21 @@ __global__ void __launch_bounds__(POOL_THREADS) pool_ln_bwd_input_kernel(const _
   }
 }
 
-// grads_j[i] += sum over the job's blocks of partials[b][i]      (grid.y = job)
+// grads_j[i] += sum over the job's blocks of partials[b][i]      (grid.y = job, grid.z = slice of the blocks)
+constexpr int RED_SLICES = 8;
 __global__ void __launch_bounds__(256) reduce_jobs_kernel(const __grid_constant__ Launch L) {
   const Job& J = L.job[blockIdx.y];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= NGRAD) return;
-  float s = 0.f;
-  for (int b = J.blk_begin; b < J.blk_begin + J.nblk; ++b) s += L.partials[(int64_t)b * NGRAD + i];
-  J.grads[i] += s;
+  float s0 = 0.f, s1 = 0.f;
+  const int end = J.blk_begin + J.nblk;
+  int b = J.blk_begin + blockIdx.z;
+  for (; b + RED_SLICES < end; b += 2 * RED_SLICES) {
+    s0 += L.partials[(int64_t)b * NGRAD + i];
+    s1 += L.partials[(int64_t)(b + RED_SLICES) * NGRAD + i];
+  }
+  if (b < end) s0 += L.partials[(int64_t)b * NGRAD + i];
+  atomicAdd(J.grads + i, s0 + s1);
 }
 
 int nblocks_for(int64_t items, int per_block, int max_blocks) {
@@ -426,7 +433,7 @@ extern "C" int pmv_pool_ln_qkv_bwd(const void* qkv, int64_t batch_stride, int64_
   L.partials = cursor;
   cudaStream_t st = (cudaStream_t)stream;
   PMV_DISPATCH_DTYPE(dtype, TT, (pool_ln_bwd_tokens_kernel<TT><<<(unsigned)total, BWD_WARPS * 32, 0, st>>>(L)));
-  reduce_jobs_kernel<<<dim3((NGRAD + 255) / 256, njobs), 256, 0, st>>>(L);
+  reduce_jobs_kernel<<<dim3((NGRAD + 255) / 256, njobs, RED_SLICES), 256, 0, st>>>(L);
   // second launch geometry: one block range per job over the INPUT tokens
   Launch L2 = L;
   int total2 = 0;

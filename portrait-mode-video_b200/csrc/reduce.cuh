@@ -9,11 +9,23 @@ static __global__ void __launch_bounds__(256) reduce_partials_kernel(const float
                                                                        float* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partials[(int64_t)b * n + i];
-  dst[i] += s;
+  // grid.y slices the partial rows; 4 independent accumulators keep 4 loads in flight per thread
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  const int step = gridDim.y;
+  int b = blockIdx.y;
+  for (; b + 3 * step < nblocks; b += 4 * step) {
+    s0 += partials[(int64_t)b * n + i];
+    s1 += partials[(int64_t)(b + step) * n + i];
+    s2 += partials[(int64_t)(b + 2 * step) * n + i];
+    s3 += partials[(int64_t)(b + 3 * step) * n + i];
+  }
+  for (; b < nblocks; b += step) s0 += partials[(int64_t)b * n + i];
+  atomicAdd(dst + i, (s0 + s1) + (s2 + s3));  // at most gridDim.y (<= 16) adds per address
 }
 
 static inline void launch_reduce_partials(const float* partials, int nblocks, int n, float* dst, cudaStream_t stream) {
-  reduce_partials_kernel<<<(n + 255) / 256, 256, 0, stream>>>(partials, nblocks, n, dst);
+  int slices = nblocks / 8;
+  if (slices < 1) slices = 1;
+  if (slices > 16) slices = 16;
+  reduce_partials_kernel<<<dim3((n + 255) / 256, slices), 256, 0, stream>>>(partials, nblocks, n, dst);
 }
