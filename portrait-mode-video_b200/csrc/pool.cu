@@ -6,14 +6,17 @@
 //
 // forward       : 8 lanes own one output token, each lane 12 consecutive channels (8/16-byte vector loads);
 //                 a warp handles 4 tokens that are neighbours along w, so the window overlap is served by L1.
-// backward (i)  : one warp per OUTPUT token, lane owns channels {lane, lane+32, lane+64}; all 27 x 3 inputs are
-//                 loaded up front (81 loads in flight: the kernel is latency-bound otherwise), the convolution
-//                 and the LN statistics are recomputed, LN backward gives the pre-LN gradient (fp32 workspace),
-//                 and dW / dgamma / dbeta are accumulated in registers -> one partial vector per CTA.
-// backward (ii) : gather form of the transposed stencil per INPUT token (no atomics), written straight into the
+// backward (i)  : one warp per OUTPUT token, lane owns channels {lane, lane+32, lane+64}: the convolution and the
+//                 LN statistics are recomputed, LN backward gives the pre-LN gradient (fp32 workspace) and the
+//                 dgamma / dbeta partials.  Light on registers on purpose: the kernel is latency-bound (one token
+//                 per warp at a time, three warp reductions on the critical path), so it lives on occupancy.
+// backward (ii) : weight gradient dW[c][tap] = sum_tok x[nb(tok, tap)][c] * dconv[tok][c]: thread = (channel,
+//                 temporal tap), 9 exclusive accumulators, no reductions and no dependences between tokens, so
+//                 loads of several tokens are in flight -> one partial [96][27] per CTA.
+// backward (iii): gather form of the transposed stencil per INPUT token (no atomics), written straight into the
 //                 interleaved dQKV buffer.
-// backward (iii): reduce_jobs_kernel folds the per-CTA partials (same-address global atomics from hundreds of
-//                 CTAs serialise in L2).
+// backward (iv) : reduce kernels fold the per-CTA partials (same-address global atomics from hundreds of CTAs
+//                 serialise in L2).
 #include "common.cuh"
 
 namespace {
@@ -26,6 +29,8 @@ constexpr int POOL_THREADS = 256;
 constexpr int TOK_PER_BLOCK = POOL_THREADS / LPT;
 constexpr int BWD_WARPS = 8;
 constexpr int NGRAD = (TAPS + 2) * HD;  // dW [96][27], dgamma [96], dbeta [96]
+constexpr int NDW = TAPS * HD;
+constexpr int DW_THREADS = 3 * HD;     // (temporal tap, channel)
 constexpr int MAX_JOBS = 3;
 
 struct Job {
@@ -42,6 +47,7 @@ struct Job {
   float* dconv;         // backward: fp32 workspace [B*heads*Lo*96]
   int s, Ho, Wo;
   int blk_begin, nblk;  // block range of this job in the current launch
+  int blk2_begin, nblk2;  // block range in the dW kernel
 };
 
 struct Launch {
@@ -50,7 +56,8 @@ struct Launch {
   int B, heads, T, H, W;
   int64_t in_bs, in_ts, in_hs;  // element strides of the input views
   float eps;
-  float* partials;              // [total blocks][NGRAD]
+  float* partials;              // token kernel: [total blocks][2 * 96] (dgamma, dbeta)
+  float* partials_dw;           // dW kernel: [total blocks][96 * 27]
 };
 
 __device__ __forceinline__ int find_job(const Launch& L) {
@@ -153,12 +160,12 @@ __global__ void __launch_bounds__(POOL_THREADS) pool_ln_fwd_kernel(const __grid_
 }
 
 template <typename T>
-__global__ void __launch_bounds__(BWD_WARPS * 32, 1) pool_ln_bwd_tokens_kernel(const __grid_constant__ Launch L) {
+__global__ void __launch_bounds__(BWD_WARPS * 32, 4) pool_ln_bwd_tokens_kernel(const __grid_constant__ Launch L) {
   __shared__ float sw[TAPS * HD];
-  __shared__ float sred[NGRAD];
+  __shared__ float sred[2 * HD];
   const Job& J = L.job[find_job(L)];
   stage_weights(J.w, sw);
-  for (int i = threadIdx.x; i < NGRAD; i += blockDim.x) sred[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * HD; i += blockDim.x) sred[i] = 0.f;
   __syncthreads();
   const T* __restrict__ in = reinterpret_cast<const T*>(J.in);
   const T* __restrict__ dout = reinterpret_cast<const T*>(J.dout);
@@ -169,11 +176,6 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 1) pool_ln_bwd_tokens_kernel(c
   float gm[3];
 #pragma unroll
   for (int j = 0; j < 3; ++j) gm[j] = J.gamma[lane + 32 * j];
-  float adw[TAPS][3];
-#pragma unroll
-  for (int k = 0; k < TAPS; ++k)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) adw[k][j] = 0.f;
   float adg[3] = {0.f, 0.f, 0.f}, adb[3] = {0.f, 0.f, 0.f};
   const int lb = blockIdx.x - J.blk_begin;
 
@@ -189,7 +191,6 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 1) pool_ln_bwd_tokens_kernel(c
 #pragma unroll
     for (int j = 0; j < 3; ++j) dy[j] = to_f32(dyr[32 * j]);
     float acc[3] = {0.f, 0.f, 0.f};
-    float xv[TAPS][3];
     if (n == 0) {
 #pragma unroll
       for (int j = 0; j < 3; ++j) acc[j] = to_f32(base[32 * j]);
@@ -198,28 +199,31 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 1) pool_ln_bwd_tokens_kernel(c
       const int wo = l % J.Wo; l /= J.Wo;
       const int ho = l % J.Ho;
       const int t = l / J.Ho;
-      // all loads first (zero for taps that fall into the padding) ...
 #pragma unroll
       for (int dt = 0; dt < 3; ++dt) {
         const int ti = t + dt - 1;
+        if (ti < 0 || ti >= L.T) continue;
 #pragma unroll
         for (int dh = 0; dh < 3; ++dh) {
           const int hi = ho * J.s + dh - 1;
+          if (hi < 0 || hi >= L.H) continue;
+          float xv[3][3];
+#pragma unroll
+          for (int dwi = 0; dwi < 3; ++dwi) {  // the three loads of a window row are issued together
+            const int wi = wo * J.s + dwi - 1;
+            const bool ok = wi >= 0 && wi < L.W;
+            const T* p = base + (int64_t)(1 + (ti * L.H + hi) * L.W + (ok ? wi : 0)) * L.in_ts;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) xv[dwi][j] = ok ? to_f32(p[32 * j]) : 0.f;
+          }
 #pragma unroll
           for (int dwi = 0; dwi < 3; ++dwi) {
-            const int wi = wo * J.s + dwi - 1;
-            const bool ok = ti >= 0 && ti < L.T && hi >= 0 && hi < L.H && wi >= 0 && wi < L.W;
-            const T* p = base + (int64_t)(1 + (ti * L.H + hi) * L.W + wi) * L.in_ts;
+            const float* wt = sw + (dt * 9 + dh * 3 + dwi) * HD + lane;
 #pragma unroll
-            for (int j = 0; j < 3; ++j) xv[dt * 9 + dh * 3 + dwi][j] = ok ? to_f32(p[32 * j]) : 0.f;
+            for (int j = 0; j < 3; ++j) acc[j] = fmaf(xv[dwi][j], wt[32 * j], acc[j]);
           }
         }
       }
-      // ... then the convolution
-#pragma unroll
-      for (int k = 0; k < TAPS; ++k)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) acc[j] = fmaf(xv[k][j], sw[k * HD + lane + 32 * j], acc[j]);
     }
     const float mu = warp_sum(acc[0] + acc[1] + acc[2]) * (1.0f / HD);
     float q = 0.f;
@@ -236,8 +240,14 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 1) pool_ln_bwd_tokens_kernel(c
       adg[j] += dy[j] * xh[j];
       adb[j] += dy[j];
     }
-    s1 = warp_sum(s1) * (1.0f / HD);
-    s2 = warp_sum(s2) * (1.0f / HD);
+    // the two remaining reductions share their five shuffle rounds
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    s1 *= (1.0f / HD);
+    s2 *= (1.0f / HD);
     float dc[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) dc[j] = rs * (gg[j] - s1 - xh[j] * s2);
@@ -250,30 +260,59 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 1) pool_ln_bwd_tokens_kernel(c
     float* dcr = J.dconv + (bh * Lo + (n - 1)) * HD + lane;
 #pragma unroll
     for (int j = 0; j < 3; ++j) dcr[32 * j] = dc[j];
-    // weight gradient: dw[tap][c] += x[neighbour(tap)][c] * dconv[c]   (padding taps hold zeros)
-#pragma unroll
-    for (int k = 0; k < TAPS; ++k)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) adw[k][j] = fmaf(xv[k][j], dc[j], adw[k][j]);
   }
-  // block reduction through shared memory, then one partial vector per block
-#pragma unroll
-  for (int k = 0; k < TAPS; ++k)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) atomicAdd(&sred[k * HD + lane + 32 * j], adw[k][j]);
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    atomicAdd(&sred[TAPS * HD + lane + 32 * j], adg[j]);
-    atomicAdd(&sred[(TAPS + 1) * HD + lane + 32 * j], adb[j]);
+    atomicAdd(&sred[lane + 32 * j], adg[j]);
+    atomicAdd(&sred[HD + lane + 32 * j], adb[j]);
   }
   __syncthreads();
-  // partial vector already in the destination order: dw in the reference layout [96][27], dgamma, dbeta
-  float* pb = L.partials + (int64_t)blockIdx.x * NGRAD;
-  for (int i = threadIdx.x; i < TAPS * HD; i += blockDim.x) {
-    const int tap = i / HD, c = i - tap * HD;
-    pb[c * TAPS + tap] = sred[i];
+  for (int i = threadIdx.x; i < 2 * HD; i += blockDim.x) L.partials[(int64_t)blockIdx.x * 2 * HD + i] = sred[i];
+}
+
+// dW: thread = (temporal tap dt, channel c); the CTA walks its share of the output tokens, all threads on the same
+// token (block-uniform index math), 9 exclusive accumulators per thread.
+template <typename T>
+__global__ void __launch_bounds__(DW_THREADS) pool_ln_bwd_dw_kernel(const __grid_constant__ Launch L) {
+  int jj = 0;
+  while (jj + 1 < L.njobs && (int)blockIdx.x >= L.job[jj + 1].blk2_begin) ++jj;
+  const Job& J = L.job[jj];
+  const T* __restrict__ in = reinterpret_cast<const T*>(J.in);
+  const int c = threadIdx.x % HD, dt = threadIdx.x / HD;
+  const int Lo = L.T * J.Ho * J.Wo;
+  const int64_t ntok = (int64_t)L.B * L.heads * Lo;
+  float a[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) a[k] = 0.f;
+  const int lb = blockIdx.x - J.blk2_begin;
+#pragma unroll 2
+  for (int64_t tok = lb; tok < ntok; tok += J.nblk2) {
+    int l = (int)(tok % Lo);
+    const int64_t bh = tok / Lo;
+    const int head = (int)(bh % L.heads);
+    const int64_t b = bh / L.heads;
+    const int wo = l % J.Wo; l /= J.Wo;
+    const int ho = l % J.Ho;
+    const int t = l / J.Ho;
+    const int ti = t + dt - 1;
+    if (ti < 0 || ti >= L.T) continue;
+    const float d = J.dconv[tok * HD + c];
+    const T* base = in + b * L.in_bs + head * L.in_hs + c;
+#pragma unroll
+    for (int dh = 0; dh < 3; ++dh) {
+      const int hi = ho * J.s + dh - 1;
+      if (hi < 0 || hi >= L.H) continue;
+#pragma unroll
+      for (int dwi = 0; dwi < 3; ++dwi) {
+        const int wi = wo * J.s + dwi - 1;
+        if (wi < 0 || wi >= L.W) continue;
+        a[dh * 3 + dwi] = fmaf(to_f32(base[(int64_t)(1 + (ti * L.H + hi) * L.W + wi) * L.in_ts]), d, a[dh * 3 + dwi]);
+      }
+    }
   }
-  for (int i = threadIdx.x; i < 2 * HD; i += blockDim.x) pb[TAPS * HD + i] = sred[TAPS * HD + i];
+  float* pb = L.partials_dw + (int64_t)blockIdx.x * NDW + c * TAPS + dt * 9;  // reference layout [96][27]
+#pragma unroll
+  for (int k = 0; k < 9; ++k) pb[k] = a[k];
 }
 
 // gather form of the transposed stencil — one 8-lane group per INPUT token:
@@ -331,20 +370,25 @@ __global__ void __launch_bounds__(POOL_THREADS) pool_ln_bwd_input_kernel(const _
   }
 }
 
-// grads_j[i] += sum over the job's blocks of partials[b][i]      (grid.y = job, grid.z = slice of the blocks)
+// grads_j[i] += sum over the job's blocks of the partial vectors: dW from the dW kernel, dgamma / dbeta from the
+// token kernel      (grid.y = job, grid.z = slice of the blocks)
 constexpr int RED_SLICES = 8;
 __global__ void __launch_bounds__(256) reduce_jobs_kernel(const __grid_constant__ Launch L) {
   const Job& J = L.job[blockIdx.y];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= NGRAD) return;
+  const bool is_dw = i < NDW;
+  const float* src = is_dw ? L.partials_dw + i : L.partials + (i - NDW);
+  const int64_t stride = is_dw ? NDW : 2 * HD;
+  const int begin = is_dw ? J.blk2_begin : J.blk_begin;
+  const int end = begin + (is_dw ? J.nblk2 : J.nblk);
   float s0 = 0.f, s1 = 0.f;
-  const int end = J.blk_begin + J.nblk;
-  int b = J.blk_begin + blockIdx.z;
+  int b = begin + blockIdx.z;
   for (; b + RED_SLICES < end; b += 2 * RED_SLICES) {
-    s0 += L.partials[(int64_t)b * NGRAD + i];
-    s1 += L.partials[(int64_t)(b + RED_SLICES) * NGRAD + i];
+    s0 += src[(int64_t)b * stride];
+    s1 += src[(int64_t)(b + RED_SLICES) * stride];
   }
-  if (b < end) s0 += L.partials[(int64_t)b * NGRAD + i];
+  if (b < end) s0 += src[(int64_t)b * stride];
   atomicAdd(J.grads + i, s0 + s1);
 }
 
@@ -358,8 +402,9 @@ int out_hw(int n, int s) { return (n - 1) / s + 1; }  // (n + 2*1 - 3) / s + 1
 
 int64_t ntok_out(int B, int heads, int T, int H, int W, int s) { return (int64_t)B * heads * (1 + (int64_t)T * out_hw(H, s) * out_hw(W, s)); }
 
-// block budget of the backward token kernel per job (shared by the workspace query and the launcher)
+// block budgets of the backward token / dW kernels per job (shared by the workspace query and the launcher)
 int bwd_token_blocks(int B, int heads, int T, int H, int W, int s) { return nblocks_for(ntok_out(B, heads, T, H, W, s), BWD_WARPS * 4, 148 * 2); }
+int bwd_dw_blocks(int B, int heads, int T, int H, int W, int s) { return nblocks_for(ntok_out(B, heads, T, H, W, s), 32, 148 * 2); }
 
 int fill_launch(Launch& L, const void* qkv, int64_t bs, int64_t ts, int64_t ws_, int64_t hs, const pmv_pool_job* jobs, int njobs,
                 int B, int heads, int T, int H, int W, float eps, int dtype) {
@@ -368,7 +413,7 @@ int fill_launch(Launch& L, const void* qkv, int64_t bs, int64_t ts, int64_t ws_,
   PMV_CHECK_ARG(ts % 4 == 0 && hs % 4 == 0 && ws_ % 4 == 0, "pool: strides must be multiples of 4 elements");
   const int esz = dtype == PMV_BF16 ? 2 : 4;
   L.njobs = njobs; L.B = B; L.heads = heads; L.T = T; L.H = H; L.W = W;
-  L.in_bs = bs; L.in_ts = ts; L.in_hs = hs; L.eps = eps; L.partials = nullptr;
+  L.in_bs = bs; L.in_ts = ts; L.in_hs = hs; L.eps = eps; L.partials = nullptr; L.partials_dw = nullptr;
   for (int i = 0; i < njobs; ++i) {
     Job& J = L.job[i];
     const pmv_pool_job& p = jobs[i];
@@ -377,7 +422,7 @@ int fill_launch(Launch& L, const void* qkv, int64_t bs, int64_t ts, int64_t ws_,
     J.w = p.w; J.gamma = p.gamma; J.beta = p.beta; J.out = p.out; J.out_ld = p.out_ld;
     J.dout = p.dout; J.dout_ld = p.dout_ld; J.din = nullptr; J.grads = p.grads; J.dconv = nullptr;
     J.s = p.stride_hw; J.Ho = out_hw(H, p.stride_hw); J.Wo = out_hw(W, p.stride_hw);
-    J.blk_begin = 0; J.nblk = 0;
+    J.blk_begin = 0; J.nblk = 0; J.blk2_begin = 0; J.nblk2 = 0;
   }
   return PMV_OK;
 }
@@ -406,7 +451,8 @@ extern "C" int64_t pmv_pool_ln_qkv_bwd_workspace_bytes(int B, int heads, int T, 
   int64_t floats = 0;
   for (int i = 0; i < njobs; ++i) {
     floats += (ntok_out(B, heads, T, H, W, strides_hw[i]) - (int64_t)B * heads) * HD;  // pre-LN gradient, non-cls tokens
-    floats += (int64_t)bwd_token_blocks(B, heads, T, H, W, strides_hw[i]) * NGRAD;
+    floats += (int64_t)bwd_token_blocks(B, heads, T, H, W, strides_hw[i]) * 2 * HD;
+    floats += (int64_t)bwd_dw_blocks(B, heads, T, H, W, strides_hw[i]) * NDW;
   }
   return floats * (int64_t)sizeof(float);
 }
@@ -419,7 +465,7 @@ extern "C" int pmv_pool_ln_qkv_bwd(const void* qkv, int64_t batch_stride, int64_
   if (rc) return rc;
   const int esz = dtype == PMV_BF16 ? 2 : 4;
   float* cursor = ws;
-  int total = 0;
+  int total = 0, total_dw = 0;
   for (int i = 0; i < njobs; ++i) {
     PMV_CHECK_ARG(jobs[i].dout != nullptr && jobs[i].grads != nullptr && jobs[i].dout_ld % 4 == 0, "pool: bad backward job");
     Job& J = L.job[i];
@@ -429,10 +475,17 @@ extern "C" int pmv_pool_ln_qkv_bwd(const void* qkv, int64_t batch_stride, int64_
     J.blk_begin = total;
     J.nblk = bwd_token_blocks(B, heads, T, H, W, J.s);
     total += J.nblk;
+    J.blk2_begin = total_dw;
+    J.nblk2 = bwd_dw_blocks(B, heads, T, H, W, J.s);
+    total_dw += J.nblk2;
   }
   L.partials = cursor;
+  L.partials_dw = cursor + (int64_t)total * 2 * HD;
   cudaStream_t st = (cudaStream_t)stream;
-  PMV_DISPATCH_DTYPE(dtype, TT, (pool_ln_bwd_tokens_kernel<TT><<<(unsigned)total, BWD_WARPS * 32, 0, st>>>(L)));
+  PMV_DISPATCH_DTYPE(dtype, TT, {
+    pool_ln_bwd_tokens_kernel<TT><<<(unsigned)total, BWD_WARPS * 32, 0, st>>>(L);
+    pool_ln_bwd_dw_kernel<TT><<<(unsigned)total_dw, DW_THREADS, 0, st>>>(L);
+  });
   reduce_jobs_kernel<<<dim3((NGRAD + 255) / 256, njobs, RED_SLICES), 256, 0, st>>>(L);
   // second launch geometry: one block range per job over the INPUT tokens
   Launch L2 = L;

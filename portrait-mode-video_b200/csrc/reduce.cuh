@@ -6,7 +6,7 @@
 #include "common.cuh"
 
 static __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, int nblocks, int n,
-                                                                       float* __restrict__ dst) {
+                                                                       int64_t stride, float* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   // grid.y slices the partial rows; 4 independent accumulators keep 4 loads in flight per thread
@@ -14,18 +14,19 @@ static __global__ void __launch_bounds__(256) reduce_partials_kernel(const float
   const int step = gridDim.y;
   int b = blockIdx.y;
   for (; b + 3 * step < nblocks; b += 4 * step) {
-    s0 += partials[(int64_t)b * n + i];
-    s1 += partials[(int64_t)(b + step) * n + i];
-    s2 += partials[(int64_t)(b + 2 * step) * n + i];
-    s3 += partials[(int64_t)(b + 3 * step) * n + i];
+    s0 += partials[(int64_t)b * stride + i];
+    s1 += partials[(int64_t)(b + step) * stride + i];
+    s2 += partials[(int64_t)(b + 2 * step) * stride + i];
+    s3 += partials[(int64_t)(b + 3 * step) * stride + i];
   }
-  for (; b < nblocks; b += step) s0 += partials[(int64_t)b * n + i];
+  for (; b < nblocks; b += step) s0 += partials[(int64_t)b * stride + i];
   atomicAdd(dst + i, (s0 + s1) + (s2 + s3));  // at most gridDim.y (<= 16) adds per address
 }
 
-static inline void launch_reduce_partials(const float* partials, int nblocks, int n, float* dst, cudaStream_t stream) {
+static inline void launch_reduce_partials(const float* partials, int nblocks, int n, float* dst, cudaStream_t stream,
+                                          int64_t stride = 0) {
   int slices = nblocks / 8;
   if (slices < 1) slices = 1;
   if (slices > 16) slices = 16;
-  reduce_partials_kernel<<<dim3((n + 255) / 256, slices), 256, 0, stream>>>(partials, nblocks, n, dst);
+  reduce_partials_kernel<<<dim3((n + 255) / 256, slices), 256, 0, stream>>>(partials, nblocks, n, stride ? stride : n, dst);
 }

@@ -101,74 +101,160 @@ __global__ void __launch_bounds__(256) relpos_augment_k_kernel(T* __restrict__ k
   }
 }
 
-// backward of augment_q.  One warp per query, lane owns channels {lane, lane+32, lane+64}.
-// dynamic smem: fp32 gradient tables [(rows)][96] accumulated with shared atomics, written out once per block.
+// backward of augment_q, two kernels that keep the table gradients in registers instead of hammering shared
+// memory with one atomic per (query, column, channel):
+//   row walk    : one warp per (bh, t, h) row of queries.  All queries of a row share their rel_pos_h and rel_pos_t
+//                 rows, so d rel_h / d rel_t accumulate in registers over the row and are flushed once per row;
+//                 the bias path's contribution to dq (all three parts) is added in place.
+//   column walk : one warp per (bh, t, w) column of queries; d rel_w accumulates in registers over the column.
+// Lane owns channels {lane, lane+32, lane+64}.  Both kernels write one partial table per CTA.
+constexpr int KMAX = 16;  // max k_h, k_w, k_t (MViTv2-S: 14 / 14 / 8, MViTv2-B: 14 / 14 / 16)
+constexpr int RW_WARPS = 16;
+
 template <typename T>
-__global__ void __launch_bounds__(AUG_WARPS * 32) relpos_augment_q_bwd_kernel(
+__global__ void __launch_bounds__(RW_WARPS * 32, 1) relpos_bwd_rows_kernel(
     T* __restrict__ dq_aug, const T* __restrict__ q_aug, int64_t ld, const float* __restrict__ rel_h,
     const float* __restrict__ rel_w, const float* __restrict__ rel_t, const int32_t* __restrict__ idx_h,
     const int32_t* __restrict__ idx_w, const int32_t* __restrict__ idx_t, float* __restrict__ partials,
     int64_t BH, RelGeom g, float inv_scale) {
-  extern __shared__ float dtab[];
+  extern __shared__ float sm[];
   const int rows = g.rows_h + g.rows_w + g.rows_t;
-  float* tab = dtab + rows * HD;  // the three tables stacked, staged once per block
+  float* tab = sm;                    // the three tables stacked [rows][96]
+  float* dtab = sm + rows * HD;       // gradients of the h and t tables [rows_h + rows_t][96]
+  const int nht = g.rows_h + g.rows_t;
   for (int i = threadIdx.x; i < rows * HD; i += blockDim.x) {
-    dtab[i] = 0.f;
     const int r = i / HD, c = i - r * HD;
     tab[i] = r < g.rows_h ? rel_h[r * HD + c]
              : r < g.rows_h + g.rows_w ? rel_w[(r - g.rows_h) * HD + c]
                                        : rel_t[(r - g.rows_h - g.rows_w) * HD + c];
   }
+  for (int i = threadIdx.x; i < nht * HD; i += blockDim.x) dtab[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int Lq = g.qt * g.qh * g.qw;
-  const int Nq = Lq + 1;
+  const int Nq = g.qt * g.qh * g.qw + 1;
   const int RK = g.kh + g.kw + g.kt;
-  const int64_t total = BH * Nq;
-  for (int64_t row = (int64_t)blockIdx.x * AUG_WARPS + warp; row < total; row += (int64_t)gridDim.x * AUG_WARPS) {
-    const int n = (int)(row % Nq);
-    if (n == 0) continue;
-    int l = n - 1;
-    const int iw = l % g.qw; l /= g.qw;
-    const int ih = l % g.qh;
-    const int it = l / g.qh;
-    T* dqp = dq_aug + row * ld;
-    const T* qp = q_aug + row * ld;
-    float qv[3], acc[3];
+  const int64_t nrows = BH * g.qt * g.qh;
+  for (int64_t rr = (int64_t)blockIdx.x * RW_WARPS + warp; rr < nrows; rr += (int64_t)gridDim.x * RW_WARPS) {
+    const int ih = (int)(rr % g.qh);
+    const int it = (int)((rr / g.qh) % g.qt);
+    const int64_t bh = rr / ((int64_t)g.qh * g.qt);
+    // table rows shared by the whole query row (lane j holds the row of column j)
+    const int my_h = lane < g.kh ? idx_h[ih * g.kh + lane] : 0;
+    const int my_t = lane < g.kt ? g.rows_h + g.rows_w + idx_t[it * g.kt + lane] : 0;
+    float gh[KMAX][3], gt[KMAX][3];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) { qv[j] = to_f32(qp[lane + 32 * j]); acc[j] = to_f32(dqp[lane + 32 * j]); }
-    // the d rq values of this query: one coalesced load, broadcast by shuffle inside the loop
-    const float d_lo = lane < RK ? to_f32(dqp[HD + lane]) * inv_scale : 0.f;
-    const float d_hi = lane + 32 < RK ? to_f32(dqp[HD + 32 + lane]) * inv_scale : 0.f;
-    // table row of column (j0 + lane): resolved once per query by the lanes, broadcast by shuffle
-    int my_row_lo = 0, my_row_hi = 0;
-    {
-      const int j = lane;
-      if (j < RK) my_row_lo = j < g.kh ? idx_h[ih * g.kh + j]
-                              : j < g.kh + g.kw ? g.rows_h + idx_w[iw * g.kw + (j - g.kh)]
-                                                : g.rows_h + g.rows_w + idx_t[it * g.kt + (j - g.kh - g.kw)];
-      const int j2 = lane + 32;
-      if (j2 < RK) my_row_hi = j2 < g.kh ? idx_h[ih * g.kh + j2]
-                               : j2 < g.kh + g.kw ? g.rows_h + idx_w[iw * g.kw + (j2 - g.kh)]
-                                                  : g.rows_h + g.rows_w + idx_t[it * g.kt + (j2 - g.kh - g.kw)];
+    for (int j = 0; j < KMAX; ++j)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { gh[j][c] = 0.f; gt[j][c] = 0.f; }
+    const int64_t row0 = bh * Nq + 1 + ((int64_t)it * g.qh + ih) * g.qw;
+    for (int iw = 0; iw < g.qw; ++iw) {
+      T* dqp = dq_aug + (row0 + iw) * ld;
+      const T* qp = q_aug + (row0 + iw) * ld;
+      float qv[3], acc[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { qv[c] = to_f32(qp[lane + 32 * c]); acc[c] = to_f32(dqp[lane + 32 * c]); }
+      const float d_lo = lane < RK ? to_f32(dqp[HD + lane]) * inv_scale : 0.f;
+      const float d_hi = lane + 32 < RK ? to_f32(dqp[HD + 32 + lane]) * inv_scale : 0.f;
+      const int my_w = lane < g.kw ? g.rows_h + idx_w[iw * g.kw + lane] : 0;
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) {
+        if (j < g.kh) {
+          const float d = __shfl_sync(0xffffffffu, d_lo, j);
+          const float* src = tab + __shfl_sync(0xffffffffu, my_h, j) * HD + lane;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { acc[c] = fmaf(d, src[32 * c], acc[c]); gh[j][c] = fmaf(d, qv[c], gh[j][c]); }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) {
+        if (j < g.kw) {
+          const int col = g.kh + j;
+          const float d = __shfl_sync(0xffffffffu, col < 32 ? d_lo : d_hi, col & 31);
+          const float* src = tab + __shfl_sync(0xffffffffu, my_w, j) * HD + lane;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) acc[c] = fmaf(d, src[32 * c], acc[c]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) {
+        if (j < g.kt) {
+          const int col = g.kh + g.kw + j;
+          const float d = __shfl_sync(0xffffffffu, col < 32 ? d_lo : d_hi, col & 31);
+          const float* src = tab + __shfl_sync(0xffffffffu, my_t, j) * HD + lane;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { acc[c] = fmaf(d, src[32 * c], acc[c]); gt[j][c] = fmaf(d, qv[c], gt[j][c]); }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) dqp[lane + 32 * c] = from_f32<T>(acc[c]);
     }
-#pragma unroll 4
-    for (int j = 0; j < RK; ++j) {
-      const float d = __shfl_sync(0xffffffffu, j < 32 ? d_lo : d_hi, j & 31);
-      const int trow = __shfl_sync(0xffffffffu, j < 32 ? my_row_lo : my_row_hi, j & 31);
-      const float* src = tab + trow * HD;
+    // flush the row's table gradients (h rows first, then t rows, in the partial layout)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        acc[c] = fmaf(d, src[lane + 32 * c], acc[c]);
-        atomicAdd(&dtab[trow * HD + lane + 32 * c], d * qv[c]);
+    for (int j = 0; j < KMAX; ++j) {
+      if (j < g.kh) {
+        float* dst = dtab + __shfl_sync(0xffffffffu, my_h, j) * HD + lane;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) atomicAdd(dst + 32 * c, gh[j][c]);
+      }
+      if (j < g.kt) {
+        float* dst = dtab + (__shfl_sync(0xffffffffu, my_t, j) - g.rows_w) * HD + lane;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) atomicAdd(dst + 32 * c, gt[j][c]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nht * HD; i += blockDim.x) partials[(int64_t)blockIdx.x * nht * HD + i] = dtab[i];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RW_WARPS * 32) relpos_bwd_cols_kernel(
+    const T* __restrict__ dq_aug, const T* __restrict__ q_aug, int64_t ld, const int32_t* __restrict__ idx_w,
+    float* __restrict__ partials, int64_t BH, RelGeom g, float inv_scale) {
+  extern __shared__ float dtab[];  // [rows_w][96]
+  for (int i = threadIdx.x; i < g.rows_w * HD; i += blockDim.x) dtab[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Nq = g.qt * g.qh * g.qw + 1;
+  const int64_t ncols = BH * g.qt * g.qw;
+  for (int64_t cc = (int64_t)blockIdx.x * RW_WARPS + warp; cc < ncols; cc += (int64_t)gridDim.x * RW_WARPS) {
+    const int iw = (int)(cc % g.qw);
+    const int it = (int)((cc / g.qw) % g.qt);
+    const int64_t bh = cc / ((int64_t)g.qw * g.qt);
+    const int my_w = lane < g.kw ? idx_w[iw * g.kw + lane] : 0;
+    float gw[KMAX][3];
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gw[j][c] = 0.f;
+    for (int ih = 0; ih < g.qh; ++ih) {
+      const int64_t row = bh * Nq + 1 + ((int64_t)it * g.qh + ih) * g.qw + iw;
+      const T* qp = q_aug + row * ld;
+      const T* dqp = dq_aug + row * ld;
+      float qv[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) qv[c] = to_f32(qp[lane + 32 * c]);
+      const float dw_ = lane < g.kw ? to_f32(dqp[HD + g.kh + lane]) * inv_scale : 0.f;
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) {
+        if (j < g.kw) {
+          const float d = __shfl_sync(0xffffffffu, dw_, j);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) gw[j][c] = fmaf(d, qv[c], gw[j][c]);
+        }
       }
     }
 #pragma unroll
-    for (int j = 0; j < 3; ++j) dqp[lane + 32 * j] = from_f32<T>(acc[j]);
+    for (int j = 0; j < KMAX; ++j) {
+      if (j < g.kw) {
+        float* dst = dtab + __shfl_sync(0xffffffffu, my_w, j) * HD + lane;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) atomicAdd(dst + 32 * c, gw[j][c]);
+      }
+    }
   }
   __syncthreads();
-  // one partial table per block ([rows_h + rows_w + rows_t][96], folded by reduce_partials_kernel)
-  for (int i = threadIdx.x; i < rows * HD; i += blockDim.x) partials[(int64_t)blockIdx.x * rows * HD + i] = dtab[i];
+  for (int i = threadIdx.x; i < g.rows_w * HD; i += blockDim.x) partials[(int64_t)blockIdx.x * g.rows_w * HD + i] = dtab[i];
 }
 
 RelGeom make_rel(int qt, int qh, int qw, int kt, int kh, int kw) {
@@ -213,15 +299,17 @@ extern "C" int pmv_relpos_augment_k(void* k_aug, int64_t ld, int BH, int kt, int
   return PMV_OK;
 }
 
-static int64_t relpos_bwd_blocks(int64_t total_rows) {
-  int64_t blocks = ceil_div64(total_rows, AUG_WARPS * 8);
-  if (blocks > 148 * 2) blocks = 148 * 2;
-  return blocks < 1 ? 1 : blocks;
+static int rw_blocks(int64_t units) {
+  int64_t b = ceil_div64(units, RW_WARPS * 2);
+  if (b > 148) b = 148;
+  return b < 1 ? 1 : (int)b;
 }
 
 extern "C" int64_t pmv_relpos_bwd_workspace_bytes(int BH, int qt, int qh, int qw, int kt, int kh, int kw) {
   RelGeom g = make_rel(qt, qh, qw, kt, kh, kw);
-  return relpos_bwd_blocks((int64_t)BH * (qt * qh * qw + 1)) * (g.rows_h + g.rows_w + g.rows_t) * HD * (int64_t)sizeof(float);
+  const int64_t r = (int64_t)rw_blocks((int64_t)BH * qt * qh) * (g.rows_h + g.rows_t) * HD;
+  const int64_t c = (int64_t)rw_blocks((int64_t)BH * qt * qw) * g.rows_w * HD;
+  return (r + c) * (int64_t)sizeof(float);
 }
 
 /* d_rel: [rows_h + rows_w + rows_t][96] fp32 (the three tables stacked), added to. */
@@ -231,17 +319,26 @@ extern "C" int pmv_relpos_augment_q_bwd(void* dq_aug, const void* q_aug, int64_t
                                         int BH, int qt, int qh, int qw, int kt, int kh, int kw,
                                         float inv_scale, int dtype, void* stream) {
   RelGeom g = make_rel(qt, qh, qw, kt, kh, kw);
-  const size_t smem = (size_t)2 * (g.rows_h + g.rows_w + g.rows_t) * HD * sizeof(float);
-  PMV_CHECK_ARG(smem <= 200 * 1024, "relpos: tables too large for shared memory");
-  PMV_CHECK_ARG(kh + kw + kt <= 64, "relpos: at most 64 bias columns");
-  const int64_t total = (int64_t)BH * (qt * qh * qw + 1);
-  const int64_t blocks = relpos_bwd_blocks(total);
+  PMV_CHECK_ARG(kh <= KMAX && kw <= KMAX && kt <= KMAX && kh + kw + kt <= 64, "relpos: k_h, k_w, k_t must be <= %d", KMAX);
+  const int rows = g.rows_h + g.rows_w + g.rows_t, nht = g.rows_h + g.rows_t;
+  const size_t smem_r = (size_t)(rows + nht) * HD * sizeof(float);
+  const size_t smem_c = (size_t)g.rows_w * HD * sizeof(float);
+  PMV_CHECK_ARG(smem_r <= 200 * 1024, "relpos: tables too large for shared memory");
+  const int nb_r = rw_blocks((int64_t)BH * qt * qh), nb_c = rw_blocks((int64_t)BH * qt * qw);
+  float* part_r = ws;
+  float* part_c = ws + (int64_t)nb_r * nht * HD;
+  cudaStream_t st = (cudaStream_t)stream;
   PMV_DISPATCH_DTYPE(dtype, T, {
-    PMV_CHECK_CUDA(cudaFuncSetAttribute(relpos_augment_q_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    relpos_augment_q_bwd_kernel<T><<<(unsigned)blocks, AUG_WARPS * 32, smem, (cudaStream_t)stream>>>(
-        (T*)dq_aug, (const T*)q_aug, ld, rel_h, rel_w, rel_t, idx_h, idx_w, idx_t, ws, BH, g, inv_scale);
+    PMV_CHECK_CUDA(cudaFuncSetAttribute(relpos_bwd_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    PMV_CHECK_CUDA(cudaFuncSetAttribute(relpos_bwd_cols_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    // the column walk reads the d rq columns, which the row walk leaves untouched (it rewrites columns [0, 96) only)
+    relpos_bwd_cols_kernel<T><<<nb_c, RW_WARPS * 32, smem_c, st>>>((const T*)dq_aug, (const T*)q_aug, ld, idx_w, part_c, BH, g, inv_scale);
+    relpos_bwd_rows_kernel<T><<<nb_r, RW_WARPS * 32, smem_r, st>>>((T*)dq_aug, (const T*)q_aug, ld, rel_h, rel_w, rel_t, idx_h, idx_w,
+                                                                    idx_t, part_r, BH, g, inv_scale);
   });
-  launch_reduce_partials(ws, (int)blocks, (g.rows_h + g.rows_w + g.rows_t) * HD, d_rel, (cudaStream_t)stream);
+  launch_reduce_partials(part_r, nb_r, g.rows_h * HD, d_rel, st, (int64_t)nht * HD);
+  launch_reduce_partials(part_r + g.rows_h * HD, nb_r, g.rows_t * HD, d_rel + (int64_t)(g.rows_h + g.rows_w) * HD, st, (int64_t)nht * HD);
+  launch_reduce_partials(part_c, nb_c, g.rows_w * HD, d_rel + (int64_t)g.rows_h * HD, st);
   PMV_CHECK_LAUNCH();
   return PMV_OK;
 }
