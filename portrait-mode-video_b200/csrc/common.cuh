@@ -42,6 +42,34 @@ void pmv_set_error(const char* fmt, ...);
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Division by a run-time constant as multiply-high + shift (dividends < 2^31).  A hardware integer division
+// costs ~25 instructions; the token decode of the memory-bound kernels did 5-25 of them per token and was
+// instruction-bound on index arithmetic (profiles/r01_pool_relpos_ncu.md).
+struct FastDiv {
+  uint32_t d, mul, shr;
+  FastDiv() : d(1), mul(0), shr(0) {}
+  explicit FastDiv(uint32_t div) : d(div), mul(0), shr(0) {
+    if (div > 1) {
+      uint32_t lg = 0;
+      while ((1ull << lg) < div) ++lg;  // ceil(log2(div))
+      const uint32_t p = 31 + lg;
+      mul = (uint32_t)(((1ull << p) + div - 1) / div);
+      shr = p - 32;
+    }
+  }
+  __host__ __device__ __forceinline__ uint32_t div(uint32_t n) const {
+#ifdef __CUDA_ARCH__
+    return d == 1 ? n : (__umulhi(n, mul) >> shr);
+#else
+    return n / d;
+#endif
+  }
+  __host__ __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
+    q = div(n);
+    r = n - q * d;
+  }
+};
+
 // ---------------------------------------------------------------------------
 // scalar conversions
 // ---------------------------------------------------------------------------

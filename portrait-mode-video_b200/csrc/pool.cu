@@ -4,34 +4,44 @@
 // [B, N, 3, heads, 96] (strided view) and write [B, heads, 1+L', ld] — the three permute().contiguous()
 // copies, the cat and the separate LayerNorm of the reference disappear.
 //
-// forward       : 8 lanes own one output token, each lane 12 consecutive channels (8/16-byte vector loads);
-//                 a warp handles 4 tokens that are neighbours along w, so the window overlap is served by L1.
-// backward (i)  : one warp per OUTPUT token, lane owns channels {lane, lane+32, lane+64}: the convolution and the
-//                 LN statistics are recomputed, LN backward gives the pre-LN gradient (fp32 workspace) and the
-//                 dgamma / dbeta partials.  Light on registers on purpose: the kernel is latency-bound (one token
-//                 per warp at a time, three warp reductions on the critical path), so it lives on occupancy.
-// backward (ii) : weight gradient dW[c][tap] = sum_tok x[nb(tok, tap)][c] * dconv[tok][c]: thread = (channel,
-//                 temporal tap), 9 exclusive accumulators, no reductions and no dependences between tokens, so
-//                 loads of several tokens are in flight -> one partial [96][27] per CTA.
-// backward (iii): gather form of the transposed stencil per INPUT token (no atomics), written straight into the
-//                 interleaved dQKV buffer.
-// backward (iv) : reduce kernels fold the per-CTA partials (same-address global atomics from hundreds of CTAs
-//                 serialise in L2).
+// All stencil kernels share one shape ("row march"): a CTA of 192 threads = 4 output rows x 48 channel PAIRS.
+// A thread keeps the 27 taps of its two channels in registers (packed fp32 pairs -> FFMA2, 27 per output pair)
+// and walks along w.  For stride 1 the 3x3 (t,h) x 3 (w) input window lives in registers and slides: 9 new
+// 4-byte loads per output instead of 27, every load of a warp is a contiguous 128-byte run of channels.
+// The convolution results of 4 rows x 6 positions are parked in shared memory; after one __syncthreads the
+// CTA re-maps to 24 tokens x 8 lanes (12 channels per lane) for the LayerNorm (3 shuffle rounds per
+// reduction) and writes 192-byte token rows.  The buffer is double-buffered: one barrier per 24 tokens.
+//
+// forward        : conv -> LN -> out.
+// backward (i)   : conv recomputed -> LN statistics -> LN backward -> pre-LN gradient `dconv` (workspace, in the
+//                  compute dtype) + dgamma / dbeta partials per CTA.  The cls token (no convolution) is handled
+//                  by a few extra CTAs, one warp per token.
+// backward (ii)  : dW[c][tap] += x[nb(tok, tap)][c] * dconv[tok][c]: the same march with the window of x and 27
+//                  exclusive accumulator pairs per thread -> one partial [96][27] per CTA.
+// backward (iii) : input gradient, gather form of the transposed stencil per INPUT row (no atomics), written
+//                  straight into the interleaved dQKV buffer.  Stride 1: the forward march over dconv with
+//                  flipped taps.  Stride >= 2: only taps with (h+1-dh) % s == 0 contribute (none for most rows at
+//                  stride 4 / 8): guarded taps, zero rows written without arithmetic.
+// backward (iv)  : a reduce kernel folds the per-CTA partials (same-address global atomics from hundreds of CTAs
+//                  serialise in L2).
 #include "common.cuh"
 
 namespace {
 
 constexpr int HD = PMV_HEAD_DIM;  // 96
 constexpr int TAPS = 27;
-constexpr int CPL = 12;           // channels per lane (forward / input-gradient kernels)
-constexpr int LPT = 8;            // lanes per token
-constexpr int POOL_THREADS = 256;
-constexpr int TOK_PER_BLOCK = POOL_THREADS / LPT;
-constexpr int BWD_WARPS = 8;
+constexpr int NCP = HD / 2;        // 48 channel pairs
+constexpr int ROWS = 4;            // output rows per CTA pass
+constexpr int CW = 6;              // positions along w between two LayerNorm phases (multiple of 3: window rotation)
+constexpr int THREADS = NCP * ROWS;  // 192
+constexpr int LNL = 8;             // lanes per token in the LayerNorm phase
+constexpr int CPL = HD / LNL;      // 12 channels per lane
+constexpr int CHUNK_TOK = ROWS * CW;  // 24 tokens per phase == THREADS / LNL
+constexpr int CLS_WARPS = THREADS / 32;
 constexpr int NGRAD = (TAPS + 2) * HD;  // dW [96][27], dgamma [96], dbeta [96]
 constexpr int NDW = TAPS * HD;
-constexpr int DW_THREADS = 3 * HD;     // (temporal tap, channel)
 constexpr int MAX_JOBS = 3;
+static_assert(CHUNK_TOK * LNL == THREADS, "LayerNorm phase mapping");
 
 struct Job {
   const void* in;       // first channel of this tensor inside the QKV buffer
@@ -44,10 +54,11 @@ struct Job {
   int64_t dout_ld;
   void* din;            // backward: gradient wrt `in` (same strides)
   float* grads;         // backward: [NGRAD] fp32, added to
-  float* dconv;         // backward: fp32 workspace [B*heads*Lo*96]
+  void* dconv;          // backward: pre-LN gradient [B*heads*Lo*96] in the compute dtype
   int s, Ho, Wo;
-  int blk_begin, nblk;  // block range of this job in the current launch
-  int blk2_begin, nblk2;  // block range in the dW kernel
+  int blk_begin, nblk, ncls_blk;  // forward / backward (i): [blk_begin, +nblk) march blocks, then ncls_blk cls blocks
+  int blk2_begin, nblk2;          // backward (ii)
+  int blk3_begin, nblk3;          // backward (iii)
 };
 
 struct Launch {
@@ -56,16 +67,21 @@ struct Launch {
   int B, heads, T, H, W;
   int64_t in_bs, in_ts, in_hs;  // element strides of the input views
   float eps;
-  float* partials;              // token kernel: [total blocks][2 * 96] (dgamma, dbeta)
-  float* partials_dw;           // dW kernel: [total blocks][96 * 27]
+  float* partials;              // backward (i): [total blocks][2 * 96] (dgamma, dbeta)
+  float* partials_dw;           // backward (ii): [total blocks][96 * 27]
 };
 
-__device__ __forceinline__ int find_job(const Launch& L) {
-  int j = 0;
-  while (j + 1 < L.njobs && (int)blockIdx.x >= L.job[j + 1].blk_begin) ++j;
-  return j;
+// ---- 2-channel loads / stores ---------------------------------------------------------------------------------
+__device__ __forceinline__ float2 ld2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+__device__ __forceinline__ float2 ld2(const bf16* p) {
+  const uint32_t u = __ldg(reinterpret_cast<const unsigned int*>(p));
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
-
+__device__ __forceinline__ void st2(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+__device__ __forceinline__ void st2(bf16* p, float2 v) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+  *reinterpret_cast<uint32_t*>(p) = *reinterpret_cast<uint32_t*>(&h);
+}
 template <typename T> __device__ __forceinline__ void load12(const T* p, float (&v)[CPL]) {
   float a[4];
 #pragma unroll
@@ -83,295 +99,517 @@ template <typename T> __device__ __forceinline__ void store12(T* p, const float 
   }
 }
 
-// weights: reference layout [96][27] -> smem [27][96]
-__device__ __forceinline__ void stage_weights(const float* __restrict__ w, float* sw) {
-  for (int i = threadIdx.x; i < HD * TAPS; i += blockDim.x) {
-    int c = i / TAPS, tap = i - c * TAPS;
-    sw[tap * HD + c] = w[i];
+// the 27 taps of channels (2cp, 2cp+1); FLIP mirrors all three axes (transposed stencil)
+template <bool FLIP> __device__ __forceinline__ void load_taps(const float* __restrict__ w, int cp, float2 (&wr)[TAPS]) {
+#pragma unroll
+  for (int tap = 0; tap < TAPS; ++tap) {
+    const int src = FLIP ? (TAPS - 1 - tap) : tap;
+    wr[tap] = make_float2(__ldg(w + (2 * cp) * TAPS + src), __ldg(w + (2 * cp + 1) * TAPS + src));
   }
 }
 
+// One row of the march: where the 3x3 (t,h) neighbourhood of the row lives.
+struct RowGeom {
+  int off9[9];      // element offset of neighbour row k = dt*3+dh relative to `base`
+  uint32_t mask9;   // bit k set: neighbour row k is inside the volume
+};
+
+// offsets / validity of the 3x3 (t,h) neighbour rows around (t, hc) in a [T][Hn][Wn] volume with token stride ts
+__device__ __forceinline__ void make_geom(RowGeom& g, int t, int hc, int T, int Hn, int Wn, int ts) {
+  g.mask9 = 0;
+#pragma unroll
+  for (int dt = 0; dt < 3; ++dt)
+#pragma unroll
+    for (int dh = 0; dh < 3; ++dh) {
+      const int tt = t + dt - 1, hh = hc + dh - 1;
+      const bool ok = tt >= 0 && tt < T && hh >= 0 && hh < Hn;
+      g.off9[dt * 3 + dh] = ((dt - 1) * Hn + (dh - 1)) * Wn * ts;
+      if (ok) g.mask9 |= 1u << (dt * 3 + dh);
+    }
+}
+
+// load column `wi` of the window (9 neighbour rows) into x[.]: zero outside the volume
 template <typename T>
-__global__ void __launch_bounds__(POOL_THREADS) pool_ln_fwd_kernel(const __grid_constant__ Launch L) {
-  __shared__ float sw[TAPS * HD];
+__device__ __forceinline__ void load_col(float2 (&x)[9], const T* __restrict__ base, const RowGeom& g, int wi, int Wn, int ts) {
+  const bool wok = wi >= 0 && wi < Wn;
+  const int woff = wi * ts;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const bool ok = wok && ((g.mask9 >> k) & 1u);
+    x[k] = ok ? ld2(base + (g.off9[k] + woff)) : make_float2(0.f, 0.f);
+  }
+}
+
+// conv value from window columns (A, B, C) = (w-1, w, w+1): three independent FFMA2 chains
+__device__ __forceinline__ float2 dot27(const float2 (&xa)[9], const float2 (&xb)[9], const float2 (&xc)[9], const float2 (&wr)[TAPS]) {
+  float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    a0 = __ffma2_rn(xa[k], wr[3 * k + 0], a0);
+    a1 = __ffma2_rn(xb[k], wr[3 * k + 1], a1);
+    a2 = __ffma2_rn(xc[k], wr[3 * k + 2], a2);
+  }
+  return make_float2(a0.x + a1.x + a2.x, a0.y + a1.y + a2.y);
+}
+
+// One march step at output position wo.
+//   stride 1: the window slides — slots (SA, SB, SC) hold columns (wo-1, wo, wo+1); only SC is loaded.
+//   stride s: all three columns wo*s-1 .. wo*s+1 are loaded (slots 0, 1, 2).
+template <typename T, bool SLIDE, int SA, int SB, int SC>
+__device__ __forceinline__ void window_step(float2 (&x)[3][9], const T* __restrict__ base, const RowGeom& g, int wo, int s, int Wn,
+                                            int ts) {
+  if (SLIDE) {
+    load_col(x[SC], base, g, wo + 1, Wn, ts);
+  } else {
+    load_col(x[SA], base, g, wo * s - 1, Wn, ts);
+    load_col(x[SB], base, g, wo * s, Wn, ts);
+    load_col(x[SC], base, g, wo * s + 1, Wn, ts);
+  }
+}
+
+__device__ __forceinline__ int find_job(const Launch& L) {
+  int j = 0;
+  while (j + 1 < L.njobs && (int)blockIdx.x >= L.job[j + 1].blk_begin) ++j;
+  return j;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward (BWD = false) and backward (i) (BWD = true)
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(THREADS, 2) pool_ln_march_kernel(const __grid_constant__ Launch L) {
+  __shared__ __align__(16) float conv_s[2][CHUNK_TOK * HD];  // 18 KB; reused for the final partial reduction
+  __shared__ float sgam[HD], sbet[HD];
+  __shared__ int64_t row_out_s[ROWS];   // output token index of the row's first position (incl. cls slots)
+  __shared__ int64_t row_dc_s[ROWS];    // dconv token index of the row's first position
   const Job& J = L.job[find_job(L)];
-  stage_weights(J.w, sw);
-  __syncthreads();
   const T* __restrict__ in = reinterpret_cast<const T*>(J.in);
-  T* __restrict__ out = reinterpret_cast<T*>(J.out);
-  const int sub = threadIdx.x & (LPT - 1);
-  const int c0 = sub * CPL;
+  const int tid = threadIdx.x;
   const int Lo = L.T * J.Ho * J.Wo;
-  const int64_t ntok = (int64_t)L.B * L.heads * (Lo + 1);
-  float gm[CPL], bt[CPL];
-#pragma unroll
-  for (int j = 0; j < CPL; ++j) { gm[j] = J.gamma[c0 + j]; bt[j] = J.beta[c0 + j]; }
   const int lb = blockIdx.x - J.blk_begin;
-  for (int64_t tok = (int64_t)lb * TOK_PER_BLOCK + threadIdx.x / LPT; tok < ntok; tok += (int64_t)J.nblk * TOK_PER_BLOCK) {
-    const int n = (int)(tok % (Lo + 1));
-    const int64_t bh = tok / (Lo + 1);
-    const int head = (int)(bh % L.heads);
-    const int64_t b = bh / L.heads;
-    const T* base = in + b * L.in_bs + head * L.in_hs + c0;
-    float acc[CPL];
-    if (n == 0) {
-      load12(base, acc);  // cls token: no convolution (attention.py:25-26)
-    } else {
-      int l = n - 1;
-      const int wo = l % J.Wo; l /= J.Wo;
-      const int ho = l % J.Ho;
-      const int t = l / J.Ho;
+
+  if (tid < HD) {
+    sgam[tid] = J.gamma[tid];
+    sbet[tid] = BWD ? 0.f : J.beta[tid];
+  }
+
+  float adg[CPL], adb[CPL];  // backward: dgamma / dbeta of this lane's 12 channels (march blocks), 3 channels (cls blocks)
 #pragma unroll
-      for (int j = 0; j < CPL; ++j) acc[j] = 0.f;
+  for (int j = 0; j < CPL; ++j) { adg[j] = 0.f; adb[j] = 0.f; }
+
+  if (lb >= J.nblk) {
+    // ---------------------------------------------------------------- cls tokens: LayerNorm only, one warp per token
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    const int ncls = L.B * L.heads;
+    for (int bh = (lb - J.nblk) * CLS_WARPS + warp; bh < ncls; bh += J.ncls_blk * CLS_WARPS) {
+      const int head = bh % L.heads, b = bh / L.heads;
+      const int64_t in_off = (int64_t)b * L.in_bs + (int64_t)head * L.in_hs + lane;
+      const int64_t tok = (int64_t)bh * (Lo + 1);
+      float v[3];
 #pragma unroll
-      for (int dt = 0; dt < 3; ++dt) {
-        const int ti = t + dt - 1;
-        if (ti < 0 || ti >= L.T) continue;
+      for (int j = 0; j < 3; ++j) v[j] = to_f32(in[in_off + 32 * j]);
+      const float mu = warp_sum(v[0] + v[1] + v[2]) * (1.0f / HD);
+      float q = 0.f;
 #pragma unroll
-        for (int dh = 0; dh < 3; ++dh) {
-          const int hi = ho * J.s + dh - 1;
-          if (hi < 0 || hi >= L.H) continue;
+      for (int j = 0; j < 3; ++j) { const float d = v[j] - mu; q += d * d; }
+      const float rs = rsqrtf(warp_sum(q) * (1.0f / HD) + L.eps);
+      if (!BWD) {
+        T* o = reinterpret_cast<T*>(J.out) + tok * J.out_ld + lane;
 #pragma unroll
-          for (int dw = 0; dw < 3; ++dw) {
-            const int wi = wo * J.s + dw - 1;
-            if (wi < 0 || wi >= L.W) continue;
-            float xv[CPL];
-            load12(base + (int64_t)(1 + (ti * L.H + hi) * L.W + wi) * L.in_ts, xv);
-            const float* wt = sw + (dt * 9 + dh * 3 + dw) * HD + c0;
+        for (int j = 0; j < 3; ++j) o[32 * j] = from_f32<T>((v[j] - mu) * rs * sgam[lane + 32 * j] + sbet[lane + 32 * j]);
+      } else {
+        const T* dyr = reinterpret_cast<const T*>(J.dout) + tok * J.dout_ld + lane;
+        float xh[3], gg[3], s1 = 0.f, s2 = 0.f;
 #pragma unroll
-            for (int j = 0; j < CPL; ++j) acc[j] = fmaf(xv[j], wt[j], acc[j]);
+        for (int j = 0; j < 3; ++j) {
+          const float dy = to_f32(dyr[32 * j]);
+          xh[j] = (v[j] - mu) * rs;
+          gg[j] = dy * sgam[lane + 32 * j];
+          s1 += gg[j];
+          s2 += gg[j] * xh[j];
+          adg[j] += dy * xh[j];
+          adb[j] += dy;
+        }
+        s1 = warp_sum(s1) * (1.0f / HD);
+        s2 = warp_sum(s2) * (1.0f / HD);
+        T* dp = reinterpret_cast<T*>(J.din) + in_off;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) dp[32 * j] = from_f32<T>(rs * (gg[j] - s1 - xh[j] * s2));
+      }
+    }
+    if (BWD) {
+      float* red = &conv_s[0][0];  // [CLS_WARPS][2*HD]
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        red[warp * 2 * HD + lane + 32 * j] = adg[j];
+        red[warp * 2 * HD + HD + lane + 32 * j] = adb[j];
+      }
+      __syncthreads();
+      if (tid < 2 * HD) {
+        float s = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < CLS_WARPS; ++wv) s += red[wv * 2 * HD + tid];
+        L.partials[(int64_t)blockIdx.x * 2 * HD + tid] = s;
+      }
+    }
+    return;
+  }
+
+  // ------------------------------------------------------------------ march blocks
+  const int cp = tid % NCP, r = tid / NCP;
+  float2 wr[TAPS];
+  load_taps<false>(J.w, cp, wr);
+  const int ts = (int)L.in_ts;
+  const bool slide = J.s == 1;
+  // LayerNorm-phase role of this thread
+  const int g = tid >> 3, sub = tid & 7;
+  const int g_row = g / CW, g_w = g - g_row * CW;
+  const int nrows = L.B * L.heads * L.T * J.Ho;
+  const int nitems = (nrows + ROWS - 1) / ROWS;
+  int buf = 0;
+
+  for (int item = lb; item < nitems; item += J.nblk) {
+    const int row = item * ROWS + r;
+    const bool rvalid = row < nrows;
+    RowGeom geo;
+    const T* base = in;
+    {
+      const int rr = rvalid ? row : 0;
+      const int ho = rr % J.Ho;
+      int q = rr / J.Ho;
+      const int t = q % L.T; q /= L.T;
+      const int head = q % L.heads, b = q / L.heads;
+      make_geom(geo, t, ho * J.s, L.T, L.H, L.W, ts);
+      if (!rvalid) geo.mask9 = 0;
+      base = in + ((int64_t)b * L.in_bs + (int64_t)head * L.in_hs + (int64_t)(1 + (t * L.H + ho * J.s) * L.W) * L.in_ts + 2 * cp);
+      if (cp == 0) {
+        const int64_t bh = (int64_t)b * L.heads + head;
+        const int64_t pos = (int64_t)(t * J.Ho + ho) * J.Wo;
+        row_out_s[r] = rvalid ? bh * (Lo + 1) + 1 + pos : -1;
+        row_dc_s[r] = bh * Lo + pos;
+      }
+    }
+    float2 x[3][9];
+    if (slide) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) x[0][k] = make_float2(0.f, 0.f);
+      load_col(x[1], base, geo, 0, L.W, ts);
+    }
+    for (int c0 = 0; c0 < J.Wo; c0 += CW) {
+      float* cb = &conv_s[buf][(r * CW) * HD + 2 * cp];
+      if (slide) {
+#pragma unroll
+        for (int j = 0; j < CW; j += 3) {
+          if (c0 + j < J.Wo) {
+            window_step<T, true, 0, 1, 2>(x, base, geo, c0 + j, 1, L.W, ts);
+            *reinterpret_cast<float2*>(cb + j * HD) = dot27(x[0], x[1], x[2], wr);
+          }
+          if (c0 + j + 1 < J.Wo) {
+            window_step<T, true, 1, 2, 0>(x, base, geo, c0 + j + 1, 1, L.W, ts);
+            *reinterpret_cast<float2*>(cb + (j + 1) * HD) = dot27(x[1], x[2], x[0], wr);
+          }
+          if (c0 + j + 2 < J.Wo) {
+            window_step<T, true, 2, 0, 1>(x, base, geo, c0 + j + 2, 1, L.W, ts);
+            *reinterpret_cast<float2*>(cb + (j + 2) * HD) = dot27(x[2], x[0], x[1], wr);
+          }
+        }
+      } else {
+#pragma unroll 2
+        for (int j = 0; j < CW; ++j) {
+          if (c0 + j < J.Wo) {
+            window_step<T, false, 0, 1, 2>(x, base, geo, c0 + j, J.s, L.W, ts);
+            *reinterpret_cast<float2*>(cb + j * HD) = dot27(x[0], x[1], x[2], wr);
           }
         }
       }
-    }
-    float s = 0.f;
+      __syncthreads();  // conv_s[buf] complete (and row_*_s of this item visible)
+      // ---- LayerNorm phase: 8 lanes per token
+      {
+        const int64_t otok = row_out_s[g_row];
+        const bool tvalid = otok >= 0 && c0 + g_w < J.Wo;
+        float v[CPL];
+        const float* src = &conv_s[buf][g * HD + sub * CPL];
 #pragma unroll
-    for (int j = 0; j < CPL; ++j) s += acc[j];
-    const float mu = group_sum<LPT>(s) * (1.0f / HD);
-    float q = 0.f;
+        for (int i = 0; i < 3; ++i) {
+          const float4 t4 = *reinterpret_cast<const float4*>(src + 4 * i);
+          v[4 * i] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
+        }
+        if (!tvalid) {  // stale buffer contents must not reach the dgamma / dbeta accumulators
 #pragma unroll
-    for (int j = 0; j < CPL; ++j) { float d = acc[j] - mu; q += d * d; }
-    const float rs = rsqrtf(group_sum<LPT>(q) * (1.0f / HD) + L.eps);
-    float o[CPL];
+          for (int j = 0; j < CPL; ++j) v[j] = 0.f;
+        }
+        float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < CPL; ++j) o[j] = (acc[j] - mu) * rs * gm[j] + bt[j];
-    store12(out + tok * J.out_ld + c0, o);
-  }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(BWD_WARPS * 32, 4) pool_ln_bwd_tokens_kernel(const __grid_constant__ Launch L) {
-  __shared__ float sw[TAPS * HD];
-  __shared__ float sred[2 * HD];
-  const Job& J = L.job[find_job(L)];
-  stage_weights(J.w, sw);
-  for (int i = threadIdx.x; i < 2 * HD; i += blockDim.x) sred[i] = 0.f;
-  __syncthreads();
-  const T* __restrict__ in = reinterpret_cast<const T*>(J.in);
-  const T* __restrict__ dout = reinterpret_cast<const T*>(J.dout);
-  T* __restrict__ din = reinterpret_cast<T*>(J.din);
-  const int lane = threadIdx.x & 31;
-  const int Lo = L.T * J.Ho * J.Wo;
-  const int64_t ntok = (int64_t)L.B * L.heads * (Lo + 1);
-  float gm[3];
+        for (int j = 0; j < CPL; ++j) s += v[j];
+        const float mu = group_sum<LNL>(s) * (1.0f / HD);
+        float q = 0.f;
 #pragma unroll
-  for (int j = 0; j < 3; ++j) gm[j] = J.gamma[lane + 32 * j];
-  float adg[3] = {0.f, 0.f, 0.f}, adb[3] = {0.f, 0.f, 0.f};
-  const int lb = blockIdx.x - J.blk_begin;
-
-  for (int64_t tok = (int64_t)lb * BWD_WARPS + (threadIdx.x >> 5); tok < ntok; tok += (int64_t)J.nblk * BWD_WARPS) {
-    const int n = (int)(tok % (Lo + 1));
-    const int64_t bh = tok / (Lo + 1);
-    const int head = (int)(bh % L.heads);
-    const int64_t b = bh / L.heads;
-    const int64_t base_off = b * L.in_bs + head * L.in_hs + lane;
-    const T* base = in + base_off;
-    const T* dyr = dout + tok * J.dout_ld + lane;
-    float dy[3];
+        for (int j = 0; j < CPL; ++j) { const float d = v[j] - mu; q += d * d; }
+        const float rs = rsqrtf(group_sum<LNL>(q) * (1.0f / HD) + L.eps);
+        if (!BWD) {
+          float o[CPL];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) dy[j] = to_f32(dyr[32 * j]);
-    float acc[3] = {0.f, 0.f, 0.f};
-    if (n == 0) {
+          for (int j = 0; j < CPL; ++j) o[j] = (v[j] - mu) * rs * sgam[sub * CPL + j] + sbet[sub * CPL + j];
+          if (tvalid) store12(reinterpret_cast<T*>(J.out) + (otok + c0 + g_w) * J.out_ld + sub * CPL, o);
+        } else {
+          float dy[CPL];
+          if (tvalid) {
+            load12(reinterpret_cast<const T*>(J.dout) + (otok + c0 + g_w) * J.dout_ld + sub * CPL, dy);
+          } else {
 #pragma unroll
-      for (int j = 0; j < 3; ++j) acc[j] = to_f32(base[32 * j]);
-    } else {
-      int l = n - 1;
-      const int wo = l % J.Wo; l /= J.Wo;
-      const int ho = l % J.Ho;
-      const int t = l / J.Ho;
+            for (int j = 0; j < CPL; ++j) dy[j] = 0.f;
+          }
+          float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int dt = 0; dt < 3; ++dt) {
-        const int ti = t + dt - 1;
-        if (ti < 0 || ti >= L.T) continue;
-#pragma unroll
-        for (int dh = 0; dh < 3; ++dh) {
-          const int hi = ho * J.s + dh - 1;
-          if (hi < 0 || hi >= L.H) continue;
-          float xv[3][3];
-#pragma unroll
-          for (int dwi = 0; dwi < 3; ++dwi) {  // the three loads of a window row are issued together
-            const int wi = wo * J.s + dwi - 1;
-            const bool ok = wi >= 0 && wi < L.W;
-            const T* p = base + (int64_t)(1 + (ti * L.H + hi) * L.W + (ok ? wi : 0)) * L.in_ts;
-#pragma unroll
-            for (int j = 0; j < 3; ++j) xv[dwi][j] = ok ? to_f32(p[32 * j]) : 0.f;
+          for (int j = 0; j < CPL; ++j) {
+            v[j] = (v[j] - mu) * rs;                      // xhat
+            const float gg = dy[j] * sgam[sub * CPL + j];
+            s1 += gg;
+            s2 += gg * v[j];
+            adg[j] += dy[j] * v[j];
+            adb[j] += dy[j];
+            dy[j] = gg;
           }
 #pragma unroll
-          for (int dwi = 0; dwi < 3; ++dwi) {
-            const float* wt = sw + (dt * 9 + dh * 3 + dwi) * HD + lane;
-#pragma unroll
-            for (int j = 0; j < 3; ++j) acc[j] = fmaf(xv[dwi][j], wt[32 * j], acc[j]);
+          for (int o = LNL / 2; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
           }
+          s1 *= (1.0f / HD);
+          s2 *= (1.0f / HD);
+          float dc[CPL];
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) dc[j] = rs * (dy[j] - s1 - v[j] * s2);
+          if (tvalid) store12(reinterpret_cast<T*>(J.dconv) + (row_dc_s[g_row] + c0 + g_w) * HD + sub * CPL, dc);
         }
       }
+      buf ^= 1;
     }
-    const float mu = warp_sum(acc[0] + acc[1] + acc[2]) * (1.0f / HD);
-    float q = 0.f;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) { float d = acc[j] - mu; q += d * d; }
-    const float rs = rsqrtf(warp_sum(q) * (1.0f / HD) + L.eps);
-    float xh[3], gg[3], s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      xh[j] = (acc[j] - mu) * rs;
-      gg[j] = dy[j] * gm[j];
-      s1 += gg[j];
-      s2 += gg[j] * xh[j];
-      adg[j] += dy[j] * xh[j];
-      adb[j] += dy[j];
-    }
-    // the two remaining reductions share their five shuffle rounds
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    }
-    s1 *= (1.0f / HD);
-    s2 *= (1.0f / HD);
-    float dc[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) dc[j] = rs * (gg[j] - s1 - xh[j] * s2);
-    if (n == 0) {
-      T* dp = din + base_off;
-#pragma unroll
-      for (int j = 0; j < 3; ++j) dp[32 * j] = from_f32<T>(dc[j]);
-      continue;
-    }
-    float* dcr = J.dconv + (bh * Lo + (n - 1)) * HD + lane;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) dcr[32 * j] = dc[j];
+    __syncthreads();  // row_*_s are rewritten by the next item
   }
+
+  if (BWD) {
+    __syncthreads();
+    float* red = &conv_s[0][0];  // [CHUNK_TOK groups][2*HD] = 4608 floats = the whole buffer
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    atomicAdd(&sred[lane + 32 * j], adg[j]);
-    atomicAdd(&sred[HD + lane + 32 * j], adb[j]);
+    for (int j = 0; j < CPL; ++j) {
+      red[g * 2 * HD + sub * CPL + j] = adg[j];
+      red[g * 2 * HD + HD + sub * CPL + j] = adb[j];
+    }
+    __syncthreads();
+    if (tid < 2 * HD) {
+      float s = 0.f;
+#pragma unroll 8
+      for (int gg = 0; gg < CHUNK_TOK; ++gg) s += red[gg * 2 * HD + tid];
+      L.partials[(int64_t)blockIdx.x * 2 * HD + tid] = s;
+    }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * HD; i += blockDim.x) L.partials[(int64_t)blockIdx.x * 2 * HD + i] = sred[i];
 }
 
-// dW: thread = (temporal tap dt, channel c); the CTA walks its share of the output tokens, all threads on the same
-// token (block-uniform index math), 9 exclusive accumulators per thread.
+// ---------------------------------------------------------------------------------------------------------------
+// backward (ii): dW partials
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dw_accum(float2 (&acc)[TAPS], const float2 (&xa)[9], const float2 (&xb)[9], const float2 (&xc)[9],
+                                         float2 d) {
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    acc[3 * k + 0] = __ffma2_rn(xa[k], d, acc[3 * k + 0]);
+    acc[3 * k + 1] = __ffma2_rn(xb[k], d, acc[3 * k + 1]);
+    acc[3 * k + 2] = __ffma2_rn(xc[k], d, acc[3 * k + 2]);
+  }
+}
+
 template <typename T>
-__global__ void __launch_bounds__(DW_THREADS) pool_ln_bwd_dw_kernel(const __grid_constant__ Launch L) {
+__global__ void __launch_bounds__(THREADS, 2) pool_ln_bwd_dw_kernel(const __grid_constant__ Launch L) {
+  __shared__ float dws[NDW];
   int jj = 0;
   while (jj + 1 < L.njobs && (int)blockIdx.x >= L.job[jj + 1].blk2_begin) ++jj;
   const Job& J = L.job[jj];
   const T* __restrict__ in = reinterpret_cast<const T*>(J.in);
-  const int c = threadIdx.x % HD, dt = threadIdx.x / HD;
+  const T* __restrict__ dconv = reinterpret_cast<const T*>(J.dconv);
+  const int tid = threadIdx.x;
+  const int cp = tid % NCP, r = tid / NCP;
   const int Lo = L.T * J.Ho * J.Wo;
-  const int64_t ntok = (int64_t)L.B * L.heads * Lo;
-  float a[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) a[k] = 0.f;
+  const int ts = (int)L.in_ts;
+  const bool slide = J.s == 1;
+  const int nrows = L.B * L.heads * L.T * J.Ho;
+  const int nitems = (nrows + ROWS - 1) / ROWS;
   const int lb = blockIdx.x - J.blk2_begin;
+  float2 acc[TAPS];
+#pragma unroll
+  for (int k = 0; k < TAPS; ++k) acc[k] = make_float2(0.f, 0.f);
+
+  for (int item = lb; item < nitems; item += J.nblk2) {
+    const int row = item * ROWS + r;
+    if (row >= nrows) continue;
+    const int ho = row % J.Ho;
+    int q = row / J.Ho;
+    const int t = q % L.T; q /= L.T;
+    const int head = q % L.heads, b = q / L.heads;
+    RowGeom geo;
+    make_geom(geo, t, ho * J.s, L.T, L.H, L.W, ts);
+    const T* base = in + ((int64_t)b * L.in_bs + (int64_t)head * L.in_hs + (int64_t)(1 + (t * L.H + ho * J.s) * L.W) * L.in_ts + 2 * cp);
+    const T* dc = dconv + (((int64_t)b * L.heads + head) * Lo + (int64_t)(t * J.Ho + ho) * J.Wo) * HD + 2 * cp;
+    float2 x[3][9];
+    if (slide) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) x[0][k] = make_float2(0.f, 0.f);
+      load_col(x[1], base, geo, 0, L.W, ts);
+      for (int wo = 0; wo < J.Wo; wo += 3) {
+        {
+          const float2 d = ld2(dc + wo * HD);
+          window_step<T, true, 0, 1, 2>(x, base, geo, wo, 1, L.W, ts);
+          dw_accum(acc, x[0], x[1], x[2], d);
+        }
+        if (wo + 1 < J.Wo) {
+          const float2 d = ld2(dc + (wo + 1) * HD);
+          window_step<T, true, 1, 2, 0>(x, base, geo, wo + 1, 1, L.W, ts);
+          dw_accum(acc, x[1], x[2], x[0], d);
+        }
+        if (wo + 2 < J.Wo) {
+          const float2 d = ld2(dc + (wo + 2) * HD);
+          window_step<T, true, 2, 0, 1>(x, base, geo, wo + 2, 1, L.W, ts);
+          dw_accum(acc, x[2], x[0], x[1], d);
+        }
+      }
+    } else {
 #pragma unroll 2
-  for (int64_t tok = lb; tok < ntok; tok += J.nblk2) {
-    int l = (int)(tok % Lo);
-    const int64_t bh = tok / Lo;
-    const int head = (int)(bh % L.heads);
-    const int64_t b = bh / L.heads;
-    const int wo = l % J.Wo; l /= J.Wo;
-    const int ho = l % J.Ho;
-    const int t = l / J.Ho;
-    const int ti = t + dt - 1;
-    if (ti < 0 || ti >= L.T) continue;
-    const float d = J.dconv[tok * HD + c];
-    const T* base = in + b * L.in_bs + head * L.in_hs + c;
-#pragma unroll
-    for (int dh = 0; dh < 3; ++dh) {
-      const int hi = ho * J.s + dh - 1;
-      if (hi < 0 || hi >= L.H) continue;
-#pragma unroll
-      for (int dwi = 0; dwi < 3; ++dwi) {
-        const int wi = wo * J.s + dwi - 1;
-        if (wi < 0 || wi >= L.W) continue;
-        a[dh * 3 + dwi] = fmaf(to_f32(base[(int64_t)(1 + (ti * L.H + hi) * L.W + wi) * L.in_ts]), d, a[dh * 3 + dwi]);
+      for (int wo = 0; wo < J.Wo; ++wo) {
+        const float2 d = ld2(dc + wo * HD);
+        window_step<T, false, 0, 1, 2>(x, base, geo, wo, J.s, L.W, ts);
+        dw_accum(acc, x[0], x[1], x[2], d);
       }
     }
   }
-  float* pb = L.partials_dw + (int64_t)blockIdx.x * NDW + c * TAPS + dt * 9;  // reference layout [96][27]
+  // fold the 4 row groups of the CTA in shared memory ([c][tap], the reference layout), then one coalesced store
+  for (int i = tid; i < NDW; i += THREADS) dws[i] = 0.f;
+  __syncthreads();
+#pragma unroll 1
+  for (int rr = 0; rr < ROWS; ++rr) {
+    if (r == rr) {
 #pragma unroll
-  for (int k = 0; k < 9; ++k) pb[k] = a[k];
+      for (int k = 0; k < TAPS; ++k) {
+        dws[(2 * cp) * TAPS + k] += acc[k].x;
+        dws[(2 * cp + 1) * TAPS + k] += acc[k].y;
+      }
+    }
+    __syncthreads();
+  }
+  float* pb = L.partials_dw + (int64_t)blockIdx.x * NDW;
+  for (int i = tid; i < NDW; i += THREADS) pb[i] = dws[i];
 }
 
-// gather form of the transposed stencil — one 8-lane group per INPUT token:
-// din[ti,hi,wi][c] = sum over taps with (hi+1-dh) % s == 0 of w[c][tap] * dconv[to,ho,wo][c].
-template <typename T>
-__global__ void __launch_bounds__(POOL_THREADS) pool_ln_bwd_input_kernel(const __grid_constant__ Launch L) {
-  __shared__ float sw[TAPS * HD];
-  const Job& J = L.job[find_job(L)];
-  stage_weights(J.w, sw);
-  __syncthreads();
-  T* __restrict__ din = reinterpret_cast<T*>(J.din);
-  const int sub = threadIdx.x & (LPT - 1);
-  const int c0 = sub * CPL;
-  const int Li = L.T * L.H * L.W;
-  const int Lo = L.T * J.Ho * J.Wo;
-  const int64_t ntok = (int64_t)L.B * L.heads * Li;
-  const int lb = blockIdx.x - J.blk_begin;
-  for (int64_t tok = (int64_t)lb * TOK_PER_BLOCK + threadIdx.x / LPT; tok < ntok; tok += (int64_t)J.nblk * TOK_PER_BLOCK) {
-    int l = (int)(tok % Li);
-    const int64_t bh = tok / Li;
-    const int head = (int)(bh % L.heads);
-    const int64_t b = bh / L.heads;
-    const int wi = l % L.W; l /= L.W;
-    const int hi = l % L.H;
-    const int ti = l / L.H;
-    float acc[CPL];
+// ---------------------------------------------------------------------------------------------------------------
+// backward (iii): input gradient.  din[ti,hi,wi][c] = sum_taps w[c][dt,dh,dw] * dconv[ti+1-dt, (hi+1-dh)/s, (wi+1-dw)/s][c]
+// over the taps whose (hi+1-dh), (wi+1-dw) are multiples of s inside the output grid.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int DH, int DW>
+__device__ __forceinline__ void tap_t(float2& acc, const T* __restrict__ p, const int (&toff)[3], uint32_t tmask, const float2 (&wr)[TAPS]) {
 #pragma unroll
-    for (int j = 0; j < CPL; ++j) acc[j] = 0.f;
+  for (int dt = 0; dt < 3; ++dt) {
+    if ((tmask >> dt) & 1u) acc = __ffma2_rn(ld2(p + toff[dt]), wr[dt * 9 + DH * 3 + DW], acc);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(THREADS, 2) pool_ln_bwd_input_kernel(const __grid_constant__ Launch L) {
+  int jj = 0;
+  while (jj + 1 < L.njobs && (int)blockIdx.x >= L.job[jj + 1].blk3_begin) ++jj;
+  const Job& J = L.job[jj];
+  const T* __restrict__ dconv = reinterpret_cast<const T*>(J.dconv);
+  T* __restrict__ din = reinterpret_cast<T*>(J.din);
+  const int tid = threadIdx.x;
+  const int cp = tid % NCP, r = tid / NCP;
+  const int Lo = L.T * J.Ho * J.Wo;
+  const int S = J.s;
+  const int nrows = L.B * L.heads * L.T * L.H;  // input rows
+  const int nitems = (nrows + ROWS - 1) / ROWS;
+  const int lb = blockIdx.x - J.blk3_begin;
+  float2 wr[TAPS];
+  if (S == 1) load_taps<true>(J.w, cp, wr); else load_taps<false>(J.w, cp, wr);
+
+  for (int item = lb; item < nitems; item += J.nblk3) {
+    const int row = item * ROWS + r;
+    if (row >= nrows) continue;
+    const int hi = row % L.H;
+    int q = row / L.H;
+    const int ti = q % L.T; q /= L.T;
+    const int head = q % L.heads, b = q / L.heads;
+    T* drow = din + ((int64_t)b * L.in_bs + (int64_t)head * L.in_hs + (int64_t)(1 + (ti * L.H + hi) * L.W) * L.in_ts + 2 * cp);
+    const T* dcb = dconv + ((int64_t)b * L.heads + head) * Lo * HD + 2 * cp;
+    if (S == 1) {
+      // forward march over dconv (Ho == H, Wo == W) with mirrored taps
+      RowGeom geo;
+      make_geom(geo, ti, hi, L.T, L.H, L.W, HD);
+      const T* base = dcb + (int64_t)((ti * L.H + hi) * L.W) * HD;
+      float2 x[3][9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) x[0][k] = make_float2(0.f, 0.f);
+      load_col(x[1], base, geo, 0, L.W, HD);
+      for (int wi = 0; wi < L.W; wi += 3) {
+        window_step<T, true, 0, 1, 2>(x, base, geo, wi, 1, L.W, HD);
+        st2(drow + (int64_t)wi * L.in_ts, dot27(x[0], x[1], x[2], wr));
+        if (wi + 1 < L.W) {
+          window_step<T, true, 1, 2, 0>(x, base, geo, wi + 1, 1, L.W, HD);
+          st2(drow + (int64_t)(wi + 1) * L.in_ts, dot27(x[1], x[2], x[0], wr));
+        }
+        if (wi + 2 < L.W) {
+          window_step<T, true, 2, 0, 1>(x, base, geo, wi + 2, 1, L.W, HD);
+          st2(drow + (int64_t)(wi + 2) * L.in_ts, dot27(x[2], x[0], x[1], wr));
+        }
+      }
+      continue;
+    }
+    // stride >= 2: which (dh -> ho) and (dt -> to) contribute to this input row
+    int toff[3];
+    uint32_t tmask = 0;
 #pragma unroll
     for (int dt = 0; dt < 3; ++dt) {
       const int to = ti + 1 - dt;
-      if (to < 0 || to >= L.T) continue;
-#pragma unroll
-      for (int dh = 0; dh < 3; ++dh) {
-        const int nh = hi + 1 - dh;
-        if (nh < 0 || nh % J.s != 0) continue;
-        const int ho = nh / J.s;
-        if (ho >= J.Ho) continue;
-#pragma unroll
-        for (int dwi = 0; dwi < 3; ++dwi) {
-          const int nw = wi + 1 - dwi;
-          if (nw < 0 || nw % J.s != 0) continue;
-          const int wo = nw / J.s;
-          if (wo >= J.Wo) continue;
-          float dv[CPL];
-          load12(J.dconv + (bh * Lo + (int64_t)(to * J.Ho + ho) * J.Wo + wo) * HD + c0, dv);
-          const float* wt = sw + (dt * 9 + dh * 3 + dwi) * HD + c0;
-#pragma unroll
-          for (int j = 0; j < CPL; ++j) acc[j] = fmaf(dv[j], wt[j], acc[j]);
-        }
-      }
+      toff[dt] = to * J.Ho * J.Wo * HD;
+      if (to >= 0 && to < L.T) tmask |= 1u << dt;
     }
-    T* dp = din + b * L.in_bs + head * L.in_hs + (int64_t)(1 + (ti * L.H + hi) * L.W + wi) * L.in_ts + c0;
-    store12(dp, acc);
+    int hoff[3];
+    uint32_t hmask = 0;
+#pragma unroll
+    for (int dh = 0; dh < 3; ++dh) {
+      const int nh = hi + 1 - dh;
+      const int ho = nh / S;
+      hoff[dh] = ho * J.Wo * HD;
+      if (nh >= 0 && nh - ho * S == 0 && ho < J.Ho) hmask |= 1u << dh;
+    }
+    if (hmask == 0) {
+      for (int wi = 0; wi < L.W; ++wi) st2(drow + (int64_t)wi * L.in_ts, make_float2(0.f, 0.f));
+      continue;
+    }
+    // incremental (wi+1-dw) mod S / div S for dw = 0, 1, 2   (wi = 0: nw = 1, 0, -1)
+    int wm[3], wd[3];
+#pragma unroll
+    for (int dw = 0; dw < 3; ++dw) {
+      const int nw = 1 - dw;
+      wm[dw] = nw < 0 ? S - 1 : nw % S;
+      wd[dw] = nw < 0 ? -1 : nw / S;
+    }
+    for (int wi = 0; wi < L.W; ++wi) {
+      float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int dw = 0; dw < 3; ++dw) {
+        if (wm[dw] == 0 && wd[dw] >= 0 && wd[dw] < J.Wo) {
+          const T* p = dcb + wd[dw] * HD;
+          if (hmask & 1u) { if (dw == 0) tap_t<T, 0, 0>(acc, p + hoff[0], toff, tmask, wr); else if (dw == 1) tap_t<T, 0, 1>(acc, p + hoff[0], toff, tmask, wr); else tap_t<T, 0, 2>(acc, p + hoff[0], toff, tmask, wr); }
+          if (hmask & 2u) { if (dw == 0) tap_t<T, 1, 0>(acc, p + hoff[1], toff, tmask, wr); else if (dw == 1) tap_t<T, 1, 1>(acc, p + hoff[1], toff, tmask, wr); else tap_t<T, 1, 2>(acc, p + hoff[1], toff, tmask, wr); }
+          if (hmask & 4u) { if (dw == 0) tap_t<T, 2, 0>(acc, p + hoff[2], toff, tmask, wr); else if (dw == 1) tap_t<T, 2, 1>(acc, p + hoff[2], toff, tmask, wr); else tap_t<T, 2, 2>(acc, p + hoff[2], toff, tmask, wr); }
+        }
+        if (++wm[dw] == S) { wm[dw] = 0; ++wd[dw]; }
+      }
+      st2(drow + (int64_t)wi * L.in_ts, acc);
+    }
   }
 }
 
-// grads_j[i] += sum over the job's blocks of the partial vectors: dW from the dW kernel, dgamma / dbeta from the
-// token kernel      (grid.y = job, grid.z = slice of the blocks)
+// grads_j[i] += sum over the job's blocks of the partial vectors: dW from backward (ii), dgamma / dbeta from
+// backward (i)      (grid.y = job, grid.z = slice of the blocks)
 constexpr int RED_SLICES = 8;
 __global__ void __launch_bounds__(256) reduce_jobs_kernel(const __grid_constant__ Launch L) {
   const Job& J = L.job[blockIdx.y];
@@ -381,7 +619,7 @@ __global__ void __launch_bounds__(256) reduce_jobs_kernel(const __grid_constant_
   const float* src = is_dw ? L.partials_dw + i : L.partials + (i - NDW);
   const int64_t stride = is_dw ? NDW : 2 * HD;
   const int begin = is_dw ? J.blk2_begin : J.blk_begin;
-  const int end = begin + (is_dw ? J.nblk2 : J.nblk);
+  const int end = begin + (is_dw ? J.nblk2 : J.nblk + J.ncls_blk);
   float s0 = 0.f, s1 = 0.f;
   int b = begin + blockIdx.z;
   for (; b + RED_SLICES < end; b += 2 * RED_SLICES) {
@@ -392,25 +630,31 @@ __global__ void __launch_bounds__(256) reduce_jobs_kernel(const __grid_constant_
   atomicAdd(J.grads + i, s0 + s1);
 }
 
-int nblocks_for(int64_t items, int per_block, int max_blocks) {
-  int64_t b = ceil_div64(items, per_block);
+int nblocks_for(int64_t items, int max_blocks) {
+  int64_t b = items;
   if (b > max_blocks) b = max_blocks;
   return b < 1 ? 1 : (int)b;
 }
 
 int out_hw(int n, int s) { return (n - 1) / s + 1; }  // (n + 2*1 - 3) / s + 1
 
-int64_t ntok_out(int B, int heads, int T, int H, int W, int s) { return (int64_t)B * heads * (1 + (int64_t)T * out_hw(H, s) * out_hw(W, s)); }
+int64_t out_rows(int B, int heads, int T, int H, int s) { return (int64_t)B * heads * T * out_hw(H, s); }
+int64_t ntok_conv(int B, int heads, int T, int H, int W, int s) { return (int64_t)B * heads * T * out_hw(H, s) * out_hw(W, s); }
 
-// block budgets of the backward token / dW kernels per job (shared by the workspace query and the launcher)
-int bwd_token_blocks(int B, int heads, int T, int H, int W, int s) { return nblocks_for(ntok_out(B, heads, T, H, W, s), BWD_WARPS * 4, 148 * 2); }
-int bwd_dw_blocks(int B, int heads, int T, int H, int W, int s) { return nblocks_for(ntok_out(B, heads, T, H, W, s), 32, 148 * 2); }
+// block budgets (shared by the workspace query and the launchers)
+int march_blocks(int B, int heads, int T, int H, int s) { return nblocks_for(ceil_div64(out_rows(B, heads, T, H, s), ROWS), 148 * 8); }
+int cls_blocks(int B, int heads) { return nblocks_for(ceil_div64((int64_t)B * heads, CLS_WARPS), 16); }
+int dw_blocks(int B, int heads, int T, int H, int s) { return nblocks_for(ceil_div64(out_rows(B, heads, T, H, s), ROWS), 148 * 2); }
+int input_blocks(int B, int heads, int T, int H) { return nblocks_for(ceil_div64((int64_t)B * heads * T * H, ROWS), 148 * 8); }
+
+int64_t align16(int64_t bytes) { return (bytes + 15) / 16 * 16; }
 
 int fill_launch(Launch& L, const void* qkv, int64_t bs, int64_t ts, int64_t ws_, int64_t hs, const pmv_pool_job* jobs, int njobs,
                 int B, int heads, int T, int H, int W, float eps, int dtype) {
   PMV_CHECK_ARG(njobs >= 1 && njobs <= MAX_JOBS, "pool: 1..3 jobs");
   PMV_CHECK_ARG(B > 0 && heads > 0 && T > 0 && H > 0 && W > 0, "pool: bad geometry");
-  PMV_CHECK_ARG(ts % 4 == 0 && hs % 4 == 0 && ws_ % 4 == 0, "pool: strides must be multiples of 4 elements");
+  PMV_CHECK_ARG(ts % 4 == 0 && hs % 4 == 0 && ws_ % 4 == 0 && bs % 4 == 0, "pool: strides must be multiples of 4 elements");
+  PMV_CHECK_ARG((int64_t)3 * H * W * ts < (1ll << 31) && (int64_t)B * heads * T * H < (1ll << 29), "pool: volume too large for 32-bit row offsets");
   const int esz = dtype == PMV_BF16 ? 2 : 4;
   L.njobs = njobs; L.B = B; L.heads = heads; L.T = T; L.H = H; L.W = W;
   L.in_bs = bs; L.in_ts = ts; L.in_hs = hs; L.eps = eps; L.partials = nullptr; L.partials_dw = nullptr;
@@ -422,7 +666,7 @@ int fill_launch(Launch& L, const void* qkv, int64_t bs, int64_t ts, int64_t ws_,
     J.w = p.w; J.gamma = p.gamma; J.beta = p.beta; J.out = p.out; J.out_ld = p.out_ld;
     J.dout = p.dout; J.dout_ld = p.dout_ld; J.din = nullptr; J.grads = p.grads; J.dconv = nullptr;
     J.s = p.stride_hw; J.Ho = out_hw(H, p.stride_hw); J.Wo = out_hw(W, p.stride_hw);
-    J.blk_begin = 0; J.nblk = 0; J.blk2_begin = 0; J.nblk2 = 0;
+    J.blk_begin = 0; J.nblk = 0; J.ncls_blk = 0; J.blk2_begin = 0; J.nblk2 = 0; J.blk3_begin = 0; J.nblk3 = 0;
   }
   return PMV_OK;
 }
@@ -439,22 +683,23 @@ extern "C" int pmv_pool_ln_qkv_fwd(const void* qkv, int64_t batch_stride, int64_
   for (int i = 0; i < njobs; ++i) {
     PMV_CHECK_ARG(jobs[i].out != nullptr && jobs[i].out_ld % 4 == 0 && jobs[i].out_ld >= HD, "pool: bad output");
     L.job[i].blk_begin = total;
-    L.job[i].nblk = nblocks_for(ntok_out(B, heads, T, H, W, jobs[i].stride_hw), TOK_PER_BLOCK, 148 * 16);
-    total += L.job[i].nblk;
+    L.job[i].nblk = march_blocks(B, heads, T, H, jobs[i].stride_hw);
+    L.job[i].ncls_blk = cls_blocks(B, heads);
+    total += L.job[i].nblk + L.job[i].ncls_blk;
   }
-  PMV_DISPATCH_DTYPE(dtype, TT, (pool_ln_fwd_kernel<TT><<<(unsigned)total, POOL_THREADS, 0, (cudaStream_t)stream>>>(L)));
+  PMV_DISPATCH_DTYPE(dtype, TT, (pool_ln_march_kernel<TT, false><<<(unsigned)total, THREADS, 0, (cudaStream_t)stream>>>(L)));
   PMV_CHECK_LAUNCH();
   return PMV_OK;
 }
 
 extern "C" int64_t pmv_pool_ln_qkv_bwd_workspace_bytes(int B, int heads, int T, int H, int W, const int* strides_hw, int njobs) {
-  int64_t floats = 0;
+  int64_t bytes = 0;
   for (int i = 0; i < njobs; ++i) {
-    floats += (ntok_out(B, heads, T, H, W, strides_hw[i]) - (int64_t)B * heads) * HD;  // pre-LN gradient, non-cls tokens
-    floats += (int64_t)bwd_token_blocks(B, heads, T, H, W, strides_hw[i]) * 2 * HD;
-    floats += (int64_t)bwd_dw_blocks(B, heads, T, H, W, strides_hw[i]) * NDW;
+    bytes += align16(ntok_conv(B, heads, T, H, W, strides_hw[i]) * HD * 4);  // pre-LN gradient (sized for fp32)
+    bytes += (int64_t)(march_blocks(B, heads, T, H, strides_hw[i]) + cls_blocks(B, heads)) * 2 * HD * 4;
+    bytes += (int64_t)dw_blocks(B, heads, T, H, strides_hw[i]) * NDW * 4;
   }
-  return floats * (int64_t)sizeof(float);
+  return bytes;
 }
 
 extern "C" int pmv_pool_ln_qkv_bwd(const void* qkv, int64_t batch_stride, int64_t token_stride, int64_t which_stride,
@@ -464,39 +709,34 @@ extern "C" int pmv_pool_ln_qkv_bwd(const void* qkv, int64_t batch_stride, int64_
   int rc = fill_launch(L, qkv, batch_stride, token_stride, which_stride, head_stride, jobs, njobs, B, heads, T, H, W, eps, dtype);
   if (rc) return rc;
   const int esz = dtype == PMV_BF16 ? 2 : 4;
-  float* cursor = ws;
-  int total = 0, total_dw = 0;
+  char* cursor = reinterpret_cast<char*>(ws);
+  int total = 0, total_dw = 0, total_in = 0;
   for (int i = 0; i < njobs; ++i) {
     PMV_CHECK_ARG(jobs[i].dout != nullptr && jobs[i].grads != nullptr && jobs[i].dout_ld % 4 == 0, "pool: bad backward job");
     Job& J = L.job[i];
     J.din = reinterpret_cast<char*>(dqkv) + (int64_t)jobs[i].which * which_stride * esz;
     J.dconv = cursor;
-    cursor += (ntok_out(B, heads, T, H, W, J.s) - (int64_t)B * heads) * HD;
+    cursor += align16(ntok_conv(B, heads, T, H, W, J.s) * HD * 4);
     J.blk_begin = total;
-    J.nblk = bwd_token_blocks(B, heads, T, H, W, J.s);
-    total += J.nblk;
+    J.nblk = march_blocks(B, heads, T, H, J.s);
+    J.ncls_blk = cls_blocks(B, heads);
+    total += J.nblk + J.ncls_blk;
     J.blk2_begin = total_dw;
-    J.nblk2 = bwd_dw_blocks(B, heads, T, H, W, J.s);
+    J.nblk2 = dw_blocks(B, heads, T, H, J.s);
     total_dw += J.nblk2;
+    J.blk3_begin = total_in;
+    J.nblk3 = input_blocks(B, heads, T, H);
+    total_in += J.nblk3;
   }
-  L.partials = cursor;
-  L.partials_dw = cursor + (int64_t)total * 2 * HD;
+  L.partials = reinterpret_cast<float*>(cursor);
+  L.partials_dw = L.partials + (int64_t)total * 2 * HD;
   cudaStream_t st = (cudaStream_t)stream;
   PMV_DISPATCH_DTYPE(dtype, TT, {
-    pool_ln_bwd_tokens_kernel<TT><<<(unsigned)total, BWD_WARPS * 32, 0, st>>>(L);
-    pool_ln_bwd_dw_kernel<TT><<<(unsigned)total_dw, DW_THREADS, 0, st>>>(L);
+    pool_ln_march_kernel<TT, true><<<(unsigned)total, THREADS, 0, st>>>(L);
+    pool_ln_bwd_dw_kernel<TT><<<(unsigned)total_dw, THREADS, 0, st>>>(L);
+    pool_ln_bwd_input_kernel<TT><<<(unsigned)total_in, THREADS, 0, st>>>(L);
   });
   reduce_jobs_kernel<<<dim3((NGRAD + 255) / 256, njobs, RED_SLICES), 256, 0, st>>>(L);
-  // second launch geometry: one block range per job over the INPUT tokens
-  Launch L2 = L;
-  int total2 = 0;
-  const int64_t ntok_in = (int64_t)B * heads * T * H * W;
-  for (int i = 0; i < njobs; ++i) {
-    L2.job[i].blk_begin = total2;
-    L2.job[i].nblk = nblocks_for(ntok_in, TOK_PER_BLOCK, 148 * 16);
-    total2 += L2.job[i].nblk;
-  }
-  PMV_DISPATCH_DTYPE(dtype, TT, (pool_ln_bwd_input_kernel<TT><<<(unsigned)total2, POOL_THREADS, 0, st>>>(L2)));
   PMV_CHECK_LAUNCH();
   return PMV_OK;
 }
