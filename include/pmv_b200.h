@@ -177,21 +177,25 @@ int pmv_maxpool_skip_bwd(const float* x, const float* dy, float* dx, int B, int 
  * (written by pmv_pool_ln_fwd with out_ld = ld).  The cls row gets zeros (attention.py:111,154).
  * idx_h [qh*kh], idx_w [qw*kw], idx_t [qt*kt] are the int32 table rows from the reference's
  * float-ratio / .long() index arithmetic (attention.py:80-99,132-139), computed on the host. */
+/* ws: pmv_relpos_fwd_workspace_bytes() bytes (the stacked, pre-scaled tables and the dense
+ * [BH*Nq, rows_h+rows_w+rows_t] product Q x Rcat^T, which runs through pmv_gemm: tc selects the tcgen05 kernel). */
+int64_t pmv_relpos_fwd_workspace_bytes(int BH, int qt, int qh, int qw, int kt, int kh, int kw);
 int pmv_relpos_augment_q(void* q_aug, int64_t ld, const float* rel_h, const float* rel_w, const float* rel_t,
-                         const int32_t* idx_h, const int32_t* idx_w, const int32_t* idx_t,
+                         const int32_t* idx_h, const int32_t* idx_w, const int32_t* idx_t, float* ws,
                          int BH, int qt, int qh, int qw, int kt, int kh, int kw,
-                         float inv_scale, int dtype, void* stream);
+                         float inv_scale, int dtype, int tc, void* stream);
 int pmv_relpos_augment_k(void* k_aug, int64_t ld, int BH, int kt, int kh, int kw, int dtype, void* stream);
 /* Backward of augment_q: given dQ' (same layout), adds the table gradients into d_rel (fp32
  * [rows_h + rows_w + rows_t][96]: the three tables stacked in that order) and adds the bias path's
  * contribution to dq in place (columns [0,96) of dq_aug, non-cls rows).
- * ws: fp32 workspace of pmv_relpos_bwd_workspace_bytes() bytes. */
+ * ws: workspace of pmv_relpos_bwd_workspace_bytes() bytes (stacked tables, their gradient, the dense dRQ;
+ * both products run through pmv_gemm). */
 int64_t pmv_relpos_bwd_workspace_bytes(int BH, int qt, int qh, int qw, int kt, int kh, int kw);
 int pmv_relpos_augment_q_bwd(void* dq_aug, const void* q_aug, int64_t ld, const float* rel_h, const float* rel_w,
                              const float* rel_t, const int32_t* idx_h, const int32_t* idx_w, const int32_t* idx_t,
                              float* d_rel, float* ws,
                              int BH, int qt, int qh, int qw, int kt, int kh, int kw,
-                             float inv_scale, int dtype, void* stream);
+                             float inv_scale, int dtype, int tc, void* stream);
 
 /* ---------------------------------------------------------------- attention ----------
  * softmax(scale * Q' K'^T) V  + residual pooling, attention.py:412,446-454, head-merged output

@@ -9,75 +9,114 @@
 // no bias, attention.py:111,154), pmv_relpos_augment_k fills columns [96, ld) of K' with the one-hot key
 // coordinates (zeros for the cls key).  R_j(q) are rows of rel_pos_h/w/t selected by the reference's index
 // arithmetic (attention.py:80-99,132-139), passed in as small int32 tables.
+//
+// The per-query dot products are themselves a GEMM against the three stacked tables:
+//     RQ[M, rows_h + rows_w + rows_t] = Q[M, 96] x (Rcat / scale)^T                     (pmv_gemm, tensor cores in bf16)
+//     Q'[q, 96 + j] = RQ[q, row_j(q)]                                                   (gather kernel)
+// and the backward is the mirror image: the d rq columns are scattered into a dense dRQ (zero elsewhere), then
+//     dQ[:, :96] += dRQ x (Rcat / scale)      (dgrad GEMM, accumulating epilogue)
+//     dRcat       = dRQ^T x Q / scale         (wgrad GEMM, split over the query rows)
+// The dense detour costs (rows_h + rows_w + rows_t) instead of (k_h + k_w + k_t) columns per query, all of it on
+// the tensor cores; the previous CUDA-core kernels (one warp per query, 96-long dot products out of shared
+// memory) ran at 3 TFLOP/s and were 10 % of the training step (profiles/r01_kernels_before.txt).
 #include "common.cuh"
-#include "reduce.cuh"
 
 namespace {
 
 constexpr int HD = PMV_HEAD_DIM;
-constexpr int AUG_WARPS = 8;
-constexpr int TPAD = HD + 1;
 
 struct RelGeom {
   int qt, qh, qw, kt, kh, kw;
   int rows_h, rows_w, rows_t;  // table lengths
 };
 
-// dynamic smem: tables [(rows_h + rows_w + rows_t)][97] fp32, then per-warp q rows [AUG_WARPS][96]
+// cat[r][c] = inv_scale * table[r][c] for the three tables stacked, zero rows up to ncat_pad
 template <typename T>
-__global__ void __launch_bounds__(AUG_WARPS * 32) relpos_augment_q_kernel(
-    T* __restrict__ q_aug, int64_t ld, const float* __restrict__ rel_h, const float* __restrict__ rel_w,
-    const float* __restrict__ rel_t, const int32_t* __restrict__ idx_h, const int32_t* __restrict__ idx_w,
-    const int32_t* __restrict__ idx_t, int64_t BH, RelGeom g, float inv_scale) {
-  extern __shared__ float sm[];
-  const int rows = g.rows_h + g.rows_w + g.rows_t;
-  float* tab = sm;
-  float* qrow = sm + (size_t)rows * TPAD;
-  for (int i = threadIdx.x; i < rows * HD; i += blockDim.x) {
-    const int r = i / HD, c = i - r * HD;
-    const float v = r < g.rows_h ? rel_h[r * HD + c]
-                    : r < g.rows_h + g.rows_w ? rel_w[(r - g.rows_h) * HD + c]
-                                              : rel_t[(r - g.rows_h - g.rows_w) * HD + c];
-    tab[r * TPAD + c] = v;
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* myq = qrow + warp * HD;
-  const int Lq = g.qt * g.qh * g.qw;
-  const int Nq = Lq + 1;
+__global__ void __launch_bounds__(256) relpos_cat_kernel(T* __restrict__ cat, const float* __restrict__ rel_h,
+                                                         const float* __restrict__ rel_w, const float* __restrict__ rel_t,
+                                                         RelGeom g, int ncat_pad, float inv_scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncat_pad * HD) return;
+  const int r = i / HD, c = i - r * HD;
+  float v = 0.f;
+  if (r < g.rows_h) v = rel_h[r * HD + c];
+  else if (r < g.rows_h + g.rows_w) v = rel_w[(r - g.rows_h) * HD + c];
+  else if (r < g.rows_h + g.rows_w + g.rows_t) v = rel_t[(r - g.rows_h - g.rows_w) * HD + c];
+  cat[i] = from_f32<T>(v * inv_scale);
+}
+
+// column of the dense RQ that bias column j of query position (it, ih, iw) reads
+__device__ __forceinline__ int rel_col(const RelGeom& g, const int32_t* __restrict__ idx_h, const int32_t* __restrict__ idx_w,
+                                       const int32_t* __restrict__ idx_t, int it, int ih, int iw, int j) {
+  if (j < g.kh) return idx_h[ih * g.kh + j];
+  if (j < g.kh + g.kw) return g.rows_h + idx_w[iw * g.kw + (j - g.kh)];
+  return g.rows_h + g.rows_w + idx_t[it * g.kt + (j - g.kh - g.kw)];
+}
+
+// Q'[row, 96 + j] = RQ[row, col_j(row)]  (zero for the cls row and the padding columns); thread = (row, j)
+template <typename T>
+__global__ void __launch_bounds__(256) relpos_gather_kernel(T* __restrict__ q_aug, int ld, const T* __restrict__ rq, int ld_rq,
+                                                            const int32_t* __restrict__ idx_h, const int32_t* __restrict__ idx_w,
+                                                            const int32_t* __restrict__ idx_t, int64_t rows, RelGeom g) {
+  const int aug = ld - HD;
+  const int Nq = g.qt * g.qh * g.qw + 1;
   const int RK = g.kh + g.kw + g.kt;
-  const int aug = (int)ld - HD;
-  const int64_t total = BH * Nq;
-  for (int64_t row = (int64_t)blockIdx.x * AUG_WARPS + warp; row < total; row += (int64_t)gridDim.x * AUG_WARPS) {
+  const int64_t total = rows * aug;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / aug;
+    const int j = (int)(i - row * aug);
     const int n = (int)(row % Nq);
-    T* qp = q_aug + row * ld;
-    if (n == 0) {
-      for (int j = lane; j < aug; j += 32) qp[HD + j] = from_f32<T>(0.f);
-      continue;
+    T v = from_f32<T>(0.f);
+    if (n > 0 && j < RK) {
+      int l = n - 1;
+      const int iw = l % g.qw; l /= g.qw;
+      const int ih = l % g.qh;
+      const int it = l / g.qh;
+      v = rq[row * ld_rq + rel_col(g, idx_h, idx_w, idx_t, it, ih, iw, j)];
     }
-    int l = n - 1;
-    const int iw = l % g.qw; l /= g.qw;
-    const int ih = l % g.qh;
-    const int it = l / g.qh;
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < 3; ++j) myq[lane + 32 * j] = to_f32(qp[lane + 32 * j]);
-    __syncwarp();
-    for (int j0 = 0; j0 < aug; j0 += 32) {
-      const int j = j0 + lane;
-      float acc = 0.f;
-      if (j < RK) {
-        int trow;
-        if (j < g.kh) trow = idx_h[ih * g.kh + j];
-        else if (j < g.kh + g.kw) trow = g.rows_h + idx_w[iw * g.kw + (j - g.kh)];
-        else trow = g.rows_h + g.rows_w + idx_t[it * g.kt + (j - g.kh - g.kw)];
-        const float* tr = tab + trow * TPAD;
-#pragma unroll 8
-        for (int c = 0; c < HD; ++c) acc = fmaf(myq[c], tr[c], acc);
-      }
-      if (j < aug) qp[HD + j] = from_f32<T>(acc * inv_scale);
-    }
+    q_aug[row * ld + HD + j] = v;
   }
+}
+
+// dRQ[row, :] = 0 except dRQ[row, col_j(row)] = dQ'[row, 96 + j]; one warp per row, the row is assembled in shared
+// memory and written with full-width stores
+constexpr int SC_WARPS = 8;
+constexpr int SC_MAXCOLS = 512;
+template <typename T>
+__global__ void __launch_bounds__(SC_WARPS * 32) relpos_scatter_kernel(const T* __restrict__ dq_aug, int ld, T* __restrict__ drq,
+                                                                       int ncat_pad, const int32_t* __restrict__ idx_h,
+                                                                       const int32_t* __restrict__ idx_w,
+                                                                       const int32_t* __restrict__ idx_t, int64_t rows, RelGeom g) {
+  __shared__ __align__(16) T buf[SC_WARPS][SC_MAXCOLS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Nq = g.qt * g.qh * g.qw + 1;
+  const int RK = g.kh + g.kw + g.kt;
+  T* mine = buf[warp];
+  for (int64_t row = (int64_t)blockIdx.x * SC_WARPS + warp; row < rows; row += (int64_t)gridDim.x * SC_WARPS) {
+    for (int c = lane; c < ncat_pad; c += 32) mine[c] = from_f32<T>(0.f);
+    __syncwarp();
+    const int n = (int)(row % Nq);
+    if (n > 0) {
+      int l = n - 1;
+      const int iw = l % g.qw; l /= g.qw;
+      const int ih = l % g.qh;
+      const int it = l / g.qh;
+      for (int j = lane; j < RK; j += 32) mine[rel_col(g, idx_h, idx_w, idx_t, it, ih, iw, j)] = dq_aug[row * ld + HD + j];
+    }
+    __syncwarp();
+    // ncat_pad % 8 == 0: 16-byte pieces
+    const int pieces = ncat_pad * (int)sizeof(T) / 16;
+    uint4* dst = reinterpret_cast<uint4*>(drq + row * ncat_pad);
+    const uint4* src = reinterpret_cast<const uint4*>(mine);
+    for (int p = lane; p < pieces; p += 32) dst[p] = src[p];
+    __syncwarp();
+  }
+}
+
+// d_rel[i] += inv_scale * dcat[i]
+__global__ void __launch_bounds__(256) relpos_dtab_kernel(float* __restrict__ d_rel, const float* __restrict__ dcat, int n, float inv_scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d_rel[i] += inv_scale * dcat[i];
 }
 
 template <typename T>
@@ -101,162 +140,6 @@ __global__ void __launch_bounds__(256) relpos_augment_k_kernel(T* __restrict__ k
   }
 }
 
-// backward of augment_q, two kernels that keep the table gradients in registers instead of hammering shared
-// memory with one atomic per (query, column, channel):
-//   row walk    : one warp per (bh, t, h) row of queries.  All queries of a row share their rel_pos_h and rel_pos_t
-//                 rows, so d rel_h / d rel_t accumulate in registers over the row and are flushed once per row;
-//                 the bias path's contribution to dq (all three parts) is added in place.
-//   column walk : one warp per (bh, t, w) column of queries; d rel_w accumulates in registers over the column.
-// Lane owns channels {lane, lane+32, lane+64}.  Both kernels write one partial table per CTA.
-constexpr int KMAX = 16;  // max k_h, k_w, k_t (MViTv2-S: 14 / 14 / 8, MViTv2-B: 14 / 14 / 16)
-constexpr int RW_WARPS = 16;
-
-template <typename T>
-__global__ void __launch_bounds__(RW_WARPS * 32, 1) relpos_bwd_rows_kernel(
-    T* __restrict__ dq_aug, const T* __restrict__ q_aug, int64_t ld, const float* __restrict__ rel_h,
-    const float* __restrict__ rel_w, const float* __restrict__ rel_t, const int32_t* __restrict__ idx_h,
-    const int32_t* __restrict__ idx_w, const int32_t* __restrict__ idx_t, float* __restrict__ partials,
-    int64_t BH, RelGeom g, float inv_scale) {
-  extern __shared__ float sm[];
-  const int rows = g.rows_h + g.rows_w + g.rows_t;
-  float* tab = sm;                    // the three tables stacked [rows][96]
-  float* dtab = sm + rows * HD;       // gradients of the h and t tables [rows_h + rows_t][96]
-  const int nht = g.rows_h + g.rows_t;
-  for (int i = threadIdx.x; i < rows * HD; i += blockDim.x) {
-    const int r = i / HD, c = i - r * HD;
-    tab[i] = r < g.rows_h ? rel_h[r * HD + c]
-             : r < g.rows_h + g.rows_w ? rel_w[(r - g.rows_h) * HD + c]
-                                       : rel_t[(r - g.rows_h - g.rows_w) * HD + c];
-  }
-  for (int i = threadIdx.x; i < nht * HD; i += blockDim.x) dtab[i] = 0.f;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int Nq = g.qt * g.qh * g.qw + 1;
-  const int RK = g.kh + g.kw + g.kt;
-  const int64_t nrows = BH * g.qt * g.qh;
-  for (int64_t rr = (int64_t)blockIdx.x * RW_WARPS + warp; rr < nrows; rr += (int64_t)gridDim.x * RW_WARPS) {
-    const int ih = (int)(rr % g.qh);
-    const int it = (int)((rr / g.qh) % g.qt);
-    const int64_t bh = rr / ((int64_t)g.qh * g.qt);
-    // table rows shared by the whole query row (lane j holds the row of column j)
-    const int my_h = lane < g.kh ? idx_h[ih * g.kh + lane] : 0;
-    const int my_t = lane < g.kt ? g.rows_h + g.rows_w + idx_t[it * g.kt + lane] : 0;
-    float gh[KMAX][3], gt[KMAX][3];
-#pragma unroll
-    for (int j = 0; j < KMAX; ++j)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { gh[j][c] = 0.f; gt[j][c] = 0.f; }
-    const int64_t row0 = bh * Nq + 1 + ((int64_t)it * g.qh + ih) * g.qw;
-    for (int iw = 0; iw < g.qw; ++iw) {
-      T* dqp = dq_aug + (row0 + iw) * ld;
-      const T* qp = q_aug + (row0 + iw) * ld;
-      float qv[3], acc[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { qv[c] = to_f32(qp[lane + 32 * c]); acc[c] = to_f32(dqp[lane + 32 * c]); }
-      const float d_lo = lane < RK ? to_f32(dqp[HD + lane]) * inv_scale : 0.f;
-      const float d_hi = lane + 32 < RK ? to_f32(dqp[HD + 32 + lane]) * inv_scale : 0.f;
-      const int my_w = lane < g.kw ? g.rows_h + idx_w[iw * g.kw + lane] : 0;
-#pragma unroll
-      for (int j = 0; j < KMAX; ++j) {
-        if (j < g.kh) {
-          const float d = __shfl_sync(0xffffffffu, d_lo, j);
-          const float* src = tab + __shfl_sync(0xffffffffu, my_h, j) * HD + lane;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) { acc[c] = fmaf(d, src[32 * c], acc[c]); gh[j][c] = fmaf(d, qv[c], gh[j][c]); }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < KMAX; ++j) {
-        if (j < g.kw) {
-          const int col = g.kh + j;
-          const float d = __shfl_sync(0xffffffffu, col < 32 ? d_lo : d_hi, col & 31);
-          const float* src = tab + __shfl_sync(0xffffffffu, my_w, j) * HD + lane;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) acc[c] = fmaf(d, src[32 * c], acc[c]);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < KMAX; ++j) {
-        if (j < g.kt) {
-          const int col = g.kh + g.kw + j;
-          const float d = __shfl_sync(0xffffffffu, col < 32 ? d_lo : d_hi, col & 31);
-          const float* src = tab + __shfl_sync(0xffffffffu, my_t, j) * HD + lane;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) { acc[c] = fmaf(d, src[32 * c], acc[c]); gt[j][c] = fmaf(d, qv[c], gt[j][c]); }
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < 3; ++c) dqp[lane + 32 * c] = from_f32<T>(acc[c]);
-    }
-    // flush the row's table gradients (h rows first, then t rows, in the partial layout)
-#pragma unroll
-    for (int j = 0; j < KMAX; ++j) {
-      if (j < g.kh) {
-        float* dst = dtab + __shfl_sync(0xffffffffu, my_h, j) * HD + lane;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) atomicAdd(dst + 32 * c, gh[j][c]);
-      }
-      if (j < g.kt) {
-        float* dst = dtab + (__shfl_sync(0xffffffffu, my_t, j) - g.rows_w) * HD + lane;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) atomicAdd(dst + 32 * c, gt[j][c]);
-      }
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < nht * HD; i += blockDim.x) partials[(int64_t)blockIdx.x * nht * HD + i] = dtab[i];
-}
-
-template <typename T>
-__global__ void __launch_bounds__(RW_WARPS * 32) relpos_bwd_cols_kernel(
-    const T* __restrict__ dq_aug, const T* __restrict__ q_aug, int64_t ld, const int32_t* __restrict__ idx_w,
-    float* __restrict__ partials, int64_t BH, RelGeom g, float inv_scale) {
-  extern __shared__ float dtab[];  // [rows_w][96]
-  for (int i = threadIdx.x; i < g.rows_w * HD; i += blockDim.x) dtab[i] = 0.f;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int Nq = g.qt * g.qh * g.qw + 1;
-  const int64_t ncols = BH * g.qt * g.qw;
-  for (int64_t cc = (int64_t)blockIdx.x * RW_WARPS + warp; cc < ncols; cc += (int64_t)gridDim.x * RW_WARPS) {
-    const int iw = (int)(cc % g.qw);
-    const int it = (int)((cc / g.qw) % g.qt);
-    const int64_t bh = cc / ((int64_t)g.qw * g.qt);
-    const int my_w = lane < g.kw ? idx_w[iw * g.kw + lane] : 0;
-    float gw[KMAX][3];
-#pragma unroll
-    for (int j = 0; j < KMAX; ++j)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) gw[j][c] = 0.f;
-    for (int ih = 0; ih < g.qh; ++ih) {
-      const int64_t row = bh * Nq + 1 + ((int64_t)it * g.qh + ih) * g.qw + iw;
-      const T* qp = q_aug + row * ld;
-      const T* dqp = dq_aug + row * ld;
-      float qv[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) qv[c] = to_f32(qp[lane + 32 * c]);
-      const float dw_ = lane < g.kw ? to_f32(dqp[HD + g.kh + lane]) * inv_scale : 0.f;
-#pragma unroll
-      for (int j = 0; j < KMAX; ++j) {
-        if (j < g.kw) {
-          const float d = __shfl_sync(0xffffffffu, dw_, j);
-#pragma unroll
-          for (int c = 0; c < 3; ++c) gw[j][c] = fmaf(d, qv[c], gw[j][c]);
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < KMAX; ++j) {
-      if (j < g.kw) {
-        float* dst = dtab + __shfl_sync(0xffffffffu, my_w, j) * HD + lane;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) atomicAdd(dst + 32 * c, gw[j][c]);
-      }
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < g.rows_w * HD; i += blockDim.x) partials[(int64_t)blockIdx.x * g.rows_w * HD + i] = dtab[i];
-}
-
 RelGeom make_rel(int qt, int qh, int qw, int kt, int kh, int kw) {
   RelGeom g;
   g.qt = qt; g.qh = qh; g.qw = qw; g.kt = kt; g.kh = kh; g.kw = kw;
@@ -266,24 +149,37 @@ RelGeom make_rel(int qt, int qh, int qw, int kt, int kh, int kw) {
   return g;
 }
 
+
+int ncat_padded(const RelGeom& g) { return (g.rows_h + g.rows_w + g.rows_t + 7) / 8 * 8; }
+int64_t align256(int64_t b) { return (b + 255) / 256 * 256; }
+
 }  // namespace
 
-extern "C" int pmv_relpos_augment_q(void* q_aug, int64_t ld, const float* rel_h, const float* rel_w, const float* rel_t,
-                                    const int32_t* idx_h, const int32_t* idx_w, const int32_t* idx_t,
-                                    int BH, int qt, int qh, int qw, int kt, int kh, int kw,
-                                    float inv_scale, int dtype, void* stream) {
-  PMV_CHECK_ARG(ld >= HD + kh + kw + kt && ld % 8 == 0, "relpos: ld=%lld too small for 96+%d bias columns", (long long)ld, kh + kw + kt);
+extern "C" int64_t pmv_relpos_fwd_workspace_bytes(int BH, int qt, int qh, int qw, int kt, int kh, int kw) {
   RelGeom g = make_rel(qt, qh, qw, kt, kh, kw);
-  const size_t smem = ((size_t)(g.rows_h + g.rows_w + g.rows_t) * TPAD + AUG_WARPS * HD) * sizeof(float);
-  PMV_CHECK_ARG(smem <= 200 * 1024, "relpos: tables too large for shared memory (%zu B)", smem);
-  const int64_t total = (int64_t)BH * (qt * qh * qw + 1);
-  int64_t blocks = ceil_div64(total, AUG_WARPS * 4);
-  if (blocks > 148 * 2) blocks = 148 * 2;
-  PMV_DISPATCH_DTYPE(dtype, T, {
-    PMV_CHECK_CUDA(cudaFuncSetAttribute(relpos_augment_q_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    relpos_augment_q_kernel<T><<<(unsigned)blocks, AUG_WARPS * 32, smem, (cudaStream_t)stream>>>(
-        (T*)q_aug, ld, rel_h, rel_w, rel_t, idx_h, idx_w, idx_t, BH, g, inv_scale);
-  });
+  const int64_t np = ncat_padded(g), M = (int64_t)BH * (qt * qh * qw + 1);
+  return align256(np * HD * 4) + align256(M * np * 4);  // sized for fp32
+}
+
+extern "C" int pmv_relpos_augment_q(void* q_aug, int64_t ld, const float* rel_h, const float* rel_w, const float* rel_t,
+                                    const int32_t* idx_h, const int32_t* idx_w, const int32_t* idx_t, float* ws,
+                                    int BH, int qt, int qh, int qw, int kt, int kh, int kw,
+                                    float inv_scale, int dtype, int tc, void* stream) {
+  PMV_CHECK_ARG(ld >= HD + kh + kw + kt && ld % 8 == 0, "relpos: ld=%lld too small for 96+%d bias columns", (long long)ld, kh + kw + kt);
+  PMV_CHECK_ARG(ws != nullptr, "relpos: workspace required");
+  RelGeom g = make_rel(qt, qh, qw, kt, kh, kw);
+  const int np = ncat_padded(g);
+  const int64_t M = (int64_t)BH * (qt * qh * qw + 1);
+  char* cat = reinterpret_cast<char*>(ws);
+  char* rq = cat + align256((int64_t)np * HD * 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  PMV_DISPATCH_DTYPE(dtype, T, (relpos_cat_kernel<T><<<(np * HD + 255) / 256, 256, 0, st>>>((T*)cat, rel_h, rel_w, rel_t, g, np, inv_scale)));
+  int rc = pmv_gemm(PMV_GEMM_TN, q_aug, ld, cat, HD, rq, np, M, np, HD, dtype, dtype, nullptr, tc, 1, stream);
+  if (rc) return rc;
+  int64_t blocks = ceil_div64(M * (ld - HD), 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  PMV_DISPATCH_DTYPE(dtype, T, (relpos_gather_kernel<T><<<(unsigned)blocks, 256, 0, st>>>((T*)q_aug, (int)ld, (const T*)rq, np, idx_h, idx_w,
+                                                                                            idx_t, M, g)));
   PMV_CHECK_LAUNCH();
   return PMV_OK;
 }
@@ -299,17 +195,11 @@ extern "C" int pmv_relpos_augment_k(void* k_aug, int64_t ld, int BH, int kt, int
   return PMV_OK;
 }
 
-static int rw_blocks(int64_t units) {
-  int64_t b = ceil_div64(units, RW_WARPS * 2);
-  if (b > 148) b = 148;
-  return b < 1 ? 1 : (int)b;
-}
 
 extern "C" int64_t pmv_relpos_bwd_workspace_bytes(int BH, int qt, int qh, int qw, int kt, int kh, int kw) {
   RelGeom g = make_rel(qt, qh, qw, kt, kh, kw);
-  const int64_t r = (int64_t)rw_blocks((int64_t)BH * qt * qh) * (g.rows_h + g.rows_t) * HD;
-  const int64_t c = (int64_t)rw_blocks((int64_t)BH * qt * qw) * g.rows_w * HD;
-  return (r + c) * (int64_t)sizeof(float);
+  const int64_t np = ncat_padded(g), M = (int64_t)BH * (qt * qh * qw + 1);
+  return 2 * align256(np * HD * 4) + align256(M * np * 4);
 }
 
 /* d_rel: [rows_h + rows_w + rows_t][96] fp32 (the three tables stacked), added to. */
@@ -317,28 +207,44 @@ extern "C" int pmv_relpos_augment_q_bwd(void* dq_aug, const void* q_aug, int64_t
                                         const float* rel_t, const int32_t* idx_h, const int32_t* idx_w, const int32_t* idx_t,
                                         float* d_rel, float* ws,
                                         int BH, int qt, int qh, int qw, int kt, int kh, int kw,
-                                        float inv_scale, int dtype, void* stream) {
+                                        float inv_scale, int dtype, int tc, void* stream) {
   RelGeom g = make_rel(qt, qh, qw, kt, kh, kw);
-  PMV_CHECK_ARG(kh <= KMAX && kw <= KMAX && kt <= KMAX && kh + kw + kt <= 64, "relpos: k_h, k_w, k_t must be <= %d", KMAX);
-  const int rows = g.rows_h + g.rows_w + g.rows_t, nht = g.rows_h + g.rows_t;
-  const size_t smem_r = (size_t)(rows + nht) * HD * sizeof(float);
-  const size_t smem_c = (size_t)g.rows_w * HD * sizeof(float);
-  PMV_CHECK_ARG(smem_r <= 200 * 1024, "relpos: tables too large for shared memory");
-  const int nb_r = rw_blocks((int64_t)BH * qt * qh), nb_c = rw_blocks((int64_t)BH * qt * qw);
-  float* part_r = ws;
-  float* part_c = ws + (int64_t)nb_r * nht * HD;
+  const int np = ncat_padded(g);
+  PMV_CHECK_ARG(np <= SC_MAXCOLS, "relpos: stacked tables too long (%d rows)", np);
+  PMV_CHECK_ARG(ws != nullptr && d_rel != nullptr, "relpos: workspace / d_rel required");
+  const int64_t M = (int64_t)BH * (qt * qh * qw + 1);
+  const int ncat = g.rows_h + g.rows_w + g.rows_t;
+  char* cat = reinterpret_cast<char*>(ws);
+  float* dcat = reinterpret_cast<float*>(cat + align256((int64_t)np * HD * 4));
+  char* drq = reinterpret_cast<char*>(dcat) + align256((int64_t)np * HD * 4);
   cudaStream_t st = (cudaStream_t)stream;
+  int64_t blocks = ceil_div64(M, SC_WARPS);
+  if (blocks > 148 * 8) blocks = 148 * 8;
   PMV_DISPATCH_DTYPE(dtype, T, {
-    PMV_CHECK_CUDA(cudaFuncSetAttribute(relpos_bwd_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    PMV_CHECK_CUDA(cudaFuncSetAttribute(relpos_bwd_cols_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    // the column walk reads the d rq columns, which the row walk leaves untouched (it rewrites columns [0, 96) only)
-    relpos_bwd_cols_kernel<T><<<nb_c, RW_WARPS * 32, smem_c, st>>>((const T*)dq_aug, (const T*)q_aug, ld, idx_w, part_c, BH, g, inv_scale);
-    relpos_bwd_rows_kernel<T><<<nb_r, RW_WARPS * 32, smem_r, st>>>((T*)dq_aug, (const T*)q_aug, ld, rel_h, rel_w, rel_t, idx_h, idx_w,
-                                                                    idx_t, part_r, BH, g, inv_scale);
+    relpos_cat_kernel<T><<<(np * HD + 255) / 256, 256, 0, st>>>((T*)cat, rel_h, rel_w, rel_t, g, np, inv_scale);
+    relpos_scatter_kernel<T><<<(unsigned)blocks, SC_WARPS * 32, 0, st>>>((const T*)dq_aug, (int)ld, (T*)drq, np, idx_h, idx_w, idx_t, M, g);
   });
-  launch_reduce_partials(part_r, nb_r, g.rows_h * HD, d_rel, st, (int64_t)nht * HD);
-  launch_reduce_partials(part_r + g.rows_h * HD, nb_r, g.rows_t * HD, d_rel + (int64_t)(g.rows_h + g.rows_w) * HD, st, (int64_t)nht * HD);
-  launch_reduce_partials(part_c, nb_c, g.rows_w * HD, d_rel + (int64_t)g.rows_h * HD, st);
+  PMV_CHECK_LAUNCH();
+  // dQ[:, :96] += dRQ x cat      (cat already carries 1/scale)
+  pmv_epilogue e;
+  memset(&e, 0, sizeof(e));
+  e.accumulate = 1;
+  int rc = pmv_gemm(PMV_GEMM_NN, drq, np, cat, HD, dq_aug, ld, M, HD, np, dtype, dtype, &e, tc, 1, stream);
+  if (rc) return rc;
+  // dcat = dRQ^T x Q, split over the query rows
+  int split = 1;
+  {
+    const int tiles = ((np + 127) / 128) * 1;
+    int want = (148 * 2) / tiles;
+    if (want < 1) want = 1;
+    const int64_t cap = M >= 512 ? M / 512 : 1;
+    split = (int)(want < cap ? want : cap);
+    if (split < 1) split = 1;
+  }
+  if (split > 1) PMV_CHECK_CUDA(cudaMemsetAsync(dcat, 0, (size_t)np * HD * 4, st));
+  rc = pmv_gemm(PMV_GEMM_NT_REDUCE_M, drq, np, q_aug, ld, dcat, HD, M, np, HD, dtype, PMV_F32, nullptr, tc, split, stream);
+  if (rc) return rc;
+  relpos_dtab_kernel<<<(ncat * HD + 255) / 256, 256, 0, st>>>(d_rel, dcat, ncat * HD, inv_scale);
   PMV_CHECK_LAUNCH();
   return PMV_OK;
 }

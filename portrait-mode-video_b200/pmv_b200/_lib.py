@@ -49,10 +49,11 @@ _SIGS = {
     "pmv_pool_ln_qkv_bwd": (_i, [_p, _i64, _i64, _i64, _i64, C.POINTER(PoolJob), _i, _p, _p, _i, _i, _i, _i, _i, _f, _i, _p]),
     "pmv_maxpool_skip_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "pmv_maxpool_skip_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
-    "pmv_relpos_augment_q": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
+    "pmv_relpos_fwd_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, _i, _i]),
+    "pmv_relpos_augment_q": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _p]),
     "pmv_relpos_augment_k": (_i, [_p, _i64, _i, _i, _i, _i, _i, _p]),
     "pmv_relpos_bwd_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, _i, _i]),
-    "pmv_relpos_augment_q_bwd": (_i, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
+    "pmv_relpos_augment_q_bwd": (_i, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _p]),
     "pmv_attention_fwd": (_i, [_p, _p, _i64, _i, _p, _i64, _p, _p, _p, _i, _i, _i, _i, _f, _i, _i, _i, _p]),
     "pmv_attention_bwd_workspace_bytes": (_i64, [_i, _i, _i, _i]),
     "pmv_attention_bwd": (_i, [_p, _p, _i64, _i, _p, _i64, _p, _p, _p, _p, _p, _i64, _p, _i64, _p, _i, _i, _i, _i, _f, _i, _i, _i, _p]),

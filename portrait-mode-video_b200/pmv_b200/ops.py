@@ -254,13 +254,18 @@ def aug_ld(k_shape) -> int:
     return 96 + ((rk + 31) // 32) * 32
 
 
-def relpos_augment_q(q_aug, q_shape, k_shape, rel_h, rel_w, rel_t, inv_scale):
+def relpos_augment_q(q_aug, q_shape, k_shape, rel_h, rel_w, rel_t, inv_scale, tc=None):
     BH, Nq, ld = q_aug.shape
     dev = q_aug.device
     ih, iw, it = (rel_index_table(q_shape[1], k_shape[1], dev), rel_index_table(q_shape[2], k_shape[2], dev),
                   rel_index_table(q_shape[0], k_shape[0], dev))
-    _run("pmv_relpos_augment_q", 1, dict(bytes=BH * Nq * ld * q_aug.element_size()), L.ptr(q_aug), ld, L.ptr(rel_h), L.ptr(rel_w), L.ptr(rel_t), L.ptr(ih), L.ptr(iw),
-                                         L.ptr(it), BH, *q_shape, *k_shape, inv_scale, L.dt(q_aug), L.stream())
+    ncat = rel_h.shape[0] + rel_w.shape[0] + rel_t.shape[0]
+    ws = _ws(L.lib().pmv_relpos_fwd_workspace_bytes(BH, *q_shape, *k_shape), dev)
+    use_tc = _tc_default(q_aug.dtype) if tc is None else int(tc)
+    e = q_aug.element_size()
+    _run("pmv_relpos_augment_q", 3, dict(bytes=BH * Nq * (ld + 2 * ncat) * e, flops=2 * BH * Nq * 96 * ncat), L.ptr(q_aug), ld,
+         L.ptr(rel_h), L.ptr(rel_w), L.ptr(rel_t), L.ptr(ih), L.ptr(iw), L.ptr(it), L.ptr(ws), BH, *q_shape, *k_shape, inv_scale,
+         L.dt(q_aug), use_tc, L.stream())
 
 
 def relpos_augment_k(k_aug, k_shape):
@@ -268,18 +273,21 @@ def relpos_augment_k(k_aug, k_shape):
     _run("pmv_relpos_augment_k", 1, dict(bytes=BH * Nk * (ld - 96) * k_aug.element_size()), L.ptr(k_aug), ld, BH, *k_shape, L.dt(k_aug), L.stream())
 
 
-def relpos_augment_q_bwd(dq_aug, q_aug, q_shape, k_shape, rel_h, rel_w, rel_t, inv_scale):
+def relpos_augment_q_bwd(dq_aug, q_aug, q_shape, k_shape, rel_h, rel_w, rel_t, inv_scale, tc=None):
     """In place: dq_aug[:, :, :96] += bias-path gradient.  Returns fp32 (d_rel_h, d_rel_w, d_rel_t)."""
     BH, Nq, ld = q_aug.shape
     dev = q_aug.device
     ih, iw, it = (rel_index_table(q_shape[1], k_shape[1], dev), rel_index_table(q_shape[2], k_shape[2], dev),
                   rel_index_table(q_shape[0], k_shape[0], dev))
     nh, nw, nt = rel_h.shape[0], rel_w.shape[0], rel_t.shape[0]
-    d_rel = torch.zeros(nh + nw + nt, 96, dtype=torch.float32, device=dev)
+    ncat = nh + nw + nt
+    d_rel = torch.zeros(ncat, 96, dtype=torch.float32, device=dev)
     ws = _ws(L.lib().pmv_relpos_bwd_workspace_bytes(BH, *q_shape, *k_shape), dev)
-    _run("pmv_relpos_augment_q_bwd", 2, dict(bytes=2 * BH * Nq * ld * q_aug.element_size()), L.ptr(dq_aug), L.ptr(q_aug), ld,
-         L.ptr(rel_h), L.ptr(rel_w), L.ptr(rel_t), L.ptr(ih), L.ptr(iw), L.ptr(it), L.ptr(d_rel), L.ptr(ws), BH,
-         *q_shape, *k_shape, inv_scale, L.dt(q_aug), L.stream())
+    use_tc = _tc_default(q_aug.dtype) if tc is None else int(tc)
+    e = q_aug.element_size()
+    _run("pmv_relpos_augment_q_bwd", 5, dict(bytes=BH * Nq * (3 * ld + 3 * ncat) * e, flops=4 * BH * Nq * 96 * ncat), L.ptr(dq_aug),
+         L.ptr(q_aug), ld, L.ptr(rel_h), L.ptr(rel_w), L.ptr(rel_t), L.ptr(ih), L.ptr(iw), L.ptr(it), L.ptr(d_rel), L.ptr(ws), BH,
+         *q_shape, *k_shape, inv_scale, L.dt(q_aug), use_tc, L.stream())
     return d_rel[:nh], d_rel[nh:nh + nw], d_rel[nh + nw:]
 
 
