@@ -18,6 +18,8 @@ struct EpiDev {
   int64_t out_skip;
   void* out;
   int64_t ldo;
+  FastDiv fd_scale;  // rows_per_scale (row indices < 2^31)
+  FastDiv fd_group;  // out_group
 };
 
 __device__ __forceinline__ int64_t epi_out_row(const EpiDev& e, int64_t row) {

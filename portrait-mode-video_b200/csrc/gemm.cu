@@ -20,6 +20,9 @@ extern "C" int pmv_gemm(int layout, const void* A, int64_t lda, const void* B, i
     e.out_group = epi->out_group; e.out_skip = epi->out_skip;
     PMV_CHECK_ARG(e.act != PMV_ACT_GELU_BWD || e.aux_in, "gemm: GELU_BWD needs aux_in");
   }
+  PMV_CHECK_ARG(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gemm: dimensions must fit 31 bits");
+  e.fd_scale = FastDiv((uint32_t)(e.rows_per_scale > 0 ? e.rows_per_scale : 1));
+  e.fd_group = FastDiv((uint32_t)(e.out_group > 0 ? e.out_group : 1));
   if (split_k > 1) {
     PMV_CHECK_ARG(layout == PMV_GEMM_NT_REDUCE_M && out_dtype == PMV_F32 && !epi, "gemm: split_k only for fp32 wgrad without epilogue");
     e.atomic = 1;

@@ -1,0 +1,428 @@
+// tcgen05 / TMEM / TMA GEMM for the Linear layers of the MViTv2 block (bf16 operands, fp32 accumulate):
+//   TN        y = x W^T            (qkv, proj, skip-proj, fc1, fc2, PatchEmbed:  attention.py:328,457,570; common.py:27-31)
+//   NN        dx = dy W            (dgrad)
+//   REDUCE_M  dW = dy^T x          (wgrad; reduction over the token rows, optional split-K with fp32 atomics)
+//
+// Persistent, warp-specialised kernel, one CTA per SM:
+//   warp 0      TMA producer   (cp.async.bulk.tensor 2-D, 128-byte swizzle, 4-stage mbarrier ring)
+//   warp 1      MMA issuer     (one elected lane issues tcgen05.mma 128 x BN x 16; accumulators double-buffered in TMEM)
+//   warps 2..9  epilogue       (tcgen05.ld 32x32b -> smem transpose -> bias / GELU / DropPath scale / residual -> global)
+//
+// Operand staging.  A "K-major" operand (reduction axis contiguous in global memory) is one TMA box of
+// [rows x 64 elements] -> rows of 128 B, 8-row swizzle atoms of 1024 B (SBO = 1024).  An "MN-major" operand
+// (row axis contiguous: W in dgrad, both operands in wgrad) is staged as 64-wide groups, each one TMA box of
+// [64 reduction rows x 64 elements]; within a group 8 reduction rows form a 1024 B atom (SBO = 1024) and the
+// groups are 8192 B apart (LBO = 8192).  The UMMA reads either through its matrix descriptor; the a_major /
+// b_major bits of the instruction descriptor select the transposed read.
+//
+// Epilogue kinds (compile time, so that each kernel carries only its own epilogue code: the all-in-one epilogue
+// was 116 KB of SASS, three times the instruction cache, and its warps stalled on instruction fetch):
+//   EK_PLAIN     out = acc (+ bias)
+//   EK_GELU      out = gelu_erf(acc + bias), optionally the pre-activation to aux_out
+//   EK_GELU_BWD  out = acc * gelu_erf'(aux_in)
+//   EK_RES       out(fp32) = residual + [row_scale *] (acc + bias)
+//   EK_ATOMIC    out(fp32) += acc   (split-K wgrad partials: one 16-byte vector reduction per lane)
+//   EK_GENERIC   every pmv_epilogue term at run time (accumulate, row remap, ...)
+#pragma once
+#include "gemm.h"
+#include "tc_common.cuh"
+
+namespace gemm_tc {
+
+enum { EK_PLAIN = 0, EK_GELU = 1, EK_GELU_BWD = 2, EK_RES = 3, EK_GENERIC = 4, EK_ATOMIC = 5 };
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int EPI_WARPS = 8;                        // two warps per TMEM lane quarter, alternating 32-column chunks
+constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;
+
+struct TcParams {
+  int64_t M, N, K;          // logical output rows / cols and reduction length
+  int tiles_m, tiles_n, splits;
+  int64_t k_per_split;      // multiple of BK
+  EpiDev e;
+};
+
+template <int BN> struct TileCfg {
+  static constexpr int BN_GROUPS = (BN + 63) / 64;
+  static constexpr int A_BYTES = BM * BK * 2;                 // 16 KB either layout
+  static constexpr int B_BYTES_K = BN * BK * 2;               // K-major box
+  static constexpr int B_BYTES_MN = BN_GROUPS * 64 * BK * 2;  // MN-major groups
+  static constexpr int B_BYTES = B_BYTES_MN;                  // reserve the larger of the two
+  static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
+  static constexpr int ACC_COLS = BN <= 128 ? 128 : 256;      // TMEM columns per accumulator stage
+  static constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;   // per-epilogue-warp transpose buffer (XOR-swizzled)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
+};
+
+// ---- packed-fp32 epilogue math -----------------------------------------------------------------------------------
+// Phi(x) = 0.5 (1 + erf(x / sqrt 2)) = 0.5 + xc * Q(xc^2), xc = clamp(x, +-3 sqrt 2): degree-8 polynomial in x^2,
+// |error| <= 1.1e-5 (oracle/fit_gelu.py), no MUFU: the exp/rcp form cost 2 MUFU + 12 FMA per element and made the
+// GELU epilogues the longest stage of the fc1 GEMMs.
+__device__ __forceinline__ float2 phi2(float2 x) {
+  const float Z = 4.242640687f;
+  float2 xc = make_float2(fminf(fmaxf(x.x, -Z), Z), fminf(fmaxf(x.y, -Z), Z));
+  const float2 s = __fmul2_rn(xc, xc);
+  float2 q = make_float2(5.6236895431e-11f, 5.6236895431e-11f);
+  q = __ffma2_rn(q, s, make_float2(-5.3744284878e-09f, -5.3744284878e-09f));
+  q = __ffma2_rn(q, s, make_float2(2.2710010238e-07f, 2.2710010238e-07f));
+  q = __ffma2_rn(q, s, make_float2(-5.6547267380e-06f, -5.6547267380e-06f));
+  q = __ffma2_rn(q, s, make_float2(9.3721011908e-05f, 9.3721011908e-05f));
+  q = __ffma2_rn(q, s, make_float2(-1.1104664642e-03f, -1.1104664642e-03f));
+  q = __ffma2_rn(q, s, make_float2(9.8226745766e-03f, 9.8226745766e-03f));
+  q = __ffma2_rn(q, s, make_float2(-6.6355885986e-02f, -6.6355885986e-02f));
+  q = __ffma2_rn(q, s, make_float2(3.9890877892e-01f, 3.9890877892e-01f));
+  return __ffma2_rn(xc, q, make_float2(0.5f, 0.5f));
+}
+__device__ __forceinline__ float2 gelu2(float2 x) { return __fmul2_rn(x, phi2(x)); }
+// gelu'(x) = Phi(x) + x * pdf(x)
+__device__ __forceinline__ float2 gelu_grad2(float2 x) {
+  const float2 cdf = phi2(x);
+  const float2 t = __fmul2_rn(__fmul2_rn(x, x), make_float2(-0.72134752044448170368f, -0.72134752044448170368f));
+  const float2 e = make_float2(exp2f(t.x), exp2f(t.y));  // exp(-x^2 / 2)
+  const float2 xp = __fmul2_rn(x, make_float2(0.39894228040143267794f, 0.39894228040143267794f));
+  return __ffma2_rn(xp, e, cdf);
+}
+__device__ __forceinline__ void st4(bf16* p, float2 a, float2 b) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(b.x, b.y);
+  uint2 t;
+  t.x = *reinterpret_cast<uint32_t*>(&lo);
+  t.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+__device__ __forceinline__ void st4(float* p, float2 a, float2 b) { *reinterpret_cast<float4*>(p) = make_float4(a.x, a.y, b.x, b.y); }
+__device__ __forceinline__ void red_add4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t u) { return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
+
+template <int BN, bool A_MN, bool B_MN, typename TOut, int KIND>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+  using Cfg = TileCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                 // [STAGES]  TMA -> MMA
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]  MMA -> TMA
+  uint64_t* acc_full = bars + 2 * STAGES;    // [2]       MMA -> epilogue
+  uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2]    epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* epi_buf = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmA);
+    tc::tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) {
+      tc::mbar_init(&full_bar[i], 1);
+      tc::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&acc_full[i], 1);
+      tc::mbar_init(&acc_empty[i], EPI_WARPS);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(tmem_slot, 2 * Cfg::ACC_COLS);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int64_t num_work = (int64_t)p.tiles_m * p.tiles_n * p.splits;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+        const int tn = (int)(wi % p.tiles_n);
+        const int tm = (int)((wi / p.tiles_n) % p.tiles_m);
+        const int sp = (int)(wi / ((int64_t)p.tiles_n * p.tiles_m));
+        const int m0 = tm * BM, n0 = tn * BN;
+        const int64_t kbeg = (int64_t)sp * p.k_per_split;
+        const int64_t kend = kbeg + p.k_per_split < p.K ? kbeg + p.k_per_split : p.K;
+        for (int64_t kb = kbeg; kb < kend; kb += BK) {
+          tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          tc::mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES + (B_MN ? Cfg::B_BYTES_MN : Cfg::B_BYTES_K));
+          if (!A_MN) {
+            tc::tma_load_2d(sa, &tmA, (int)kb, m0, &full_bar[stage]);
+          } else {
+#pragma unroll
+            for (int g = 0; g < BM / 64; ++g) tc::tma_load_2d(sa + g * 8192, &tmA, m0 + g * 64, (int)kb, &full_bar[stage]);
+          }
+          if (!B_MN) {
+            tc::tma_load_2d(sb, &tmB, (int)kb, n0, &full_bar[stage]);
+          } else {
+#pragma unroll
+            for (int g = 0; g < Cfg::BN_GROUPS; ++g) tc::tma_load_2d(sb + g * 8192, &tmB, n0 + g * 64, (int)kb, &full_bar[stage]);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int64_t it = 0;
+      for (int64_t wi = blockIdx.x; wi < num_work; wi += gridDim.x, ++it) {
+        const int sp = (int)(wi / ((int64_t)p.tiles_n * p.tiles_m));
+        const int64_t kbeg = (int64_t)sp * p.k_per_split;
+        const int64_t kend = kbeg + p.k_per_split < p.K ? kbeg + p.k_per_split : p.K;
+        const int as = (int)(it & 1);
+        const uint32_t aphase = (uint32_t)((it >> 1) & 1);
+        tc::mbar_wait(&acc_empty[as], aphase ^ 1);
+        tc::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * Cfg::ACC_COLS;
+        for (int64_t kb = kbeg; kb < kend; kb += BK) {
+          tc::mbar_wait(&full_bar[stage], phase);
+          tc::tc_fence_after();
+          const uint32_t sa = tc::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const int64_t rem = kend - kb;
+          const int nk = rem >= BK ? BK / 16 : (int)((rem + 15) / 16);
+#pragma unroll 4
+          for (int k = 0; k < nk; ++k) {
+            const uint64_t da = A_MN ? tc::make_smem_desc(sa + k * 2048, 8192, 1024, tc::SWIZZLE_128B)
+                                     : tc::make_smem_desc(sa + k * 32, 16, 1024, tc::SWIZZLE_128B);
+            const uint64_t db = B_MN ? tc::make_smem_desc(sb + k * 2048, 8192, 1024, tc::SWIZZLE_128B)
+                                     : tc::make_smem_desc(sb + k * 32, 16, 1024, tc::SWIZZLE_128B);
+            tc::umma_ss(tmem_d, da, db, idesc, (kb > kbeg || k > 0) ? 1u : 0u);
+          }
+          tc::umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc::umma_commit(&acc_full[as]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4)
+    // Work items are (tile, 32-column chunk); the warp walks them as one flat sequence.  While the accumulator of
+    // item i is on its way out of TMEM, the global operands of item i+1 (residual, GELU' pre-activation, DropPath
+    // scale) are already being fetched into a second register set, so the epilogue is not exposed to a DRAM
+    // round trip per chunk.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;  // which of the two warps of this lane quarter
+    float* stage_buf = epi_buf + (warp - 2) * (32 * 32);
+    const int lr = lane >> 3, lc = lane & 7;
+    const EpiDev& e = p.e;
+    constexpr bool PRE_RES = KIND == EK_RES, PRE_AUX = KIND == EK_GELU_BWD;
+    const bool has_scale = (KIND == EK_RES || KIND == EK_GENERIC) && e.row_scale != nullptr;
+
+    struct Cursor {
+      int64_t wi, it;
+      int c;
+    };
+    struct Pre {     // operands of one chunk fetched ahead: fp32 residual (16 B) or bf16 pre-activation (8 B) per itr
+      uint4 buf[(PRE_RES || PRE_AUX) ? 8 : 1];
+      float sc[KIND == EK_RES ? 8 : 1];
+    };
+    auto valid = [&](const Cursor& cu) { return cu.wi < num_work; };
+    auto advance = [&](Cursor& cu) {
+      cu.c += 64;
+      if (cu.c >= BN) { cu.c = half * 32; cu.wi += gridDim.x; ++cu.it; }
+    };
+    auto coords = [&](const Cursor& cu, int64_t& row0, int64_t& col) {
+      const int tn = (int)(cu.wi % p.tiles_n);
+      const int tm = (int)((cu.wi / p.tiles_n) % p.tiles_m);
+      row0 = (int64_t)tm * BM + q * 32 + lr;
+      col = (int64_t)tn * BN + cu.c + lc * 4;
+    };
+    auto prefetch = [&](const Cursor& cu, Pre& pre) {
+      if constexpr (PRE_RES || PRE_AUX) {
+        if (!valid(cu)) return;
+        int64_t row0, col;
+        coords(cu, row0, col);
+        const bool colok = col < p.N;
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr) {
+          const int64_t row = row0 + itr * 4;
+          const bool ok = colok && row < p.M;
+          if constexpr (PRE_RES) {
+            pre.buf[itr] = ok ? __ldg(reinterpret_cast<const uint4*>(e.residual + row * e.ld_residual + col)) : make_uint4(0u, 0u, 0u, 0u);
+            pre.sc[itr] = (ok && has_scale) ? __ldg(e.row_scale + e.fd_scale.div((uint32_t)row)) : 1.f;
+          } else {
+            const uint2 t2 = ok ? __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(e.aux_in) + row * e.ld_aux + col)) : make_uint2(0u, 0u);
+            pre.buf[itr].x = t2.x; pre.buf[itr].y = t2.y;
+          }
+        }
+      }
+    };
+    auto process = [&](const Cursor& cu, const Pre& pre) {
+      int64_t row0, col;
+      coords(cu, row0, col);
+      const int as = (int)(cu.it & 1);
+      const bool first_chunk = cu.c == half * 32, last_chunk = cu.c + 64 >= BN;
+      if (first_chunk) {
+        tc::mbar_wait(&acc_full[as], (uint32_t)((cu.it >> 1) & 1));
+        tc::tc_fence_after();
+      }
+      uint32_t r[32];
+      tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * Cfg::ACC_COLS + cu.c, r);
+      tc::tmem_ld_wait();
+      if (last_chunk) {  // the accumulator stage is in registers: hand it back to the MMA warp
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&acc_empty[as]);
+      }
+      // transpose through shared memory (XOR-swizzled 16-byte groups: conflict-free both ways) so that 8
+      // consecutive lanes cover one 32-column row segment: every global access of the epilogue is a full
+      // 64/128-byte run per row
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        *reinterpret_cast<float4*>(stage_buf + lane * 32 + ((g ^ (lane & 7)) << 2)) =
+            make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
+      __syncwarp();
+      const bool colok = col < p.N;
+      float2 b01 = make_float2(0.f, 0.f), b23 = b01;
+      if (KIND != EK_GELU_BWD && KIND != EK_ATOMIC && e.bias && colok) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+        b01 = make_float2(b4.x, b4.y); b23 = make_float2(b4.z, b4.w);
+      }
+#pragma unroll
+      for (int itr = 0; itr < 8; ++itr) {
+        const int rr = itr * 4 + lr;
+        const int64_t row = row0 + itr * 4;
+        const float4 a4 = *reinterpret_cast<const float4*>(stage_buf + rr * 32 + ((lc ^ (rr & 7)) << 2));
+        if (!(colok && row < p.M)) continue;
+        float2 v01 = make_float2(a4.x, a4.y), v23 = make_float2(a4.z, a4.w);
+        if constexpr (KIND == EK_ATOMIC) {
+          red_add4(reinterpret_cast<float*>(e.out) + row * e.ldo + col, a4);
+        } else if constexpr (KIND == EK_PLAIN) {
+          v01 = __fadd2_rn(v01, b01); v23 = __fadd2_rn(v23, b23);
+          st4(reinterpret_cast<TOut*>(e.out) + row * e.ldo + col, v01, v23);
+        } else if constexpr (KIND == EK_GELU) {
+          v01 = __fadd2_rn(v01, b01); v23 = __fadd2_rn(v23, b23);
+          if (e.aux_out) st4(reinterpret_cast<bf16*>(e.aux_out) + row * e.ld_aux + col, v01, v23);
+          st4(reinterpret_cast<TOut*>(e.out) + row * e.ldo + col, gelu2(v01), gelu2(v23));
+        } else if constexpr (KIND == EK_GELU_BWD) {
+          v01 = __fmul2_rn(v01, gelu_grad2(bf2_to_f2(pre.buf[itr].x)));
+          v23 = __fmul2_rn(v23, gelu_grad2(bf2_to_f2(pre.buf[itr].y)));
+          st4(reinterpret_cast<TOut*>(e.out) + row * e.ldo + col, v01, v23);
+        } else if constexpr (KIND == EK_RES) {
+          const float2 sc = make_float2(pre.sc[itr], pre.sc[itr]);
+          const float2 r01 = make_float2(__uint_as_float(pre.buf[itr].x), __uint_as_float(pre.buf[itr].y));
+          const float2 r23 = make_float2(__uint_as_float(pre.buf[itr].z), __uint_as_float(pre.buf[itr].w));
+          v01 = __ffma2_rn(__fadd2_rn(v01, b01), sc, r01);
+          v23 = __ffma2_rn(__fadd2_rn(v23, b23), sc, r23);
+          st4(reinterpret_cast<TOut*>(e.out) + row * e.ldo + col, v01, v23);
+        } else {
+          float v[4] = {a4.x + b01.x, a4.y + b01.y, a4.z + b23.x, a4.w + b23.y};
+          if (e.atomic) {
+            float* o = reinterpret_cast<float*>(e.out) + row * e.ldo + col;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) atomicAdd(o + j, v[j]);
+            continue;
+          }
+          if (e.aux_out) store4(reinterpret_cast<bf16*>(e.aux_out) + row * e.ld_aux + col, v);
+          if (e.act == PMV_ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = gelu_fast(v[j]);
+          } else if (e.act == PMV_ACT_GELU_BWD) {
+            float u[4];
+            load4(reinterpret_cast<const bf16*>(e.aux_in) + row * e.ld_aux + col, u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] *= gelu_fast_grad(u[j]);
+          }
+          if (has_scale) {
+            const float s = e.row_scale[e.fd_scale.div((uint32_t)row)];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] *= s;
+          }
+          if (e.residual) {
+            float rv[4];
+            load4(e.residual + row * e.ld_residual + col, rv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] += rv[j];
+          }
+          const int64_t orow = e.out_group > 0 ? row + (int64_t)(e.fd_group.div((uint32_t)row) + 1) * e.out_skip : row;
+          TOut* o = reinterpret_cast<TOut*>(e.out) + orow * e.ldo + col;
+          if (e.accumulate) {
+            float pv[4];
+            load4(o, pv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] += pv[j];
+          }
+          store4(o, v);
+        }
+      }
+      __syncwarp();
+    };
+
+    Cursor cur{(int64_t)blockIdx.x, 0, half * 32};
+    if (cur.c < BN) {
+      Pre pa, pb;
+      prefetch(cur, pa);
+      while (valid(cur)) {
+        Cursor nxt = cur;
+        advance(nxt);
+        prefetch(nxt, pb);
+        process(cur, pa);
+        pa = pb;
+        cur = nxt;
+      }
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, 2 * Cfg::ACC_COLS);
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN, typename TOut, int KIND>
+int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int num_sms, cudaStream_t stream) {
+  using Cfg = TileCfg<BN>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, TOut, KIND>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    PMV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  int64_t work = (int64_t)p.tiles_m * p.tiles_n * p.splits;
+  unsigned grid = (unsigned)(work < num_sms ? work : num_sms);
+  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  PMV_CHECK_LAUNCH();
+  return PMV_OK;
+}
+
+// (layout, output type, epilogue kind) combinations that exist as kernels; anything else runs EK_GENERIC
+template <int BN>
+int launch_bn(int layout, int out_dtype, int kind, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int num_sms,
+              cudaStream_t s) {
+  const bool f32 = out_dtype == PMV_F32;
+  if (layout == PMV_GEMM_TN) {
+    if (kind == EK_PLAIN) return f32 ? launch_cfg<BN, false, false, float, EK_PLAIN>(tmA, tmB, p, num_sms, s)
+                                     : launch_cfg<BN, false, false, bf16, EK_PLAIN>(tmA, tmB, p, num_sms, s);
+    if (kind == EK_GELU && !f32) return launch_cfg<BN, false, false, bf16, EK_GELU>(tmA, tmB, p, num_sms, s);
+    if (kind == EK_RES && f32) return launch_cfg<BN, false, false, float, EK_RES>(tmA, tmB, p, num_sms, s);
+    return f32 ? launch_cfg<BN, false, false, float, EK_GENERIC>(tmA, tmB, p, num_sms, s)
+               : launch_cfg<BN, false, false, bf16, EK_GENERIC>(tmA, tmB, p, num_sms, s);
+  }
+  if (layout == PMV_GEMM_NN) {
+    if (kind == EK_PLAIN && !f32) return launch_cfg<BN, false, true, bf16, EK_PLAIN>(tmA, tmB, p, num_sms, s);
+    if (kind == EK_GELU_BWD && !f32) return launch_cfg<BN, false, true, bf16, EK_GELU_BWD>(tmA, tmB, p, num_sms, s);
+    return f32 ? launch_cfg<BN, false, true, float, EK_GENERIC>(tmA, tmB, p, num_sms, s)
+               : launch_cfg<BN, false, true, bf16, EK_GENERIC>(tmA, tmB, p, num_sms, s);
+  }
+  if (kind == EK_PLAIN) return launch_cfg<BN, true, true, float, EK_PLAIN>(tmA, tmB, p, num_sms, s);
+  if (kind == EK_ATOMIC) return launch_cfg<BN, true, true, float, EK_ATOMIC>(tmA, tmB, p, num_sms, s);
+  return launch_cfg<BN, true, true, float, EK_GENERIC>(tmA, tmB, p, num_sms, s);
+}
+
+}  // namespace gemm_tc
