@@ -24,42 +24,18 @@
 //                  stride 4 / 8): guarded taps, zero rows written without arithmetic.
 // backward (iv)  : a reduce kernel folds the per-CTA partials (same-address global atomics from hundreds of CTAs
 //                  serialise in L2).
-#include "common.cuh"
+#include <cstdlib>
 
+#include "pool_common.cuh"
+
+namespace pool {
 namespace {
 
-constexpr int HD = PMV_HEAD_DIM;  // 96
-constexpr int TAPS = 27;
-constexpr int NCP = HD / 2;        // 48 channel pairs
-constexpr int ROWS = 4;            // output rows per CTA pass
 constexpr int CW = 6;              // positions along w between two LayerNorm phases (multiple of 3: window rotation)
 constexpr int THREADS = NCP * ROWS;  // 192
-constexpr int LNL = 8;             // lanes per token in the LayerNorm phase
-constexpr int CPL = HD / LNL;      // 12 channels per lane
 constexpr int CHUNK_TOK = ROWS * CW;  // 24 tokens per phase == THREADS / LNL
 constexpr int CLS_WARPS = THREADS / 32;
-constexpr int NGRAD = (TAPS + 2) * HD;  // dW [96][27], dgamma [96], dbeta [96]
-constexpr int NDW = TAPS * HD;
-constexpr int MAX_JOBS = 3;
 static_assert(CHUNK_TOK * LNL == THREADS, "LayerNorm phase mapping");
-
-struct Job {
-  const void* in;       // first channel of this tensor inside the QKV buffer
-  const float* w;       // [96,1,3,3,3]
-  const float* gamma;
-  const float* beta;
-  void* out;            // forward output [B, heads, 1+Lo, out_ld]
-  int64_t out_ld;
-  const void* dout;     // backward: gradient of `out`
-  int64_t dout_ld;
-  void* din;            // backward: gradient wrt `in` (same strides)
-  float* grads;         // backward: [NGRAD] fp32, added to
-  void* dconv;          // backward: pre-LN gradient [B*heads*Lo*96] in the compute dtype
-  int s, Ho, Wo;
-  int blk_begin, nblk, ncls_blk;  // forward / backward (i): [blk_begin, +nblk) march blocks, then ncls_blk cls blocks
-  int blk2_begin, nblk2;          // backward (ii)
-  int blk3_begin, nblk3;          // backward (iii)
-};
 
 struct Launch {
   Job job[MAX_JOBS];
@@ -67,46 +43,7 @@ struct Launch {
   int B, heads, T, H, W;
   int64_t in_bs, in_ts, in_hs;  // element strides of the input views
   float eps;
-  float* partials;              // backward (i): [total blocks][2 * 96] (dgamma, dbeta)
-  float* partials_dw;           // backward (ii): [total blocks][96 * 27]
 };
-
-// ---- 2-channel loads / stores ---------------------------------------------------------------------------------
-__device__ __forceinline__ float2 ld2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
-__device__ __forceinline__ float2 ld2(const bf16* p) {
-  const uint32_t u = __ldg(reinterpret_cast<const unsigned int*>(p));
-  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
-}
-__device__ __forceinline__ void st2(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
-__device__ __forceinline__ void st2(bf16* p, float2 v) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
-  *reinterpret_cast<uint32_t*>(p) = *reinterpret_cast<uint32_t*>(&h);
-}
-template <typename T> __device__ __forceinline__ void load12(const T* p, float (&v)[CPL]) {
-  float a[4];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    load4(p + 4 * i, a);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v[4 * i + j] = a[j];
-  }
-}
-template <typename T> __device__ __forceinline__ void store12(T* p, const float (&v)[CPL]) {
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    float a[4] = {v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]};
-    store4(p + 4 * i, a);
-  }
-}
-
-// the 27 taps of channels (2cp, 2cp+1); FLIP mirrors all three axes (transposed stencil)
-template <bool FLIP> __device__ __forceinline__ void load_taps(const float* __restrict__ w, int cp, float2 (&wr)[TAPS]) {
-#pragma unroll
-  for (int tap = 0; tap < TAPS; ++tap) {
-    const int src = FLIP ? (TAPS - 1 - tap) : tap;
-    wr[tap] = make_float2(__ldg(w + (2 * cp) * TAPS + src), __ldg(w + (2 * cp + 1) * TAPS + src));
-  }
-}
 
 // One row of the march: where the 3x3 (t,h) neighbourhood of the row lives.
 struct RowGeom {
@@ -250,7 +187,7 @@ __global__ void __launch_bounds__(THREADS, 2) pool_ln_march_kernel(const __grid_
         float s = 0.f;
 #pragma unroll
         for (int wv = 0; wv < CLS_WARPS; ++wv) s += red[wv * 2 * HD + tid];
-        L.partials[(int64_t)blockIdx.x * 2 * HD + tid] = s;
+        J.part_ln[(int64_t)lb * 2 * HD + tid] = s;
       }
     }
     return;
@@ -402,7 +339,7 @@ __global__ void __launch_bounds__(THREADS, 2) pool_ln_march_kernel(const __grid_
       float s = 0.f;
 #pragma unroll 8
       for (int gg = 0; gg < CHUNK_TOK; ++gg) s += red[gg * 2 * HD + tid];
-      L.partials[(int64_t)blockIdx.x * 2 * HD + tid] = s;
+      J.part_ln[(int64_t)lb * 2 * HD + tid] = s;
     }
   }
 }
@@ -424,7 +361,7 @@ template <typename T>
 __global__ void __launch_bounds__(THREADS, 2) pool_ln_bwd_dw_kernel(const __grid_constant__ Launch L) {
   __shared__ float dws[NDW];
   int jj = 0;
-  while (jj + 1 < L.njobs && (int)blockIdx.x >= L.job[jj + 1].blk2_begin) ++jj;
+  while (jj + 1 < L.njobs && (int)blockIdx.x >= L.job[jj + 1].blk_begin) ++jj;
   const Job& J = L.job[jj];
   const T* __restrict__ in = reinterpret_cast<const T*>(J.in);
   const T* __restrict__ dconv = reinterpret_cast<const T*>(J.dconv);
@@ -435,12 +372,12 @@ __global__ void __launch_bounds__(THREADS, 2) pool_ln_bwd_dw_kernel(const __grid
   const bool slide = J.s == 1;
   const int nrows = L.B * L.heads * L.T * J.Ho;
   const int nitems = (nrows + ROWS - 1) / ROWS;
-  const int lb = blockIdx.x - J.blk2_begin;
+  const int lb = blockIdx.x - J.blk_begin;
   float2 acc[TAPS];
 #pragma unroll
   for (int k = 0; k < TAPS; ++k) acc[k] = make_float2(0.f, 0.f);
 
-  for (int item = lb; item < nitems; item += J.nblk2) {
+  for (int item = lb; item < nitems; item += J.nblk) {
     const int row = item * ROWS + r;
     if (row >= nrows) continue;
     const int ho = row % J.Ho;
@@ -496,7 +433,7 @@ __global__ void __launch_bounds__(THREADS, 2) pool_ln_bwd_dw_kernel(const __grid
     }
     __syncthreads();
   }
-  float* pb = L.partials_dw + (int64_t)blockIdx.x * NDW;
+  float* pb = J.part_dw + (int64_t)lb * NDW;
   for (int i = tid; i < NDW; i += THREADS) pb[i] = dws[i];
 }
 
@@ -515,7 +452,7 @@ __device__ __forceinline__ void tap_t(float2& acc, const T* __restrict__ p, cons
 template <typename T>
 __global__ void __launch_bounds__(THREADS, 2) pool_ln_bwd_input_kernel(const __grid_constant__ Launch L) {
   int jj = 0;
-  while (jj + 1 < L.njobs && (int)blockIdx.x >= L.job[jj + 1].blk3_begin) ++jj;
+  while (jj + 1 < L.njobs && (int)blockIdx.x >= L.job[jj + 1].blk_begin) ++jj;
   const Job& J = L.job[jj];
   const T* __restrict__ dconv = reinterpret_cast<const T*>(J.dconv);
   T* __restrict__ din = reinterpret_cast<T*>(J.din);
@@ -525,11 +462,11 @@ __global__ void __launch_bounds__(THREADS, 2) pool_ln_bwd_input_kernel(const __g
   const int S = J.s;
   const int nrows = L.B * L.heads * L.T * L.H;  // input rows
   const int nitems = (nrows + ROWS - 1) / ROWS;
-  const int lb = blockIdx.x - J.blk3_begin;
+  const int lb = blockIdx.x - J.blk_begin;
   float2 wr[TAPS];
   if (S == 1) load_taps<true>(J.w, cp, wr); else load_taps<false>(J.w, cp, wr);
 
-  for (int item = lb; item < nitems; item += J.nblk3) {
+  for (int item = lb; item < nitems; item += J.nblk) {
     const int row = item * ROWS + r;
     if (row >= nrows) continue;
     const int hi = row % L.H;
@@ -608,20 +545,19 @@ __global__ void __launch_bounds__(THREADS, 2) pool_ln_bwd_input_kernel(const __g
   }
 }
 
-// grads_j[i] += sum over the job's blocks of the partial vectors: dW from backward (ii), dgamma / dbeta from
-// backward (i)      (grid.y = job, grid.z = slice of the blocks)
+// grads_j[i] += sum over the job's partial vectors: dW from backward (ii), dgamma / dbeta from backward (i)
+// (grid.y = job, grid.z = slice of the partial vectors)
 constexpr int RED_SLICES = 8;
 __global__ void __launch_bounds__(256) reduce_jobs_kernel(const __grid_constant__ Launch L) {
   const Job& J = L.job[blockIdx.y];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= NGRAD) return;
   const bool is_dw = i < NDW;
-  const float* src = is_dw ? L.partials_dw + i : L.partials + (i - NDW);
+  const float* src = is_dw ? J.part_dw + i : J.part_ln + (i - NDW);
   const int64_t stride = is_dw ? NDW : 2 * HD;
-  const int begin = is_dw ? J.blk2_begin : J.blk_begin;
-  const int end = begin + (is_dw ? J.nblk2 : J.nblk + J.ncls_blk);
+  const int end = is_dw ? J.nblk_dw : J.nblk_ln;
   float s0 = 0.f, s1 = 0.f;
-  int b = begin + blockIdx.z;
+  int b = blockIdx.z;
   for (; b + RED_SLICES < end; b += 2 * RED_SLICES) {
     s0 += src[(int64_t)b * stride];
     s1 += src[(int64_t)(b + RED_SLICES) * stride];
@@ -641,63 +577,125 @@ int out_hw(int n, int s) { return (n - 1) / s + 1; }  // (n + 2*1 - 3) / s + 1
 int64_t out_rows(int B, int heads, int T, int H, int s) { return (int64_t)B * heads * T * out_hw(H, s); }
 int64_t ntok_conv(int B, int heads, int T, int H, int W, int s) { return (int64_t)B * heads * T * out_hw(H, s) * out_hw(W, s); }
 
-// block budgets (shared by the workspace query and the launchers)
-int march_blocks(int B, int heads, int T, int H, int s) { return nblocks_for(ceil_div64(out_rows(B, heads, T, H, s), ROWS), 148 * 8); }
-int cls_blocks(int B, int heads) { return nblocks_for(ceil_div64((int64_t)B * heads, CLS_WARPS), 16); }
-int dw_blocks(int B, int heads, int T, int H, int s) { return nblocks_for(ceil_div64(out_rows(B, heads, T, H, s), ROWS), 148 * 2); }
+// block budgets.  The partial-vector buffers in the workspace are sized for the caps.
+constexpr int MAX_LN_BLOCKS = 148 * 8;
+constexpr int MAX_CLS_BLOCKS = 16;
+constexpr int MAX_DW_BLOCKS = 148 * 2;
+int march_blocks(int B, int heads, int T, int H, int s) { return nblocks_for(ceil_div64(out_rows(B, heads, T, H, s), ROWS), MAX_LN_BLOCKS); }
+int cls_blocks(int B, int heads) { return nblocks_for(ceil_div64((int64_t)B * heads, CLS_WARPS), MAX_CLS_BLOCKS); }
+int dw_blocks(int B, int heads, int T, int H, int s) { return nblocks_for(ceil_div64(out_rows(B, heads, T, H, s), ROWS), MAX_DW_BLOCKS); }
 int input_blocks(int B, int heads, int T, int H) { return nblocks_for(ceil_div64((int64_t)B * heads * T * H, ROWS), 148 * 8); }
 
 int64_t align16(int64_t bytes) { return (bytes + 15) / 16 * 16; }
 
-int fill_launch(Launch& L, const void* qkv, int64_t bs, int64_t ts, int64_t ws_, int64_t hs, const pmv_pool_job* jobs, int njobs,
-                int B, int heads, int T, int H, int W, float eps, int dtype) {
+struct Geom {
+  int B, heads, T, H, W;
+  int64_t bs, ts, hs;
+  float eps;
+  int dtype;
+};
+
+int fill_jobs(Job* J, const void* qkv, int64_t ws_, const pmv_pool_job* jobs, int njobs, const Geom& g) {
   PMV_CHECK_ARG(njobs >= 1 && njobs <= MAX_JOBS, "pool: 1..3 jobs");
-  PMV_CHECK_ARG(B > 0 && heads > 0 && T > 0 && H > 0 && W > 0, "pool: bad geometry");
-  PMV_CHECK_ARG(ts % 4 == 0 && hs % 4 == 0 && ws_ % 4 == 0 && bs % 4 == 0, "pool: strides must be multiples of 4 elements");
-  PMV_CHECK_ARG((int64_t)3 * H * W * ts < (1ll << 31) && (int64_t)B * heads * T * H < (1ll << 29), "pool: volume too large for 32-bit row offsets");
-  const int esz = dtype == PMV_BF16 ? 2 : 4;
-  L.njobs = njobs; L.B = B; L.heads = heads; L.T = T; L.H = H; L.W = W;
-  L.in_bs = bs; L.in_ts = ts; L.in_hs = hs; L.eps = eps; L.partials = nullptr; L.partials_dw = nullptr;
+  PMV_CHECK_ARG(g.B > 0 && g.heads > 0 && g.T > 0 && g.H > 0 && g.W > 0, "pool: bad geometry");
+  PMV_CHECK_ARG(g.ts % 8 == 0 && g.hs % 4 == 0 && ws_ % 4 == 0 && g.bs % 8 == 0, "pool: strides must be multiples of 8 elements");
+  PMV_CHECK_ARG((int64_t)3 * g.H * g.W * g.ts < (1ll << 31) && (int64_t)g.B * g.heads * g.T * g.H < (1ll << 29),
+                "pool: volume too large for 32-bit row offsets");
+  const int esz = g.dtype == PMV_BF16 ? 2 : 4;
   for (int i = 0; i < njobs; ++i) {
-    Job& J = L.job[i];
     const pmv_pool_job& p = jobs[i];
     PMV_CHECK_ARG(p.stride_hw >= 1, "pool: bad stride");
-    J.in = reinterpret_cast<const char*>(qkv) + (int64_t)p.which * ws_ * esz;
-    J.w = p.w; J.gamma = p.gamma; J.beta = p.beta; J.out = p.out; J.out_ld = p.out_ld;
-    J.dout = p.dout; J.dout_ld = p.dout_ld; J.din = nullptr; J.grads = p.grads; J.dconv = nullptr;
-    J.s = p.stride_hw; J.Ho = out_hw(H, p.stride_hw); J.Wo = out_hw(W, p.stride_hw);
-    J.blk_begin = 0; J.nblk = 0; J.ncls_blk = 0; J.blk2_begin = 0; J.nblk2 = 0; J.blk3_begin = 0; J.nblk3 = 0;
+    memset(&J[i], 0, sizeof(Job));
+    J[i].in = reinterpret_cast<const char*>(qkv) + (int64_t)p.which * ws_ * esz;
+    J[i].w = p.w; J[i].gamma = p.gamma; J[i].beta = p.beta; J[i].out = p.out; J[i].out_ld = p.out_ld;
+    J[i].dout = p.dout; J[i].dout_ld = p.dout_ld; J[i].grads = p.grads;
+    J[i].s = p.stride_hw; J[i].Ho = out_hw(g.H, p.stride_hw); J[i].Wo = out_hw(g.W, p.stride_hw);
+  }
+  return PMV_OK;
+}
+
+// Runs one mode over the jobs: those the TMA t-march can take go to pool_tma.cu, the rest to the direct kernels here.
+// mode 0 forward, 1 backward (i), 2 backward (ii), 3 backward (iii).
+int run_mode(int mode, Job* all, int njobs, const Geom& g, cudaStream_t st) {
+  Job tj[MAX_JOBS], dj[MAX_JOBS];
+  int ti[MAX_JOBS], di[MAX_JOBS];
+  int nt = 0, nd = 0;
+  const bool tma_ok = pmv_has_tcgen05() && std::getenv("PMV_POOL_DIRECT") == nullptr;
+  for (int i = 0; i < njobs; ++i) {
+    if (tma_ok && tma_eligible(all[i].s, mode)) { ti[nt] = i; tj[nt++] = all[i]; } else { di[nd] = i; dj[nd++] = all[i]; }
+  }
+  if (nt > 0) {
+    // balanced waves over 2 CTAs per SM
+    int64_t items_total = 0;
+    int items[MAX_JOBS];
+    for (int i = 0; i < nt; ++i) {
+      items[i] = tma_items(g.B, g.heads, mode == 3 ? g.H : tj[i].Ho, mode == 3 ? g.W : tj[i].Wo);
+      items_total += items[i];
+    }
+    const int64_t waves = ceil_div64(items_total, 148 * 2);
+    int total = 0;
+    for (int i = 0; i < nt; ++i) {
+      tj[i].blk_begin = total;
+      tj[i].nblk = nblocks_for(ceil_div64(items[i], waves), mode == 2 ? MAX_DW_BLOCKS : MAX_LN_BLOCKS);
+      tj[i].ncls_blk = (mode == 0 || mode == 1) ? cls_blocks(g.B, g.heads) : 0;
+      total += tj[i].nblk + tj[i].ncls_blk;
+      if (mode == 1) all[ti[i]].nblk_ln = tj[i].nblk + tj[i].ncls_blk;
+      if (mode == 2) all[ti[i]].nblk_dw = tj[i].nblk;
+    }
+    int rc = tma_launch(mode, tj, nt, g.B, g.heads, g.T, g.H, g.W, g.bs, g.ts, g.hs, g.eps, g.dtype, st);
+    if (rc) return rc;
+  }
+  if (nd > 0) {
+    Launch L;
+    L.njobs = nd; L.B = g.B; L.heads = g.heads; L.T = g.T; L.H = g.H; L.W = g.W;
+    L.in_bs = g.bs; L.in_ts = g.ts; L.in_hs = g.hs; L.eps = g.eps;
+    int total = 0;
+    for (int i = 0; i < nd; ++i) {
+      Job& J = dj[i];
+      J.blk_begin = total;
+      J.nblk = mode == 2 ? dw_blocks(g.B, g.heads, g.T, g.H, J.s)
+               : mode == 3 ? input_blocks(g.B, g.heads, g.T, g.H) : march_blocks(g.B, g.heads, g.T, g.H, J.s);
+      J.ncls_blk = (mode == 0 || mode == 1) ? cls_blocks(g.B, g.heads) : 0;
+      total += J.nblk + J.ncls_blk;
+      if (mode == 1) all[di[i]].nblk_ln = J.nblk + J.ncls_blk;
+      if (mode == 2) all[di[i]].nblk_dw = J.nblk;
+      L.job[i] = J;
+    }
+    PMV_DISPATCH_DTYPE(g.dtype, TT, {
+      if (mode == 0) pool_ln_march_kernel<TT, false><<<(unsigned)total, THREADS, 0, st>>>(L);
+      else if (mode == 1) pool_ln_march_kernel<TT, true><<<(unsigned)total, THREADS, 0, st>>>(L);
+      else if (mode == 2) pool_ln_bwd_dw_kernel<TT><<<(unsigned)total, THREADS, 0, st>>>(L);
+      else pool_ln_bwd_input_kernel<TT><<<(unsigned)total, THREADS, 0, st>>>(L);
+    });
+    PMV_CHECK_LAUNCH();
   }
   return PMV_OK;
 }
 
 }  // namespace
+}  // namespace pool
+
+using namespace pool;
 
 extern "C" int pmv_pool_ln_qkv_fwd(const void* qkv, int64_t batch_stride, int64_t token_stride, int64_t which_stride,
                                    int64_t head_stride, const pmv_pool_job* jobs, int njobs,
                                    int B, int heads, int T, int H, int W, float eps, int dtype, void* stream) {
-  Launch L;
-  int rc = fill_launch(L, qkv, batch_stride, token_stride, which_stride, head_stride, jobs, njobs, B, heads, T, H, W, eps, dtype);
+  PMV_CHECK_ARG(dtype == PMV_BF16 || dtype == PMV_F32, "pool: bad dtype");
+  Geom g{B, heads, T, H, W, batch_stride, token_stride, head_stride, eps, dtype};
+  Job J[MAX_JOBS];
+  int rc = fill_jobs(J, qkv, which_stride, jobs, njobs, g);
   if (rc) return rc;
-  int total = 0;
-  for (int i = 0; i < njobs; ++i) {
+  for (int i = 0; i < njobs; ++i)
     PMV_CHECK_ARG(jobs[i].out != nullptr && jobs[i].out_ld % 4 == 0 && jobs[i].out_ld >= HD, "pool: bad output");
-    L.job[i].blk_begin = total;
-    L.job[i].nblk = march_blocks(B, heads, T, H, jobs[i].stride_hw);
-    L.job[i].ncls_blk = cls_blocks(B, heads);
-    total += L.job[i].nblk + L.job[i].ncls_blk;
-  }
-  PMV_DISPATCH_DTYPE(dtype, TT, (pool_ln_march_kernel<TT, false><<<(unsigned)total, THREADS, 0, (cudaStream_t)stream>>>(L)));
-  PMV_CHECK_LAUNCH();
-  return PMV_OK;
+  return run_mode(0, J, njobs, g, (cudaStream_t)stream);
 }
 
 extern "C" int64_t pmv_pool_ln_qkv_bwd_workspace_bytes(int B, int heads, int T, int H, int W, const int* strides_hw, int njobs) {
   int64_t bytes = 0;
   for (int i = 0; i < njobs; ++i) {
     bytes += align16(ntok_conv(B, heads, T, H, W, strides_hw[i]) * HD * 4);  // pre-LN gradient (sized for fp32)
-    bytes += (int64_t)(march_blocks(B, heads, T, H, strides_hw[i]) + cls_blocks(B, heads)) * 2 * HD * 4;
-    bytes += (int64_t)dw_blocks(B, heads, T, H, strides_hw[i]) * NDW * 4;
+    bytes += (int64_t)(MAX_LN_BLOCKS + MAX_CLS_BLOCKS) * 2 * HD * 4;
+    bytes += (int64_t)MAX_DW_BLOCKS * NDW * 4;
   }
   return bytes;
 }
@@ -705,37 +703,32 @@ extern "C" int64_t pmv_pool_ln_qkv_bwd_workspace_bytes(int B, int heads, int T, 
 extern "C" int pmv_pool_ln_qkv_bwd(const void* qkv, int64_t batch_stride, int64_t token_stride, int64_t which_stride,
                                    int64_t head_stride, const pmv_pool_job* jobs, int njobs, void* dqkv, float* ws,
                                    int B, int heads, int T, int H, int W, float eps, int dtype, void* stream) {
-  Launch L;
-  int rc = fill_launch(L, qkv, batch_stride, token_stride, which_stride, head_stride, jobs, njobs, B, heads, T, H, W, eps, dtype);
+  PMV_CHECK_ARG(dtype == PMV_BF16 || dtype == PMV_F32, "pool: bad dtype");
+  Geom g{B, heads, T, H, W, batch_stride, token_stride, head_stride, eps, dtype};
+  Job J[MAX_JOBS];
+  int rc = fill_jobs(J, qkv, which_stride, jobs, njobs, g);
   if (rc) return rc;
   const int esz = dtype == PMV_BF16 ? 2 : 4;
   char* cursor = reinterpret_cast<char*>(ws);
-  int total = 0, total_dw = 0, total_in = 0;
   for (int i = 0; i < njobs; ++i) {
     PMV_CHECK_ARG(jobs[i].dout != nullptr && jobs[i].grads != nullptr && jobs[i].dout_ld % 4 == 0, "pool: bad backward job");
-    Job& J = L.job[i];
-    J.din = reinterpret_cast<char*>(dqkv) + (int64_t)jobs[i].which * which_stride * esz;
-    J.dconv = cursor;
-    cursor += align16(ntok_conv(B, heads, T, H, W, J.s) * HD * 4);
-    J.blk_begin = total;
-    J.nblk = march_blocks(B, heads, T, H, J.s);
-    J.ncls_blk = cls_blocks(B, heads);
-    total += J.nblk + J.ncls_blk;
-    J.blk2_begin = total_dw;
-    J.nblk2 = dw_blocks(B, heads, T, H, J.s);
-    total_dw += J.nblk2;
-    J.blk3_begin = total_in;
-    J.nblk3 = input_blocks(B, heads, T, H);
-    total_in += J.nblk3;
+    J[i].din = reinterpret_cast<char*>(dqkv) + (int64_t)jobs[i].which * which_stride * esz;
+    J[i].dconv = cursor;
+    cursor += align16(ntok_conv(B, heads, T, H, W, J[i].s) * HD * 4);
+    J[i].part_ln = reinterpret_cast<float*>(cursor);
+    cursor += (int64_t)(MAX_LN_BLOCKS + MAX_CLS_BLOCKS) * 2 * HD * 4;
+    J[i].part_dw = reinterpret_cast<float*>(cursor);
+    cursor += (int64_t)MAX_DW_BLOCKS * NDW * 4;
   }
-  L.partials = reinterpret_cast<float*>(cursor);
-  L.partials_dw = L.partials + (int64_t)total * 2 * HD;
   cudaStream_t st = (cudaStream_t)stream;
-  PMV_DISPATCH_DTYPE(dtype, TT, {
-    pool_ln_march_kernel<TT, true><<<(unsigned)total, THREADS, 0, st>>>(L);
-    pool_ln_bwd_dw_kernel<TT><<<(unsigned)total_dw, THREADS, 0, st>>>(L);
-    pool_ln_bwd_input_kernel<TT><<<(unsigned)total_in, THREADS, 0, st>>>(L);
-  });
+  for (int mode = 1; mode <= 3; ++mode) {
+    rc = run_mode(mode, J, njobs, g, st);
+    if (rc) return rc;
+  }
+  Launch L;
+  L.njobs = njobs; L.B = B; L.heads = heads; L.T = T; L.H = H; L.W = W;
+  L.in_bs = batch_stride; L.in_ts = token_stride; L.in_hs = head_stride; L.eps = eps;
+  for (int i = 0; i < njobs; ++i) L.job[i] = J[i];
   reduce_jobs_kernel<<<dim3((NGRAD + 255) / 256, njobs, RED_SLICES), 256, 0, st>>>(L);
   PMV_CHECK_LAUNCH();
   return PMV_OK;

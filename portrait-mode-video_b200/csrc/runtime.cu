@@ -81,3 +81,13 @@ int pmv_make_tensor_map_3d(CUtensorMap* out, const void* base, int elem_bytes, u
   cuuint32_t box[3] = {box0, box1, box2};
   return encode(out, base, elem_bytes, 3, dims, strides, box, swizzle);
 }
+
+int pmv_make_tensor_map_5d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
+                           uint64_t d4, uint64_t s1_elems, uint64_t s2_elems, uint64_t s3_elems, uint64_t s4_elems, uint32_t b0,
+                           uint32_t b1, uint32_t b2, uint32_t b3, uint32_t b4) {
+  cuuint64_t dims[5] = {d0, d1, d2, d3, d4};
+  cuuint64_t strides[4] = {s1_elems * (uint64_t)elem_bytes, s2_elems * (uint64_t)elem_bytes, s3_elems * (uint64_t)elem_bytes,
+                           s4_elems * (uint64_t)elem_bytes};
+  cuuint32_t box[5] = {b0, b1, b2, b3, b4};
+  return encode(out, base, elem_bytes, 5, dims, strides, box, 0);
+}
