@@ -151,6 +151,8 @@ typedef struct {
   float* grads;        /* backward */
   int stride_hw;
   int which;           /* 0 = q, 1 = k, 2 = v */
+  void* xhat;          /* optional [B, heads, 1+T*Ho*Wo, 96] (dtype): forward saves the normalised pre-affine tokens, */
+  float* rstd;         /* optional [B, heads, 1+T*Ho*Wo]: ... and 1/sigma; backward then skips the convolution recompute */
 } pmv_pool_job;
 int pmv_pool_ln_qkv_fwd(const void* qkv, int64_t batch_stride, int64_t token_stride, int64_t which_stride, int64_t head_stride,
                         const pmv_pool_job* jobs, int njobs, int B, int heads, int T, int H, int W, float eps, int dtype,

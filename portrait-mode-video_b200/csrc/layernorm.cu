@@ -1,6 +1,6 @@
 // LayerNorm forward / backward over the channel axis of the fp32 residual stream.
 // Replaces native_layer_norm at attention.py:567,578 and video_model_builder.py:2163.
-// Memory-bound: one warp per row, 16-byte loads, two-pass (mean, then centred variance) in fp32.
+// Memory-bound: 8 / 16 / 32 lanes per row, 16-byte loads, two-pass (mean, then centred variance) in fp32.
 #include "common.cuh"
 #include "reduce.cuh"
 
@@ -8,157 +8,210 @@ namespace {
 
 constexpr int LN_WARPS = 8;
 
-template <typename TOut>
+// A row of C = 4 * LPR * VPL channels is owned by LPR lanes (LPR in {8, 16, 32}), each with VPL float4: a warp
+// works on 32 / LPR rows at once, every lane has VPL independent 16-byte loads in flight and consecutive lanes read
+// consecutive 16-byte pieces.  (The first version gave one row to one warp whatever C was: at C = 96 a warp had
+// 384 bytes in flight and 8 idle lanes, 1.0 TB/s.)
+template <int LPR, int VPL, typename TOut>
 __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_fwd_kernel(
     const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-    TOut* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int64_t rows, int C, float eps) {
+    TOut* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int64_t rows, float eps) {
+  constexpr int C = 4 * LPR * VPL;
+  constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
-  const int64_t warp0 = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.x * LN_WARPS;
-  const int nvec = C >> 2;  // C % 4 == 0 checked on the host
-  for (int64_t r = warp0; r < rows; r += nwarps) {
-    const float* xr = x + r * C;
-    // C <= 768 in MViTv2: at most 6 float4 per lane; keep the row in registers
-    float v[8][4];
+  const int sub = lane % LPR, rw = lane / LPR;
+  const int64_t row0 = ((int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5)) * RPW + rw;
+  const int64_t rstep = (int64_t)gridDim.x * LN_WARPS * RPW;
+  float g[VPL][4], b[VPL][4];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    load4(gamma + (sub + i * LPR) * 4, g[i]);
+    load4(beta + (sub + i * LPR) * 4, b[i]);
+  }
+  for (int64_t r0 = row0 - rw; r0 < rows; r0 += rstep) {  // warp-uniform trip count (shuffles inside)
+    const int64_t r = r0 + rw;
+    const bool ok = r < rows;
+    const float* xr = x + (ok ? r : 0) * C;
+    float v[VPL][4];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int c4 = lane + i * 32;
-      if (c4 < nvec) {
-        load4(xr + c4 * 4, v[i]);
-        s += v[i][0] + v[i][1] + v[i][2] + v[i][3];
-      }
+    for (int i = 0; i < VPL; ++i) {
+      load4(xr + (sub + i * LPR) * 4, v[i]);
+      s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
     }
-    const float mu = warp_sum(s) / (float)C;
+    const float mu = group_sum<LPR>(s) * (1.0f / C);
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int c4 = lane + i * 32;
-      if (c4 < nvec) {
+    for (int i = 0; i < VPL; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { float d = v[i][j] - mu; q += d * d; }
-      }
-    }
-    const float rs = rsqrtf(warp_sum(q) / (float)C + eps);
-    if (lane == 0 && mean != nullptr) { mean[r] = mu; rstd[r] = rs; }
+      for (int j = 0; j < 4; ++j) { const float d = v[i][j] - mu; q += d * d; }
+    const float rs = rsqrtf(group_sum<LPR>(q) * (1.0f / C) + eps);
+    if (!ok) continue;
+    if (sub == 0 && mean != nullptr) { mean[r] = mu; rstd[r] = rs; }
     TOut* yr = y + r * C;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int c4 = lane + i * 32;
-      if (c4 < nvec) {
-        float g[4], b[4], o[4];
-        load4(gamma + c4 * 4, g);
-        load4(beta + c4 * 4, b);
+    for (int i = 0; i < VPL; ++i) {
+      float o[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = (v[i][j] - mu) * rs * g[j] + b[j];
-        store4(yr + c4 * 4, o);
-      }
+      for (int j = 0; j < 4; ++j) o[j] = (v[i][j] - mu) * rs * g[i][j] + b[i][j];
+      store4(yr + (sub + i * LPR) * 4, o);
     }
   }
 }
 
 // Backward.  Per row:  xhat = (x-mu)*rstd, g = dy*gamma,
 //   dx = rstd * (g - mean(g) - xhat*mean(g*xhat));  dgamma += dy*xhat; dbeta += dy.
-// dgamma/dbeta: per-thread partials over the rows this warp visits -> smem reduce over warps ->
-// one partial vector per block (folded by reduce_partials_kernel; dgamma and dbeta must be adjacent: [2][C]).
-template <typename TDy>
+// dgamma/dbeta: per-lane partials over the rows this lane visits -> shuffle over the rows of the warp -> smem over
+// the warps -> one partial vector [2][C] per block (folded by reduce_partials_kernel).
+template <int LPR, int VPL, typename TDy>
 __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(
     const TDy* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
     const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dx, int accumulate,
-    float* __restrict__ partials, int64_t rows, int C) {
-  extern __shared__ float red[];  // [2][C]
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int64_t warp0 = (int64_t)blockIdx.x * LN_WARPS + warp;
-  const int64_t nwarps = (int64_t)gridDim.x * LN_WARPS;
-  const int nvec = C >> 2;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
-  float dg[8][4], db[8][4];
+    float* __restrict__ partials, int64_t rows) {
+  constexpr int C = 4 * LPR * VPL;
+  constexpr int RPW = 32 / LPR;
+  __shared__ float red[LN_WARPS][2 * C];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane % LPR, rw = lane / LPR;
+  const int64_t row0 = ((int64_t)blockIdx.x * LN_WARPS + warp) * RPW;
+  const int64_t rstep = (int64_t)gridDim.x * LN_WARPS * RPW;
+  float gm[VPL][4], dg[VPL][4], db[VPL][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < VPL; ++i) {
+    load4(gamma + (sub + i * LPR) * 4, gm[i]);
 #pragma unroll
     for (int j = 0; j < 4; ++j) dg[i][j] = db[i][j] = 0.f;
-
-  for (int64_t r = warp0; r < rows; r += nwarps) {
-    const float mu = mean[r], rs = rstd[r];
-    const float* xr = x + r * C;
-    const TDy* dyr = dy + r * C;
-    float xh[8][4], g[8][4];
+  }
+  for (int64_t r0 = row0; r0 < rows; r0 += rstep) {
+    const int64_t r = r0 + rw;
+    const bool ok = r < rows;
+    const int64_t rr = ok ? r : 0;
+    const float mu = mean[rr], rs = ok ? rstd[rr] : 0.f;
+    const float* xr = x + rr * C;
+    const TDy* dyr = dy + rr * C;
+    float xh[VPL][4], g[VPL][4];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int c4 = lane + i * 32;
-      if (c4 < nvec) {
-        float xv[4], dv[4], gm[4];
-        load4(xr + c4 * 4, xv);
-        load4(dyr + c4 * 4, dv);
-        load4(gamma + c4 * 4, gm);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          xh[i][j] = (xv[j] - mu) * rs;
-          g[i][j] = dv[j] * gm[j];
-          s1 += g[i][j];
-          s2 += g[i][j] * xh[i][j];
-          dg[i][j] += dv[j] * xh[i][j];
-          db[i][j] += dv[j];
-        }
-      }
-    }
-    s1 = warp_sum(s1) / (float)C;
-    s2 = warp_sum(s2) / (float)C;
-    float* dxr = dx + r * C;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int c4 = lane + i * 32;
-      if (c4 < nvec) {
-        float o[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = rs * (g[i][j] - s1 - xh[i][j] * s2);
-        if (accumulate) {
-          float p[4];
-          load4(dxr + c4 * 4, p);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] += p[j];
-        }
-        store4(dxr + c4 * 4, o);
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    int c4 = lane + i * 32;
-    if (c4 < nvec) {
+    for (int i = 0; i < VPL; ++i) {
+      float xv[4], dv[4];
+      load4(xr + (sub + i * LPR) * 4, xv);
+      load4(dyr + (sub + i * LPR) * 4, dv);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        atomicAdd(&red[c4 * 4 + j], dg[i][j]);
-        atomicAdd(&red[C + c4 * 4 + j], db[i][j]);
+        if (!ok) dv[j] = 0.f;
+        xh[i][j] = (xv[j] - mu) * rs;
+        g[i][j] = dv[j] * gm[i][j];
+        s1 += g[i][j];
+        s2 += g[i][j] * xh[i][j];
+        dg[i][j] += dv[j] * xh[i][j];
+        db[i][j] += dv[j];
       }
     }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    s1 *= (1.0f / C);
+    s2 *= (1.0f / C);
+    if (!ok) continue;
+    float* dxr = dx + r * C;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = rs * (g[i][j] - s1 - xh[i][j] * s2);
+      if (accumulate) {
+        float p[4];
+        load4(dxr + (sub + i * LPR) * 4, p);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] += p[j];
+      }
+      store4(dxr + (sub + i * LPR) * 4, o);
+    }
+  }
+  // fold the RPW rows of the warp (lanes with the same `sub`), then the warps
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int o = LPR; o < 32; o <<= 1) {
+        dg[i][j] += __shfl_xor_sync(0xffffffffu, dg[i][j], o);
+        db[i][j] += __shfl_xor_sync(0xffffffffu, db[i][j], o);
+      }
+    }
+  if (rw == 0) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        red[warp][(sub + i * LPR) * 4 + j] = dg[i][j];
+        red[warp][C + (sub + i * LPR) * 4 + j] = db[i][j];
+      }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) partials[(int64_t)blockIdx.x * 2 * C + i] = red[i];
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < LN_WARPS; ++w) s += red[w][i];
+    partials[(int64_t)blockIdx.x * 2 * C + i] = s;
+  }
 }
+
+template <int LPR, int VPL>
+int launch_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_dtype, float* mean, float* rstd, int64_t rows,
+               float eps, cudaStream_t st) {
+  int64_t blocks = ceil_div64(rows, LN_WARPS * (32 / LPR) * 2);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  PMV_DISPATCH_DTYPE(y_dtype, T, (layernorm_fwd_kernel<LPR, VPL, T><<<(unsigned)blocks, LN_WARPS * 32, 0, st>>>(
+                                     x, gamma, beta, (T*)y, mean, rstd, rows, eps)));
+  PMV_CHECK_LAUNCH();
+  return PMV_OK;
+}
+
+int64_t ln_bwd_blocks(int64_t rows) {
+  int64_t blocks = ceil_div64(rows, LN_WARPS * 4);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  return blocks < 1 ? 1 : blocks;
+}
+
+template <int LPR, int VPL>
+int launch_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma, const float* mean, const float* rstd, float* dx,
+               int accumulate, float* ws, int64_t rows, cudaStream_t st) {
+  const int64_t blocks = ln_bwd_blocks(rows);
+  PMV_DISPATCH_DTYPE(dy_dtype, T, (layernorm_bwd_kernel<LPR, VPL, T><<<(unsigned)blocks, LN_WARPS * 32, 0, st>>>(
+                                      (const T*)dy, x, gamma, mean, rstd, dx, accumulate, ws, rows)));
+  PMV_CHECK_LAUNCH();
+  return PMV_OK;
+}
+
+// C -> (lanes per row, float4 per lane)
+#define PMV_LN_DISPATCH(C, CALL)                                   \
+  switch (C) {                                                     \
+    case 96: { constexpr int LPR = 8, VPL = 3; CALL; } break;      \
+    case 192: { constexpr int LPR = 16, VPL = 3; CALL; } break;    \
+    case 384: { constexpr int LPR = 32, VPL = 3; CALL; } break;    \
+    case 768: { constexpr int LPR = 32, VPL = 6; CALL; } break;    \
+    case 128: { constexpr int LPR = 32, VPL = 1; CALL; } break;    \
+    case 256: { constexpr int LPR = 32, VPL = 2; CALL; } break;    \
+    case 512: { constexpr int LPR = 32, VPL = 4; CALL; } break;    \
+    case 32: { constexpr int LPR = 8, VPL = 1; CALL; } break;      \
+    case 64: { constexpr int LPR = 16, VPL = 1; CALL; } break;     \
+    default:                                                       \
+      pmv_set_error("layernorm: unsupported channel count %d (supported: 32 64 96 128 192 256 384 512 768)", C); \
+      return PMV_ERR_UNSUPPORTED;                                  \
+  }
 
 }  // namespace
 
 extern "C" int pmv_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_dtype,
                                  float* mean, float* rstd, int64_t rows, int C, float eps, void* stream) {
-  PMV_CHECK_ARG(C % 4 == 0 && C <= 1024 && C > 0, "layernorm: C=%d must be a multiple of 4 and <= 1024", C);
   PMV_CHECK_ARG((mean == nullptr) == (rstd == nullptr), "layernorm: mean and rstd must both be given or both NULL");
   if (rows == 0) return PMV_OK;
-  int64_t blocks = ceil_div64(rows, LN_WARPS);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  PMV_DISPATCH_DTYPE(y_dtype, T, (layernorm_fwd_kernel<T><<<(unsigned)blocks, LN_WARPS * 32, 0, (cudaStream_t)stream>>>(
-                                     x, gamma, beta, (T*)y, mean, rstd, rows, C, eps)));
-  PMV_CHECK_LAUNCH();
-  return PMV_OK;
-}
-
-static int64_t ln_bwd_blocks(int64_t rows) {
-  int64_t blocks = ceil_div64(rows, LN_WARPS * 4);
-  if (blocks > 148 * 2) blocks = 148 * 2;
-  return blocks < 1 ? 1 : blocks;
+  int rc = PMV_OK;
+  PMV_LN_DISPATCH(C, (rc = launch_fwd<LPR, VPL>(x, gamma, beta, y, y_dtype, mean, rstd, rows, eps, (cudaStream_t)stream)));
+  return rc;
 }
 
 extern "C" int64_t pmv_layernorm_bwd_workspace_bytes(int64_t rows, int C) { return ln_bwd_blocks(rows) * 2 * C * (int64_t)sizeof(float); }
@@ -166,13 +219,11 @@ extern "C" int64_t pmv_layernorm_bwd_workspace_bytes(int64_t rows, int C) { retu
 extern "C" int pmv_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma,
                                  const float* mean, const float* rstd, float* dx, int accumulate,
                                  float* dgamma_dbeta, float* ws, int64_t rows, int C, void* stream) {
-  PMV_CHECK_ARG(C % 4 == 0 && C <= 1024 && C > 0, "layernorm: C=%d must be a multiple of 4 and <= 1024", C);
   if (rows == 0) return PMV_OK;
-  const int64_t blocks = ln_bwd_blocks(rows);
-  size_t smem = 2 * (size_t)C * sizeof(float);
-  PMV_DISPATCH_DTYPE(dy_dtype, T, (layernorm_bwd_kernel<T><<<(unsigned)blocks, LN_WARPS * 32, smem, (cudaStream_t)stream>>>(
-                                      (const T*)dy, x, gamma, mean, rstd, dx, accumulate, ws, rows, C)));
-  launch_reduce_partials(ws, (int)blocks, 2 * C, dgamma_dbeta, (cudaStream_t)stream);
+  int rc = PMV_OK;
+  PMV_LN_DISPATCH(C, (rc = launch_bwd<LPR, VPL>(dy, dy_dtype, x, gamma, mean, rstd, dx, accumulate, ws, rows, (cudaStream_t)stream)));
+  if (rc) return rc;
+  launch_reduce_partials(ws, (int)ln_bwd_blocks(rows), 2 * C, dgamma_dbeta, (cudaStream_t)stream);
   PMV_CHECK_LAUNCH();
   return PMV_OK;
 }

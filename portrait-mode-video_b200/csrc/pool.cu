@@ -155,6 +155,12 @@ __global__ void __launch_bounds__(THREADS, 2) pool_ln_march_kernel(const __grid_
         T* o = reinterpret_cast<T*>(J.out) + tok * J.out_ld + lane;
 #pragma unroll
         for (int j = 0; j < 3; ++j) o[32 * j] = from_f32<T>((v[j] - mu) * rs * sgam[lane + 32 * j] + sbet[lane + 32 * j]);
+        if (J.xhat) {
+          T* xo = reinterpret_cast<T*>(J.xhat) + tok * HD + lane;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) xo[32 * j] = from_f32<T>((v[j] - mu) * rs);
+          if (lane == 0) J.rstd[tok] = rs;
+        }
       } else {
         const T* dyr = reinterpret_cast<const T*>(J.dout) + tok * J.dout_ld + lane;
         float xh[3], gg[3], s1 = 0.f, s2 = 0.f;
@@ -287,8 +293,14 @@ __global__ void __launch_bounds__(THREADS, 2) pool_ln_march_kernel(const __grid_
         if (!BWD) {
           float o[CPL];
 #pragma unroll
-          for (int j = 0; j < CPL; ++j) o[j] = (v[j] - mu) * rs * sgam[sub * CPL + j] + sbet[sub * CPL + j];
-          if (tvalid) store12(reinterpret_cast<T*>(J.out) + (otok + c0 + g_w) * J.out_ld + sub * CPL, o);
+          for (int j = 0; j < CPL; ++j) { v[j] = (v[j] - mu) * rs; o[j] = v[j] * sgam[sub * CPL + j] + sbet[sub * CPL + j]; }
+          if (tvalid) {
+            store12(reinterpret_cast<T*>(J.out) + (otok + c0 + g_w) * J.out_ld + sub * CPL, o);
+            if (J.xhat) {
+              store12(reinterpret_cast<T*>(J.xhat) + (otok + c0 + g_w) * HD + sub * CPL, v);
+              if (sub == 0) J.rstd[otok + c0 + g_w] = rs;
+            }
+          }
         } else {
           float dy[CPL];
           if (tvalid) {
@@ -545,6 +557,85 @@ __global__ void __launch_bounds__(THREADS, 2) pool_ln_bwd_input_kernel(const __g
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// backward (i) from saved statistics: the forward kept xhat (normalised, pre-affine) and 1/sigma, so the LayerNorm
+// backward is a plain token-wise pass (no convolution recompute): 8 lanes per token, 12 channels per lane.
+//   g = dy * gamma;  dconv = rstd * (g - mean(g) - xhat * mean(g * xhat));  dgamma += dy * xhat;  dbeta += dy
+// cls tokens write their gradient straight into din (no convolution in front of them).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SV_THREADS = 256;
+constexpr int SV_TOK = SV_THREADS / LNL;  // 32 tokens per pass
+template <typename T>
+__global__ void __launch_bounds__(SV_THREADS) pool_ln_bwd_saved_kernel(const __grid_constant__ Launch L) {
+  __shared__ float red[SV_TOK * 2 * HD];
+  __shared__ float sgam[HD];
+  const Job& J = L.job[find_job(L)];
+  const int tid = threadIdx.x;
+  const int lb = blockIdx.x - J.blk_begin;
+  if (tid < HD) sgam[tid] = J.gamma[tid];
+  __syncthreads();
+  const int g = tid >> 3, sub = tid & 7;
+  const int Lo = L.T * J.Ho * J.Wo;
+  const int64_t ntok = (int64_t)L.B * L.heads * (Lo + 1);
+  const T* __restrict__ xhat = reinterpret_cast<const T*>(J.xhat);
+  const T* __restrict__ dout = reinterpret_cast<const T*>(J.dout);
+  float gm[CPL], adg[CPL], adb[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) { gm[j] = sgam[sub * CPL + j]; adg[j] = 0.f; adb[j] = 0.f; }
+  for (int64_t t0 = (int64_t)lb * SV_TOK; t0 < ntok; t0 += (int64_t)J.nblk * SV_TOK) {
+    const int64_t tok = t0 + g;
+    const bool ok = tok < ntok;
+    const int64_t tk = ok ? tok : 0;
+    float xh[CPL], dy[CPL];
+    load12(xhat + tk * HD + sub * CPL, xh);
+    load12(dout + tk * J.dout_ld + sub * CPL, dy);
+    const float rs = ok ? J.rstd[tk] : 0.f;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      if (!ok) dy[j] = 0.f;
+      const float gg = dy[j] * gm[j];
+      s1 += gg;
+      s2 += gg * xh[j];
+      adg[j] += dy[j] * xh[j];
+      adb[j] += dy[j];
+      dy[j] = gg;
+    }
+#pragma unroll
+    for (int o = LNL / 2; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    s1 *= (1.0f / HD);
+    s2 *= (1.0f / HD);
+    if (!ok) continue;
+    float dc[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) dc[j] = rs * (dy[j] - s1 - xh[j] * s2);
+    const int64_t bh = tok / (Lo + 1);
+    const int n = (int)(tok - bh * (Lo + 1));
+    if (n == 0) {
+      const int head = (int)(bh % L.heads);
+      const int64_t b = bh / L.heads;
+      store12(reinterpret_cast<T*>(J.din) + b * L.in_bs + head * L.in_hs + sub * CPL, dc);
+    } else {
+      store12(reinterpret_cast<T*>(J.dconv) + (bh * Lo + (n - 1)) * HD + sub * CPL, dc);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    red[g * 2 * HD + sub * CPL + j] = adg[j];
+    red[g * 2 * HD + HD + sub * CPL + j] = adb[j];
+  }
+  __syncthreads();
+  if (tid < 2 * HD) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int gg = 0; gg < SV_TOK; ++gg) s += red[gg * 2 * HD + tid];
+    J.part_ln[(int64_t)lb * 2 * HD + tid] = s;
+  }
+}
+
 // grads_j[i] += sum over the job's partial vectors: dW from backward (ii), dgamma / dbeta from backward (i)
 // (grid.y = job, grid.z = slice of the partial vectors)
 constexpr int RED_SLICES = 8;
@@ -608,7 +699,7 @@ int fill_jobs(Job* J, const void* qkv, int64_t ws_, const pmv_pool_job* jobs, in
     memset(&J[i], 0, sizeof(Job));
     J[i].in = reinterpret_cast<const char*>(qkv) + (int64_t)p.which * ws_ * esz;
     J[i].w = p.w; J[i].gamma = p.gamma; J[i].beta = p.beta; J[i].out = p.out; J[i].out_ld = p.out_ld;
-    J[i].dout = p.dout; J[i].dout_ld = p.dout_ld; J[i].grads = p.grads;
+    J[i].dout = p.dout; J[i].dout_ld = p.dout_ld; J[i].grads = p.grads; J[i].xhat = p.xhat; J[i].rstd = p.rstd;
     J[i].s = p.stride_hw; J[i].Ho = out_hw(g.H, p.stride_hw); J[i].Wo = out_hw(g.W, p.stride_hw);
   }
   return PMV_OK;
@@ -721,7 +812,39 @@ extern "C" int pmv_pool_ln_qkv_bwd(const void* qkv, int64_t batch_stride, int64_
     cursor += (int64_t)MAX_DW_BLOCKS * NDW * 4;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  for (int mode = 1; mode <= 3; ++mode) {
+  // backward (i): token-wise from the saved statistics where the forward kept them, otherwise with the recompute
+  {
+    Job rj[MAX_JOBS];
+    int ri[MAX_JOBS];
+    int nr = 0;
+    Launch LS;
+    LS.njobs = 0; LS.B = B; LS.heads = heads; LS.T = T; LS.H = H; LS.W = W;
+    LS.in_bs = batch_stride; LS.in_ts = token_stride; LS.in_hs = head_stride; LS.eps = eps;
+    int total = 0;
+    for (int i = 0; i < njobs; ++i) {
+      if (J[i].xhat != nullptr && J[i].rstd != nullptr) {
+        const int64_t ntok = (int64_t)B * heads * (1 + (int64_t)T * J[i].Ho * J[i].Wo);
+        J[i].blk_begin = total;
+        J[i].nblk = nblocks_for(ceil_div64(ntok, SV_TOK * 4), 148 * 4);
+        J[i].nblk_ln = J[i].nblk;
+        total += J[i].nblk;
+        LS.job[LS.njobs++] = J[i];
+      } else {
+        ri[nr] = i;
+        rj[nr++] = J[i];
+      }
+    }
+    if (LS.njobs > 0) {
+      PMV_DISPATCH_DTYPE(dtype, TT, (pool_ln_bwd_saved_kernel<TT><<<(unsigned)total, SV_THREADS, 0, st>>>(LS)));
+      PMV_CHECK_LAUNCH();
+    }
+    if (nr > 0) {
+      rc = run_mode(1, rj, nr, g, st);
+      if (rc) return rc;
+      for (int k = 0; k < nr; ++k) J[ri[k]].nblk_ln = rj[k].nblk_ln;
+    }
+  }
+  for (int mode = 2; mode <= 3; ++mode) {
     rc = run_mode(mode, J, njobs, g, st);
     if (rc) return rc;
   }

@@ -28,6 +28,8 @@ struct Job {
   void* din;            // backward: gradient wrt `in` (same strides)
   float* grads;         // backward: [NGRAD] fp32, added to
   void* dconv;          // backward: pre-LN gradient [B*heads*Lo*96] in the compute dtype
+  void* xhat;           // optional: normalised pre-affine tokens [B*heads*(1+Lo)][96] (forward writes, backward reads)
+  float* rstd;          // optional: [B*heads*(1+Lo)]
   float* part_ln;       // backward (i): [nblk + ncls_blk][2 * 96] per-CTA partials (dgamma, dbeta)
   float* part_dw;       // backward (ii): [nblk2][96 * 27] per-CTA partials
   int s, Ho, Wo;

@@ -239,8 +239,15 @@ __device__ __forceinline__ void march(const TLaunch& L, const Job& J, const CUte
         if (MODE == M_FWD) {
           float o[CPL];
 #pragma unroll
-          for (int j = 0; j < CPL; ++j) o[j] = (v[j] - mu) * rs * sgam[sub * CPL + j] + sbet[sub * CPL + j];
-          if (tvalid) store12(reinterpret_cast<T*>(J.out) + (bh * (Lo + 1) + 1 + pos) * J.out_ld + sub * CPL, o);
+          for (int j = 0; j < CPL; ++j) { v[j] = (v[j] - mu) * rs; o[j] = v[j] * sgam[sub * CPL + j] + sbet[sub * CPL + j]; }
+          if (tvalid) {
+            const int64_t otok = bh * (Lo + 1) + 1 + pos;
+            store12(reinterpret_cast<T*>(J.out) + otok * J.out_ld + sub * CPL, o);
+            if (J.xhat) {
+              store12(reinterpret_cast<T*>(J.xhat) + otok * HD + sub * CPL, v);
+              if (sub == 0) J.rstd[otok] = rs;
+            }
+          }
         } else {
           float dy[CPL];
           if (tvalid) {
@@ -371,6 +378,12 @@ __global__ void __launch_bounds__(THREADS, 2) pool_tma_kernel(const __grid_const
         T* o = reinterpret_cast<T*>(J.out) + tok * J.out_ld + lane;
 #pragma unroll
         for (int j = 0; j < 3; ++j) o[32 * j] = from_f32<T>((v[j] - mu) * rs * sgam[lane + 32 * j] + sbet[lane + 32 * j]);
+        if (J.xhat) {
+          T* xo = reinterpret_cast<T*>(J.xhat) + tok * HD + lane;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) xo[32 * j] = from_f32<T>((v[j] - mu) * rs);
+          if (lane == 0) J.rstd[tok] = rs;
+        }
       } else {
         const T* dyr = reinterpret_cast<const T*>(J.dout) + tok * J.dout_ld + lane;
         float xh[3], gg[3], s1 = 0.f, s2 = 0.f;

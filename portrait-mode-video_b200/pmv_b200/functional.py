@@ -183,24 +183,31 @@ class PoolAttentionFn(Function):
         q_aug = torch.empty(B * heads, Nq, ld, dtype=T, device=dev)
         k_aug = torch.empty(B * heads, Nk, ld, dtype=T, device=dev)
         v = torch.empty(B * heads, Nk, 96, dtype=T, device=dev)
-        ops.pool_ln_qkv_fwd(qkv5, heads, thw, [(0, stride_q, wq, gq, bq, q_aug.view(B, heads, Nq, ld)),
-                                               (1, stride_kv, wk, gk, bk, k_aug.view(B, heads, Nk, ld)),
-                                               (2, stride_kv, wv, gv, bv, v.view(B, heads, Nk, 96))], eps)
+        need = any(ctx.needs_input_grad)
+        saved = []
+        if need:  # normalised pre-affine tokens + 1/sigma: the backward LayerNorm needs no convolution recompute
+            for n_tok in (Nq, Nk, Nk):
+                saved += [torch.empty(B, heads, n_tok, 96, dtype=T, device=dev),
+                          torch.empty(B, heads, n_tok, dtype=torch.float32, device=dev)]
+        extra = [tuple(saved[2 * i:2 * i + 2]) for i in range(3)] if need else [(), (), ()]
+        ops.pool_ln_qkv_fwd(qkv5, heads, thw, [(0, stride_q, wq, gq, bq, q_aug.view(B, heads, Nq, ld)) + extra[0],
+                                               (1, stride_kv, wk, gk, bk, k_aug.view(B, heads, Nk, ld)) + extra[1],
+                                               (2, stride_kv, wv, gv, bv, v.view(B, heads, Nk, 96)) + extra[2]], eps)
         if has_rel:
             ops.relpos_augment_q(q_aug, q_shape, k_shape, rel_h, rel_w, rel_t, 1.0 / scale)
             ops.relpos_augment_k(k_aug, k_shape)
-        need = any(ctx.needs_input_grad)
         out, out_pre, lse = ops.attention_fwd(q_aug, k_aug, v, B, heads, ld, scale, residual=residual, want_lse=need,
                                      tc=(1 if (use_tc_attn and T == torch.bfloat16) else 0))
         if need:
-            ctx.save_for_backward(qkv5, q_aug, k_aug, v, out_pre, lse, wq, wk, wv, gq, gk, gv, rel_h, rel_w, rel_t)
+            ctx.save_for_backward(qkv5, q_aug, k_aug, v, out_pre, lse, wq, wk, wv, gq, gk, gv, rel_h, rel_w, rel_t, *saved)
         ctx.meta = (heads, tuple(thw), stride_q, stride_kv, q_shape, k_shape, scale, residual, ld, has_rel, eps,
                     bool(use_tc_attn and T == torch.bfloat16 and ld in (128, 160)))
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        qkv5, q_aug, k_aug, v, out, lse, wq, wk, wv, gq, gk, gv, rel_h, rel_w, rel_t = ctx.saved_tensors
+        qkv5, q_aug, k_aug, v, out, lse, wq, wk, wv, gq, gk, gv, rel_h, rel_w, rel_t, *saved = ctx.saved_tensors
+        extra = [tuple(saved[2 * i:2 * i + 2]) for i in range(3)]
         heads, thw, sq, skv, q_shape, k_shape, scale, residual, ld, has_rel, eps, tc_bwd = ctx.meta
         B, N = qkv5.shape[0], qkv5.shape[1]
         Nq, Nk = q_aug.shape[1], k_aug.shape[1]
@@ -211,9 +218,9 @@ class PoolAttentionFn(Function):
             drh, drw, drt = ops.relpos_augment_q_bwd(dq_aug, q_aug, q_shape, k_shape, rel_h, rel_w, rel_t, 1.0 / scale)
         dqkv = torch.empty_like(qkv5)
         g = torch.zeros(3, 96 * 27 + 192, dtype=torch.float32, device=qkv5.device)
-        ops.pool_ln_qkv_bwd(qkv5, heads, thw, [(0, sq, wq, gq, dq_aug.view(B, heads, Nq, ld), g[0]),
-                                               (1, skv, wk, gk, dk.view(B, heads, Nk, 96), g[1]),
-                                               (2, skv, wv, gv, dv.view(B, heads, Nk, 96), g[2])], dqkv, eps)
+        ops.pool_ln_qkv_bwd(qkv5, heads, thw, [(0, sq, wq, gq, dq_aug.view(B, heads, Nq, ld), g[0]) + extra[0],
+                                               (1, skv, wk, gk, dk.view(B, heads, Nk, 96), g[1]) + extra[1],
+                                               (2, skv, wv, gv, dv.view(B, heads, Nk, 96), g[2]) + extra[2]], dqkv, eps)
         dw = [g[i, :2592].view(96, 1, 3, 3, 3) for i in range(3)]
         dg = [g[i, 2592:2688] for i in range(3)]
         db = [g[i, 2688:] for i in range(3)]

@@ -183,28 +183,36 @@ def pool_ln_bwd(qkv, which, heads, thw, stride_hw, w, gamma, dout, dqkv, grads, 
 
 
 def pool_ln_qkv_fwd(qkv, heads, thw, jobs, eps=LN_EPS):
-    """q / k / v pooled in one launch.  qkv: [B, N, 3, heads, 96]; jobs: list of (which, stride_hw, w, gamma, beta, out)
-    with out [B, heads, 1+L', ld]."""
+    """q / k / v pooled in one launch.  qkv: [B, N, 3, heads, 96]; jobs: list of (which, stride_hw, w, gamma, beta, out
+    [, xhat, rstd]) with out [B, heads, 1+L', ld]; xhat [B, heads, 1+L', 96] / rstd [B, heads, 1+L'] (optional) receive the
+    normalised pre-affine tokens and 1/sigma for the backward pass."""
     B, N = qkv.shape[0], qkv.shape[1]
     T, H, W = thw
     arr = (L.PoolJob * len(jobs))()
     nbytes = 0
-    for i, (which, s, w, gamma, beta, out) in enumerate(jobs):
-        arr[i] = L.PoolJob(L.ptr(w), L.ptr(gamma), L.ptr(beta), L.ptr(out), out.stride(2), None, 0, None, s, which)
+    for i, job in enumerate(jobs):
+        which, s, w, gamma, beta, out = job[:6]
+        xhat, rstd = (job[6], job[7]) if len(job) > 6 else (None, None)
+        arr[i] = L.PoolJob(L.ptr(w), L.ptr(gamma), L.ptr(beta), L.ptr(out), out.stride(2), None, 0, None, s, which,
+                           L.ptr(xhat), L.ptr(rstd))
         nbytes += (B * N * heads * 96 + out.shape[0] * out.shape[1] * out.shape[2] * 96) * qkv.element_size()
     _run("pmv_pool_ln_qkv_fwd", 1, dict(bytes=nbytes, shape=(B, heads, T, H, W, [j[1] for j in jobs])), L.ptr(qkv), qkv.stride(0),
          qkv.stride(1), qkv.stride(2), qkv.stride(3), arr, len(jobs), B, heads, T, H, W, eps, L.dt(qkv), L.stream())
 
 
 def pool_ln_qkv_bwd(qkv, heads, thw, jobs, dqkv, eps=LN_EPS):
-    """jobs: list of (which, stride_hw, w, gamma, dout, grads) — grads fp32 [96*27 + 192], added to."""
+    """jobs: list of (which, stride_hw, w, gamma, dout, grads [, xhat, rstd]) — grads fp32 [96*27 + 192], added to.
+    With xhat / rstd (saved by the forward) the LayerNorm backward skips the convolution recompute."""
     B, N = qkv.shape[0], qkv.shape[1]
     T, H, W = thw
     arr = (L.PoolJob * len(jobs))()
     strides = (C.c_int * len(jobs))(*[j[1] for j in jobs])
     nbytes = 0
-    for i, (which, s, w, gamma, dout, grads) in enumerate(jobs):
-        arr[i] = L.PoolJob(L.ptr(w), L.ptr(gamma), None, None, 0, L.ptr(dout), dout.stride(2), L.ptr(grads), s, which)
+    for i, job in enumerate(jobs):
+        which, s, w, gamma, dout, grads = job[:6]
+        xhat, rstd = (job[6], job[7]) if len(job) > 6 else (None, None)
+        arr[i] = L.PoolJob(L.ptr(w), L.ptr(gamma), None, None, 0, L.ptr(dout), dout.stride(2), L.ptr(grads), s, which,
+                           L.ptr(xhat), L.ptr(rstd))
         nbytes += (2 * B * N * heads * 96 + dout.shape[0] * dout.shape[1] * dout.shape[2] * 96) * qkv.element_size()
     ws = _ws(L.lib().pmv_pool_ln_qkv_bwd_workspace_bytes(B, heads, T, H, W, strides, len(jobs)), qkv.device)
     _run("pmv_pool_ln_qkv_bwd", 3, dict(bytes=nbytes, shape=(B, heads, T, H, W, [j[1] for j in jobs])), L.ptr(qkv), qkv.stride(0),

@@ -66,10 +66,14 @@ def bench_pool():
         dqkv = torch.empty_like(qkv)
         e = qkv.element_size()
         fwd_bytes = (3 * (N - 1) * heads * 96 + sum(Ls) * heads * 96) * B * e   # read 3(N-1)C, write (Lq+2Lk+3)C
+        xh = [torch.empty(B, heads, Ls[i], 96, dtype=dt, device=dev) for i in range(3)]
+        rs = [torch.empty(B, heads, Ls[i], device=dev) for i in range(3)]
         us = timeit(lambda: ops.pool_ln_qkv_fwd(qkv, heads, thw, [(i, strides[i], ws[i], gs[i], bs[i], outs[i]) for i in range(3)]))
+        report("pool_ln_qkv_fwd (infer)", (B, heads, thw, strides), us, nbytes=fwd_bytes)
+        us = timeit(lambda: ops.pool_ln_qkv_fwd(qkv, heads, thw, [(i, strides[i], ws[i], gs[i], bs[i], outs[i], xh[i], rs[i]) for i in range(3)]))
         report("pool_ln_qkv_fwd", (B, heads, thw, strides), us, nbytes=fwd_bytes)
         bwd_bytes = (2 * 3 * (N - 1) * heads * 96 + sum(Ls) * heads * 96) * B * e
-        us = timeit(lambda: ops.pool_ln_qkv_bwd(qkv, heads, thw, [(i, strides[i], ws[i], gs[i], douts[i], grads[i]) for i in range(3)], dqkv))
+        us = timeit(lambda: ops.pool_ln_qkv_bwd(qkv, heads, thw, [(i, strides[i], ws[i], gs[i], douts[i], grads[i], xh[i], rs[i]) for i in range(3)], dqkv))
         report("pool_ln_qkv_bwd", (B, heads, thw, strides), us, nbytes=bwd_bytes)
 
 

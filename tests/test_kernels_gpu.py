@@ -308,7 +308,9 @@ def test_pool_ln_qkv_fused_launch(dtype):
     Ls = [1 + T * ops.pooled_hw(H, s) * ops.pooled_hw(W, s) for s in strides]
     lds = [128, 128, 96]
     outs = [torch.zeros(B, heads, Ls[i], lds[i], dtype=dtype, device="cuda") for i in range(3)]
-    ops.pool_ln_qkv_fwd(qkv, heads, thw, [(i, strides[i], ws[i], gs[i], bs[i], outs[i]) for i in range(3)])
+    xhats = [torch.empty(B, heads, Ls[i], 96, dtype=dtype, device="cuda") for i in range(3)]
+    rstds = [torch.empty(B, heads, Ls[i], device="cuda") for i in range(3)]
+    ops.pool_ln_qkv_fwd(qkv, heads, thw, [(i, strides[i], ws[i], gs[i], bs[i], outs[i], xhats[i], rstds[i]) for i in range(3)])
     douts = [torch.zeros_like(o) for o in outs]
     grads = torch.zeros(3, 96 * 27 + 192, device="cuda")
     dqkv = torch.full_like(qkv, float("nan"))
@@ -321,9 +323,14 @@ def test_pool_ln_qkv_fused_launch(dtype):
         douts[i][..., :96] = randn(B, heads, Ls[i], 96, seed=90 + i).to(dtype)
         ref.backward(douts[i][..., :96].float())
         refs.append((xin, wr, gr, br))
-    ops.pool_ln_qkv_bwd(qkv, heads, thw, [(i, strides[i], ws[i], gs[i], douts[i], grads[i]) for i in range(3)], dqkv)
-    for i, (xin, wr, gr, br) in enumerate(refs):
-        assert nerr(dqkv[:, :, i].permute(0, 2, 1, 3).float(), xin.grad) < TOL[dtype], i
-        assert nerr(grads[i, :2592].view(96, 27), wr.grad.view(96, 27)) < TOL[dtype], i
-        assert nerr(grads[i, 2592:2688], gr.grad) < TOL[dtype], i
-        assert nerr(grads[i, 2688:], br.grad) < TOL[dtype], i
+    # once with the convolution recompute, once from the statistics the forward saved
+    for saved in (False, True):
+        grads.zero_()
+        dqkv.fill_(float("nan"))
+        extra = [(xhats[i], rstds[i]) if saved else () for i in range(3)]
+        ops.pool_ln_qkv_bwd(qkv, heads, thw, [(i, strides[i], ws[i], gs[i], douts[i], grads[i]) + extra[i] for i in range(3)], dqkv)
+        for i, (xin, wr, gr, br) in enumerate(refs):
+            assert nerr(dqkv[:, :, i].permute(0, 2, 1, 3).float(), xin.grad) < TOL[dtype], (i, saved)
+            assert nerr(grads[i, :2592].view(96, 27), wr.grad.view(96, 27)) < TOL[dtype], (i, saved)
+            assert nerr(grads[i, 2592:2688], gr.grad) < TOL[dtype], (i, saved)
+            assert nerr(grads[i, 2688:], br.grad) < TOL[dtype], (i, saved)
