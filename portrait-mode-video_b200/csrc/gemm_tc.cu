@@ -4,10 +4,14 @@
 
 using namespace gemm_tc;
 
-int gemm_tc_launch_bn96(int, int, int, const CUtensorMap&, const CUtensorMap&, const TcParams&, int, cudaStream_t);
-int gemm_tc_launch_bn128(int, int, int, const CUtensorMap&, const CUtensorMap&, const TcParams&, int, cudaStream_t);
-int gemm_tc_launch_bn192(int, int, int, const CUtensorMap&, const CUtensorMap&, const TcParams&, int, cudaStream_t);
-int gemm_tc_launch_bn256(int, int, int, const CUtensorMap&, const CUtensorMap&, const TcParams&, int, cudaStream_t);
+int gemm_tc_launch_bn96(int, int, int, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
+                         const TcParams&, int, cudaStream_t);
+int gemm_tc_launch_bn128(int, int, int, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
+                         const TcParams&, int, cudaStream_t);
+int gemm_tc_launch_bn192(int, int, int, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
+                         const TcParams&, int, cudaStream_t);
+int gemm_tc_launch_bn256(int, int, int, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
+                         const TcParams&, int, cudaStream_t);
 
 static int g_num_sms = 0;
 
@@ -81,11 +85,30 @@ int gemm_tc_launch(int layout, const void* A, int64_t lda, const void* B, int64_
     PMV_CHECK_CUDA(cudaGetDevice(&dev));
     PMV_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int kind = pick_kind(e);
+  int kind = pick_kind(e);
+  // TMA-store epilogues: output (and pre-activation) tensor maps with 32 x 32 boxes in the swizzle the epilogue writes
+  CUtensorMap tmC = tmA, tmD = tmA;
+  if (kind_tma(kind)) {
+    const int osz = out_dtype == PMV_F32 ? 4 : 2;
+    const bool ok_out = ((uintptr_t)e.out & 15) == 0 && (e.ldo * osz) % 16 == 0;
+    const void* aux = kind == EK_GELU ? e.aux_out : kind == EK_GELU_BWD ? e.aux_in : nullptr;
+    const bool ok_aux = aux == nullptr || (((uintptr_t)aux & 15) == 0 && (e.ld_aux * 2) % 16 == 0);
+    // kernels exist for: TN PLAIN bf16/f32, TN GELU bf16, NN PLAIN bf16, NN GELU_BWD bf16, wgrad PLAIN f32
+    if (!ok_out || !ok_aux) {
+      kind = EK_GENERIC;
+    } else {
+      rc = pmv_make_tensor_map_2d(&tmC, e.out, osz, (uint64_t)NN, (uint64_t)MM, (uint64_t)e.ldo, 32, 32, osz == 2 ? 64 : 128);
+      if (rc) return rc;
+      if (aux) {
+        rc = pmv_make_tensor_map_2d(&tmD, aux, 2, (uint64_t)NN, (uint64_t)MM, (uint64_t)e.ld_aux, 32, 32, 64);
+        if (rc) return rc;
+      }
+    }
+  }
   switch (BN) {
-    case 96: return gemm_tc_launch_bn96(layout, out_dtype, kind, tmA, tmB, p, g_num_sms, stream);
-    case 128: return gemm_tc_launch_bn128(layout, out_dtype, kind, tmA, tmB, p, g_num_sms, stream);
-    case 192: return gemm_tc_launch_bn192(layout, out_dtype, kind, tmA, tmB, p, g_num_sms, stream);
-    default: return gemm_tc_launch_bn256(layout, out_dtype, kind, tmA, tmB, p, g_num_sms, stream);
+    case 96: return gemm_tc_launch_bn96(layout, out_dtype, kind, tmA, tmB, tmC, tmD, p, g_num_sms, stream);
+    case 128: return gemm_tc_launch_bn128(layout, out_dtype, kind, tmA, tmB, tmC, tmD, p, g_num_sms, stream);
+    case 192: return gemm_tc_launch_bn192(layout, out_dtype, kind, tmA, tmB, tmC, tmD, p, g_num_sms, stream);
+    default: return gemm_tc_launch_bn256(layout, out_dtype, kind, tmA, tmB, tmC, tmD, p, g_num_sms, stream);
   }
 }

@@ -33,7 +33,7 @@ enum { EK_PLAIN = 0, EK_GELU = 1, EK_GELU_BWD = 2, EK_RES = 3, EK_GENERIC = 4, E
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 4;
 constexpr int EPI_WARPS = 8;                        // two warps per TMEM lane quarter, alternating 32-column chunks
 constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;
 
@@ -44,7 +44,10 @@ struct TcParams {
   EpiDev e;
 };
 
-template <int BN> struct TileCfg {
+// kinds whose epilogue goes registers -> swizzled smem tile -> TMA store (thread = accumulator row)
+__host__ __device__ constexpr bool kind_tma(int kind) { return kind == EK_PLAIN || kind == EK_GELU || kind == EK_GELU_BWD; }
+
+template <int BN, int KIND = EK_GENERIC> struct TileCfg {
   static constexpr int BN_GROUPS = (BN + 63) / 64;
   static constexpr int A_BYTES = BM * BK * 2;                 // 16 KB either layout
   static constexpr int B_BYTES_K = BN * BK * 2;               // K-major box
@@ -52,8 +55,12 @@ template <int BN> struct TileCfg {
   static constexpr int B_BYTES = B_BYTES_MN;                  // reserve the larger of the two
   static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
   static constexpr int ACC_COLS = BN <= 128 ? 128 : 256;      // TMEM columns per accumulator stage
-  static constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;   // per-epilogue-warp transpose buffer (XOR-swizzled)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
+  // per-epilogue-warp staging: 4 KB transpose buffer / one fp32 or two bf16 32x32 output tiles; the GELU kinds keep two
+  // tiles per chunk (output + pre-activation), double-buffered: 8 KB
+  static constexpr int EPI_WARP_BYTES = (KIND == EK_GELU || KIND == EK_GELU_BWD) ? 8192 : 4096;
+  static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
+  static constexpr int STAGES = (MAX_STAGES * STAGE_BYTES + 2048 + EPI_BYTES <= 227 * 1024) ? MAX_STAGES : MAX_STAGES - 1;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 1024 /*barriers*/ + EPI_BYTES;
 };
 
 // ---- packed-fp32 epilogue math -----------------------------------------------------------------------------------
@@ -95,12 +102,27 @@ __device__ __forceinline__ void st4(float* p, float2 a, float2 b) { *reinterpret
 __device__ __forceinline__ void red_add4(float* p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(tc::smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint32_t pack_bf2(float2 v) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
 __device__ __forceinline__ float2 bf2_to_f2(uint32_t u) { return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
 
 template <int BN, bool A_MN, bool B_MN, typename TOut, int KIND>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
-  using Cfg = TileCfg<BN>;
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD, TcParams p) {
+  // tmC: output (32 x 32 boxes, swizzled); tmD: aux_out (EK_GELU) / aux_in (EK_GELU_BWD); unused by the other kinds
+  using Cfg = TileCfg<BN, KIND>;
+  constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
@@ -109,7 +131,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* acc_full = bars + 2 * STAGES;    // [2]       MMA -> epilogue
   uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2]    epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* epi_buf = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
+  uint64_t* aux_bar = bars + 2 * STAGES + 6;  // [EPI_WARPS][2]  EK_GELU_BWD: pre-activation tiles landed
+  uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES + 1024;  // 1024-aligned: the swizzle patterns are address based
+  float* epi_buf = reinterpret_cast<float*>(epi_smem);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -124,6 +148,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&acc_full[i], 1);
       tc::mbar_init(&acc_empty[i], EPI_WARPS);
+    }
+    for (int i = 0; i < 2 * EPI_WARPS; ++i) tc::mbar_init(&aux_bar[i], 1);
+    if (kind_tma(KIND)) {
+      tc::tma_prefetch_desc(&tmC);
+      if (KIND != EK_PLAIN) tc::tma_prefetch_desc(&tmD);
     }
     tc::fence_barrier_init();
   }
@@ -207,6 +236,150 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tc::umma_commit(&acc_full[as]);  // accumulator complete -> epilogue
       }
+    }
+  } else if constexpr (kind_tma(KIND)) {
+    // ------------------------------------------------------------ epilogue warps, TMA-store form
+    // thread = accumulator row (the TMEM lane), 32 consecutive columns per chunk in registers: bias / GELU in packed
+    // fp32, 16-byte stores into a 32 x 32 tile in the swizzle pattern of the output tensor map (conflict-free:
+    // 64B swizzle for bf16 rows of 64 B, 128B swizzle for fp32 rows of 128 B), then ONE bulk tensor store per
+    // tile issued by lane 0.  No shared-memory read-back, no per-row global addressing, no bounds predicates (the
+    // TMA clips rows >= M and columns >= N).  ~60 instructions per 32 x 32 chunk instead of ~450.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const EpiDev& e = p.e;
+    uint8_t* wbuf = epi_smem + (warp - 2) * Cfg::EPI_WARP_BYTES;
+    constexpr int OUT_TILE = 32 * 32 * (int)sizeof(TOut);           // 2 KB (bf16) / 4 KB (fp32)
+    constexpr int OUT_BUFS = (KIND == EK_PLAIN) ? (4096 / OUT_TILE) : 2;
+    // EK_GELU: out tiles at [0, 4 KB), aux tiles at [4 KB, 8 KB).  EK_GELU_BWD: out tiles at [0, 4 KB), aux_in at [4 KB, 8 KB)
+    uint64_t* my_aux_bar = aux_bar + (warp - 2) * 2;
+    const int row = lane;  // row inside the warp's 32-row slab
+    auto sw16 = [&](int j) -> int {  // byte offset of 16-byte piece j of this thread's row inside a tile
+      if (sizeof(TOut) == 2) return row * 64 + ((j ^ ((row >> 1) & 3)) << 4);
+      return row * 128 + ((j ^ (row & 7)) << 4);
+    };
+    auto sw16_bf = [&](int j) -> int { return row * 64 + ((j ^ ((row >> 1) & 3)) << 4); };
+
+    struct Cursor {
+      int64_t wi, it;
+      int c;
+    };
+    auto valid = [&](const Cursor& cu) { return cu.wi < num_work; };
+    auto advance = [&](Cursor& cu) {
+      cu.c += 64;
+      if (cu.c >= BN) { cu.c = half * 32; cu.wi += gridDim.x; ++cu.it; }
+    };
+    auto coords = [&](const Cursor& cu, int& row0, int& col0) {
+      const int tn = (int)(cu.wi % p.tiles_n);
+      const int tm = (int)((cu.wi / p.tiles_n) % p.tiles_m);
+      row0 = tm * BM + q * 32;
+      col0 = tn * BN + cu.c;
+    };
+    int n_item = 0;    // live chunks stored so far (staging-buffer parity)
+    int n_loaded = 0;  // EK_GELU_BWD: pre-activation tiles requested so far (the k-th request feeds the k-th live chunk)
+    auto load_aux = [&](const Cursor& cu) {  // EK_GELU_BWD, warp-uniform: pre-activation tile of a live chunk -> aux buffer
+      int row0, col0;
+      coords(cu, row0, col0);
+      if (col0 >= p.N || row0 >= p.M) return;
+      if (lane == 0) {
+        tc::mbar_expect_tx(&my_aux_bar[n_loaded & 1], 2048);
+        tc::tma_load_2d(wbuf + 4096 + (n_loaded & 1) * 2048, &tmD, col0, row0, &my_aux_bar[n_loaded & 1]);
+      }
+      ++n_loaded;
+    };
+
+    Cursor cur{(int64_t)blockIdx.x, 0, half * 32};
+    if (cur.c < BN) {
+      if (KIND == EK_GELU_BWD && valid(cur)) load_aux(cur);
+      while (valid(cur)) {
+        Cursor nxt = cur;
+        advance(nxt);
+        int row0, col0;
+        coords(cur, row0, col0);
+        const int as = (int)(cur.it & 1);
+        const bool first_chunk = cur.c == half * 32, last_chunk = cur.c + 64 >= BN;
+        const bool live = col0 < p.N && row0 < p.M;
+        if (KIND == EK_GELU_BWD) {
+          __syncwarp();  // everyone has consumed the aux buffer the next request overwrites (two requests back)
+          if (valid(nxt)) load_aux(nxt);
+        }
+        if (first_chunk) {
+          tc::mbar_wait(&acc_full[as], (uint32_t)((cur.it >> 1) & 1));
+          tc::tc_fence_after();
+        }
+        uint32_t r[32];
+        if (live) {
+          tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * Cfg::ACC_COLS + cur.c, r);
+          tc::tmem_ld_wait();
+        }
+        if (last_chunk) {  // the accumulator stage is in registers: hand it back to the MMA warp
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&acc_empty[as]);
+        }
+        if (live) {
+          float2 v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+          if (KIND != EK_GELU_BWD && e.bias) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              if (col0 + 4 * g < p.N) {  // N % 4 == 0
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + 4 * g));
+                v[2 * g] = __fadd2_rn(v[2 * g], make_float2(b4.x, b4.y));
+                v[2 * g + 1] = __fadd2_rn(v[2 * g + 1], make_float2(b4.z, b4.w));
+              }
+            }
+          }
+          const int ob = n_item % OUT_BUFS;
+          uint8_t* otile = wbuf + ob * OUT_TILE;
+          // the bulk store that last read this buffer must be done with it
+          if (lane == 0) bulk_wait_read<OUT_BUFS - 1>();
+          __syncwarp();
+          if (KIND == EK_GELU && e.aux_out) {
+            uint8_t* atile = wbuf + 4096 + ob * 2048;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(atile + sw16_bf(j)) =
+                  make_uint4(pack_bf2(v[4 * j]), pack_bf2(v[4 * j + 1]), pack_bf2(v[4 * j + 2]), pack_bf2(v[4 * j + 3]));
+          }
+          if (KIND == EK_GELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = gelu2(v[i]);
+          }
+          if (KIND == EK_GELU_BWD) {
+            tc::mbar_wait(&my_aux_bar[n_item & 1], (uint32_t)((n_item >> 1) & 1));
+            const uint8_t* atile = wbuf + 4096 + (n_item & 1) * 2048;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = *reinterpret_cast<const uint4*>(atile + sw16_bf(j));
+              v[4 * j] = __fmul2_rn(v[4 * j], gelu_grad2(bf2_to_f2(u.x)));
+              v[4 * j + 1] = __fmul2_rn(v[4 * j + 1], gelu_grad2(bf2_to_f2(u.y)));
+              v[4 * j + 2] = __fmul2_rn(v[4 * j + 2], gelu_grad2(bf2_to_f2(u.z)));
+              v[4 * j + 3] = __fmul2_rn(v[4 * j + 3], gelu_grad2(bf2_to_f2(u.w)));
+            }
+          }
+          if (sizeof(TOut) == 2) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(otile + sw16(j)) =
+                  make_uint4(pack_bf2(v[4 * j]), pack_bf2(v[4 * j + 1]), pack_bf2(v[4 * j + 2]), pack_bf2(v[4 * j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(otile + sw16(j)) = make_float4(v[2 * j].x, v[2 * j].y, v[2 * j + 1].x, v[2 * j + 1].y);
+          }
+          tc::fence_proxy_async();  // generic-proxy writes -> visible to the bulk store
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, otile, col0, row0);
+            if (KIND == EK_GELU && e.aux_out) tma_store_2d(&tmD, wbuf + 4096 + ob * 2048, col0, row0);
+            bulk_commit();
+          }
+          ++n_item;
+        }
+        cur = nxt;
+      }
+      if (lane == 0) bulk_wait_all();  // global writes complete before the CTA retires its shared memory
     }
   } else {
     // ------------------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4)
@@ -386,8 +559,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 template <int BN, bool A_MN, bool B_MN, typename TOut, int KIND>
-int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int num_sms, cudaStream_t stream) {
-  using Cfg = TileCfg<BN>;
+int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmD, const TcParams& p,
+               int num_sms, cudaStream_t stream) {
+  using Cfg = TileCfg<BN, KIND>;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, TOut, KIND>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
@@ -396,33 +570,33 @@ int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p
   }
   int64_t work = (int64_t)p.tiles_m * p.tiles_n * p.splits;
   unsigned grid = (unsigned)(work < num_sms ? work : num_sms);
-  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmD, p);
   PMV_CHECK_LAUNCH();
   return PMV_OK;
 }
 
 // (layout, output type, epilogue kind) combinations that exist as kernels; anything else runs EK_GENERIC
 template <int BN>
-int launch_bn(int layout, int out_dtype, int kind, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int num_sms,
-              cudaStream_t s) {
+int launch_bn(int layout, int out_dtype, int kind, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+              const CUtensorMap& tmD, const TcParams& p, int num_sms, cudaStream_t s) {
   const bool f32 = out_dtype == PMV_F32;
   if (layout == PMV_GEMM_TN) {
-    if (kind == EK_PLAIN) return f32 ? launch_cfg<BN, false, false, float, EK_PLAIN>(tmA, tmB, p, num_sms, s)
-                                     : launch_cfg<BN, false, false, bf16, EK_PLAIN>(tmA, tmB, p, num_sms, s);
-    if (kind == EK_GELU && !f32) return launch_cfg<BN, false, false, bf16, EK_GELU>(tmA, tmB, p, num_sms, s);
-    if (kind == EK_RES && f32) return launch_cfg<BN, false, false, float, EK_RES>(tmA, tmB, p, num_sms, s);
-    return f32 ? launch_cfg<BN, false, false, float, EK_GENERIC>(tmA, tmB, p, num_sms, s)
-               : launch_cfg<BN, false, false, bf16, EK_GENERIC>(tmA, tmB, p, num_sms, s);
+    if (kind == EK_PLAIN) return f32 ? launch_cfg<BN, false, false, float, EK_PLAIN>(tmA, tmB, tmC, tmD, p, num_sms, s)
+                                     : launch_cfg<BN, false, false, bf16, EK_PLAIN>(tmA, tmB, tmC, tmD, p, num_sms, s);
+    if (kind == EK_GELU && !f32) return launch_cfg<BN, false, false, bf16, EK_GELU>(tmA, tmB, tmC, tmD, p, num_sms, s);
+    if (kind == EK_RES && f32) return launch_cfg<BN, false, false, float, EK_RES>(tmA, tmB, tmC, tmD, p, num_sms, s);
+    return f32 ? launch_cfg<BN, false, false, float, EK_GENERIC>(tmA, tmB, tmC, tmD, p, num_sms, s)
+               : launch_cfg<BN, false, false, bf16, EK_GENERIC>(tmA, tmB, tmC, tmD, p, num_sms, s);
   }
   if (layout == PMV_GEMM_NN) {
-    if (kind == EK_PLAIN && !f32) return launch_cfg<BN, false, true, bf16, EK_PLAIN>(tmA, tmB, p, num_sms, s);
-    if (kind == EK_GELU_BWD && !f32) return launch_cfg<BN, false, true, bf16, EK_GELU_BWD>(tmA, tmB, p, num_sms, s);
-    return f32 ? launch_cfg<BN, false, true, float, EK_GENERIC>(tmA, tmB, p, num_sms, s)
-               : launch_cfg<BN, false, true, bf16, EK_GENERIC>(tmA, tmB, p, num_sms, s);
+    if (kind == EK_PLAIN && !f32) return launch_cfg<BN, false, true, bf16, EK_PLAIN>(tmA, tmB, tmC, tmD, p, num_sms, s);
+    if (kind == EK_GELU_BWD && !f32) return launch_cfg<BN, false, true, bf16, EK_GELU_BWD>(tmA, tmB, tmC, tmD, p, num_sms, s);
+    return f32 ? launch_cfg<BN, false, true, float, EK_GENERIC>(tmA, tmB, tmC, tmD, p, num_sms, s)
+               : launch_cfg<BN, false, true, bf16, EK_GENERIC>(tmA, tmB, tmC, tmD, p, num_sms, s);
   }
-  if (kind == EK_PLAIN) return launch_cfg<BN, true, true, float, EK_PLAIN>(tmA, tmB, p, num_sms, s);
-  if (kind == EK_ATOMIC) return launch_cfg<BN, true, true, float, EK_ATOMIC>(tmA, tmB, p, num_sms, s);
-  return launch_cfg<BN, true, true, float, EK_GENERIC>(tmA, tmB, p, num_sms, s);
+  if (kind == EK_PLAIN) return launch_cfg<BN, true, true, float, EK_PLAIN>(tmA, tmB, tmC, tmD, p, num_sms, s);
+  if (kind == EK_ATOMIC) return launch_cfg<BN, true, true, float, EK_ATOMIC>(tmA, tmB, tmC, tmD, p, num_sms, s);
+  return launch_cfg<BN, true, true, float, EK_GENERIC>(tmA, tmB, tmC, tmD, p, num_sms, s);
 }
 
 }  // namespace gemm_tc
