@@ -26,7 +26,8 @@ namespace {
 
 constexpr int HD = PMV_HEAD_DIM;
 constexpr int BT = 128;  // tile edge (queries and keys)
-constexpr int THREADS = 256;
+constexpr int THREADS = 384;  // warp 0 TMA, 1 MMA, 2 TMEM allocation, 4..11 softmax (two warps per TMEM lane quarter)
+constexpr int SM_WARPS = 8;
 constexpr int X96_BYTES = 2 * BT * 128;  // a [128 x 96] operand staged as two 64-column blocks (second half-used)
 
 struct BwdGeom {
@@ -89,7 +90,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tc::mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&kv_full[i], 1); tc::mbar_init(&kv_empty[i], 1); }
     tc::mbar_init(sdp_full, 1);
-    tc::mbar_init(ds_full, 4);
+    tc::mbar_init(ds_full, SM_WARPS);
     tc::mbar_init(dq_final, 1);
     tc::fence_barrier_init();
   }
@@ -146,9 +147,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const uint32_t idesc_32 = tc::make_idesc_bf16(BT, 32, false, true);
         for (int ks = 0; ks < nks; ++ks) {
           const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
-          tc::umma_ts(tmem_dq, tmem_s + ks * 8, tc::make_smem_desc(sk_addr + ks * 2048, 16384, 1024, tc::SWIZZLE_128B), idesc_128, acc);
+          const uint32_t a_col = ks < 4 ? ks * 8 : 64 + (ks - 4) * 8;  // see the softmax warps: where dS of these 16 keys sits
+          tc::umma_ts(tmem_dq, tmem_s + a_col, tc::make_smem_desc(sk_addr + ks * 2048, 16384, 1024, tc::SWIZZLE_128B), idesc_128, acc);
           if (KD == 160)
-            tc::umma_ts(tmem_dq + 128, tmem_s + ks * 8, tc::make_smem_desc(sk_addr + 32768 + ks * 1024, 8192, 512, tc::SWIZZLE_64B), idesc_32, acc);
+            tc::umma_ts(tmem_dq + 128, tmem_s + a_col, tc::make_smem_desc(sk_addr + 32768 + ks * 1024, 8192, 512, tc::SWIZZLE_64B), idesc_32, acc);
         }
         tc::umma_commit(&kv_empty[st]);
       }
@@ -156,6 +158,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else if (warp >= 4) {
     const int qd = warp & 3;
+    const int half = (warp - 4) >> 2;  // the two warps of a lane quarter take alternate 32-column chunks
     const int row = qd * 32 + lane;
     const int n = q0 + row;
     const bool rvalid = n < g.Nq;
@@ -178,7 +181,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           delta = fmaf(__high2float(a2[i]), __high2float(b2[i]), delta);
         }
       }
-      delta_out[(int64_t)bh * g.Nq + n] = delta;
+      if (half == 0) delta_out[(int64_t)bh * g.Nq + n] = delta;
       lse2 = lse[(int64_t)bh * g.Nq + n] * 1.4426950408889634f;
     }
     for (int j = 0; j < ntiles; ++j) {
@@ -186,7 +189,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc::tc_fence_after();
       const int nvalid = min(BT, g.Nk - j * BT);
       const int nchunks = (nvalid + 31) >> 5;
-      for (int ch = 0; ch < nchunks; ++ch) {
+      // warp `half` owns score columns [64 half, 64 half + 64) and writes its packed bf16 dS over the first 32 columns
+      // of that range, behind its own reads: keys 0..63 -> columns [0, 32), keys 64..127 -> columns [64, 96)
+      for (int ch = 2 * half; ch < nchunks && ch < 2 * half + 2; ++ch) {
         uint32_t s[32], dp[32], pk[16];
         tc::tmem_ld32(tmem_s + lane_addr + ch * 32, s);
         tc::tmem_ld32(tmem_dp + lane_addr + ch * 32, dp);
@@ -203,7 +208,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           __nv_bfloat162 pp = __floats2bfloat162_rn(d[0], d[1]);
           pk[i] = *reinterpret_cast<uint32_t*>(&pp);
         }
-        tc::tmem_st16(tmem_s + lane_addr + ch * 16, pk);
+        tc::tmem_st16(tmem_s + lane_addr + half * 64 + (ch - 2 * half) * 16, pk);
       }
       tc::tmem_st_wait();
       tc::tc_fence_before();
@@ -216,7 +221,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     bf16* dqp = dq_aug + ((int64_t)bh * g.Nq + n) * g.ld_qk;
     const bool add_do = g.residual && n >= 1;
 #pragma unroll 1
-    for (int ch = 0; ch < KD / 32; ++ch) {
+    for (int ch = half; ch < KD / 32; ch += 2) {
       uint32_t o[32];
       tc::tmem_ld32(tmem_dq + lane_addr + ch * 32, o);
       tc::tmem_ld_wait();
@@ -286,7 +291,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tc::mbar_init(k_full, 1);
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&q_full[i], 1); tc::mbar_init(&q_empty[i], 1); }
     tc::mbar_init(sdp_full, 1);
-    tc::mbar_init(pds_full, 4);
+    tc::mbar_init(pds_full, SM_WARPS);
     tc::mbar_init(final_bar, 1);
     tc::fence_barrier_init();
   }
@@ -344,8 +349,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int ks = 0; ks < nks; ++ks) {
           const uint32_t acc = (i > 0 || ks > 0) ? 1u : 0u;
           // dV += P^T dO ; dK += dS^T Q'[:, :96]   (B tiles read MN-major: 64-column groups 16384 B apart)
-          tc::umma_ts(tmem_dv, tmem_st + ks * 8, tc::make_smem_desc(sdo_addr + ks * 2048, 16384, 1024, tc::SWIZZLE_128B), idesc_o, acc);
-          tc::umma_ts(tmem_dk, tmem_dpt + ks * 8, tc::make_smem_desc(sq_addr + ks * 2048, 16384, 1024, tc::SWIZZLE_128B), idesc_o, acc);
+          const uint32_t a_col = ks < 4 ? ks * 8 : 64 + (ks - 4) * 8;
+          tc::umma_ts(tmem_dv, tmem_st + a_col, tc::make_smem_desc(sdo_addr + ks * 2048, 16384, 1024, tc::SWIZZLE_128B), idesc_o, acc);
+          tc::umma_ts(tmem_dk, tmem_dpt + a_col, tc::make_smem_desc(sq_addr + ks * 2048, 16384, 1024, tc::SWIZZLE_128B), idesc_o, acc);
         }
         tc::umma_commit(&q_empty[st]);
       }
@@ -353,8 +359,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
   } else if (warp >= 4) {
     const int qd = warp & 3;
+    const int half = (warp - 4) >> 2;
     const int row = qd * 32 + lane;  // key row of this thread
-    const int tid128 = threadIdx.x - 128;
+    const int tid128 = threadIdx.x - 128;  // 0..255; the first 128 stage lse / delta
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
     const float c = g.scale * 1.4426950408889634f;
     for (int i = 0; i < nq_tiles; ++i) {
@@ -362,17 +369,17 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int nqv = min(BT, g.Nq - q0);
       float* lse_t = s_lse + (i & 1) * 128;
       float* del_t = s_delta + (i & 1) * 128;
-      {
+      if (tid128 < 128) {
         const int n = q0 + tid128;
         const bool ok = n < g.Nq;
         lse_t[tid128] = ok ? lse[(int64_t)bh * g.Nq + n] * 1.4426950408889634f : 0.f;
         del_t[tid128] = ok ? delta[(int64_t)bh * g.Nq + n] : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four softmax warps only
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight softmax warps only
       tc::mbar_wait(sdp_full, i & 1);
       tc::tc_fence_after();
       const int nchunks = (nqv + 31) >> 5;
-      for (int ch = 0; ch < nchunks; ++ch) {
+      for (int ch = 2 * half; ch < nchunks && ch < 2 * half + 2; ++ch) {
         uint32_t s[32], dp[32], pk[16], dk[16];
         tc::tmem_ld32(tmem_st + lane_addr + ch * 32, s);
         tc::tmem_ld32(tmem_dpt + lane_addr + ch * 32, dp);
@@ -391,8 +398,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           pk[e] = *reinterpret_cast<uint32_t*>(&pp);
           dk[e] = *reinterpret_cast<uint32_t*>(&dd);
         }
-        tc::tmem_st16(tmem_st + lane_addr + ch * 16, pk);
-        tc::tmem_st16(tmem_dpt + lane_addr + ch * 16, dk);
+        tc::tmem_st16(tmem_st + lane_addr + half * 64 + (ch - 2 * half) * 16, pk);
+        tc::tmem_st16(tmem_dpt + lane_addr + half * 64 + (ch - 2 * half) * 16, dk);
       }
       tc::tmem_st_wait();
       tc::tc_fence_before();
@@ -405,16 +412,18 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     float* dkp = dk_ws + ((int64_t)bh * g.Nk + key) * HD;
     float* dvp = dv_ws + ((int64_t)bh * g.Nk + key) * HD;
 #pragma unroll 1
-    for (int ch = 0; ch < 3; ++ch) {
+    for (int ch = half; ch < 3; ch += 2) {
       uint32_t a[32], b[32];
       tc::tmem_ld32(tmem_dv + lane_addr + ch * 32, a);
       tc::tmem_ld32(tmem_dk + lane_addr + ch * 32, b);
       tc::tmem_ld_wait();
       if (key < g.Nk) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          atomicAdd(dvp + ch * 32 + e, __uint_as_float(a[e]));
-          atomicAdd(dkp + ch * 32 + e, __uint_as_float(b[e]));
+        for (int e = 0; e < 32; e += 4) {  // 16-byte vector reductions (rows are 384-byte aligned)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dvp + ch * 32 + e), "f"(__uint_as_float(a[e])),
+                       "f"(__uint_as_float(a[e + 1])), "f"(__uint_as_float(a[e + 2])), "f"(__uint_as_float(a[e + 3])) : "memory");
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dkp + ch * 32 + e), "f"(__uint_as_float(b[e])),
+                       "f"(__uint_as_float(b[e + 1])), "f"(__uint_as_float(b[e + 2])), "f"(__uint_as_float(b[e + 3])) : "memory");
         }
       }
     }
