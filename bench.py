@@ -177,6 +177,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="clips per GPU per step")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -220,7 +221,7 @@ def main():
     if train:
         model.train()
         reducer = GradAllReducer(model, bucket_mb=25.0)
-        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.05, fused=True)
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.05, fused=True, capturable=True)
     else:
         model.eval()
         model.head.act = None
@@ -236,10 +237,31 @@ def main():
         with torch.no_grad():
             return model([c])
 
+    eager_step = step
+    graphed = None
+    for _ in range(max(args.warmup, 3)):
+        eager_step(clips, labels)
+    if not args.no_graph:
+        # the whole step (forward [+ backward + bucketed all-reduce + AdamW]) as one CUDA graph: ~750 launches per
+        # step issued from Python were the bottleneck (host-bound), see pmv_b200/graphs.py
+        try:
+            from pmv_b200.graphs import GraphedStep
+            graphed = GraphedStep(eager_step, [clips, labels])
+            step = graphed
+        except Exception as exc:  # noqa: BLE001  (capture is an optimisation: fall back to eager launches, say so)
+            print(f"[bench] CUDA-graph capture failed ({type(exc).__name__}: {exc}); running eager", file=sys.stderr)
+            torch.cuda.synchronize()
+            graphed = None
+
     def e2e_step():
-        c = host_clips.to(dev, non_blocking=True)
-        l = host_labels.to(dev, non_blocking=True)
-        out = step(c, l)
+        if graphed is not None:  # H2D straight into the graph's static input buffers
+            graphed.static_inputs[0].copy_(host_clips, non_blocking=True)
+            graphed.static_inputs[1].copy_(host_labels, non_blocking=True)
+            out = graphed(graphed.static_inputs[0], graphed.static_inputs[1])
+        else:
+            c = host_clips.to(dev, non_blocking=True)
+            l = host_labels.to(dev, non_blocking=True)
+            out = step(c, l)
         return out.float().cpu()  # D2H read of the loss (train) / logits (infer)
 
     def barrier():
@@ -265,16 +287,17 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = ops.LAUNCHES
     ms_dev = timed(lambda: step(clips, labels), args.steps)
-    launches = (ops.LAUNCHES - l0) // args.steps
+    l0 = ops.LAUNCHES
+    eager_step(clips, labels)  # launch count of one step (the graph replays exactly these launches)
+    launches = ops.LAUNCHES - l0
     ms_e2e = timed(e2e_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
     # per-kernel CUDA-event times over two more passes of the same step (events on the launching stream)
     with ops.record_kernels() as rec:
         for _ in range(2):
-            step(clips, labels)
+            eager_step(clips, labels)
         torch.cuda.synchronize()
         roof, shares, detail = summarize_kernels(rec, peaks)
 
@@ -293,6 +316,7 @@ def main():
         "config": {"workload": workload, "per_gpu_batch": B, "global_batch": total_clips, "mode": args.mode,
                    "parallelism": f"dp{world} (batch-sharded; {'bucketed NCCL grad all-reduce overlapped with backward' if train else 'no collective'})",
                    "l2": "no explicit flush: per-step activations (>2 GB) exceed the 126 MB L2",
+                   "launch": "one CUDA graph per step" if graphed is not None else "eager (one Python call per kernel)",
                    "model_tflops_per_gpu": round(flop_per_clip * B / (ms_dev * 1e-3) / 1e3, 1)},
         "e2e": {"value": round(e2e_v, 2), "unit": "clips/s", "h2d_bytes_per_step": host_clips.numel() * 4 + host_labels.numel() * 8,
                 "d2h_bytes_per_step": 4 if train else B * 400 * 4, "ms_per_step": round(ms_e2e, 3)},
