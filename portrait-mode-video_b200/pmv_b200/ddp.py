@@ -4,11 +4,10 @@ Mirrors what the reference gets from ``torch.nn.parallel.DistributedDataParallel
 models/build.py:71-79 (bucketed all-reduce launched as gradients become ready, mean over ranks,
 find_unused_parameters=False) and the optional fp16-compressed hook of build.py:80-83 (here: bf16).
 
-Design: parameters are packed, in reverse registration order (the order backward produces gradients),
-into flat fp32 buckets; each parameter's ``.grad`` is a view into its bucket, so no gather copy is needed.
-A post-accumulate-grad hook counts down the bucket; when the last gradient of a bucket has been written,
-the bucket is all-reduced on a dedicated communication stream (NCCL over NVLink / NVSwitch) while backward
-keeps running on the compute stream.  ``finish()`` makes the compute stream wait for the reductions.
+Design: parameters are grouped, in reverse registration order (the order backward produces gradients), into
+buckets with a flat fp32 staging buffer.  A post-accumulate-grad hook counts down the bucket; when its last gradient
+has been produced the bucket is packed (one multi-tensor copy) and all-reduced on a dedicated communication stream
+(NCCL over NVLink / NVSwitch) while backward keeps running on the compute stream.  ``finish()`` makes the compute stream wait for the reductions.
 Inference needs no collective (pure batch partitioning, tools/test_net.py:131-132 gathers logits only).
 """
 from __future__ import annotations
@@ -20,26 +19,37 @@ import torch.distributed as dist
 
 
 class _Bucket:
-    def __init__(self, params, device, compress_dtype):
+    def __init__(self, params, device, compress_dtype, need_flat):
         self.params = params
         n = sum(p.numel() for p in params)
-        self.flat = torch.zeros(n, dtype=torch.float32, device=device)
-        off = 0
-        for p in params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        # flat fp32 staging buffer of the bucket (only needed when there is something to reduce)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=device) if need_flat else None
+        self.views = []
+        if need_flat:
+            off = 0
+            for p in params:
+                self.views.append(self.flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
         self.pending = len(params)
         self.work = None
+        self.avg_done = False
         self.event = torch.cuda.Event() if device.type == "cuda" else None
-        self.compressed = torch.empty(n, dtype=compress_dtype, device=device) if compress_dtype is not None else None
+        self.compressed = torch.empty(n, dtype=compress_dtype, device=device) if (compress_dtype is not None and need_flat) else None
 
 
 class GradAllReducer:
+    """Gradients are NOT pre-allocated views: ``zero_grad()`` sets ``p.grad = None`` so autograd adopts each freshly
+    computed gradient tensor as is (no ``grad += dW`` kernel and no zero-fill per parameter: 397 + 200 launches per
+    MViTv2-S step otherwise).  When the last gradient of a bucket has arrived the bucket is packed into its flat
+    buffer with one multi-tensor copy on the communication stream and all-reduced there; ``finish()`` re-points
+    ``p.grad`` at the reduced flat views.  With one rank nothing is copied at all."""
+
     def __init__(self, module: torch.nn.Module, bucket_mb: float = 25.0, compress_dtype=None, process_group=None):
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         params = [p for p in module.parameters() if p.requires_grad]
         assert params, "no trainable parameters"
+        self.params = params
         self.device = params[0].device
         self.stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
         self.buckets: List[_Bucket] = []
@@ -48,10 +58,10 @@ class GradAllReducer:
             cur.append(p)
             cur_bytes += p.numel() * 4
             if cur_bytes >= limit:
-                self.buckets.append(_Bucket(cur, self.device, compress_dtype))
+                self.buckets.append(_Bucket(cur, self.device, compress_dtype, self.world > 1))
                 cur, cur_bytes = [], 0
         if cur:
-            self.buckets.append(_Bucket(cur, self.device, compress_dtype))
+            self.buckets.append(_Bucket(cur, self.device, compress_dtype, self.world > 1))
         self._owner = {}
         for b in self.buckets:
             for p in b.params:
@@ -64,7 +74,8 @@ class GradAllReducer:
 
     def zero_grad(self):
         for b in self.buckets:
-            b.flat.zero_()
+            for p in b.params:
+                p.grad = None
             b.pending = len(b.params)
             b.work = None
 
@@ -84,6 +95,7 @@ class GradAllReducer:
             self._reduce(b)
 
     def _reduce(self, b: _Bucket):
+        torch._foreach_copy_(b.views, [p.grad for p in b.params])  # pack: one multi-tensor copy
         buf = b.flat
         if b.compressed is not None:
             b.compressed.copy_(b.flat)
@@ -109,5 +121,7 @@ class GradAllReducer:
                     b.flat.copy_(b.compressed)
                 if not b.avg_done:
                     b.flat.div_(self.world)
+            for p, v in zip(b.params, b.views):
+                p.grad = v
         if self.stream is not None:
             torch.cuda.current_stream(self.device).wait_stream(self.stream)
