@@ -689,7 +689,7 @@ struct Geom {
 int fill_jobs(Job* J, const void* qkv, int64_t ws_, const pmv_pool_job* jobs, int njobs, const Geom& g) {
   PMV_CHECK_ARG(njobs >= 1 && njobs <= MAX_JOBS, "pool: 1..3 jobs");
   PMV_CHECK_ARG(g.B > 0 && g.heads > 0 && g.T > 0 && g.H > 0 && g.W > 0, "pool: bad geometry");
-  PMV_CHECK_ARG(g.ts % 8 == 0 && g.hs % 4 == 0 && ws_ % 4 == 0 && g.bs % 8 == 0, "pool: strides must be multiples of 8 elements");
+  PMV_CHECK_ARG(g.ts % 8 == 0 && g.hs % 8 == 0 && ws_ % 8 == 0 && g.bs % 8 == 0, "pool: strides must be multiples of 8 elements");
   PMV_CHECK_ARG((int64_t)3 * g.H * g.W * g.ts < (1ll << 31) && (int64_t)g.B * g.heads * g.T * g.H < (1ll << 29),
                 "pool: volume too large for 32-bit row offsets");
   const int esz = g.dtype == PMV_BF16 ? 2 : 4;
@@ -713,7 +713,7 @@ int run_mode(int mode, Job* all, int njobs, const Geom& g, cudaStream_t st) {
   int nt = 0, nd = 0;
   const bool tma_ok = pmv_has_tcgen05() && std::getenv("PMV_POOL_DIRECT") == nullptr;
   for (int i = 0; i < njobs; ++i) {
-    if (tma_ok && tma_eligible(all[i].s, mode)) { ti[nt] = i; tj[nt++] = all[i]; } else { di[nd] = i; dj[nd++] = all[i]; }
+    if (tma_ok && tma_eligible(all[i].s, mode, g.dtype == PMV_BF16 ? 2 : 4)) { ti[nt] = i; tj[nt++] = all[i]; } else { di[nd] = i; dj[nd++] = all[i]; }
   }
   if (nt > 0) {
     // balanced waves over 2 CTAs per SM

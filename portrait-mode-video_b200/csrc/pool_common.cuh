@@ -76,7 +76,7 @@ template <bool FLIP> __device__ __forceinline__ void load_taps(const float* __re
 
 // pool_tma.cu
 int tma_items(int B, int heads, int Ho, int Wo);
-bool tma_eligible(int stride_hw, int mode);
+bool tma_eligible(int stride_hw, int mode, int elem_bytes);
 int tma_launch(int mode, const Job* jobs, int njobs, int B, int heads, int T, int H, int W, int64_t bs, int64_t ts, int64_t hs,
                float eps, int dtype, cudaStream_t st);
 

@@ -38,10 +38,19 @@ struct TLaunch {
   float eps;
 };
 
+// S = 1, 2: one dense halo plane per frame.  S = 0 stands for "any stride >= 3": the 3 x 3 windows do not overlap, so
+// a plane is fetched as nine tap tiles of [ROWS][CW] tokens, each by one TMA load that walks the tensor with element
+// strides (1, s, s, 1, 1) from the tap's own origin — exactly the tokens the stencil touches, zero-filled by
+// coordinate outside the frame.
 template <int S> struct Geo {
   static constexpr int BH = 3 + (ROWS - 1) * S;
   static constexpr int BW = 3 + (CW - 1) * S;
   static constexpr int PLANE_ELEMS = BH * BW * HD;
+};
+template <> struct Geo<0> {
+  static constexpr int BH = ROWS, BW = CW;
+  static constexpr int TILE_ELEMS = ROWS * CW * HD;
+  static constexpr int PLANE_ELEMS = 9 * TILE_ELEMS;
 };
 
 __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m, int c0, int c1, int c2, int c3, int c4, uint64_t* bar) {
@@ -100,7 +109,15 @@ __device__ __forceinline__ void march(const TLaunch& L, const Job& J, const CUte
     // M_BWD_IN reads dconv [bh][T][H][W][96]: channel coordinate 0, outermost coordinate bh
     const int c0 = MODE == M_BWD_IN ? 0 : head * HD;
     const int c4 = MODE == M_BWD_IN ? b * L.heads + head : b;
-    tma_load_5d(sm.planes + (size_t)(k % NST) * PLANE_STRIDE, tm, c0, tw * CW * S - 1, th * ROWS * S - 1, tin, c4, bar);
+    if constexpr (S == 0) {
+      constexpr uint32_t TILE_BYTES = Geo<0>::TILE_ELEMS * sizeof(T);
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap)
+        tma_load_5d(sm.planes + (size_t)(k % NST) * PLANE_STRIDE + tap * TILE_BYTES, tm, c0, tw * CW * J.s + tap % 3 - 1,
+                    th * ROWS * J.s + tap / 3 - 1, tin, c4, bar);
+    } else {
+      tma_load_5d(sm.planes + (size_t)(k % NST) * PLANE_STRIDE, tm, c0, tw * CW * S - 1, th * ROWS * S - 1, tin, c4, bar);
+    }
   };
 
   if (tid == 0) {
@@ -160,15 +177,23 @@ __device__ __forceinline__ void march(const TLaunch& L, const Job& J, const CUte
           const T* plane = reinterpret_cast<const T*>(sm.planes + (size_t)(k % NST) * PLANE_STRIDE) + 2 * cp;
 #pragma unroll
           for (int dh = 0; dh < 3; ++dh) {
-            float2 x[G::BW];
-            const T* prow = plane + (r * S + dh) * (G::BW * HD);
+            constexpr int NX = S == 0 ? 3 * CW : G::BW;
+            float2 x[NX];
+            if constexpr (S == 0) {  // tap tiles (dh, dw): [ROWS][CW] tokens each
 #pragma unroll
-            for (int c = 0; c < G::BW; ++c) x[c] = lds2(prow + c * HD);
+              for (int dw = 0; dw < 3; ++dw)
+#pragma unroll
+                for (int j = 0; j < CW; ++j) x[dw * CW + j] = lds2(plane + (((dh * 3 + dw) * ROWS + r) * CW + j) * HD);
+            } else {
+              const T* prow = plane + (r * S + dh) * (G::BW * HD);
+#pragma unroll
+              for (int c = 0; c < G::BW; ++c) x[c] = lds2(prow + c * HD);
+            }
 #pragma unroll
             for (int j = 0; j < CW; ++j)
 #pragma unroll
               for (int dw = 0; dw < 3; ++dw) {
-                const float2 xv = x[j * S + dw];
+                const float2 xv = S == 0 ? x[dw * CW + j] : x[j * S + dw];
                 if (MODE == M_BWD_DW) {
                   accw[0 * 9 + dh * 3 + dw] = __ffma2_rn(xv, acc[SLOT_P1][j], accw[0 * 9 + dh * 3 + dw]);
                   accw[1 * 9 + dh * 3 + dw] = __ffma2_rn(xv, acc[SLOT_0][j], accw[1 * 9 + dh * 3 + dw]);
@@ -426,22 +451,196 @@ __global__ void __launch_bounds__(THREADS, 2) pool_tma_kernel(const __grid_const
   if (MODE == M_BWD_LN) partial = J.part_ln + (int64_t)lb * 2 * HD;
   if (MODE == M_BWD_DW) partial = J.part_dw + (int64_t)lb * NDW;
   if (J.s == 1) march<T, MODE, 1>(L, J, &L.tm[jj], sm, lb, J.nblk, sgam, sbet, partial);
-  else if (MODE != M_BWD_IN) march<T, MODE, 2>(L, J, &L.tm[jj], sm, lb, J.nblk, sgam, sbet, partial);
+  else if (MODE != M_BWD_IN && J.s == 2) march<T, MODE, 2>(L, J, &L.tm[jj], sm, lb, J.nblk, sgam, sbet, partial);
+  else if (MODE != M_BWD_IN) march<T, MODE, 0>(L, J, &L.tm[jj], sm, lb, J.nblk, sgam, sbet, partial);
 }
 
-size_t smem_bytes(int max_s, int esz) {
-  const size_t plane = (size_t)(3 + (ROWS - 1) * max_s) * (3 + (CW - 1) * max_s) * HD * esz;
-  return 128 + 2 * TOK * HD * sizeof(float) + NST * ((plane + 127) / 128 * 128);
+
+// ---------------------------------------------------------------------------------------------------------------
+// backward (iii), stride 2: gather form over an INPUT tile of 8 rows x 14 columns (= the 4 x 7 output tile it feeds,
+// plus one halo output row / column).  The pre-LN gradient planes [5 x 8 tokens] of the three frames t-1, t, t+1 sit
+// in a 4-deep TMA ring; a thread owns one even and one odd input row and a channel pair, so the tap pattern of every
+// (row parity, column parity) is static: 1, 2, 2 or 4 (dh, dw) taps x 3 frames, 6.75 FFMA2 per input element.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int S2_NST = 4;
+constexpr int S2_BH = ROWS + 1, S2_BW = CW + 1;
+constexpr int S2_THREADS = ROWS * NCP;  // 192
+
+template <typename T>
+__global__ void __launch_bounds__(S2_THREADS, 3) pool_din_s2_kernel(const __grid_constant__ TLaunch L) {
+  constexpr uint32_t PLANE_BYTES = S2_BH * S2_BW * HD * sizeof(T);
+  constexpr uint32_t PLANE_STRIDE = (PLANE_BYTES + 127u) & ~127u;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* planes = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  __shared__ __align__(8) uint64_t full_bar[S2_NST];
+  int jj = 0;
+  while (jj + 1 < L.njobs && (int)blockIdx.x >= L.job[jj + 1].blk_begin) ++jj;
+  const Job& J = L.job[jj];
+  const CUtensorMap* tm = &L.tm[jj];
+  const int tid = threadIdx.x;
+  const int lb = blockIdx.x - J.blk_begin;
+  const int cp = tid % NCP, r = tid / NCP;
+  const int Tn = L.T, Ho = J.Ho, Wo = J.Wo;
+  if (tid == 0) {
+    tc::tma_prefetch_desc(tm);
+    for (int i = 0; i < S2_NST; ++i) tc::mbar_init(&full_bar[i], 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  float2 wr[TAPS];
+  load_taps<false>(J.w, cp, wr);
+  const int n_th = (L.H + 2 * ROWS - 1) / (2 * ROWS), n_tw = (L.W + 2 * CW - 1) / (2 * CW);
+  const int per_bh = n_th * n_tw;
+  const int nitems = L.B * L.heads * per_bh;
+  int nload = 0;  // planes requested so far by this CTA (ring slot / parity bookkeeping, uniform)
+  for (int item = lb; item < nitems; item += J.nblk) {
+    const int bh = item / per_bh;
+    const int rem = item - bh * per_bh;
+    const int th = rem / n_tw, tw = rem - th * n_tw;
+    const int b = bh / L.heads, head = bh - b * L.heads;
+    const int base_load = nload;  // plane `to` of this item is request base_load + to
+    auto issue = [&](int to) {
+      if (tid == 0) {
+        uint64_t* bar = &full_bar[(base_load + to) % S2_NST];
+        tc::mbar_expect_tx(bar, PLANE_BYTES);
+        tma_load_5d(planes + (size_t)((base_load + to) % S2_NST) * PLANE_STRIDE, tm, 0, tw * CW, th * ROWS, to, bh, bar);
+      }
+    };
+    issue(0);
+    if (Tn > 1) issue(1);
+    const int hi0 = th * 2 * ROWS + 2 * r;  // even input row of this thread; hi0 + 1 is its odd row
+    T* dbase = reinterpret_cast<T*>(J.din) + ((int64_t)b * L.in_bs + (int64_t)head * L.in_hs + 2 * cp);
+    for (int ti = 0; ti < Tn; ++ti) {
+      // frames ti-1, ti, ti+1 are needed; ti+1 arrives now, ti+2 is requested after the barrier below
+      if (ti + 1 < Tn) tc::mbar_wait(&full_bar[(base_load + ti + 1) % S2_NST], (uint32_t)(((base_load + ti + 1) / S2_NST) & 1));
+      else if (Tn == 1 || ti == 0) { /* single frame: plane 0 waited below */ }
+      if (ti == 0) tc::mbar_wait(&full_bar[base_load % S2_NST], (uint32_t)((base_load / S2_NST) & 1));
+      const T* pl[3];  // dt = 0, 1, 2  <->  output frame to = ti + 1 - dt
+      bool pv[3];
+#pragma unroll
+      for (int dt = 0; dt < 3; ++dt) {
+        const int to = ti + 1 - dt;
+        pv[dt] = to >= 0 && to < Tn;
+        pl[dt] = reinterpret_cast<const T*>(planes + (size_t)((base_load + (pv[dt] ? to : 0)) % S2_NST) * PLANE_STRIDE) + 2 * cp;
+      }
+      // tile-local output rows: even input row -> (dh = 1, row r); odd input row -> (dh = 0, row r + 1), (dh = 2, row r)
+#pragma unroll
+      for (int par = 0; par < 2; ++par) {
+        const int hi = hi0 + par;
+        if (hi >= L.H) continue;
+        T* drow = dbase + (int64_t)(1 + (ti * L.H + hi) * L.W + tw * 2 * CW) * L.in_ts;
+#pragma unroll
+        for (int c = 0; c < 2 * CW; ++c) {
+          if (tw * 2 * CW + c >= L.W) continue;
+          float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int dt = 0; dt < 3; ++dt) {
+            if (!pv[dt]) continue;
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {      // row taps
+              if (par == 0 && a == 1) continue;
+              const int dh = par == 0 ? 1 : (a == 0 ? 0 : 2);
+              const int orow = par == 0 ? r : (a == 0 ? r + 1 : r);
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {    // column taps
+                if ((c & 1) == 0 && e == 1) continue;
+                const int dw = (c & 1) == 0 ? 1 : (e == 0 ? 0 : 2);
+                const int ocol = (c & 1) == 0 ? c / 2 : (e == 0 ? (c + 1) / 2 : (c - 1) / 2);
+                acc = __ffma2_rn(lds2(pl[dt] + (orow * S2_BW + ocol) * HD), wr[dt * 9 + dh * 3 + dw], acc);
+              }
+            }
+          }
+          st2(drow + (int64_t)c * L.in_ts, acc);
+        }
+      }
+      __syncthreads();  // frame ti-1 is no longer needed: its ring slot takes frame ti+2
+      if (ti + 2 < Tn) issue(ti + 2);
+    }
+    nload += Tn;
+  }
 }
 
-int make_map(CUtensorMap* tm, const void* base, int esz, int64_t dims[5], int64_t strides_elems[4], int box_w, int box_h) {
+// ---------------------------------------------------------------------------------------------------------------
+// backward (iii), stride >= 3: the 3 x 3 windows do not overlap, so every input position is fed by at most one
+// output position: din[t, ho s + dh - 1, wo s + dw - 1] = sum_dt w[dt,dh,dw] dconv[t + 1 - dt, ho, wo], all other
+// positions are zero.  One kernel zero-fills the job's slice of dQKV (16-byte stores, cls token skipped), a second
+// one walks the frames per (output position, channel pair) with the three dconv values in registers.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) pool_din_zero_kernel(const __grid_constant__ TLaunch L) {
+  constexpr int PIECES = HD * sizeof(T) / 16;  // 16-byte pieces per (token, head)
+  const Job& J = L.job[blockIdx.y];
+  const int64_t ntok = (int64_t)L.T * L.H * L.W;
+  const int64_t total = (int64_t)L.B * ntok * L.heads * PIECES;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int piece = (int)(i % PIECES);
+    int64_t q = i / PIECES;
+    const int head = (int)(q % L.heads); q /= L.heads;
+    const int64_t n = q % ntok;
+    const int64_t b = q / ntok;
+    T* p = reinterpret_cast<T*>(J.din) + b * L.in_bs + (1 + n) * L.in_ts + head * L.in_hs;
+    reinterpret_cast<uint4*>(p)[piece] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(S2_THREADS) pool_din_scatter_kernel(const __grid_constant__ TLaunch L) {
+  int jj = 0;
+  while (jj + 1 < L.njobs && (int)blockIdx.x >= L.job[jj + 1].blk_begin) ++jj;
+  const Job& J = L.job[jj];
+  const int tid = threadIdx.x;
+  const int cp = tid % NCP, r = tid / NCP;
+  const int Tn = L.T, Ho = J.Ho, Wo = J.Wo, S = J.s;
+  const int Lo = Tn * Ho * Wo;
+  float2 wr[TAPS];
+  load_taps<false>(J.w, cp, wr);
+  const int npos = L.B * L.heads * Ho * Wo;
+  for (int pos = (blockIdx.x - J.blk_begin) * ROWS + r; pos < npos; pos += J.nblk * ROWS) {
+    const int wo = pos % Wo;
+    int q = pos / Wo;
+    const int ho = q % Ho; q /= Ho;
+    const int head = q % L.heads, b = q / L.heads;
+    const T* dc = reinterpret_cast<const T*>(J.dconv) + (((int64_t)b * L.heads + head) * Lo + (int64_t)ho * Wo + wo) * HD + 2 * cp;
+    T* dbase = reinterpret_cast<T*>(J.din) + ((int64_t)b * L.in_bs + (int64_t)head * L.in_hs + 2 * cp);
+    float2 d_m1 = make_float2(0.f, 0.f), d_0 = ld2(dc), d_p1;
+    for (int ti = 0; ti < Tn; ++ti) {
+      d_p1 = ti + 1 < Tn ? ld2(dc + (int64_t)(ti + 1) * Ho * Wo * HD) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int dh = 0; dh < 3; ++dh) {
+        const int hi = ho * S + dh - 1;
+        if (hi < 0 || hi >= L.H) continue;
+#pragma unroll
+        for (int dw = 0; dw < 3; ++dw) {
+          const int wi = wo * S + dw - 1;
+          if (wi < 0 || wi >= L.W) continue;
+          float2 v = __fmul2_rn(d_p1, wr[0 * 9 + dh * 3 + dw]);
+          v = __ffma2_rn(d_0, wr[1 * 9 + dh * 3 + dw], v);
+          v = __ffma2_rn(d_m1, wr[2 * 9 + dh * 3 + dw], v);
+          st2(dbase + (int64_t)(1 + (ti * L.H + hi) * L.W + wi) * L.in_ts, v);
+        }
+      }
+      d_m1 = d_0;
+      d_0 = d_p1;
+    }
+  }
+}
+
+size_t plane_bytes(int s, int esz) {
+  if (s >= 3) return (size_t)9 * ROWS * CW * HD * esz;
+  return (size_t)(3 + (ROWS - 1) * s) * (3 + (CW - 1) * s) * HD * esz;
+}
+size_t smem_bytes(size_t max_plane) { return 128 + 2 * TOK * HD * sizeof(float) + NST * ((max_plane + 127) / 128 * 128); }
+
+int make_map(CUtensorMap* tm, const void* base, int esz, int64_t dims[5], int64_t strides_elems[4], int box_w, int box_h,
+             int walk = 1) {
   return pmv_make_tensor_map_5d(tm, base, esz, (uint64_t)dims[0], (uint64_t)dims[1], (uint64_t)dims[2], (uint64_t)dims[3],
                                 (uint64_t)dims[4], (uint64_t)strides_elems[0], (uint64_t)strides_elems[1],
-                                (uint64_t)strides_elems[2], (uint64_t)strides_elems[3], HD, (uint32_t)box_w, (uint32_t)box_h, 1, 1);
+                                (uint64_t)strides_elems[2], (uint64_t)strides_elems[3], HD, (uint32_t)box_w, (uint32_t)box_h, 1, 1,
+                                (uint32_t)walk);
 }
 
-template <typename T, int MODE> int launch_mode(const TLaunch& L, int total_blocks, int max_s, cudaStream_t st) {
-  const size_t smem = smem_bytes(max_s, (int)sizeof(T));
+template <typename T, int MODE> int launch_mode(const TLaunch& L, int total_blocks, size_t max_plane, cudaStream_t st) {
+  const size_t smem = smem_bytes(max_plane);
   auto kern = pool_tma_kernel<T, MODE>;
   static size_t attr = 0;
   if (smem > attr) {
@@ -457,10 +656,68 @@ template <typename T, int MODE> int launch_mode(const TLaunch& L, int total_bloc
 
 int tma_items(int B, int heads, int Ho, int Wo) { return B * heads * ((Ho + ROWS - 1) / ROWS) * ((Wo + CW - 1) / CW); }
 
-bool tma_eligible(int stride_hw, int mode) {
-  if (mode == 3) return stride_hw == 1;
-  return stride_hw == 1 || stride_hw == 2;
+bool tma_eligible(int stride_hw, int mode, int elem_bytes) {
+  if (stride_hw < 1 || stride_hw > 8) return false;  // element strides of a tensor map go up to 8
+  // nine fp32 tap tiles x 3 ring slots exceed the shared memory of an SM: fp32 mode keeps the direct kernels there
+  if (mode != 3 && stride_hw >= 3 && elem_bytes != 2) return false;
+  return true;
 }
+
+namespace {
+int nblk_for(int64_t items, int64_t cap) { return (int)(items < 1 ? 1 : (items > cap ? cap : items)); }
+
+// backward (iii) for the stride-2 jobs and the stride >= 3 jobs of a launch (stride 1 goes through the t-march)
+template <typename T>
+int launch_din_strided(const Job* jobs, int njobs, TLaunch& L, int esz, cudaStream_t st) {
+  const int B = L.B, heads = L.heads, Tn = L.T, H = L.H, W = L.W;
+  // ---- stride 2
+  TLaunch L2 = L;
+  L2.njobs = 0;
+  int total = 0;
+  for (int i = 0; i < njobs; ++i) {
+    if (jobs[i].s != 2) continue;
+    Job J = jobs[i];
+    int64_t dims[5] = {HD, J.Wo, J.Ho, Tn, (int64_t)B * heads};
+    int64_t str[4] = {HD, (int64_t)J.Wo * HD, (int64_t)J.Ho * J.Wo * HD, (int64_t)Tn * J.Ho * J.Wo * HD};
+    int rc = make_map(&L2.tm[L2.njobs], J.dconv, esz, dims, str, S2_BW, S2_BH);
+    if (rc) return rc;
+    const int64_t items = (int64_t)B * heads * ((H + 2 * ROWS - 1) / (2 * ROWS)) * ((W + 2 * CW - 1) / (2 * CW));
+    J.blk_begin = total;
+    J.nblk = nblk_for(items, 148 * 6);
+    total += J.nblk;
+    L2.job[L2.njobs++] = J;
+  }
+  if (L2.njobs > 0) {
+    const size_t smem = 128 + (size_t)S2_NST * ((S2_BH * S2_BW * HD * sizeof(T) + 127) / 128 * 128);
+    auto kern = pool_din_s2_kernel<T>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      PMV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    kern<<<(unsigned)total, S2_THREADS, smem, st>>>(L2);
+    PMV_CHECK_LAUNCH();
+  }
+  // ---- stride >= 3
+  TLaunch L3 = L;
+  L3.njobs = 0;
+  total = 0;
+  for (int i = 0; i < njobs; ++i) {
+    if (jobs[i].s < 3) continue;
+    Job J = jobs[i];
+    J.blk_begin = total;
+    J.nblk = nblk_for(ceil_div64((int64_t)B * heads * J.Ho * J.Wo, ROWS), 148 * 8);
+    total += J.nblk;
+    L3.job[L3.njobs++] = J;
+  }
+  if (L3.njobs > 0) {
+    pool_din_zero_kernel<T><<<dim3(148 * 8, (unsigned)L3.njobs), 256, 0, st>>>(L3);
+    pool_din_scatter_kernel<T><<<(unsigned)total, S2_THREADS, 0, st>>>(L3);
+    PMV_CHECK_LAUNCH();
+  }
+  return PMV_OK;
+}
+}  // namespace
 
 // mode: 0 forward, 1 backward (i), 2 backward (ii), 3 backward (iii).  `jobs` hold their block ranges for this launch
 // (blk_begin / nblk / ncls_blk) and, for the backward modes, part_ln / part_dw / dconv / din.
@@ -471,12 +728,35 @@ int tma_launch(int mode, const Job* jobs, int njobs, int B, int heads, int T, in
   L.njobs = njobs; L.B = B; L.heads = heads; L.T = T; L.H = H; L.W = W;
   L.in_bs = bs; L.in_ts = ts; L.in_hs = hs; L.eps = eps;
   const int esz = dtype == PMV_BF16 ? 2 : 4;
-  int total = 0, max_s = 1;
+  if (mode == 3) {
+    // stride 1 jobs: t-march over dconv below; stride 2 / >= 3: dedicated kernels
+    Job s1[MAX_JOBS];
+    int n1 = 0, nother = 0, tot1 = 0;
+    for (int i = 0; i < njobs; ++i) {
+      if (jobs[i].s == 1) {
+        s1[n1] = jobs[i];
+        s1[n1].blk_begin = tot1;
+        tot1 += s1[n1].nblk;
+        ++n1;
+      } else {
+        ++nother;
+      }
+    }
+    if (nother > 0) {
+      int rc = dtype == PMV_BF16 ? launch_din_strided<bf16>(jobs, njobs, L, esz, st) : launch_din_strided<float>(jobs, njobs, L, esz, st);
+      if (rc) return rc;
+    }
+    if (n1 == 0) return PMV_OK;
+    if (n1 < njobs) return tma_launch(3, s1, n1, B, heads, T, H, W, bs, ts, hs, eps, dtype, st);
+  }
+  int total = 0;
+  size_t max_plane = 0;
   for (int i = 0; i < njobs; ++i) {
     L.job[i] = jobs[i];
     const Job& J = jobs[i];
-    if (J.s > max_s) max_s = J.s;
     const int S = J.s;
+    const size_t pb = plane_bytes(mode == 3 ? 1 : S, esz);
+    if (pb > max_plane) max_plane = pb;
     int rc;
     if (mode == 3) {
       int64_t dims[5] = {HD, W, H, T, (int64_t)B * heads};
@@ -486,24 +766,26 @@ int tma_launch(int mode, const Job* jobs, int njobs, int B, int heads, int T, in
       int64_t dims[5] = {(int64_t)heads * HD, W, H, T, B};
       int64_t str[4] = {ts, (int64_t)W * ts, (int64_t)H * W * ts, bs};
       // token 0 is the cls token: the spatial volume starts one token in
-      rc = make_map(&L.tm[i], reinterpret_cast<const char*>(J.in) + ts * esz, esz, dims, str, 3 + (CW - 1) * S, 3 + (ROWS - 1) * S);
+      const char* vol = reinterpret_cast<const char*>(J.in) + ts * esz;
+      if (S >= 3) rc = make_map(&L.tm[i], vol, esz, dims, str, (CW - 1) * S + 1, (ROWS - 1) * S + 1, S);  // walks every S-th token
+      else rc = make_map(&L.tm[i], vol, esz, dims, str, 3 + (CW - 1) * S, 3 + (ROWS - 1) * S);
     }
     if (rc) return rc;
     total = J.blk_begin + J.nblk + ((mode == 0 || mode == 1) ? J.ncls_blk : 0);
   }
   if (dtype == PMV_BF16) {
     switch (mode) {
-      case 0: return launch_mode<bf16, M_FWD>(L, total, max_s, st);
-      case 1: return launch_mode<bf16, M_BWD_LN>(L, total, max_s, st);
-      case 2: return launch_mode<bf16, M_BWD_DW>(L, total, max_s, st);
-      default: return launch_mode<bf16, M_BWD_IN>(L, total, 1, st);
+      case 0: return launch_mode<bf16, M_FWD>(L, total, max_plane, st);
+      case 1: return launch_mode<bf16, M_BWD_LN>(L, total, max_plane, st);
+      case 2: return launch_mode<bf16, M_BWD_DW>(L, total, max_plane, st);
+      default: return launch_mode<bf16, M_BWD_IN>(L, total, max_plane, st);
     }
   }
   switch (mode) {
-    case 0: return launch_mode<float, M_FWD>(L, total, max_s, st);
-    case 1: return launch_mode<float, M_BWD_LN>(L, total, max_s, st);
-    case 2: return launch_mode<float, M_BWD_DW>(L, total, max_s, st);
-    default: return launch_mode<float, M_BWD_IN>(L, total, 1, st);
+    case 0: return launch_mode<float, M_FWD>(L, total, max_plane, st);
+    case 1: return launch_mode<float, M_BWD_LN>(L, total, max_plane, st);
+    case 2: return launch_mode<float, M_BWD_DW>(L, total, max_plane, st);
+    default: return launch_mode<float, M_BWD_IN>(L, total, max_plane, st);
   }
 }
 

@@ -40,7 +40,7 @@ static EncodeTiledFn get_encode() {
 }
 
 static int encode(CUtensorMap* out, const void* base, int elem_bytes, int rank, const cuuint64_t* dims,
-                  const cuuint64_t* strides_bytes, const cuuint32_t* box, int swizzle) {
+                  const cuuint64_t* strides_bytes, const cuuint32_t* box, int swizzle, const cuuint32_t* walk = nullptr) {
   EncodeTiledFn fn = get_encode();
   if (!fn) {
     pmv_set_error("cuTensorMapEncodeTiled entry point not available");
@@ -54,6 +54,9 @@ static int encode(CUtensorMap* out, const void* base, int elem_bytes, int rank, 
                           : swizzle == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
                                           : CU_TENSOR_MAP_SWIZZLE_NONE;
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (walk) {
+    for (int i = 0; i < rank; ++i) estr[i] = walk[i];
+  }
   CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -84,10 +87,11 @@ int pmv_make_tensor_map_3d(CUtensorMap* out, const void* base, int elem_bytes, u
 
 int pmv_make_tensor_map_5d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
                            uint64_t d4, uint64_t s1_elems, uint64_t s2_elems, uint64_t s3_elems, uint64_t s4_elems, uint32_t b0,
-                           uint32_t b1, uint32_t b2, uint32_t b3, uint32_t b4) {
+                           uint32_t b1, uint32_t b2, uint32_t b3, uint32_t b4, uint32_t walk_hw) {
   cuuint64_t dims[5] = {d0, d1, d2, d3, d4};
+  cuuint32_t walk[5] = {1, walk_hw, walk_hw, 1, 1};  // element strides along w and h (strided pooling windows)
   cuuint64_t strides[4] = {s1_elems * (uint64_t)elem_bytes, s2_elems * (uint64_t)elem_bytes, s3_elems * (uint64_t)elem_bytes,
                            s4_elems * (uint64_t)elem_bytes};
   cuuint32_t box[5] = {b0, b1, b2, b3, b4};
-  return encode(out, base, elem_bytes, 5, dims, strides, box, 0);
+  return encode(out, base, elem_bytes, 5, dims, strides, box, 0, walk_hw > 1 ? walk : nullptr);
 }

@@ -163,7 +163,8 @@ int pmv_make_tensor_map_2d(CUtensorMap* out, const void* base, int elem_bytes, u
 int pmv_make_tensor_map_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t dim0, uint64_t dim1, uint64_t dim2,
                            uint64_t stride1_elems, uint64_t stride2_elems, uint32_t box0, uint32_t box1, uint32_t box2,
                            int swizzle);
-// 5-D, no swizzle (pooling planes: channel, w, h, t, batch; out-of-bounds elements read as zero)
+// 5-D, no swizzle (pooling planes: channel, w, h, t, batch; out-of-bounds elements read as zero).  walk_hw > 1: the box is
+// traversed with that element stride along dims 1 and 2 (b1 / b2 are the traversed extents, ceil(b / walk) tokens land).
 int pmv_make_tensor_map_5d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
                            uint64_t d4, uint64_t s1_elems, uint64_t s2_elems, uint64_t s3_elems, uint64_t s4_elems, uint32_t b0,
-                           uint32_t b1, uint32_t b2, uint32_t b3, uint32_t b4);
+                           uint32_t b1, uint32_t b2, uint32_t b3, uint32_t b4, uint32_t walk_hw = 1);
