@@ -301,9 +301,26 @@ def main():
         torch.cuda.synchronize()
         roof, shares, detail = summarize_kernels(rec, peaks)
 
+    def shutdown():
+        """Leave the process group without hanging: the captured graph holds NCCL kernels, so release it first; a
+        watchdog ends the process if the communicator teardown still blocks (the result line is already out)."""
+        nonlocal graphed, step
+        if world == 1:
+            return
+        sys.stdout.flush()
+        import gc
+        import threading
+        threading.Timer(30.0, lambda: os._exit(0)).start()
+        step = eager_step
+        graphed = None
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
+        os._exit(0)
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown()
         return
     total_clips = B * world
     value = total_clips / (ms_dev * 1e-3)
@@ -328,8 +345,7 @@ def main():
                                 "sample": f"oracle port of the reference MViT ({args.mode}), 1 clip per step, fp32, "
                                           f"{2 if train else 3} steps after 1 warm-up ({ms:.0f} ms/step)"}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 if __name__ == "__main__":

@@ -44,10 +44,12 @@ template <int KD> struct BCfg {
   static constexpr int SMEM_BYTES = 3 * STAGE_BYTES + 1024 /*align*/ + 2048 /*lse, delta*/ + 256;
 };
 
-// K-major descriptor of k-step ks (16 columns) inside a [rows x KD] tile
-template <int KD> __device__ __forceinline__ uint64_t kmajor_desc(uint32_t base, int ks) {
-  if (ks < 8) return tc::make_smem_desc(base + (uint32_t)(ks >> 2) * 16384 + (uint32_t)(ks & 3) * 32, 16, 1024, tc::SWIZZLE_128B);
-  return tc::make_smem_desc(base + 32768 + (uint32_t)(ks - 8) * 32, 16, 512, tc::SWIZZLE_64B);
+// K-major descriptor of k-step ks (16 columns) inside a [rows x KD] tile, starting `half` * 64 rows into the tile
+// (128B-swizzle blocks: 64 rows = 8192 B; the 64B-swizzle block of the bias columns: 64 rows = 4096 B)
+template <int KD> __device__ __forceinline__ uint64_t kmajor_desc(uint32_t base, int ks, int half = 0) {
+  if (ks < 8)
+    return tc::make_smem_desc(base + (uint32_t)(ks >> 2) * 16384 + (uint32_t)half * 8192 + (uint32_t)(ks & 3) * 32, 16, 1024, tc::SWIZZLE_128B);
+  return tc::make_smem_desc(base + 32768 + (uint32_t)half * 4096 + (uint32_t)(ks - 8) * 32, 16, 512, tc::SWIZZLE_64B);
 }
 
 __device__ __forceinline__ void load_tile_qk(uint8_t* dst, const CUtensorMap* m128, const CUtensorMap* m64, int kd, int row0,
@@ -56,6 +58,16 @@ __device__ __forceinline__ void load_tile_qk(uint8_t* dst, const CUtensorMap* m1
   tc::tma_load_3d(dst + 16384, m128, 64, row0, bh, bar);
   if (kd == 160) tc::tma_load_3d(dst + 32768, m64, 128, row0, bh, bar);
 }
+
+// Software pipeline shared by both kernels.  A 128-wide tile of the "other" axis (keys in the dQ kernel, queries in
+// the dK/dV kernel) is processed as two halves of 64; the score-like accumulators S and dP are double-buffered in
+// TMEM (2 x 64 columns each), so the tensor core computes S / dP of half h+1 while the softmax warps turn half h
+// into P / dS, and the products that consume P / dS of half h are issued right after.  Before this the chain
+// MMA -> softmax -> MMA ran serially per tile (profiles/r01_kernels_after.txt: 80-230 TFLOP/s).
+constexpr int HK = 64;
+// where the 16-element k-step ks of a half sits after the softmax warps packed it to bf16: warp-half 0 (elements 0..31)
+// writes columns [0, 16) of the S buffer, warp-half 1 (elements 32..63) columns [32, 48) — each behind its own reads
+__device__ __forceinline__ uint32_t packed_col(int ks) { return ks < 2 ? ks * 8 : 32 + (ks - 2) * 8; }
 
 // ================================================================================================ dQ kernel
 template <int KD>
@@ -75,10 +87,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* q_full = bars;        // [1]
   uint64_t* kv_full = bars + 1;   // [2]
   uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* sdp_full = bars + 5;  // [1]  S and dP of the current tile are in TMEM
-  uint64_t* ds_full = bars + 6;   // [1]  dS written (4 warps)
-  uint64_t* dq_final = bars + 7;  // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* sdp_full = bars + 5;  // [2]  S and dP of a half are in TMEM buffer b
+  uint64_t* ds_full = bars + 7;   // [2]  dS of buffer b written (8 warps)
+  uint64_t* dq_final = bars + 9;  // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
@@ -88,9 +100,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (warp == 0 && lane == 0) {
     tc::mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&kv_full[i], 1); tc::mbar_init(&kv_empty[i], 1); }
-    tc::mbar_init(sdp_full, 1);
-    tc::mbar_init(ds_full, SM_WARPS);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&kv_full[i], 1);
+      tc::mbar_init(&kv_empty[i], 1);
+      tc::mbar_init(&sdp_full[i], 1);
+      tc::mbar_init(&ds_full[i], SM_WARPS);
+    }
     tc::mbar_init(dq_final, 1);
     tc::fence_barrier_init();
   }
@@ -99,7 +114,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dq = tmem_base + 256;
+  const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dq = tmem_base + 256;  // S / dP: buffer b at + 64 b
 
   if (warp == 0) {
     if (lane == 0) {
@@ -121,44 +136,62 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t sq_addr = tc::smem_u32(sQ), sdo_addr = tc::smem_u32(sdO);
+      const uint32_t idesc_128 = tc::make_idesc_bf16(BT, 128, false, true);
+      const uint32_t idesc_32 = tc::make_idesc_bf16(BT, 32, false, true);
       tc::mbar_wait(q_full, 0);
       tc::tc_fence_after();
+      int hh = 0;  // live halves issued so far
+      bool have_prev = false, first_dq = true;
+      int p_b = 0, p_hh = 0, p_nks = 0, p_half = 0, p_st = 0;
+      bool p_last = false;
+      uint32_t p_sk = 0;
+      // dQ' += dS K' for the half recorded in p_*: A = dS (TMEM, packed bf16), B = K' rows of that half read MN-major
+      auto retire = [&]() {
+        tc::mbar_wait(&ds_full[p_b], (uint32_t)((p_hh >> 1) & 1));
+        tc::tc_fence_after();
+        for (int ks = 0; ks < p_nks; ++ks) {
+          const uint32_t acc = first_dq ? 0u : 1u;
+          first_dq = false;
+          const uint32_t a = tmem_s + p_b * HK + packed_col(ks);
+          const int kk = 4 * p_half + ks;
+          tc::umma_ts(tmem_dq, a, tc::make_smem_desc(p_sk + kk * 2048, 16384, 1024, tc::SWIZZLE_128B), idesc_128, acc);
+          if (KD == 160) tc::umma_ts(tmem_dq + 128, a, tc::make_smem_desc(p_sk + 32768 + kk * 1024, 8192, 512, tc::SWIZZLE_64B), idesc_32, acc);
+        }
+        if (p_last) tc::umma_commit(&kv_empty[p_st]);
+      };
       for (int j = 0; j < ntiles; ++j) {
         const int st = j & 1;
         tc::mbar_wait(&kv_full[st], (j >> 1) & 1);
         tc::tc_fence_after();
         const int nvalid = min(BT, g.Nk - j * BT);
-        const int n16 = (nvalid + 15) & ~15;
         const uint32_t sk_addr = tc::smem_u32(sStage + st * Cfg::STAGE_BYTES);
         const uint32_t sv_addr = sk_addr + Cfg::QK_BYTES;
-        const uint32_t idesc_s = tc::make_idesc_bf16(BT, n16, false, false);
+        for (int half = 0; half < 2; ++half) {
+          const int nv = min(HK, nvalid - HK * half);
+          if (nv <= 0) break;
+          const int n16 = (nv + 15) & ~15;
+          const int b = hh & 1;
+          const uint32_t idesc_s = tc::make_idesc_bf16(BT, n16, false, false);
 #pragma unroll
-        for (int ks = 0; ks < KD / 16; ++ks)  // S = Q' K'^T
-          tc::umma_ss(tmem_s, kmajor_desc<KD>(sq_addr, ks), kmajor_desc<KD>(sk_addr, ks), idesc_s, ks > 0);
+          for (int ks = 0; ks < KD / 16; ++ks)  // S = Q' K'^T (keys of this half)
+            tc::umma_ss(tmem_s + b * HK, kmajor_desc<KD>(sq_addr, ks), kmajor_desc<KD>(sk_addr, ks, half), idesc_s, ks > 0);
 #pragma unroll
-        for (int ks = 0; ks < HD / 16; ++ks)  // dP = dO V^T
-          tc::umma_ss(tmem_dp, kmajor_desc<128>(sdo_addr, ks), kmajor_desc<128>(sv_addr, ks), idesc_s, ks > 0);
-        tc::umma_commit(sdp_full);
-        tc::mbar_wait(ds_full, j & 1);
-        tc::tc_fence_after();
-        // dQ' += dS K' : A = dS (TMEM, packed bf16 over the S columns), B = K' tile read MN-major
-        const int nks = n16 >> 4;
-        const uint32_t idesc_128 = tc::make_idesc_bf16(BT, 128, false, true);
-        const uint32_t idesc_32 = tc::make_idesc_bf16(BT, 32, false, true);
-        for (int ks = 0; ks < nks; ++ks) {
-          const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
-          const uint32_t a_col = ks < 4 ? ks * 8 : 64 + (ks - 4) * 8;  // see the softmax warps: where dS of these 16 keys sits
-          tc::umma_ts(tmem_dq, tmem_s + a_col, tc::make_smem_desc(sk_addr + ks * 2048, 16384, 1024, tc::SWIZZLE_128B), idesc_128, acc);
-          if (KD == 160)
-            tc::umma_ts(tmem_dq + 128, tmem_s + a_col, tc::make_smem_desc(sk_addr + 32768 + ks * 1024, 8192, 512, tc::SWIZZLE_64B), idesc_32, acc);
+          for (int ks = 0; ks < HD / 16; ++ks)  // dP = dO V^T
+            tc::umma_ss(tmem_dp + b * HK, kmajor_desc<128>(sdo_addr, ks), kmajor_desc<128>(sv_addr, ks, half), idesc_s, ks > 0);
+          tc::umma_commit(&sdp_full[b]);
+          if (have_prev) retire();
+          have_prev = true;
+          p_b = b; p_hh = hh; p_nks = n16 >> 4; p_half = half; p_st = st; p_sk = sk_addr;
+          p_last = (half == 1) || (nvalid <= HK);
+          ++hh;
         }
-        tc::umma_commit(&kv_empty[st]);
       }
+      if (have_prev) retire();
       tc::umma_commit(dq_final);
     }
   } else if (warp >= 4) {
     const int qd = warp & 3;
-    const int half = (warp - 4) >> 2;  // the two warps of a lane quarter take alternate 32-column chunks
+    const int wh = (warp - 4) >> 2;  // which 32 elements of a half this warp converts
     const int row = qd * 32 + lane;
     const int n = q0 + row;
     const bool rvalid = n < g.Nq;
@@ -181,39 +214,43 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           delta = fmaf(__high2float(a2[i]), __high2float(b2[i]), delta);
         }
       }
-      if (half == 0) delta_out[(int64_t)bh * g.Nq + n] = delta;
+      if (wh == 0) delta_out[(int64_t)bh * g.Nq + n] = delta;
       lse2 = lse[(int64_t)bh * g.Nq + n] * 1.4426950408889634f;
     }
+    int hh = 0;
     for (int j = 0; j < ntiles; ++j) {
-      tc::mbar_wait(sdp_full, j & 1);
-      tc::tc_fence_after();
       const int nvalid = min(BT, g.Nk - j * BT);
-      const int nchunks = (nvalid + 31) >> 5;
-      // warp `half` owns score columns [64 half, 64 half + 64) and writes its packed bf16 dS over the first 32 columns
-      // of that range, behind its own reads: keys 0..63 -> columns [0, 32), keys 64..127 -> columns [64, 96)
-      for (int ch = 2 * half; ch < nchunks && ch < 2 * half + 2; ++ch) {
-        uint32_t s[32], dp[32], pk[16];
-        tc::tmem_ld32(tmem_s + lane_addr + ch * 32, s);
-        tc::tmem_ld32(tmem_dp + lane_addr + ch * 32, dp);
-        tc::tmem_ld_wait();
+      for (int half = 0; half < 2; ++half) {
+        const int nv = min(HK, nvalid - HK * half);
+        if (nv <= 0) break;
+        const int b = hh & 1;
+        tc::mbar_wait(&sdp_full[b], (uint32_t)((hh >> 1) & 1));
+        tc::tc_fence_after();
+        if (wh * 32 < nv) {
+          uint32_t s[32], dp[32], pk[16];
+          tc::tmem_ld32(tmem_s + lane_addr + b * HK + wh * 32, s);
+          tc::tmem_ld32(tmem_dp + lane_addr + b * HK + wh * 32, dp);
+          tc::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float d[2];
+          for (int i = 0; i < 16; ++i) {
+            float d[2];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int col = ch * 32 + 2 * i + h;
-            const float p = (rvalid && col < nvalid) ? exp2f(fmaf(__uint_as_float(s[2 * i + h]), c, -lse2)) : 0.f;
-            d[h] = p * (__uint_as_float(dp[2 * i + h]) - delta) * g.scale;
+            for (int h = 0; h < 2; ++h) {
+              const int col = wh * 32 + 2 * i + h;
+              const float p = (rvalid && col < nv) ? exp2f(fmaf(__uint_as_float(s[2 * i + h]), c, -lse2)) : 0.f;
+              d[h] = p * (__uint_as_float(dp[2 * i + h]) - delta) * g.scale;
+            }
+            __nv_bfloat162 pp = __floats2bfloat162_rn(d[0], d[1]);
+            pk[i] = *reinterpret_cast<uint32_t*>(&pp);
           }
-          __nv_bfloat162 pp = __floats2bfloat162_rn(d[0], d[1]);
-          pk[i] = *reinterpret_cast<uint32_t*>(&pp);
+          tc::tmem_st16(tmem_s + lane_addr + b * HK + wh * 32, pk);
+          tc::tmem_st_wait();
         }
-        tc::tmem_st16(tmem_s + lane_addr + half * 64 + (ch - 2 * half) * 16, pk);
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&ds_full[b]);
+        ++hh;
       }
-      tc::tmem_st_wait();
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(ds_full);
     }
     // epilogue: dQ' (+ dO on the first 96 columns for rows >= 1: residual pooling) -> bf16
     tc::mbar_wait(dq_final, 0);
@@ -221,7 +258,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     bf16* dqp = dq_aug + ((int64_t)bh * g.Nq + n) * g.ld_qk;
     const bool add_do = g.residual && n >= 1;
 #pragma unroll 1
-    for (int ch = half; ch < KD / 32; ch += 2) {
+    for (int ch = wh; ch < KD / 32; ch += 2) {
       uint32_t o[32];
       tc::tmem_ld32(tmem_dq + lane_addr + ch * 32, o);
       tc::tmem_ld_wait();
@@ -273,10 +310,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* k_full = bars;       // [1]
   uint64_t* q_full = bars + 1;   // [2]
   uint64_t* q_empty = bars + 3;  // [2]
-  uint64_t* sdp_full = bars + 5;
-  uint64_t* pds_full = bars + 6;  // P^T and dS^T written (4 warps)
-  uint64_t* final_bar = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* sdp_full = bars + 5;  // [2]
+  uint64_t* pds_full = bars + 7;  // [2]  P^T and dS^T of buffer b written (8 warps)
+  uint64_t* final_bar = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
@@ -289,9 +326,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   if (warp == 0 && lane == 0) {
     tc::mbar_init(k_full, 1);
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&q_full[i], 1); tc::mbar_init(&q_empty[i], 1); }
-    tc::mbar_init(sdp_full, 1);
-    tc::mbar_init(pds_full, SM_WARPS);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&q_full[i], 1);
+      tc::mbar_init(&q_empty[i], 1);
+      tc::mbar_init(&sdp_full[i], 1);
+      tc::mbar_init(&pds_full[i], SM_WARPS);
+    }
     tc::mbar_init(final_bar, 1);
     tc::fence_barrier_init();
   }
@@ -326,44 +366,63 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tc::mbar_wait(k_full, 0);
       tc::tc_fence_after();
       const uint32_t idesc_o = tc::make_idesc_bf16(BT, HD, false, true);  // N = 96 channels, B read MN-major
+      int hh = 0;
+      bool have_prev = false, first_acc = true;
+      int p_b = 0, p_hh = 0, p_nks = 0, p_half = 0, p_st = 0;
+      bool p_last = false;
+      uint32_t p_sq = 0, p_sdo = 0;
+      // dV += P^T dO ; dK += dS^T Q'[:, :96] for the recorded half (B tiles read MN-major: 16-query steps are 2048 B apart)
+      auto retire = [&]() {
+        tc::mbar_wait(&pds_full[p_b], (uint32_t)((p_hh >> 1) & 1));
+        tc::tc_fence_after();
+        for (int ks = 0; ks < p_nks; ++ks) {
+          const uint32_t acc = first_acc ? 0u : 1u;
+          first_acc = false;
+          const int kk = 4 * p_half + ks;
+          tc::umma_ts(tmem_dv, tmem_st + p_b * HK + packed_col(ks), tc::make_smem_desc(p_sdo + kk * 2048, 16384, 1024, tc::SWIZZLE_128B), idesc_o, acc);
+          tc::umma_ts(tmem_dk, tmem_dpt + p_b * HK + packed_col(ks), tc::make_smem_desc(p_sq + kk * 2048, 16384, 1024, tc::SWIZZLE_128B), idesc_o, acc);
+        }
+        if (p_last) tc::umma_commit(&q_empty[p_st]);
+      };
       for (int i = 0; i < nq_tiles; ++i) {
         const int st = i & 1;
         const int q0 = (qt_begin + i) * BT;
         tc::mbar_wait(&q_full[st], (i >> 1) & 1);
         tc::tc_fence_after();
         const int nqv = min(BT, g.Nq - q0);
-        const int n16 = (nqv + 15) & ~15;
         const uint32_t sq_addr = tc::smem_u32(sStage + st * Cfg::STAGE_BYTES);
         const uint32_t sdo_addr = sq_addr + Cfg::QK_BYTES;
-        const uint32_t idesc_s = tc::make_idesc_bf16(BT, n16, false, false);
+        for (int half = 0; half < 2; ++half) {
+          const int nv = min(HK, nqv - HK * half);
+          if (nv <= 0) break;
+          const int n16 = (nv + 15) & ~15;
+          const int b = hh & 1;
+          const uint32_t idesc_s = tc::make_idesc_bf16(BT, n16, false, false);
 #pragma unroll
-        for (int ks = 0; ks < KD / 16; ++ks)  // S^T = K' Q'^T
-          tc::umma_ss(tmem_st, kmajor_desc<KD>(sk_addr, ks), kmajor_desc<KD>(sq_addr, ks), idesc_s, ks > 0);
+          for (int ks = 0; ks < KD / 16; ++ks)  // S^T = K' Q'^T (queries of this half)
+            tc::umma_ss(tmem_st + b * HK, kmajor_desc<KD>(sk_addr, ks), kmajor_desc<KD>(sq_addr, ks, half), idesc_s, ks > 0);
 #pragma unroll
-        for (int ks = 0; ks < HD / 16; ++ks)  // dP^T = V dO^T
-          tc::umma_ss(tmem_dpt, kmajor_desc<128>(sv_addr, ks), kmajor_desc<128>(sdo_addr, ks), idesc_s, ks > 0);
-        tc::umma_commit(sdp_full);
-        tc::mbar_wait(pds_full, i & 1);
-        tc::tc_fence_after();
-        const int nks = n16 >> 4;
-        for (int ks = 0; ks < nks; ++ks) {
-          const uint32_t acc = (i > 0 || ks > 0) ? 1u : 0u;
-          // dV += P^T dO ; dK += dS^T Q'[:, :96]   (B tiles read MN-major: 64-column groups 16384 B apart)
-          const uint32_t a_col = ks < 4 ? ks * 8 : 64 + (ks - 4) * 8;
-          tc::umma_ts(tmem_dv, tmem_st + a_col, tc::make_smem_desc(sdo_addr + ks * 2048, 16384, 1024, tc::SWIZZLE_128B), idesc_o, acc);
-          tc::umma_ts(tmem_dk, tmem_dpt + a_col, tc::make_smem_desc(sq_addr + ks * 2048, 16384, 1024, tc::SWIZZLE_128B), idesc_o, acc);
+          for (int ks = 0; ks < HD / 16; ++ks)  // dP^T = V dO^T
+            tc::umma_ss(tmem_dpt + b * HK, kmajor_desc<128>(sv_addr, ks), kmajor_desc<128>(sdo_addr, ks, half), idesc_s, ks > 0);
+          tc::umma_commit(&sdp_full[b]);
+          if (have_prev) retire();
+          have_prev = true;
+          p_b = b; p_hh = hh; p_nks = n16 >> 4; p_half = half; p_st = st; p_sq = sq_addr; p_sdo = sdo_addr;
+          p_last = (half == 1) || (nqv <= HK);
+          ++hh;
         }
-        tc::umma_commit(&q_empty[st]);
       }
+      if (have_prev) retire();
       tc::umma_commit(final_bar);
     }
   } else if (warp >= 4) {
     const int qd = warp & 3;
-    const int half = (warp - 4) >> 2;
+    const int wh = (warp - 4) >> 2;
     const int row = qd * 32 + lane;  // key row of this thread
     const int tid128 = threadIdx.x - 128;  // 0..255; the first 128 stage lse / delta
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
     const float c = g.scale * 1.4426950408889634f;
+    int hh = 0;
     for (int i = 0; i < nq_tiles; ++i) {
       const int q0 = (qt_begin + i) * BT;
       const int nqv = min(BT, g.Nq - q0);
@@ -376,35 +435,41 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         del_t[tid128] = ok ? delta[(int64_t)bh * g.Nq + n] : 0.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight softmax warps only
-      tc::mbar_wait(sdp_full, i & 1);
-      tc::tc_fence_after();
-      const int nchunks = (nqv + 31) >> 5;
-      for (int ch = 2 * half; ch < nchunks && ch < 2 * half + 2; ++ch) {
-        uint32_t s[32], dp[32], pk[16], dk[16];
-        tc::tmem_ld32(tmem_st + lane_addr + ch * 32, s);
-        tc::tmem_ld32(tmem_dpt + lane_addr + ch * 32, dp);
-        tc::tmem_ld_wait();
+      for (int half = 0; half < 2; ++half) {
+        const int nv = min(HK, nqv - HK * half);
+        if (nv <= 0) break;
+        const int b = hh & 1;
+        tc::mbar_wait(&sdp_full[b], (uint32_t)((hh >> 1) & 1));
+        tc::tc_fence_after();
+        if (wh * 32 < nv) {
+          uint32_t s[32], dp[32], pk[16], dk[16];
+          tc::tmem_ld32(tmem_st + lane_addr + b * HK + wh * 32, s);
+          tc::tmem_ld32(tmem_dpt + lane_addr + b * HK + wh * 32, dp);
+          tc::tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          float p[2], d[2];
+          for (int e = 0; e < 16; ++e) {
+            float p[2], d[2];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int col = ch * 32 + 2 * e + h;  // query inside the tile
-            p[h] = col < nqv ? exp2f(fmaf(__uint_as_float(s[2 * e + h]), c, -lse_t[col])) : 0.f;
-            d[h] = p[h] * (__uint_as_float(dp[2 * e + h]) - del_t[col]) * g.scale;
+            for (int h = 0; h < 2; ++h) {
+              const int cl = wh * 32 + 2 * e + h;        // query inside the half
+              const int col = half * HK + cl;            // query inside the tile
+              p[h] = cl < nv ? exp2f(fmaf(__uint_as_float(s[2 * e + h]), c, -lse_t[col])) : 0.f;
+              d[h] = p[h] * (__uint_as_float(dp[2 * e + h]) - del_t[col]) * g.scale;
+            }
+            __nv_bfloat162 pp = __floats2bfloat162_rn(p[0], p[1]);
+            __nv_bfloat162 dd = __floats2bfloat162_rn(d[0], d[1]);
+            pk[e] = *reinterpret_cast<uint32_t*>(&pp);
+            dk[e] = *reinterpret_cast<uint32_t*>(&dd);
           }
-          __nv_bfloat162 pp = __floats2bfloat162_rn(p[0], p[1]);
-          __nv_bfloat162 dd = __floats2bfloat162_rn(d[0], d[1]);
-          pk[e] = *reinterpret_cast<uint32_t*>(&pp);
-          dk[e] = *reinterpret_cast<uint32_t*>(&dd);
+          tc::tmem_st16(tmem_st + lane_addr + b * HK + wh * 32, pk);
+          tc::tmem_st16(tmem_dpt + lane_addr + b * HK + wh * 32, dk);
+          tc::tmem_st_wait();
         }
-        tc::tmem_st16(tmem_st + lane_addr + half * 64 + (ch - 2 * half) * 16, pk);
-        tc::tmem_st16(tmem_dpt + lane_addr + half * 64 + (ch - 2 * half) * 16, dk);
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&pds_full[b]);
+        ++hh;
       }
-      tc::tmem_st_wait();
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(pds_full);
     }
     tc::mbar_wait(final_bar, 0);
     tc::tc_fence_after();
@@ -412,7 +477,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     float* dkp = dk_ws + ((int64_t)bh * g.Nk + key) * HD;
     float* dvp = dv_ws + ((int64_t)bh * g.Nk + key) * HD;
 #pragma unroll 1
-    for (int ch = half; ch < 3; ch += 2) {
+    for (int ch = wh; ch < 3; ch += 2) {
       uint32_t a[32], b[32];
       tc::tmem_ld32(tmem_dv + lane_addr + ch * 32, a);
       tc::tmem_ld32(tmem_dk + lane_addr + ch * 32, b);
