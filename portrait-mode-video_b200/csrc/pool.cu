@@ -716,25 +716,40 @@ int run_mode(int mode, Job* all, int njobs, const Geom& g, cudaStream_t st) {
     if (tma_ok && tma_eligible(all[i].s, mode, g.dtype == PMV_BF16 ? 2 : 4)) { ti[nt] = i; tj[nt++] = all[i]; } else { di[nd] = i; dj[nd++] = all[i]; }
   }
   if (nt > 0) {
-    // balanced waves over 2 CTAs per SM
-    int64_t items_total = 0;
-    int items[MAX_JOBS];
-    for (int i = 0; i < nt; ++i) {
-      items[i] = tma_items(g.B, g.heads, mode == 3 ? g.H : tj[i].Ho, mode == 3 ? g.W : tj[i].Wo);
-      items_total += items[i];
+    // One launch per job class, so that a class with large shared-memory planes (stride >= 3 tap tiles) does not
+    // take the second CTA per SM away from the big stride-1 / stride-2 jobs, and the block budget of a launch is
+    // computed from the jobs that are really in it (profiles/r01_pool_ncu.md: 0.3 waves on the stride-1 input gradient).
+    //   class 0: dense planes (stride 1, 2; mode 3: stride 1 only)   class 1: everything else of this mode
+    for (int cls = 0; cls < 2; ++cls) {
+      Job cj[MAX_JOBS];
+      int ci[MAX_JOBS];
+      int nc = 0;
+      for (int i = 0; i < nt; ++i) {
+        const bool dense = mode == 3 ? tj[i].s == 1 : tj[i].s <= 2;
+        if (dense == (cls == 0)) { ci[nc] = ti[i]; cj[nc++] = tj[i]; }
+      }
+      if (nc == 0) continue;
+      int64_t items_total = 0;
+      int items[MAX_JOBS];
+      for (int i = 0; i < nc; ++i) {
+        items[i] = tma_items(g.B, g.heads, mode == 3 ? g.H : cj[i].Ho, mode == 3 ? g.W : cj[i].Wo);
+        items_total += items[i];
+      }
+      // balanced rounds over the CTA slots of the machine (2 per SM for dense planes, 1 for the tap-tile class)
+      const int slots = 148 * (cls == 0 ? 2 : 1);
+      const int64_t rounds = ceil_div64(items_total, slots);
+      int total = 0;
+      for (int i = 0; i < nc; ++i) {
+        cj[i].blk_begin = total;
+        cj[i].nblk = nblocks_for(ceil_div64(items[i], rounds), mode == 2 ? MAX_DW_BLOCKS : MAX_LN_BLOCKS);
+        cj[i].ncls_blk = (mode == 0 || mode == 1) ? cls_blocks(g.B, g.heads) : 0;
+        total += cj[i].nblk + cj[i].ncls_blk;
+        if (mode == 1) all[ci[i]].nblk_ln = cj[i].nblk + cj[i].ncls_blk;
+        if (mode == 2) all[ci[i]].nblk_dw = cj[i].nblk;
+      }
+      int rc = tma_launch(mode, cj, nc, g.B, g.heads, g.T, g.H, g.W, g.bs, g.ts, g.hs, g.eps, g.dtype, st);
+      if (rc) return rc;
     }
-    const int64_t waves = ceil_div64(items_total, 148 * 2);
-    int total = 0;
-    for (int i = 0; i < nt; ++i) {
-      tj[i].blk_begin = total;
-      tj[i].nblk = nblocks_for(ceil_div64(items[i], waves), mode == 2 ? MAX_DW_BLOCKS : MAX_LN_BLOCKS);
-      tj[i].ncls_blk = (mode == 0 || mode == 1) ? cls_blocks(g.B, g.heads) : 0;
-      total += tj[i].nblk + tj[i].ncls_blk;
-      if (mode == 1) all[ti[i]].nblk_ln = tj[i].nblk + tj[i].ncls_blk;
-      if (mode == 2) all[ti[i]].nblk_dw = tj[i].nblk;
-    }
-    int rc = tma_launch(mode, tj, nt, g.B, g.heads, g.T, g.H, g.W, g.bs, g.ts, g.hs, g.eps, g.dtype, st);
-    if (rc) return rc;
   }
   if (nd > 0) {
     Launch L;

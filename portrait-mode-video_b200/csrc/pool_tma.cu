@@ -163,7 +163,13 @@ __device__ __forceinline__ void march(const TLaunch& L, const Job& J, const CUte
         dst[j] = ok ? ld2(dc + j * HD) : make_float2(0.f, 0.f);
       }
     };
-    if (MODE == M_BWD_DW) load_dc(acc[0], 0);
+    // M_BWD_DW: step tin needs the pre-LN gradient of frames tin-1, tin, tin+1.  Frame tin+2 is requested at the END of
+    // step tin, into the register slot frame tin-1 just vacated, so the loads fly during the barrier and the wait for the
+    // next plane (they used to be consumed right after issue: 37 % of the samples, profiles/r01_pool_ncu.md)
+    if constexpr (MODE == M_BWD_DW) {
+      load_dc(acc[0], 0);
+      load_dc(acc[1], 1);
+    }
 
     auto step = [&](auto ptag, int tin) {
       constexpr int P = decltype(ptag)::value;
@@ -171,7 +177,6 @@ __device__ __forceinline__ void march(const TLaunch& L, const Job& J, const CUte
       if (tin > Tn) return;
       const int k = i * Tn + tin;
       if (tin < Tn) {
-        if (MODE == M_BWD_DW) load_dc(acc[SLOT_P1], tin + 1);
         tc::mbar_wait(&sm.full[k % NST], (uint32_t)((k / NST) & 1));
         if (conv_thread) {
           const T* plane = reinterpret_cast<const T*>(sm.planes + (size_t)(k % NST) * PLANE_STRIDE) + 2 * cp;
@@ -189,10 +194,11 @@ __device__ __forceinline__ void march(const TLaunch& L, const Job& J, const CUte
 #pragma unroll
               for (int c = 0; c < G::BW; ++c) x[c] = lds2(prow + c * HD);
             }
+            // dw outside j: consecutive FFMA2 of one accumulator are 21 instructions apart (7 positions x 3 frames)
 #pragma unroll
-            for (int j = 0; j < CW; ++j)
+            for (int dw = 0; dw < 3; ++dw)
 #pragma unroll
-              for (int dw = 0; dw < 3; ++dw) {
+              for (int j = 0; j < CW; ++j) {
                 const float2 xv = S == 0 ? x[dw * CW + j] : x[j * S + dw];
                 if (MODE == M_BWD_DW) {
                   accw[0 * 9 + dh * 3 + dw] = __ffma2_rn(xv, acc[SLOT_P1][j], accw[0 * 9 + dh * 3 + dw]);
@@ -208,7 +214,8 @@ __device__ __forceinline__ void march(const TLaunch& L, const Job& J, const CUte
         }
       }
       const int tout = tin - 1;
-      if (MODE == M_BWD_DW) {
+      if constexpr (MODE == M_BWD_DW) {
+        if (tin < Tn) load_dc(acc[SLOT_M1], tin + 2);
         __syncthreads();  // everyone is done with plane k: its ring slot may be refilled
         if (tid == 0 && tin < Tn && k + NST < total) issue(k + NST);
         return;

@@ -1,31 +1,34 @@
-"""Micro-driver for ncu: pool backward / rel-pos kernels at the MViTv2-S mid-stage shape (blocks 4-13)."""
+"""Micro-driver for ncu: pooling forward / backward at the MViTv2-S mid-stage shape (blocks 4-13) and at block 0."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "portrait-mode-video_b200"))
 import torch
 from pmv_b200 import ops
 torch.manual_seed(0)
-B, heads, thw, sq, skv = 8, 4, (8, 14, 14), 1, 2
-T, H, W = thw
-N = 1 + T * H * W
 dt = torch.bfloat16
-qkv = torch.randn(B, N, 3, heads, 96, device="cuda").to(dt)
-ws = [torch.randn(96, 1, 3, 3, 3, device="cuda") * 0.2 for _ in range(3)]
-gs = [torch.ones(96, device="cuda") for _ in range(3)]
-bs = [torch.zeros(96, device="cuda") for _ in range(3)]
-strides = [sq, skv, skv]
-Ls = [1 + T * ops.pooled_hw(H, s) * ops.pooled_hw(W, s) for s in strides]
-lds = [128, 128, 96]
-outs = [torch.zeros(B, heads, Ls[i], lds[i], dtype=dt, device="cuda") for i in range(3)]
-douts = [torch.randn_like(o) for o in outs]
-grads = torch.zeros(3, 96 * 27 + 192, device="cuda")
-dqkv = torch.empty_like(qkv)
-q_shape, k_shape = (8, 14, 14), (8, 7, 7)
-rh, rw, rt = torch.randn(27, 96, device="cuda") * .02, torch.randn(27, 96, device="cuda") * .02, torch.randn(15, 96, device="cuda") * .02
+def case(B, heads, thw, sq, skv):
+    T, H, W = thw
+    N = 1 + T * H * W
+    qkv = torch.randn(B, N, 3, heads, 96, device="cuda").to(dt)
+    ws = [torch.randn(96, 1, 3, 3, 3, device="cuda") * 0.2 for _ in range(3)]
+    gs = [torch.ones(96, device="cuda") for _ in range(3)]
+    bs = [torch.zeros(96, device="cuda") for _ in range(3)]
+    strides = [sq, skv, skv]
+    Ls = [1 + T * ops.pooled_hw(H, s) * ops.pooled_hw(W, s) for s in strides]
+    lds = [128, 128, 96]
+    outs = [torch.zeros(B, heads, Ls[i], lds[i], dtype=dt, device="cuda") for i in range(3)]
+    xh = [torch.empty(B, heads, Ls[i], 96, dtype=dt, device="cuda") for i in range(3)]
+    rs = [torch.empty(B, heads, Ls[i], device="cuda") for i in range(3)]
+    douts = [torch.randn_like(o) for o in outs]
+    grads = torch.zeros(3, 96 * 27 + 192, device="cuda")
+    dqkv = torch.empty_like(qkv)
+    def run():
+        ops.pool_ln_qkv_fwd(qkv, heads, thw, [(i, strides[i], ws[i], gs[i], bs[i], outs[i], xh[i], rs[i]) for i in range(3)])
+        ops.pool_ln_qkv_bwd(qkv, heads, thw, [(i, strides[i], ws[i], gs[i], douts[i], grads[i], xh[i], rs[i]) for i in range(3)], dqkv)
+    return run
+runs = [case(8, 4, (8, 14, 14), 1, 2), case(8, 1, (8, 56, 56), 1, 8)]
 for it in range(3):
-    ops.pool_ln_qkv_fwd(qkv, heads, thw, [(i, strides[i], ws[i], gs[i], bs[i], outs[i]) for i in range(3)])
-    ops.relpos_augment_q(outs[0].view(B * heads, Ls[0], 128), q_shape, k_shape, rh, rw, rt, 96 ** 0.5)
-    ops.pool_ln_qkv_bwd(qkv, heads, thw, [(i, strides[i], ws[i], gs[i], douts[i], grads[i]) for i in range(3)], dqkv)
-    ops.relpos_augment_q_bwd(douts[0].view(B * heads, Ls[0], 128), outs[0].view(B * heads, Ls[0], 128), q_shape, k_shape, rh, rw, rt, 96 ** 0.5)
+    for r in runs:
+        r()
 torch.cuda.synchronize()
 print("ok")
