@@ -17,6 +17,8 @@ static int g_num_sms = 0;
 
 static int pick_kind(const EpiDev& e) {
   if (e.atomic) return EK_ATOMIC;  // only instantiated for the wgrad layout; other layouts fall back to EK_GENERIC
+  if (e.accumulate && e.out_group == 0 && !e.bias && !e.row_scale && !e.residual && !e.aux_out && e.act == PMV_ACT_NONE)
+    return EK_ACCUM;  // only instantiated for NN / bf16 (the rel-pos dQ product); everything else falls back to EK_GENERIC
   if (e.accumulate || e.out_group > 0) return EK_GENERIC;
   const bool scale = e.row_scale != nullptr, res = e.residual != nullptr;
   if (e.act == PMV_ACT_GELU) return (!scale && !res) ? EK_GELU : EK_GENERIC;
@@ -91,16 +93,17 @@ int gemm_tc_launch(int layout, const void* A, int64_t lda, const void* B, int64_
   if (kind_tma(kind)) {
     const int osz = out_dtype == PMV_F32 ? 4 : 2;
     const bool ok_out = ((uintptr_t)e.out & 15) == 0 && (e.ldo * osz) % 16 == 0;
-    const void* aux = kind == EK_GELU ? e.aux_out : kind == EK_GELU_BWD ? e.aux_in : nullptr;
-    const bool ok_aux = aux == nullptr || (((uintptr_t)aux & 15) == 0 && (e.ld_aux * 2) % 16 == 0);
+    const void* aux = kind == EK_GELU ? e.aux_out : kind == EK_GELU_BWD ? e.aux_in : kind == EK_ACCUM ? e.out : nullptr;
+    const int64_t ld_auxmap = kind == EK_ACCUM ? e.ldo : e.ld_aux;
+    const bool ok_aux = aux == nullptr || (((uintptr_t)aux & 15) == 0 && (ld_auxmap * 2) % 16 == 0);
     // kernels exist for: TN PLAIN bf16/f32, TN GELU bf16, NN PLAIN bf16, NN GELU_BWD bf16, wgrad PLAIN f32
-    if (!ok_out || !ok_aux) {
+    if (!ok_out || !ok_aux || (kind == EK_ACCUM && (layout != PMV_GEMM_NN || out_dtype != PMV_BF16))) {
       kind = EK_GENERIC;
     } else {
       rc = pmv_make_tensor_map_2d(&tmC, e.out, osz, (uint64_t)NN, (uint64_t)MM, (uint64_t)e.ldo, 32, 32, osz == 2 ? 64 : 128);
       if (rc) return rc;
       if (aux) {
-        rc = pmv_make_tensor_map_2d(&tmD, aux, 2, (uint64_t)NN, (uint64_t)MM, (uint64_t)e.ld_aux, 32, 32, 64);
+        rc = pmv_make_tensor_map_2d(&tmD, aux, 2, (uint64_t)NN, (uint64_t)MM, (uint64_t)ld_auxmap, 32, 32, 64);
         if (rc) return rc;
       }
     }

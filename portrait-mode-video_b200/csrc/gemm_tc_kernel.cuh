@@ -20,6 +20,7 @@
 //   EK_PLAIN     out = acc (+ bias)
 //   EK_GELU      out = gelu_erf(acc + bias), optionally the pre-activation to aux_out
 //   EK_GELU_BWD  out = acc * gelu_erf'(aux_in)
+//   EK_ACCUM     out(bf16) += acc            (rel-pos bias gradient added into dQ'; the previous tile arrives by TMA load)
 //   EK_RES       out(fp32) = residual + [row_scale *] (acc + bias)
 //   EK_ATOMIC    out(fp32) += acc   (split-K wgrad partials: one 16-byte vector reduction per lane)
 //   EK_GENERIC   every pmv_epilogue term at run time (accumulate, row remap, ...)
@@ -29,7 +30,7 @@
 
 namespace gemm_tc {
 
-enum { EK_PLAIN = 0, EK_GELU = 1, EK_GELU_BWD = 2, EK_RES = 3, EK_GENERIC = 4, EK_ATOMIC = 5 };
+enum { EK_PLAIN = 0, EK_GELU = 1, EK_GELU_BWD = 2, EK_RES = 3, EK_GENERIC = 4, EK_ATOMIC = 5, EK_ACCUM = 6 };
 
 constexpr int BM = 128;
 constexpr int BK = 64;
@@ -45,7 +46,7 @@ struct TcParams {
 };
 
 // kinds whose epilogue goes registers -> swizzled smem tile -> TMA store (thread = accumulator row)
-__host__ __device__ constexpr bool kind_tma(int kind) { return kind == EK_PLAIN || kind == EK_GELU || kind == EK_GELU_BWD; }
+__host__ __device__ constexpr bool kind_tma(int kind) { return kind == EK_PLAIN || kind == EK_GELU || kind == EK_GELU_BWD || kind == EK_ACCUM; }
 
 template <int BN, int KIND = EK_GENERIC> struct TileCfg {
   static constexpr int BN_GROUPS = (BN + 63) / 64;
@@ -57,7 +58,7 @@ template <int BN, int KIND = EK_GENERIC> struct TileCfg {
   static constexpr int ACC_COLS = BN <= 128 ? 128 : 256;      // TMEM columns per accumulator stage
   // per-epilogue-warp staging: 4 KB transpose buffer / one fp32 or two bf16 32x32 output tiles; the GELU kinds keep two
   // tiles per chunk (output + pre-activation), double-buffered: 8 KB
-  static constexpr int EPI_WARP_BYTES = (KIND == EK_GELU || KIND == EK_GELU_BWD) ? 8192 : 4096;
+  static constexpr int EPI_WARP_BYTES = (KIND == EK_GELU || KIND == EK_GELU_BWD || KIND == EK_ACCUM) ? 8192 : 4096;
   static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
   static constexpr int STAGES = (MAX_STAGES * STAGE_BYTES + 2048 + EPI_BYTES <= 227 * 1024) ? MAX_STAGES : MAX_STAGES - 1;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 1024 /*barriers*/ + EPI_BYTES;
@@ -289,7 +290,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     Cursor cur{(int64_t)blockIdx.x, 0, half * 32};
     if (cur.c < BN) {
-      if (KIND == EK_GELU_BWD && valid(cur)) load_aux(cur);
+      if ((KIND == EK_GELU_BWD || KIND == EK_ACCUM) && valid(cur)) load_aux(cur);
       while (valid(cur)) {
         Cursor nxt = cur;
         advance(nxt);
@@ -298,7 +299,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int as = (int)(cur.it & 1);
         const bool first_chunk = cur.c == half * 32, last_chunk = cur.c + 64 >= BN;
         const bool live = col0 < p.N && row0 < p.M;
-        if (KIND == EK_GELU_BWD) {
+        if (KIND == EK_GELU_BWD || KIND == EK_ACCUM) {
           __syncwarp();  // everyone has consumed the aux buffer the next request overwrites (two requests back)
           if (valid(nxt)) load_aux(nxt);
         }
@@ -320,7 +321,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float2 v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-          if (KIND != EK_GELU_BWD && e.bias) {
+          if (KIND != EK_GELU_BWD && KIND != EK_ACCUM && e.bias) {
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
               if (col0 + 4 * g < p.N) {  // N % 4 == 0
@@ -345,6 +346,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (KIND == EK_GELU) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = gelu2(v[i]);
+          }
+          if (KIND == EK_ACCUM) {
+            tc::mbar_wait(&my_aux_bar[n_item & 1], (uint32_t)((n_item >> 1) & 1));
+            const uint8_t* atile = wbuf + 4096 + (n_item & 1) * 2048;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = *reinterpret_cast<const uint4*>(atile + sw16_bf(j));
+              v[4 * j] = __fadd2_rn(v[4 * j], bf2_to_f2(u.x));
+              v[4 * j + 1] = __fadd2_rn(v[4 * j + 1], bf2_to_f2(u.y));
+              v[4 * j + 2] = __fadd2_rn(v[4 * j + 2], bf2_to_f2(u.z));
+              v[4 * j + 3] = __fadd2_rn(v[4 * j + 3], bf2_to_f2(u.w));
+            }
           }
           if (KIND == EK_GELU_BWD) {
             tc::mbar_wait(&my_aux_bar[n_item & 1], (uint32_t)((n_item >> 1) & 1));
@@ -591,6 +604,7 @@ int launch_bn(int layout, int out_dtype, int kind, const CUtensorMap& tmA, const
   if (layout == PMV_GEMM_NN) {
     if (kind == EK_PLAIN && !f32) return launch_cfg<BN, false, true, bf16, EK_PLAIN>(tmA, tmB, tmC, tmD, p, num_sms, s);
     if (kind == EK_GELU_BWD && !f32) return launch_cfg<BN, false, true, bf16, EK_GELU_BWD>(tmA, tmB, tmC, tmD, p, num_sms, s);
+    if (kind == EK_ACCUM && !f32) return launch_cfg<BN, false, true, bf16, EK_ACCUM>(tmA, tmB, tmC, tmD, p, num_sms, s);
     return f32 ? launch_cfg<BN, false, true, float, EK_GENERIC>(tmA, tmB, tmC, tmD, p, num_sms, s)
                : launch_cfg<BN, false, true, bf16, EK_GENERIC>(tmA, tmB, tmC, tmD, p, num_sms, s);
   }
