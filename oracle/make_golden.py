@@ -171,6 +171,34 @@ def run_full_model(seed=4321):
     return dict(logits=logits.numpy(), seed=seed, nparam=nparam), {"logits": norm_err(lo, logits)}
 
 
+PM_CFG = dict(orc.MVITV2_S, crop=(128, 96), hw_switch_auto=True)
+
+
+def run_pm_model(seed=977):
+    """Portrait / landscape routing (video_model_builder.py:2075-2096) on a rectangular crop with
+    TRAIN_CROP_SIZE_RECT_SWITCH_AUTO: 3 clips, two of them portrait (stored transposed, as the loader delivers them)."""
+    model, cfg = ref_loader.load_full_model("configs/Kinetics/MVITv2_S_16x4.yaml", overrides={
+        "DATA.TRAIN_CROP_SIZE_RECT": [128, 96], "DATA.TEST_CROP_SIZE_RECT": [128, 96],
+        "DATA.TRAIN_CROP_SIZE_RECT_SWITCH_AUTO": True, "TEST.PROCESS": False})
+    shapes = orc.param_shapes(PM_CFG)
+    ref_shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert ref_shapes == shapes, set(ref_shapes) ^ set(shapes)
+    params = detgen.det_params(shapes, seed)
+    model.load_state_dict(params, strict=True)
+    model.eval()
+    model.head.act = None
+    clip = detgen.det_normal((3, 3, 16, 128, 96), seed, "clip")
+    pm = torch.tensor([True, False, True])
+    with torch.no_grad():
+        logits = model([clip], pm=[pm])
+        lo = orc.mvit_forward_pm(clip, pm, params, PM_CFG)
+        # routing really matters: the same clips all treated as landscape give different logits
+        plain = model([clip])
+    assert float((plain[0] - logits[0]).abs().max()) > 1e-3
+    assert float((plain[1] - logits[1]).abs().max()) < 1e-5
+    return dict(logits=logits.numpy(), pm=pm.numpy(), seed=seed), {"pm_logits": norm_err(lo, logits)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--check", action="store_true")
@@ -200,6 +228,12 @@ def main():
         worst = max(worst, max(errs.values()))
         if not args.check:
             np.savez_compressed(os.path.join(GOLDEN, "mvitv2_s_logits.npz"), **full)
+    if not args.skip_full:
+        pmres, errs = run_pm_model()
+        print("portrait/landscape routing, rect 128x96:", {k: f"{v:.1e}" for k, v in errs.items()})
+        worst = max(worst, max(errs.values()))
+        if not args.check:
+            np.savez_compressed(os.path.join(GOLDEN, "mvitv2_s_pm_logits.npz"), **pmres)
     print(f"worst oracle-vs-reference error {worst:.2e}")
     assert worst < 5e-5, worst
 

@@ -368,10 +368,28 @@ def mvit_forward(clip: torch.Tensor, p: Params, cfg: dict, softmax_head: bool = 
         assert thw == blk["thw"], (thw, blk["thw"])
         ds = None if drop_scale is None else drop_scale[i]
         x, thw = multiscale_block(x, thw, p, f"blocks.{i}.", blk["num_heads"], blk["stride_q"], blk["stride_kv"],
-                                  drop_scale=ds)
+                                  drop_scale=ds, hw_switch_auto=cfg.get("hw_switch_auto", False))
     x = layer_norm(x, p["norm.weight"], p["norm.bias"])[:, 0]  # :2163-2165
     y = F.linear(x, p["head.projection.weight"], p["head.projection.bias"])
     return y.softmax(dim=1) if softmax_head else y
+
+
+def mvit_forward_pm(clip: torch.Tensor, pm: torch.Tensor, p: Params, cfg: dict, softmax_head: bool = False) -> torch.Tensor:
+    """MViT.forward with the portrait-mode mask (video_model_builder.py:2075-2096): portrait samples (pm == True)
+    arrive transposed inside a landscape-shaped batch; they are transposed back and run with H and W swapped
+    (the rel-pos tables swap inside the blocks when hw_switch_auto is set, attention.py:414-435), the landscape
+    samples run as they are, and the outputs are scattered back into batch order."""
+    if pm is None or int(pm.sum()) == 0:
+        return mvit_forward(clip, p, cfg, softmax_head)
+    pm_index = torch.where(pm)[0]
+    lm_index = torch.where(~pm)[0]
+    cfg_p = dict(cfg, crop=(cfg["crop"][1], cfg["crop"][0]))
+    pm_x = mvit_forward(clip[pm_index].transpose(-2, -1), p, cfg_p, softmax_head)
+    out = torch.empty((len(pm),) + tuple(pm_x.shape[1:]), dtype=pm_x.dtype, device=pm_x.device)
+    out[pm_index] = pm_x
+    if len(lm_index) != 0:
+        out[lm_index] = mvit_forward(clip[lm_index], p, cfg, softmax_head)
+    return out
 
 
 def param_shapes(cfg: dict) -> Dict[str, Tuple[int, ...]]:

@@ -84,7 +84,7 @@ class _Node(dict):
         self[k] = v
 
 
-def load_full_model(yaml_rel: str = "configs/Kinetics/MVITv2_S_16x4.yaml"):
+def load_full_model(yaml_rel: str = "configs/Kinetics/MVITv2_S_16x4.yaml", overrides: dict = None):
     """Build the reference ``MViT`` from its own YAML with stubbed third-party imports.
     Returns (model, cfg).  Must run in a process that has NOT called load_attention()."""
     import torch
@@ -152,5 +152,11 @@ def load_full_model(yaml_rel: str = "configs/Kinetics/MVITv2_S_16x4.yaml"):
 
     merge(C, yaml.safe_load(open(os.path.join(REF_ROOT, yaml_rel))))
     C.NUM_GPUS = 0
+    for dotted, v in (overrides or {}).items():  # e.g. {"DATA.TRAIN_CROP_SIZE_RECT": [128, 96]}
+        *path, leaf = dotted.split(".")
+        node = C
+        for q in path:
+            node = node.setdefault(q, _Node())
+        node[leaf] = v
     model = vmb.MViT(C)
     return model, C

@@ -124,17 +124,32 @@ class MViT(nn.Module):
             nn.init.constant_(m.bias, 0)
             nn.init.constant_(m.weight, 1.0)
 
-    def forward_features(self, clip):
+    def forward_features(self, clip, thw_expected=None):
         x, thw = self.patch_embed.forward_tokens(clip, self.cls_token)        # :2100-2121
-        assert tuple(thw) == (self.T, self.H, self.W), thw                    # :2106
+        assert tuple(thw) == tuple(thw_expected or (self.T, self.H, self.W)), thw  # :2106
         for blk in self.blocks:                                               # :2144-2146
             x, thw = blk(x, thw)
         x = Fn.layer_norm(x, self.norm.weight, self.norm.bias, torch.float32, self.norm.eps)  # :2163
         return x[:, 0]                                                        # :2165
 
     def forward(self, x, pm=None):
-        clip = x[0] if isinstance(x, (list, tuple)) else x                    # :2099 takes a list
-        if pm is not None:
-            raise NotImplementedError("portrait/landscape batch routing (video_model_builder.py:2075-2096) "
-                                      "is row f1 of SURVEY.md section 8 (next)")
-        return self.head(self.forward_features(clip))
+        """``x``: clip tensor or the reference's one-element list (:2099).  ``pm``: portrait-mode mask, a bool tensor
+        [B] or the reference's list of per-loader-batch tensors (:2076-2077).  Portrait samples arrive transposed
+        inside the landscape-shaped batch; they are transposed back and run with H and W swapped (the blocks swap
+        their rel-pos tables when built with hw_switch_auto), the landscape samples run as they are, and the rows
+        are scattered back into batch order (video_model_builder.py:2075-2096)."""
+        clip = x[0] if isinstance(x, (list, tuple)) else x
+        if pm is not None and isinstance(pm, (list, tuple)):
+            pm = torch.cat(list(pm))
+        if pm is None or int(pm.sum()) == 0:
+            return self.head(self.forward_features(clip))
+        assert len(pm) == clip.shape[0]
+        pm = pm.to(device=clip.device, dtype=torch.bool)
+        pm_index = torch.where(pm)[0]
+        lm_index = torch.where(~pm)[0]
+        pm_x = self.head(self.forward_features(clip[pm_index].transpose(-2, -1), (self.T, self.W, self.H)))
+        out = torch.empty((len(pm),) + tuple(pm_x.shape[1:]), device=pm_x.device, dtype=pm_x.dtype)
+        out[pm_index] = pm_x
+        if len(lm_index) != 0:
+            out[lm_index] = self.head(self.forward_features(clip[lm_index]))
+        return out

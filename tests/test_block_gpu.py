@@ -175,3 +175,29 @@ def test_full_model_logits_match_reference_fixture(dtype):
         logits = model([clip])
     assert nerr(logits, z["logits"]) < OUT_TOL[dtype]
     assert int(logits.argmax()) == int(np.argmax(z["logits"]))  # top-1 agrees
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_pm_routing_matches_reference_fixture(dtype):
+    """portrait / landscape mixed batch (video_model_builder.py:2075-2096) on a rectangular
+    128x96 crop with hw_switch_auto, logits vs the unmodified reference MViT (tests/golden/mvitv2_s_pm_logits.npz)."""
+    from oracle import detgen, mvit_oracle as orc
+    from pmv_b200 import mvit
+    z = np.load(os.path.join(GOLDEN, "mvitv2_s_pm_logits.npz"))
+    cfg = dict(mvit.MVITV2_S, crop=(128, 96), hw_switch_auto=True)
+    model = mvit.MViT(cfg, compute_dtype=dtype)
+    seed = int(z["seed"])
+    params = detgen.det_params(orc.param_shapes(dict(orc.MVITV2_S, crop=(128, 96))), seed)
+    model.load_state_dict(params, strict=True)
+    model.cuda().eval()
+    model.head.act = None
+    clip = detgen.det_normal((3, 3, 16, 128, 96), seed, "clip").cuda()
+    pm = torch.from_numpy(z["pm"]).cuda()
+    with torch.no_grad():
+        logits = model([clip], pm=[pm])
+        plain = model([clip])
+    assert nerr(logits, z["logits"]) < OUT_TOL[dtype]
+    assert (logits.argmax(1).cpu().numpy() == np.argmax(z["logits"], 1)).all()  # top-1 agrees per clip
+    assert nerr(plain[1:2], z["logits"][1:2]) < OUT_TOL[dtype]                   # the landscape clip is unaffected
+    assert float((plain[0] - logits[0]).abs().max()) > 1e-3                      # the routing really changes the portrait ones

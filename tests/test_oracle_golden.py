@@ -110,3 +110,22 @@ def test_block_schedule_matches_survey_appendix_a():
     assert rows[15] == (768, 768, 8, (8, 7, 7), (1, 1, 1), (1, 1, 1))
     b = orc.block_schedule(orc.MVITV2_B)
     assert len(b) == 24 and b[2]["dim_out"] == 192 and b[21]["dim_out"] == 768 and b[0]["thw"] == [16, 56, 56]
+
+
+def test_pm_routing_logits_oracle_vs_reference():
+    """Portrait / landscape batch routing (video_model_builder.py:2075-2096) on a rectangular crop with
+    hw_switch_auto: oracle restatement against logits of the unmodified reference MViT (oracle/make_golden.py)."""
+    from oracle import detgen, mvit_oracle as orc
+    z = np.load(os.path.join(GOLDEN, "mvitv2_s_pm_logits.npz"))
+    cfg = dict(orc.MVITV2_S, crop=(128, 96), hw_switch_auto=True)
+    seed = int(z["seed"])
+    params = detgen.det_params(orc.param_shapes(cfg), seed)
+    clip = detgen.det_normal((3, 3, 16, 128, 96), seed, "clip")
+    pm = torch.from_numpy(z["pm"])
+    with torch.no_grad():
+        out = orc.mvit_forward_pm(clip, pm, params, cfg)
+    assert nerr(out, z["logits"]) < TOL
+    # all-landscape mask == plain forward
+    with torch.no_grad():
+        a = orc.mvit_forward_pm(clip[1:2], torch.tensor([False]), params, cfg)
+    assert nerr(a, z["logits"][1:2]) < TOL
