@@ -62,12 +62,13 @@ int pmv_has_tcgen05(void);
  * (may be NULL in inference). */
 int pmv_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_dtype,
                       float* mean, float* rstd, int64_t rows, int C, float eps, void* stream);
-/* dx (fp32) = LN'(dy) [+ dx if accumulate]; dgamma_dbeta (fp32 [2][C]: dgamma then dbeta) is added to.
+/* dx (fp32) = LN'(dy) [+ dx_base: the gradient arriving over the residual connection, NULL for none, may alias dx];
+ * dgamma_dbeta (fp32 [2][C]: dgamma then dbeta) is OVERWRITTEN.
  * ws: fp32 workspace of pmv_layernorm_bwd_workspace_bytes() bytes (one partial vector per CTA, folded by a
  * second small kernel: same-address global atomics from hundreds of CTAs serialise in L2). */
 int64_t pmv_layernorm_bwd_workspace_bytes(int64_t rows, int C);
 int pmv_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma,
-                      const float* mean, const float* rstd, float* dx, int accumulate,
+                      const float* mean, const float* rstd, float* dx, const float* dx_base,
                       float* dgamma_dbeta, float* ws, int64_t rows, int C, void* stream);
 
 /* ---------------------------------------------------------------- GEMM family --------
@@ -106,9 +107,9 @@ int pmv_gemm(int layout, const void* A, int64_t lda, const void* B, int64_t ldb,
              int64_t M, int64_t N, int64_t K, int io_dtype, int out_dtype, const pmv_epilogue* epi,
              int tc, int split_k, void* stream);
 
-/* column sums: out_sum[c] += sum_r in[r, c] * (row_scale ? row_scale[r / rows_per_scale] : 1); also
+/* column sums: out_sum[c] = sum_r in[r, c] * (row_scale ? row_scale[r / rows_per_scale] : 1); also
  * optionally writes the scaled copy cast to cast_dtype (bias gradients + operand cast of the fp32
- * residual-stream gradient in one pass). out_sum may be NULL; otherwise ws must hold
+ * residual-stream gradient in one pass). out_sum is OVERWRITTEN; it may be NULL; otherwise ws must hold
  * pmv_colsum_workspace_bytes() bytes. */
 int64_t pmv_colsum_workspace_bytes(int64_t rows, int64_t cols);
 int pmv_colsum_cast(const void* in, int in_dtype, int64_t ld_in, int64_t rows, int64_t cols,

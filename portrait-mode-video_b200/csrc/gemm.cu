@@ -48,8 +48,13 @@ template <typename TIn, typename TCast>
 __global__ void __launch_bounds__(CS_THREADS) colsum_cast_kernel(const TIn* __restrict__ in, int64_t ld_in, int64_t rows, int64_t cols,
                                                                  const float* __restrict__ row_scale, FastDiv fd_scale,
                                                                  float* __restrict__ out_sum, TCast* __restrict__ cast_out, int64_t ld_cast,
-                                                                 int64_t rows_per_block, int cx) {
+                                                                 int64_t rows_per_block, int cx, float* __restrict__ final_sum) {
   __shared__ float red[CS_THREADS * 4];
+  // the fold kernel that follows ADDS the per-slice partials into final_sum: clear it here (saves a fill launch)
+  if (final_sum != nullptr && blockIdx.y == 0) {
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    for (int64_t i = c; i < cols; i += (int64_t)gridDim.x * blockDim.x) final_sum[i] = 0.f;
+  }
   const int ry = CS_THREADS / cx;
   const int tx = threadIdx.x % cx, ty = threadIdx.x / cx;
   const int64_t c4 = ((int64_t)blockIdx.x * cx + tx) * 4;
@@ -139,7 +144,7 @@ extern "C" int pmv_colsum_cast(const void* in, int in_dtype, int64_t ld_in, int6
   const FastDiv fd((uint32_t)rows_per_scale);
   PMV_CHECK_ARG(out_sum == nullptr || ws != nullptr, "colsum: workspace required when out_sum is given");
 #define LAUNCH(TI, TC) colsum_cast_kernel<TI, TC><<<grid, CS_THREADS, 0, (cudaStream_t)stream>>>( \
-      (const TI*)in, ld_in, rows, cols, row_scale, fd, out_sum ? ws : nullptr, (TC*)cast_out, ld_cast, rpb, cx)
+      (const TI*)in, ld_in, rows, cols, row_scale, fd, out_sum ? ws : nullptr, (TC*)cast_out, ld_cast, rpb, cx, out_sum)
   if (in_dtype == PMV_F32 && cast_dtype == PMV_F32) LAUNCH(float, float);
   else if (in_dtype == PMV_F32 && cast_dtype == PMV_BF16) LAUNCH(float, bf16);
   else if (in_dtype == PMV_BF16 && cast_dtype == PMV_BF16) LAUNCH(bf16, bf16);

@@ -66,8 +66,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_fwd_kernel(
 template <int LPR, int VPL, typename TDy>
 __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(
     const TDy* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
-    const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dx, int accumulate,
-    float* __restrict__ partials, int64_t rows) {
+    const float* __restrict__ mean, const float* __restrict__ rstd, float* dx, const float* dx_base,
+    float* __restrict__ partials, float* __restrict__ dgb, int64_t rows) {
   constexpr int C = 4 * LPR * VPL;
   constexpr int RPW = 32 / LPR;
   __shared__ float red[LN_WARPS][2 * C];
@@ -75,6 +75,9 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(
   const int sub = lane % LPR, rw = lane / LPR;
   const int64_t row0 = ((int64_t)blockIdx.x * LN_WARPS + warp) * RPW;
   const int64_t rstep = (int64_t)gridDim.x * LN_WARPS * RPW;
+  // the fold kernel that follows ADDS the per-CTA partials into dgamma / dbeta: clear them here (saves a fill launch)
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) dgb[i] = 0.f;
   float gm[VPL][4], dg[VPL][4], db[VPL][4];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
@@ -121,9 +124,9 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(
       float o[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[j] = rs * (g[i][j] - s1 - xh[i][j] * s2);
-      if (accumulate) {
+      if (dx_base != nullptr) {  // gradient arriving over the residual connection (may alias dx)
         float p[4];
-        load4(dxr + (sub + i * LPR) * 4, p);
+        load4(dx_base + r * C + (sub + i * LPR) * 4, p);
 #pragma unroll
         for (int j = 0; j < 4; ++j) o[j] += p[j];
       }
@@ -178,10 +181,10 @@ int64_t ln_bwd_blocks(int64_t rows) {
 
 template <int LPR, int VPL>
 int launch_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma, const float* mean, const float* rstd, float* dx,
-               int accumulate, float* ws, int64_t rows, cudaStream_t st) {
+               const float* dx_base, float* ws, float* dgb, int64_t rows, cudaStream_t st) {
   const int64_t blocks = ln_bwd_blocks(rows);
   PMV_DISPATCH_DTYPE(dy_dtype, T, (layernorm_bwd_kernel<LPR, VPL, T><<<(unsigned)blocks, LN_WARPS * 32, 0, st>>>(
-                                      (const T*)dy, x, gamma, mean, rstd, dx, accumulate, ws, rows)));
+                                      (const T*)dy, x, gamma, mean, rstd, dx, dx_base, ws, dgb, rows)));
   PMV_CHECK_LAUNCH();
   return PMV_OK;
 }
@@ -217,11 +220,11 @@ extern "C" int pmv_layernorm_fwd(const float* x, const float* gamma, const float
 extern "C" int64_t pmv_layernorm_bwd_workspace_bytes(int64_t rows, int C) { return ln_bwd_blocks(rows) * 2 * C * (int64_t)sizeof(float); }
 
 extern "C" int pmv_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma,
-                                 const float* mean, const float* rstd, float* dx, int accumulate,
+                                 const float* mean, const float* rstd, float* dx, const float* dx_base,
                                  float* dgamma_dbeta, float* ws, int64_t rows, int C, void* stream) {
   if (rows == 0) return PMV_OK;
   int rc = PMV_OK;
-  PMV_LN_DISPATCH(C, (rc = launch_bwd<LPR, VPL>(dy, dy_dtype, x, gamma, mean, rstd, dx, accumulate, ws, rows, (cudaStream_t)stream)));
+  PMV_LN_DISPATCH(C, (rc = launch_bwd<LPR, VPL>(dy, dy_dtype, x, gamma, mean, rstd, dx, dx_base, ws, dgamma_dbeta, rows, (cudaStream_t)stream)));
   if (rc) return rc;
   launch_reduce_partials(ws, (int)ln_bwd_blocks(rows), 2 * C, dgamma_dbeta, (cudaStream_t)stream);
   PMV_CHECK_LAUNCH();

@@ -37,7 +37,7 @@ _SIGS = {
     "pmv_has_tcgen05": (_i, []),
     "pmv_layernorm_fwd": (_i, [_p, _p, _p, _p, _i, _p, _p, _i64, _i, _f, _p]),
     "pmv_layernorm_bwd_workspace_bytes": (_i64, [_i64, _i]),
-    "pmv_layernorm_bwd": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _p, _p, _i64, _i, _p]),
+    "pmv_layernorm_bwd": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _p]),
     "pmv_gemm": (_i, [_i, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _i, _i, C.POINTER(Epilogue), _i, _i, _p]),
     "pmv_colsum_workspace_bytes": (_i64, [_i64, _i64]),
     "pmv_colsum_cast": (_i, [_p, _i, _i64, _i64, _i64, _p, _i64, _p, _p, _p, _i, _i64, _p]),

@@ -195,13 +195,13 @@ class MultiScaleBlock(nn.Module):
         B = x.shape[0]
         x = x.float() if x.dtype != torch.float32 else x
         thw = list(thw_shape)
-        x_norm = Fn.layer_norm(x, self.norm1.weight, self.norm1.bias, T, self.norm1.eps)                     # :567
+        x, x_norm = Fn.layer_norm_residual(x, self.norm1.weight, self.norm1.bias, T, self.norm1.eps)         # :567
         if self.dim_mul_in_att and self.dim != self.dim_out:
             x = Fn.linear(x_norm, self.proj.weight, self.proj.bias, out_fp32=True)           # :569-570
         x_res = Fn.maxpool_skip(x, thw) if self.pool_skip is not None else x                  # :571-573
         ds1 = drop_path_scale(B, self.drop_path_prob, self.training, x.device)
         x, thw_new = self.attn(x_norm, thw, residual=x_res, row_scale=ds1)                    # :568,577
-        x_norm2 = Fn.layer_norm(x, self.norm2.weight, self.norm2.bias, T, self.norm2.eps)                     # :578
+        x, x_norm2 = Fn.layer_norm_residual(x, self.norm2.weight, self.norm2.bias, T, self.norm2.eps)        # :578
         ds2 = drop_path_scale(B, self.drop_path_prob, self.training, x.device)
         x = self.mlp(x_norm2, residual=x, row_scale=ds2, rows_per_scale=x.shape[1])           # :579,585
         if thw_shape:

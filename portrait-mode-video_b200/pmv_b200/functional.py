@@ -40,8 +40,39 @@ class LayerNormFn(Function):
         return dx, dg, db, None, None
 
 
+class ResidualLayerNormFn(Function):
+    """(x, LayerNorm(x)): the residual stream passes through unchanged next to its normalised copy, so that the
+    backward kernel adds the gradient arriving over the residual connection on the fly (one pass instead of
+    LayerNorm-backward + a separate fp32 add) — attention.py:567-577 / 578-585."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, out_dtype, eps):
+        x = x.contiguous()
+        need = any(ctx.needs_input_grad)
+        y, mean, rstd = ops.layernorm_fwd(x, gamma, beta, out_dtype, save_stats=need, eps=eps)
+        if need:
+            ctx.save_for_backward(x, gamma, mean, rstd)
+        return x.view_as(x), y
+
+    @staticmethod
+    def backward(ctx, dx_res, dy):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        if dy is None:
+            return dx_res, None, None, None, None
+        base = None
+        if dx_res is not None:
+            base = dx_res if (dx_res.dtype == torch.float32 and dx_res.is_contiguous()) else dx_res.float().contiguous()
+        dx, dg, db = ops.layernorm_bwd(dy, x, gamma, mean, rstd, dx_base=base)
+        return dx, dg, db, None, None
+
+
 def layer_norm(x, gamma, beta, out_dtype, eps=1e-6):
     return LayerNormFn.apply(x, gamma, beta, out_dtype, float(eps))
+
+
+def layer_norm_residual(x, gamma, beta, out_dtype, eps=1e-6):
+    """Returns (x, LayerNorm(x)); use the returned x for the residual connection."""
+    return ResidualLayerNormFn.apply(x, gamma, beta, out_dtype, float(eps))
 
 
 class LinearFn(Function):

@@ -71,17 +71,20 @@ def layernorm_fwd(x: torch.Tensor, gamma, beta, out_dtype, save_stats=True, eps=
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dx_accum: Optional[torch.Tensor] = None):
-    """Returns (dx fp32, dgamma, dbeta).  If dx_accum is given the input gradient is added into it in place."""
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx_accum: Optional[torch.Tensor] = None, dx_base: Optional[torch.Tensor] = None):
+    """Returns (dx fp32, dgamma, dbeta).  ``dx_base`` (the gradient arriving over the residual connection) is added
+    into a fresh dx; ``dx_accum`` adds the input gradient into that tensor in place."""
     Cdim = x.shape[-1]
     rows = x.numel() // Cdim
     dy = dy.contiguous()
+    base = dx_accum if dx_accum is not None else dx_base
+    if base is not None:
+        assert base.dtype == torch.float32 and base.is_contiguous() and base.numel() == x.numel()
     dx = dx_accum if dx_accum is not None else torch.empty_like(x)
-    dgb = torch.zeros(2, Cdim, dtype=torch.float32, device=x.device)
+    dgb = torch.empty(2, Cdim, dtype=torch.float32, device=x.device)  # overwritten by the kernel
     ws = _ws(L.lib().pmv_layernorm_bwd_workspace_bytes(rows, Cdim), x.device)
-    _run("pmv_layernorm_bwd", 2, dict(bytes=rows * Cdim * (8 + dy.element_size() + (4 if dx_accum is not None else 0))), L.ptr(dy), L.dt(dy), L.ptr(x), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), L.ptr(dx),
-                                      1 if dx_accum is not None else 0, L.ptr(dgb), L.ptr(ws), rows, Cdim,
-                                      L.stream())
+    _run("pmv_layernorm_bwd", 2, dict(bytes=rows * Cdim * (8 + dy.element_size() + (4 if base is not None else 0))), L.ptr(dy), L.dt(dy),
+         L.ptr(x), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), L.ptr(dx), L.ptr(base), L.ptr(dgb), L.ptr(ws), rows, Cdim, L.stream())
     return dx, dgb[0], dgb[1]
 
 
@@ -145,7 +148,7 @@ def linear_wgrad(dy2d, x2d, tc=None):
 
 def colsum_cast(x2d, cast_dtype=None, row_scale=None, rows_per_scale=1, want_sum=True):
     rows, cols = x2d.shape
-    s = torch.zeros(cols, dtype=torch.float32, device=x2d.device) if want_sum else None
+    s = torch.empty(cols, dtype=torch.float32, device=x2d.device) if want_sum else None  # overwritten by the kernel
     c = torch.empty(rows, cols, dtype=cast_dtype, device=x2d.device) if cast_dtype is not None else None
     ws = _ws(L.lib().pmv_colsum_workspace_bytes(rows, cols), x2d.device) if want_sum else None
     _run("pmv_colsum_cast", 2 if want_sum else 1, dict(bytes=rows * cols * (x2d.element_size() + (c.element_size() if c is not None else 0))), L.ptr(x2d), L.dt(x2d), x2d.stride(0), rows, cols, L.ptr(row_scale), rows_per_scale,
