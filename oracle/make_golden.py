@@ -199,6 +199,36 @@ def run_pm_model(seed=977):
     return dict(logits=logits.numpy(), pm=pm.numpy(), seed=seed), {"pm_logits": norm_err(lo, logits)}
 
 
+def run_checkpoint_case(seed=555):
+    """Row f4: the reference's own load_checkpoint (utils/checkpoint.py:191-563) loading a 224-crop MViTv2-S checkpoint
+    into a 160-crop model: rel-pos tables of a different length are interpolated.  Stores the resulting tables of three
+    blocks and a checksum of every tensor."""
+    import tempfile
+    model224, _ = ref_loader.load_full_model("configs/Kinetics/MVITv2_S_16x4.yaml")
+    params = detgen.det_params(orc.param_shapes(orc.MVITV2_S), seed)
+    model224.load_state_dict(params, strict=True)
+    path = os.path.join(tempfile.mkdtemp(), "ck.pyth")
+    torch.save({"model_state": model224.state_dict(), "epoch": 3}, path)
+    model160, _ = ref_loader.load_full_model("configs/Kinetics/MVITv2_S_16x4.yaml",
+                                             overrides={"DATA.TRAIN_CROP_SIZE": 160, "DATA.TEST_CROP_SIZE": 160})
+    import slowfast.utils.checkpoint as cu
+
+    class _PM:
+        exists = staticmethod(os.path.exists)
+        open = staticmethod(open)
+    cu.pathmgr = _PM
+    epoch = cu.load_checkpoint(path, model160, data_parallel=False, optimizer=None, inflation=False,
+                               convert_from_caffe2=False, epoch_reset=False, clear_name_pattern=(), image_init=False)
+    sd = model160.state_dict()
+    out = dict(seed=seed, epoch=int(epoch))
+    for blk in (0, 3, 15):
+        for n in ("rel_pos_h", "rel_pos_w", "rel_pos_t"):
+            out[f"blocks.{blk}.attn.{n}"] = sd[f"blocks.{blk}.attn.{n}"].numpy()
+    out["checksum"] = np.array([float(v.double().sum()) for v in sd.values()])
+    out["names"] = np.array(list(sd.keys()))
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--check", action="store_true")
@@ -234,6 +264,10 @@ def main():
         worst = max(worst, max(errs.values()))
         if not args.check:
             np.savez_compressed(os.path.join(GOLDEN, "mvitv2_s_pm_logits.npz"), **pmres)
+    if not args.skip_full and not args.check:
+        ck = run_checkpoint_case()
+        print("checkpoint surgery case: epoch", ck["epoch"], "tables", [k for k in ck if k.startswith("blocks")][:3], "...")
+        np.savez_compressed(os.path.join(GOLDEN, "checkpoint_surgery.npz"), **ck)
     print(f"worst oracle-vs-reference error {worst:.2e}")
     assert worst < 5e-5, worst
 

@@ -1,5 +1,7 @@
 // Host side of the tcgen05 GEMM: tensor maps, tile-width choice, epilogue-kind choice.  The kernel template lives in
 // gemm_tc_kernel.cuh and is instantiated per tile width in gemm_tc_bn*.cu.
+#include <cstdlib>
+
 #include "gemm_tc_kernel.cuh"
 
 using namespace gemm_tc;
@@ -12,6 +14,13 @@ int gemm_tc_launch_bn192(int, int, int, const CUtensorMap&, const CUtensorMap&, 
                          const TcParams&, int, cudaStream_t);
 int gemm_tc_launch_bn256(int, int, int, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
                          const TcParams&, int, cudaStream_t);
+
+int gemm_tc_launch_pair_bn128(int, int, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const TcParams&,
+                              int, cudaStream_t);
+int gemm_tc_launch_pair_bn192(int, int, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const TcParams&,
+                              int, cudaStream_t);
+int gemm_tc_launch_pair_bn256(int, int, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const TcParams&,
+                              int, cudaStream_t);
 
 static int g_num_sms = 0;
 
@@ -105,6 +114,29 @@ int gemm_tc_launch(int layout, const void* A, int64_t lda, const void* B, int64_
       if (aux) {
         rc = pmv_make_tensor_map_2d(&tmD, aux, 2, (uint64_t)NN, (uint64_t)MM, (uint64_t)ld_auxmap, 32, 32, 64);
         if (rc) return rc;
+      }
+    }
+  }
+  // CTA pairs (cta_group::2, 256-row tiles, the B tile crosses L2 -> SM once per pair): forward layout, when the problem
+  // has at least one full round of pair tiles
+  {
+    static int pair_mode = -1;  // PMV_GEMM_PAIR: 0 = never, 1 = when eligible (default 0 until validated on the model)
+    if (pair_mode < 0) {
+      const char* ev = std::getenv("PMV_GEMM_PAIR");
+      pair_mode = ev ? atoi(ev) : 0;
+    }
+    const bool kind_ok = (kind == EK_PLAIN && out_dtype == PMV_BF16) || (kind == EK_GELU && out_dtype == PMV_BF16) ||
+                         (kind == EK_RES && out_dtype == PMV_F32);
+    if (pair_mode && layout == PMV_GEMM_TN && p.splits == 1 && kind_ok && BN >= 128 && MM >= 256 * 37) {
+      TcParams pp = p;
+      pp.tiles_m = (int)ceil_div64(MM, 2 * BM);
+      CUtensorMap tmBh;
+      rc = pmv_make_tensor_map_2d(&tmBh, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, (uint32_t)(BN / 2), 128);
+      if (rc) return rc;
+      switch (BN) {
+        case 128: return gemm_tc_launch_pair_bn128(out_dtype, kind, tmA, tmBh, tmC, tmD, pp, g_num_sms, stream);
+        case 192: return gemm_tc_launch_pair_bn192(out_dtype, kind, tmA, tmBh, tmC, tmD, pp, g_num_sms, stream);
+        default: return gemm_tc_launch_pair_bn256(out_dtype, kind, tmA, tmBh, tmC, tmD, pp, g_num_sms, stream);
       }
     }
   }

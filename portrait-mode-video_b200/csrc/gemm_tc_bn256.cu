@@ -5,3 +5,8 @@ int gemm_tc_launch_bn256(int layout, int out_dtype, int kind, const CUtensorMap&
                           const CUtensorMap& tmD,                           const gemm_tc::TcParams& p, int num_sms, cudaStream_t s) {
   return gemm_tc::launch_bn<256>(layout, out_dtype, kind, tmA, tmB, tmC, tmD, p, num_sms, s);
 }
+
+int gemm_tc_launch_pair_bn256(int out_dtype, int kind, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                              const CUtensorMap& tmD, const gemm_tc::TcParams& p, int num_sms, cudaStream_t s) {
+  return gemm_tc::launch_bn_pair<256>(out_dtype, kind, tmA, tmB, tmC, tmD, p, num_sms, s);
+}

@@ -48,19 +48,21 @@ struct TcParams {
 // kinds whose epilogue goes registers -> swizzled smem tile -> TMA store (thread = accumulator row)
 __host__ __device__ constexpr bool kind_tma(int kind) { return kind == EK_PLAIN || kind == EK_GELU || kind == EK_GELU_BWD || kind == EK_ACCUM; }
 
-template <int BN, int KIND = EK_GENERIC> struct TileCfg {
+template <int BN, int KIND = EK_GENERIC, bool PAIR = false> struct TileCfg {
   static constexpr int BN_GROUPS = (BN + 63) / 64;
   static constexpr int A_BYTES = BM * BK * 2;                 // 16 KB either layout
   static constexpr int B_BYTES_K = BN * BK * 2;               // K-major box
   static constexpr int B_BYTES_MN = BN_GROUPS * 64 * BK * 2;  // MN-major groups
   static constexpr int B_BYTES = B_BYTES_MN;                  // reserve the larger of the two
-  static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
+  // a CTA of a pair stages only half of the B tile: smaller stages, more of them in flight
+  static constexpr int STAGE_BYTES = A_BYTES + (((PAIR ? B_BYTES_K / 2 : B_BYTES) + 1023) / 1024) * 1024;
   static constexpr int ACC_COLS = BN <= 128 ? 128 : 256;      // TMEM columns per accumulator stage
   // per-epilogue-warp staging: 4 KB transpose buffer / one fp32 or two bf16 32x32 output tiles; the GELU kinds keep two
   // tiles per chunk (output + pre-activation), double-buffered: 8 KB
   static constexpr int EPI_WARP_BYTES = (KIND == EK_GELU || KIND == EK_GELU_BWD || KIND == EK_ACCUM) ? 8192 : 4096;
   static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
-  static constexpr int STAGES = (MAX_STAGES * STAGE_BYTES + 2048 + EPI_BYTES <= 227 * 1024) ? MAX_STAGES : MAX_STAGES - 1;
+  static constexpr int FIT_STAGES = (227 * 1024 - 2048 - EPI_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = PAIR ? (FIT_STAGES > 8 ? 8 : FIT_STAGES) : (FIT_STAGES >= MAX_STAGES ? MAX_STAGES : MAX_STAGES - 1);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 1024 /*barriers*/ + EPI_BYTES;
 };
 
@@ -117,12 +119,15 @@ __device__ __forceinline__ uint32_t pack_bf2(float2 v) {
 }
 __device__ __forceinline__ float2 bf2_to_f2(uint32_t u) { return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
 
-template <int BN, bool A_MN, bool B_MN, typename TOut, int KIND>
+// PAIR: launched as clusters of two CTAs; a work item is a 256 x BN tile computed by ONE cta_group::2 MMA stream issued
+// by the leader CTA (rank 0).  Each CTA stages its own 128 rows of A and half of the B tile, owns the accumulator of its
+// 128 rows in its own TMEM and runs its own epilogue.  Implemented for the TN (forward) layout.
+template <int BN, bool A_MN, bool B_MN, typename TOut, int KIND, bool PAIR = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD, TcParams p) {
   // tmC: output (32 x 32 boxes, swizzled); tmD: aux_out (EK_GELU) / aux_in (EK_GELU_BWD); unused by the other kinds
-  using Cfg = TileCfg<BN, KIND>;
+  using Cfg = TileCfg<BN, KIND, PAIR>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -138,6 +143,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  static_assert(!PAIR || (!A_MN && !B_MN), "CTA pairs: TN layout only");
+  const uint32_t cta_rank = PAIR ? tc::cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  constexpr int BM_TILE = PAIR ? 2 * BM : BM;                 // rows of a work item
+  const int64_t work0 = PAIR ? (blockIdx.x >> 1) : blockIdx.x;  // first work item / stride of this CTA (pair)
+  const int64_t work_step = PAIR ? (gridDim.x >> 1) : gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmA);
@@ -148,7 +159,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&acc_full[i], 1);
-      tc::mbar_init(&acc_empty[i], EPI_WARPS);
+      tc::mbar_init(&acc_empty[i], PAIR ? 2 * EPI_WARPS : EPI_WARPS);  // PAIR: both CTAs' epilogue warps arrive at the leader
     }
     for (int i = 0; i < 2 * EPI_WARPS; ++i) tc::mbar_init(&aux_bar[i], 1);
     if (kind_tma(KIND)) {
@@ -158,11 +169,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc::fence_barrier_init();
   }
   if (warp == 1) {
-    tc::tmem_alloc(tmem_slot, 2 * Cfg::ACC_COLS);
-    tc::tmem_relinquish();
+    if (PAIR) {
+      tc::tmem_alloc2(tmem_slot, 2 * Cfg::ACC_COLS);
+      tc::tmem_relinquish2();
+    } else {
+      tc::tmem_alloc(tmem_slot, 2 * Cfg::ACC_COLS);
+      tc::tmem_relinquish();
+    }
   }
   tc::tc_fence_before();
-  __syncthreads();
+  if (PAIR) tc::cluster_sync_all(); else __syncthreads();  // PAIR: the peer's barriers must exist before anyone signals them
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -173,17 +189,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+      const uint32_t full_bar0_cl = PAIR ? tc::mapa_u32(&full_bar[0], 0) : 0u;  // the leader's full barriers
+      for (int64_t wi = work0; wi < num_work; wi += work_step) {
         const int tn = (int)(wi % p.tiles_n);
         const int tm = (int)((wi / p.tiles_n) % p.tiles_m);
         const int sp = (int)(wi / ((int64_t)p.tiles_n * p.tiles_m));
-        const int m0 = tm * BM, n0 = tn * BN;
+        const int m0 = tm * BM_TILE + (int)cta_rank * BM, n0 = tn * BN;
         const int64_t kbeg = (int64_t)sp * p.k_per_split;
         const int64_t kend = kbeg + p.k_per_split < p.K ? kbeg + p.k_per_split : p.K;
         for (int64_t kb = kbeg; kb < kend; kb += BK) {
           tc::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
+          if constexpr (PAIR) {
+            // both CTAs load into their own smem and credit the LEADER's barrier; the leader expects both halves
+            if (leader) tc::mbar_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES_K / 2));
+            const uint32_t fb = full_bar0_cl + stage * 8;
+            tc::tma_load_2d_2sm(sa, &tmA, (int)kb, m0, fb);
+            tc::tma_load_2d_2sm(sb, &tmB, (int)kb, n0 + (int)cta_rank * (BN / 2), fb);  // box of BN / 2 rows
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           tc::mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES + (B_MN ? Cfg::B_BYTES_MN : Cfg::B_BYTES_K));
           if (!A_MN) {
             tc::tma_load_2d(sa, &tmA, (int)kb, m0, &full_bar[stage]);
@@ -203,12 +229,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc_bf16(BM, BN, A_MN, B_MN);
+    if (lane == 0 && leader) {
+      const uint32_t idesc = tc::make_idesc_bf16(BM_TILE, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int64_t it = 0;
-      for (int64_t wi = blockIdx.x; wi < num_work; wi += gridDim.x, ++it) {
+      for (int64_t wi = work0; wi < num_work; wi += work_step, ++it) {
         const int sp = (int)(wi / ((int64_t)p.tiles_n * p.tiles_m));
         const int64_t kbeg = (int64_t)sp * p.k_per_split;
         const int64_t kend = kbeg + p.k_per_split < p.K ? kbeg + p.k_per_split : p.K;
@@ -230,12 +256,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                      : tc::make_smem_desc(sa + k * 32, 16, 1024, tc::SWIZZLE_128B);
             const uint64_t db = B_MN ? tc::make_smem_desc(sb + k * 2048, 8192, 1024, tc::SWIZZLE_128B)
                                      : tc::make_smem_desc(sb + k * 32, 16, 1024, tc::SWIZZLE_128B);
-            tc::umma_ss(tmem_d, da, db, idesc, (kb > kbeg || k > 0) ? 1u : 0u);
+            if (PAIR) tc::umma_ss2(tmem_d, da, db, idesc, (kb > kbeg || k > 0) ? 1u : 0u);
+            else tc::umma_ss(tmem_d, da, db, idesc, (kb > kbeg || k > 0) ? 1u : 0u);
           }
-          tc::umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
+          // frees the smem stage (PAIR: in both CTAs) once these MMAs have read it
+          if (PAIR) tc::umma_commit2_mc(&empty_bar[stage], 3); else tc::umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc::umma_commit(&acc_full[as]);  // accumulator complete -> epilogue
+        if (PAIR) tc::umma_commit2_mc(&acc_full[as], 3); else tc::umma_commit(&acc_full[as]);  // accumulator complete -> epilogue(s)
       }
     }
   } else if constexpr (kind_tma(KIND)) {
@@ -267,13 +295,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto valid = [&](const Cursor& cu) { return cu.wi < num_work; };
     auto advance = [&](Cursor& cu) {
       cu.c += 64;
-      if (cu.c >= BN) { cu.c = half * 32; cu.wi += gridDim.x; ++cu.it; }
+      if (cu.c >= BN) { cu.c = half * 32; cu.wi += work_step; ++cu.it; }
     };
     auto coords = [&](const Cursor& cu, int& row0, int& col0) {
       const int tn = (int)(cu.wi % p.tiles_n);
       const int tm = (int)((cu.wi / p.tiles_n) % p.tiles_m);
-      row0 = tm * BM + q * 32;
+      row0 = tm * BM_TILE + (int)cta_rank * BM + q * 32;
       col0 = tn * BN + cu.c;
+    };
+    const uint32_t acc_empty0_cl = PAIR ? tc::mapa_u32(&acc_empty[0], 0) : 0u;
+    auto release_acc = [&](int as) {  // lane 0: this warp has its part of accumulator stage `as` in registers
+      if (PAIR) tc::mbar_arrive_cluster(acc_empty0_cl + as * 8); else tc::mbar_arrive(&acc_empty[as]);
     };
     int n_item = 0;    // live chunks stored so far (staging-buffer parity)
     int n_loaded = 0;  // EK_GELU_BWD: pre-activation tiles requested so far (the k-th request feeds the k-th live chunk)
@@ -288,7 +320,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ++n_loaded;
     };
 
-    Cursor cur{(int64_t)blockIdx.x, 0, half * 32};
+    Cursor cur{work0, 0, half * 32};
     if (cur.c < BN) {
       if ((KIND == EK_GELU_BWD || KIND == EK_ACCUM) && valid(cur)) load_aux(cur);
       while (valid(cur)) {
@@ -315,7 +347,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (last_chunk) {  // the accumulator stage is in registers: hand it back to the MMA warp
           tc::tc_fence_before();
           __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&acc_empty[as]);
+          if (lane == 0) release_acc(as);
         }
         if (live) {
           float2 v[16];
@@ -419,14 +451,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto valid = [&](const Cursor& cu) { return cu.wi < num_work; };
     auto advance = [&](Cursor& cu) {
       cu.c += 64;
-      if (cu.c >= BN) { cu.c = half * 32; cu.wi += gridDim.x; ++cu.it; }
+      if (cu.c >= BN) { cu.c = half * 32; cu.wi += work_step; ++cu.it; }
     };
     auto coords = [&](const Cursor& cu, int64_t& row0, int64_t& col) {
       const int tn = (int)(cu.wi % p.tiles_n);
       const int tm = (int)((cu.wi / p.tiles_n) % p.tiles_m);
-      row0 = (int64_t)tm * BM + q * 32 + lr;
+      row0 = (int64_t)tm * BM_TILE + (int64_t)cta_rank * BM + q * 32 + lr;
       col = (int64_t)tn * BN + cu.c + lc * 4;
     };
+    const uint32_t acc_empty0_cl = PAIR ? tc::mapa_u32(&acc_empty[0], 0) : 0u;
     auto prefetch = [&](const Cursor& cu, Pre& pre) {
       if constexpr (PRE_RES || PRE_AUX) {
         if (!valid(cu)) return;
@@ -462,7 +495,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (last_chunk) {  // the accumulator stage is in registers: hand it back to the MMA warp
         tc::tc_fence_before();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&acc_empty[as]);
+        if (lane == 0) {
+          if (PAIR) tc::mbar_arrive_cluster(acc_empty0_cl + as * 8); else tc::mbar_arrive(&acc_empty[as]);
+        }
       }
       // transpose through shared memory (XOR-swizzled 16-byte groups: conflict-free both ways) so that 8
       // consecutive lanes cover one 32-column row segment: every global access of the epilogue is a full
@@ -548,7 +583,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
     };
 
-    Cursor cur{(int64_t)blockIdx.x, 0, half * 32};
+    Cursor cur{work0, 0, half * 32};
     if (cur.c < BN) {
       Pre pa, pb;
       prefetch(cur, pa);
@@ -564,28 +599,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 
   tc::tc_fence_before();
-  __syncthreads();
+  if (PAIR) tc::cluster_sync_all(); else __syncthreads();  // PAIR: nobody leaves while the peer may still signal its barriers
   if (warp == 1) {
     tc::tc_fence_after();
-    tc::tmem_dealloc(tmem_base, 2 * Cfg::ACC_COLS);
+    if (PAIR) tc::tmem_dealloc2(tmem_base, 2 * Cfg::ACC_COLS); else tc::tmem_dealloc(tmem_base, 2 * Cfg::ACC_COLS);
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, typename TOut, int KIND>
+template <int BN, bool A_MN, bool B_MN, typename TOut, int KIND, bool PAIR = false>
 int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmD, const TcParams& p,
                int num_sms, cudaStream_t stream) {
-  using Cfg = TileCfg<BN, KIND>;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, TOut, KIND>;
+  using Cfg = TileCfg<BN, KIND, PAIR>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, TOut, KIND, PAIR>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     PMV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   int64_t work = (int64_t)p.tiles_m * p.tiles_n * p.splits;
+  if (PAIR) {
+    const int pairs = num_sms / 2;
+    const unsigned grid = 2u * (unsigned)(work < pairs ? work : pairs);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PMV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmD, p));
+    return PMV_OK;
+  }
   unsigned grid = (unsigned)(work < num_sms ? work : num_sms);
   kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmD, p);
   PMV_CHECK_LAUNCH();
   return PMV_OK;
+}
+
+// CTA-pair kernels (TN layout): tmB must have been encoded with a box of BN / 2 rows, p.tiles_m counts 256-row tiles
+template <int BN>
+int launch_bn_pair(int out_dtype, int kind, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                   const CUtensorMap& tmD, const TcParams& p, int num_sms, cudaStream_t s) {
+  const bool f32 = out_dtype == PMV_F32;
+  if (kind == EK_PLAIN && !f32) return launch_cfg<BN, false, false, bf16, EK_PLAIN, true>(tmA, tmB, tmC, tmD, p, num_sms, s);
+  if (kind == EK_GELU && !f32) return launch_cfg<BN, false, false, bf16, EK_GELU, true>(tmA, tmB, tmC, tmD, p, num_sms, s);
+  if (kind == EK_RES && f32) return launch_cfg<BN, false, false, float, EK_RES, true>(tmA, tmB, tmC, tmD, p, num_sms, s);
+  pmv_set_error("gemm(tc): no CTA-pair kernel for this epilogue");
+  return PMV_ERR_UNSUPPORTED;
 }
 
 // (layout, output type, epilogue kind) combinations that exist as kernels; anything else runs EK_GENERIC

@@ -8,7 +8,7 @@ torch.manual_seed(0)
 dt = torch.bfloat16
 def mk(M, N, K):
     return (torch.randn(M, K, device="cuda").to(dt), (torch.randn(N, K, device="cuda") * .05).to(dt), torch.randn(N, device="cuda"))
-x1, w1, b1 = mk(200712, 288, 96)
+x1, w1, b1 = mk(12552, 1152, 384)
 x2, w2, b2 = mk(12552, 1536, 384)
 dy3 = torch.randn(12552, 384, device="cuda").to(dt); w3 = (torch.randn(384, 1536, device="cuda") * .05).to(dt); u3 = torch.randn(12552, 1536, device="cuda").to(dt)
 for it in range(2):

@@ -63,3 +63,40 @@ def test_rel_index_table_matches_oracle(q, k):
 def test_aug_ld():
     from pmv_b200 import ops
     assert ops.aug_ld((8, 7, 7)) == 128 and ops.aug_ld((8, 14, 14)) == 160 and ops.aug_ld((16, 7, 7)) == 128
+
+
+def test_checkpoint_loader_matches_reference_surgery(tmp_path):
+    """a 224-crop MViTv2-S checkpoint loaded into a 160-crop model.  The rel-pos tables change
+    length and are interpolated; the result must equal what the reference's own load_checkpoint produced
+    (tests/golden/checkpoint_surgery.npz, oracle/make_golden.py::run_checkpoint_case)."""
+    import numpy as np
+    import torch
+    from oracle import detgen, mvit_oracle as orc
+    from pmv_b200 import mvit
+    from pmv_b200.checkpoint import load_checkpoint
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "checkpoint_surgery.npz"))
+    seed = int(z["seed"])
+    params = detgen.det_params(orc.param_shapes(orc.MVITV2_S), seed)
+    path = str(tmp_path / "ck.pyth")
+    torch.save({"model_state": {"module." + k: v for k, v in params.items()}, "epoch": 3}, path)  # DDP-style names
+    model = mvit.MViT(dict(mvit.MVITV2_S, crop=(160, 160)))
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    epoch = load_checkpoint(path, model)
+    assert epoch == int(z["epoch"]) == 3
+    sd = model.state_dict()
+    for k in z.files:
+        if k.startswith("blocks."):
+            assert tuple(sd[k].shape) == z[k].shape and sd[k].shape != params[k].shape or "rel_pos_t" in k
+            assert float((sd[k] - torch.from_numpy(z[k])).abs().max()) < 1e-6, k
+    names = list(z["names"])
+    assert names == list(sd.keys())
+    got = np.array([float(v.double().sum()) for v in sd.values()])
+    assert np.allclose(got, z["checksum"], rtol=1e-6, atol=1e-6)
+    rep = load_checkpoint.last_report
+    assert rep["not_used"] == [] and rep["not_loaded"] == [] and rep["missing"] == []
+    assert any(float((before[k] - sd[k]).abs().max()) > 0 for k in sd)
+    # same-shape load == strict load; epoch_reset
+    model224 = mvit.MViT(mvit.MVITV2_S)
+    assert load_checkpoint({"model_state": params, "epoch": 7}, model224, epoch_reset=True) == -1
+    for k, v in model224.state_dict().items():
+        assert torch.equal(v, params[k]), k
