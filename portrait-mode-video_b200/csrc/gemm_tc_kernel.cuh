@@ -335,6 +335,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();  // everyone has consumed the aux buffer the next request overwrites (two requests back)
           if (valid(nxt)) load_aux(nxt);
         }
+        // the chunk's bias slice is requested before the accumulator wait (it used to be consumed right after issue: the
+        // FADD2 behind it carried most of the long-scoreboard samples of the epilogue, profiles/r01_gemm_ncu_full_summary.txt)
+        float4 bq[8];
+        const bool use_bias = KIND != EK_GELU_BWD && KIND != EK_ACCUM && e.bias != nullptr && live;
+        if (use_bias) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            bq[g] = (col0 + 4 * g < p.N) ? __ldg(reinterpret_cast<const float4*>(e.bias + col0 + 4 * g)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         if (first_chunk) {
           tc::mbar_wait(&acc_full[as], (uint32_t)((cur.it >> 1) & 1));
           tc::tc_fence_after();
@@ -353,14 +362,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float2 v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-          if (KIND != EK_GELU_BWD && KIND != EK_ACCUM && e.bias) {
+          if (use_bias) {
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-              if (col0 + 4 * g < p.N) {  // N % 4 == 0
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + 4 * g));
-                v[2 * g] = __fadd2_rn(v[2 * g], make_float2(b4.x, b4.y));
-                v[2 * g + 1] = __fadd2_rn(v[2 * g + 1], make_float2(b4.z, b4.w));
-              }
+              v[2 * g] = __fadd2_rn(v[2 * g], make_float2(bq[g].x, bq[g].y));
+              v[2 * g + 1] = __fadd2_rn(v[2 * g + 1], make_float2(bq[g].z, bq[g].w));
             }
           }
           const int ob = n_item % OUT_BUFS;
