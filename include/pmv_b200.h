@@ -129,7 +129,7 @@ int pmv_pool_ln_fwd(const void* in, int64_t in_batch_stride, int64_t in_token_st
                     int B, int heads, int T, int H, int W, int stride_hw, float eps, int dtype, void* stream);
 /* Backward.  din is written (not accumulated) with the same strides as `in` (so q/k/v gradients land
  * interleaved in the dQKV buffer); dw_dgamma_dbeta is fp32 [96*27 + 96 + 96] (Conv3d weight gradient in the
- * reference layout, then the LayerNorm weight and bias gradients) and is added to.
+ * reference layout, then the LayerNorm weight and bias gradients) and is OVERWRITTEN.
  * ws: fp32 workspace of pmv_pool_ln_bwd_workspace_bytes() bytes (pre-LN gradient + per-CTA partial sums). */
 int64_t pmv_pool_ln_bwd_workspace_bytes(int B, int heads, int T, int H, int W, int stride_hw);
 int pmv_pool_ln_bwd(const void* in, int64_t in_batch_stride, int64_t in_token_stride, int64_t in_head_stride,
@@ -149,11 +149,13 @@ typedef struct {
   int64_t out_ld;
   const void* dout;    /* backward: gradient of out */
   int64_t dout_ld;
-  float* grads;        /* backward */
+  float* grads;        /* backward: [96*27 + 96 + 96] fp32 (dW, dgamma, dbeta), OVERWRITTEN */
   int stride_hw;
   int which;           /* 0 = q, 1 = k, 2 = v */
   void* xhat;          /* optional [B, heads, 1+T*Ho*Wo, 96] (dtype): forward saves the normalised pre-affine tokens, */
   float* rstd;         /* optional [B, heads, 1+T*Ho*Wo]: ... and 1/sigma; backward then skips the convolution recompute */
+  int dout_f32;        /* backward, saved-statistics path only: dout is fp32 whatever the compute dtype (e.g. the fp32
+                        * dk / dv accumulators pmv_attention_bwd leaves in its workspace when dk == dv == NULL) */
 } pmv_pool_job;
 int pmv_pool_ln_qkv_fwd(const void* qkv, int64_t batch_stride, int64_t token_stride, int64_t which_stride, int64_t head_stride,
                         const pmv_pool_job* jobs, int njobs, int B, int heads, int T, int H, int W, float eps, int dtype,
@@ -164,11 +166,11 @@ int pmv_pool_ln_qkv_bwd(const void* qkv, int64_t batch_stride, int64_t token_str
                         float eps, int dtype, void* stream);
 
 /* Skip-path MaxPool3d k (1,3,3) s (1,2,2) p (0,1,1) on [B, 1+T*H*W, C] fp32 tokens (cls copied):
- * attention.py:500-502,558-564,571-573.  Backward recomputes the arg-max (first maximum in window
- * scan order, like ATen) and ATOMICALLY accumulates into dx (caller zero-initialises; dx may alias
- * an accumulation buffer). */
-int pmv_maxpool_skip_fwd(const float* x, float* y, int B, int T, int H, int W, int C, void* stream);
-int pmv_maxpool_skip_bwd(const float* x, const float* dy, float* dx, int B, int T, int H, int W, int C, void* stream);
+ * attention.py:500-502,558-564,571-573.  The forward records the winning window position (0..8, first
+ * maximum in window scan order, like ATen) of every output element in `win` (uint8, same shape as y;
+ * NULL = not needed); the backward gathers through it and OVERWRITES dx (no atomics, no zero fill). */
+int pmv_maxpool_skip_fwd(const float* x, float* y, uint8_t* win, int B, int T, int H, int W, int C, void* stream);
+int pmv_maxpool_skip_bwd(const uint8_t* win, const float* dy, float* dx, int B, int T, int H, int W, int C, void* stream);
 
 /* ---------------------------------------------------------------- rel-pos augmentation
  * Decomposed relative position bias, cal_rel_pos_spatial / cal_rel_pos_temporal
@@ -215,7 +217,9 @@ int pmv_attention_fwd(const void* q_aug, const void* k_aug, int64_t ld_qk, int k
 /* Backward: dout [B, Nq, heads*96]; `out` is the PRE-residual output (out_pre of the forward call).  Writes dQ' [B*heads, Nq, ld_qk] (columns [0,kd): the first 96 are dq
  * incl. the residual-pooling path (dout added to rows >= 1), the rest d(rq/scale)), dk [B*heads, Nk, ld_dk]
  * (96 columns; the one-hot columns of K' carry no gradient) and dv [B*heads, Nk, ld_dv].
- * ws: fp32 workspace of pmv_attention_bwd_workspace_bytes() bytes (row deltas + dk/dv accumulators). */
+ * ws: fp32 workspace of pmv_attention_bwd_workspace_bytes() bytes (row deltas + dk/dv accumulators).
+ * tc path: dk == dv == NULL skips the down-cast; the gradients are then the fp32 arrays ws[0 : BH*Nk*96) (dk) and
+ * ws[BH*Nk*96 : 2*BH*Nk*96) (dv), row stride 96 — the pooling backward reads them directly (pmv_pool_job.dout_f32). */
 int64_t pmv_attention_bwd_workspace_bytes(int B, int heads, int Nq, int Nk);
 int pmv_attention_bwd(const void* q_aug, const void* k_aug, int64_t ld_qk, int kd, const void* v, int64_t ld_v,
                       const void* out, const void* dout, const float* lse,
@@ -230,6 +234,34 @@ int pmv_attention_bwd(const void* q_aug, const void* k_aug, int64_t ld_qk, int k
 int pmv_patch_im2col(const float* clip, void* col, int64_t ld_col, int B, int Cin, int T, int H, int W,
                      int kt, int kh, int kw, int st, int sh, int sw, int pt, int ph, int pw,
                      int dtype, void* stream);
+
+/* Programmatic dependent launch for the library's kernels: bit mask of kernel families (1 attention fwd, 2 attention
+ * bwd, 4 GEMM, 8 column sums, 16 LayerNorm, 32 | 64 pooling, 128 rel-pos, 256 others); 0 = off (default), -1 = all.
+ * Also settable with the PMV_PDL environment variable before the first launch. */
+void pmv_set_pdl(int family_mask);
+
+/* ---------------------------------------------------------------- optimizer step (row f3) ----
+ * Multi-tensor AdamW exactly as torch.optim.AdamW (decoupled weight decay, bias correction, eps outside the
+ * square root) — models/optimizer.py:124-131 — with a weight decay PER TENSOR (the reference's zero-WD group for
+ * 1-D parameters / biases / no_weight_decay() names, optimizer.py:42-57) and optional global L2-norm clipping of
+ * the gradients first (torch.nn.utils.clip_grad_norm_, tools/train_net.py:196-199).  One pass also refreshes the
+ * bf16 operand copy (`shadow`) of each weight, so the next forward casts nothing.
+ *   lr: DEVICE scalar (fp32) so that a captured CUDA graph follows the schedule; step: DEVICE int32, incremented by
+ *   the call; grad_norm_out: optional DEVICE fp32 scalar receiving the pre-clip global gradient norm;
+ *   max_grad_norm <= 0: no clipping.  ws: pmv_adamw_workspace_bytes() bytes.  Gradients are not modified. */
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  void* shadow;       /* optional bf16 [numel] */
+  int64_t numel;
+  float weight_decay;
+  float lr_scale;     /* multiplies lr (layer-wise decay); 1 otherwise */
+} pmv_adamw_tensor;
+int64_t pmv_adamw_workspace_bytes(const pmv_adamw_tensor* tensors, int ntensors);
+int pmv_adamw_step(const pmv_adamw_tensor* tensors, int ntensors, const float* lr, float beta1, float beta2, float eps,
+                   float max_grad_norm, int32_t* step, float* grad_norm_out, float* ws, void* stream);
 
 /* ---------------------------------------------------------------- bring-up probes ----
  * Single-tile tcgen05 probes used by tests/test_tcgen05_probe.py to pin the shared-memory /

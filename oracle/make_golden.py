@@ -229,6 +229,40 @@ def run_checkpoint_case(seed=555):
     return out
 
 
+def run_optimizer_case(seed=8642, steps=3):
+    """Row f3 pin: the reference's own construct_optimizer (models/optimizer.py:14-131) on its MViTv2-S, and the
+    reference's step sequence (tools/train_net.py:190-199: clip_grad_norm_(CLIP_GRAD_L2NORM) then optimizer.step()) on
+    deterministic parameters / gradients.  Stored: group membership by parameter name, the hyper-parameters, the
+    gradient norm of every step and per-tensor fp64 (sum, sum of squares) of the parameters after `steps` steps."""
+    model, cfg = ref_loader.load_full_model("configs/Kinetics/MVITv2_S_16x4.yaml")
+    import slowfast.models.optimizer as ropt
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    model.load_state_dict(detgen.det_params(shapes, seed), strict=True)
+    opt = ropt.construct_optimizer(model, cfg)
+    names = {id(p): n for n, p in model.named_parameters()}
+    out = dict(seed=seed, steps=steps, clip=float(cfg.SOLVER.CLIP_GRAD_L2NORM), lr=float(cfg.SOLVER.BASE_LR),
+               betas=np.asarray(cfg.SOLVER.BETAS, np.float64), eps=float(opt.param_groups[0]["eps"]),
+               optimizer=type(opt).__name__)
+    for gi, g in enumerate(opt.param_groups):
+        out[f"group{gi}_weight_decay"] = float(g["weight_decay"])
+        out[f"group{gi}_names"] = np.asarray([names[id(p)] for p in g["params"]])
+    out["ngroups"] = len(opt.param_groups)
+    norms = []
+    for it in range(steps):
+        for n, p in model.named_parameters():
+            # gradients large enough that the clip at 1.0 is active, different every step
+            p.grad = detgen.det_normal(p.shape, seed + 1 + it, n, 0.01)
+        norms.append(float(torch.nn.utils.clip_grad_norm_(model.parameters(), cfg.SOLVER.CLIP_GRAD_L2NORM)))
+        opt.step()
+    out["grad_norms"] = np.asarray(norms, np.float64)
+    pn = sorted(n for n, _ in model.named_parameters())
+    out["param_names"] = np.asarray(pn)
+    sd = dict(model.named_parameters())
+    out["param_sum"] = np.asarray([float(sd[n].detach().double().sum()) for n in pn], np.float64)
+    out["param_sumsq"] = np.asarray([float((sd[n].detach().double() ** 2).sum()) for n in pn], np.float64)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--check", action="store_true")
@@ -268,6 +302,10 @@ def main():
         ck = run_checkpoint_case()
         print("checkpoint surgery case: epoch", ck["epoch"], "tables", [k for k in ck if k.startswith("blocks")][:3], "...")
         np.savez_compressed(os.path.join(GOLDEN, "checkpoint_surgery.npz"), **ck)
+        og = run_optimizer_case()
+        print("optimizer case:", og["optimizer"], "groups", [(og[f"group{i}_weight_decay"], len(og[f"group{i}_names"])) for i in range(og["ngroups"])],
+              "grad norms", og["grad_norms"])
+        np.savez_compressed(os.path.join(GOLDEN, "optimizer_reference.npz"), **og)
     print(f"worst oracle-vs-reference error {worst:.2e}")
     assert worst < 5e-5, worst
 

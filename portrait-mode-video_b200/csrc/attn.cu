@@ -51,6 +51,7 @@ extern "C" int pmv_attention_bwd(const void* q_aug, const void* k_aug, int64_t l
     return attn_tc_bwd(q_aug, k_aug, ld_qk, kd, v, ld_v, out, dout, lse, dq_aug, dk, ld_dk, dv, ld_dv, ws, B, heads, Nq, Nk,
                        scale, residual, (cudaStream_t)stream);
   }
+  PMV_CHECK_ARG(dk != nullptr && dv != nullptr, "attention bwd: only the tcgen05 path can leave dk / dv in the workspace");
   return attn_simt_bwd(q_aug, k_aug, ld_qk, kd, v, ld_v, out, dout, lse, dq_aug, dk, ld_dk, dv, ld_dv, ws, B, heads, Nq, Nk, scale,
                        residual, dtype, stream);
 }

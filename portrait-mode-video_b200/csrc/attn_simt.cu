@@ -41,6 +41,7 @@ template <typename T>
 __global__ void __launch_bounds__(THREADS) attn_fwd_kernel(const T* __restrict__ q_aug, const T* __restrict__ k_aug,
                                                            const T* __restrict__ v, T* __restrict__ out,
                                                            T* __restrict__ out_pre, float* __restrict__ lse, AttnGeom g) {
+  pdl_wait();
   extern __shared__ float sm[];
   const int KP = g.kd + 1;
   float* Qs = sm;                 // [64][KP]
@@ -166,6 +167,7 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_kernel(const T* __restrict__
                                                            const T* __restrict__ dout, const float* __restrict__ lse,
                                                            T* __restrict__ dq_aug, float* __restrict__ dk_ws,
                                                            float* __restrict__ dv_ws, AttnGeom g) {
+  pdl_wait();
   extern __shared__ float sm[];
   const int KP = g.kd + 1;
   float* Qs = sm;                  // [64][KP]
@@ -325,6 +327,7 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_kernel(const T* __restrict__
 
 template <typename T>
 __global__ void __launch_bounds__(256) cast_rows_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t rows, int64_t ld) {
+  pdl_wait();
   const int64_t total = rows * (HD / 4);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / (HD / 4);
@@ -344,7 +347,7 @@ int attn_simt_fwd(const void* q_aug, const void* k_aug, int64_t ld_qk, int kd, c
   dim3 grid((unsigned)ceil_div64(Nq, BQ), (unsigned)(B * heads));
   PMV_DISPATCH_DTYPE(dtype, T, {
     PMV_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attn_fwd_kernel<T><<<grid, THREADS, smem, stream>>>((const T*)q_aug, (const T*)k_aug, (const T*)v, (T*)out, (T*)out_pre, lse, g);
+    pmv_launch(attn_fwd_kernel<T>, grid, THREADS, smem, stream, (const T*)q_aug, (const T*)k_aug, (const T*)v, (T*)out, (T*)out_pre, lse, g);
   });
   PMV_CHECK_LAUNCH();
   return PMV_OK;
@@ -366,10 +369,10 @@ int attn_simt_bwd(const void* q_aug, const void* k_aug, int64_t ld_qk, int kd, c
   if (cblocks > 148 * 8) cblocks = 148 * 8;
   PMV_DISPATCH_DTYPE(dtype, T, {
     PMV_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attn_bwd_kernel<T><<<grid, THREADS, smem, st>>>((const T*)q_aug, (const T*)k_aug, (const T*)v, (const T*)out,
+    pmv_launch(attn_bwd_kernel<T>, grid, THREADS, smem, st, (const T*)q_aug, (const T*)k_aug, (const T*)v, (const T*)out,
                                                     (const T*)dout, lse, (T*)dq_aug, dk_ws, dv_ws, g);
-    cast_rows_kernel<T><<<(unsigned)cblocks, 256, 0, st>>>(dk_ws, (T*)dk, rows, ld_dk);
-    cast_rows_kernel<T><<<(unsigned)cblocks, 256, 0, st>>>(dv_ws, (T*)dv, rows, ld_dv);
+    pmv_launch(cast_rows_kernel<T>, (unsigned)cblocks, 256, 0, st, dk_ws, (T*)dk, rows, ld_dk);
+    pmv_launch(cast_rows_kernel<T>, (unsigned)cblocks, 256, 0, st, dv_ws, (T*)dv, rows, ld_dv);
   });
   PMV_CHECK_LAUNCH();
   return PMV_OK;

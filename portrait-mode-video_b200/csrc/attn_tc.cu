@@ -1,3 +1,4 @@
+#define PMV_PDL_FAMILY 1
 // tcgen05 / TMEM / TMA pooling attention, forward (bf16 operands, fp32 softmax and accumulation):
 //     O = softmax(scale * Q' K'^T) V  (+ q for rows >= 1: residual pooling), head-merged store.
 // The decomposed relative-position bias rides in the augmented columns of Q'/K' (relpos.cu), so the score
@@ -91,6 +92,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base + 256;
+  pdl_wait();  // the prologue above overlaps the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -314,7 +316,7 @@ int launch(const void* q_aug, const void* k_aug, int64_t ld_qk, const void* v, i
     attr_set = true;
   }
   dim3 grid((unsigned)((g.Nq + BQ - 1) / BQ), (unsigned)BH);
-  kern<<<grid, THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmQ2, tmK, tmK2, tmV, (bf16*)out, (bf16*)out_pre, lse, g);
+  pmv_launch(kern, grid, THREADS, Cfg::SMEM_BYTES, stream, tmQ, tmQ2, tmK, tmK2, tmV, (bf16*)out, (bf16*)out_pre, lse, g);
   PMV_CHECK_LAUNCH();
   return PMV_OK;
 }

@@ -1,3 +1,4 @@
+#define PMV_PDL_FAMILY 2
 // tcgen05 / TMEM / TMA pooling attention, backward (bf16 operands, fp32 accumulation).
 //
 // Two kernels, both structured like the forward kernel (attn_tc.cu) and both free of the [Nq, Nk] score
@@ -73,6 +74,7 @@ __device__ __forceinline__ uint32_t packed_col(int ks) { return ks < 2 ? ks * 8 
 // 16-byte loads per tensor) each, 8 rows per warp: both tensors are read once, fully coalesced.
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ o_pre,
                                                          float* __restrict__ delta, int B, int heads, int Nq) {
+  pdl_wait();
   const int64_t rows = (int64_t)B * Nq * heads;  // (b, n, head) in memory order
   const int sub = threadIdx.x & 3;
   for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2; r < ((rows + 7) & ~(int64_t)7); r += ((int64_t)gridDim.x * blockDim.x) >> 2) {
@@ -150,6 +152,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dq = tmem_base + 256;  // S / dP: buffer b at + 64 b
+  pdl_wait();  // the prologue above overlaps the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -366,6 +369,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_st = tmem_base, tmem_dpt = tmem_base + 128, tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 384;
+  pdl_wait();  // the prologue above overlaps the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -525,6 +529,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
 template <typename T>
 __global__ void __launch_bounds__(256) cast_rows96_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t rows, int64_t ld) {
+  pdl_wait();
   const int64_t total = rows * (HD / 4);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / (HD / 4);
@@ -571,9 +576,9 @@ int launch_bwd(const void* q_aug, const void* k_aug, int64_t ld_qk, const void* 
     const int64_t rows = (int64_t)g.B * g.Nq * g.heads;
     int64_t dblocks = ceil_div64(rows * 4, 256);
     if (dblocks > 148 * 16) dblocks = 148 * 16;
-    attn_delta_kernel<<<(unsigned)dblocks, 256, 0, stream>>>((const bf16*)dout, (const bf16*)o_pre, delta, g.B, g.heads, g.Nq);
+    pmv_launch(attn_delta_kernel, (unsigned)dblocks, 256, 0, stream, (const bf16*)dout, (const bf16*)o_pre, delta, g.B, g.heads, g.Nq);
   }
-  kq<<<dim3((unsigned)q_tiles, (unsigned)BH), THREADS, Cfg::SMEM_BYTES, stream>>>(
+  pmv_launch(kq, dim3((unsigned)q_tiles, (unsigned)BH), THREADS, Cfg::SMEM_BYTES, stream, 
       tmQ, tmQ2, tmK, tmK2, tmV, tmdO, (const bf16*)dout, lse, delta, (bf16*)dq_aug, g);
   // split the query tiles so that about 3 CTAs per SM exist
   int chunks = (int)((148 * 3 + (int64_t)k_tiles * BH - 1) / ((int64_t)k_tiles * BH));
@@ -581,12 +586,12 @@ int launch_bwd(const void* q_aug, const void* k_aug, int64_t ld_qk, const void* 
   if (chunks > q_tiles) chunks = q_tiles;
   g.q_tiles_per_chunk = (q_tiles + chunks - 1) / chunks;
   chunks = (q_tiles + g.q_tiles_per_chunk - 1) / g.q_tiles_per_chunk;
-  kkv<<<dim3((unsigned)k_tiles, (unsigned)BH, (unsigned)chunks), THREADS, Cfg::SMEM_BYTES, stream>>>(
+  pmv_launch(kkv, dim3((unsigned)k_tiles, (unsigned)BH, (unsigned)chunks), THREADS, Cfg::SMEM_BYTES, stream, 
       tmQ, tmQ2, tmK, tmK2, tmV, tmdO, lse, delta, dk_ws, dv_ws, g);
   int64_t cblocks = ceil_div64(krows * (HD / 4), 256);
   if (cblocks > 148 * 8) cblocks = 148 * 8;
-  cast_rows96_kernel<bf16><<<(unsigned)cblocks, 256, 0, stream>>>(dk_ws, (bf16*)dk, krows, ld_dk);
-  cast_rows96_kernel<bf16><<<(unsigned)cblocks, 256, 0, stream>>>(dv_ws, (bf16*)dv, krows, ld_dv);
+  if (dk != nullptr) pmv_launch(cast_rows96_kernel<bf16>, (unsigned)cblocks, 256, 0, stream, dk_ws, (bf16*)dk, krows, ld_dk);
+  if (dv != nullptr) pmv_launch(cast_rows96_kernel<bf16>, (unsigned)cblocks, 256, 0, stream, dv_ws, (bf16*)dv, krows, ld_dv);
   PMV_CHECK_LAUNCH();
   return PMV_OK;
 }

@@ -40,6 +40,35 @@ void pmv_set_error(const char* fmt, ...);
     }                                                                                     \
   } while (0)
 
+// ---------------------------------------------------------------------------
+// launches.  Every kernel of the library is launched through pmv_launch and calls pdl_wait() before it touches global
+// memory.  With programmatic dependent launch enabled for its family (runtime.cu: pmv_set_pdl / PMV_PDL, default off)
+// the CTAs of kernel N+1 are scheduled while kernel N drains - their prologue (barrier init, TMEM allocation,
+// descriptor prefetch) overlaps its tail - and griddepcontrol.wait blocks until kernel N has completed and flushed;
+// without the launch attribute the instruction is a no-op.  scripts/pdl_probe.cu measures the edge cost.
+// ---------------------------------------------------------------------------
+#ifndef PMV_PDL_FAMILY
+#define PMV_PDL_FAMILY 256
+#endif
+bool pmv_pdl_enabled(int family);  // runtime.cu: reads PMV_PDL (bit mask of kernel families) once
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t pmv_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pmv_pdl_enabled(PMV_PDL_FAMILY) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // Division by a run-time constant as multiply-high + shift (dividends < 2^31).  A hardware integer division

@@ -1,3 +1,4 @@
+#define PMV_PDL_FAMILY 8
 // pmv_gemm dispatcher (fp32 FFMA kernel vs tcgen05 kernel) and the column-sum / cast helper.
 #include "gemm.h"
 #include "reduce.cuh"
@@ -49,6 +50,7 @@ __global__ void __launch_bounds__(CS_THREADS) colsum_cast_kernel(const TIn* __re
                                                                  const float* __restrict__ row_scale, FastDiv fd_scale,
                                                                  float* __restrict__ out_sum, TCast* __restrict__ cast_out, int64_t ld_cast,
                                                                  int64_t rows_per_block, int cx, float* __restrict__ final_sum) {
+  pdl_wait();
   __shared__ float red[CS_THREADS * 4];
   // the fold kernel that follows ADDS the per-slice partials into final_sum: clear it here (saves a fill launch)
   if (final_sum != nullptr && blockIdx.y == 0) {
@@ -143,7 +145,7 @@ extern "C" int pmv_colsum_cast(const void* in, int in_dtype, int64_t ld_in, int6
   dim3 grid(bx, by);
   const FastDiv fd((uint32_t)rows_per_scale);
   PMV_CHECK_ARG(out_sum == nullptr || ws != nullptr, "colsum: workspace required when out_sum is given");
-#define LAUNCH(TI, TC) colsum_cast_kernel<TI, TC><<<grid, CS_THREADS, 0, (cudaStream_t)stream>>>( \
+#define LAUNCH(TI, TC) pmv_launch(colsum_cast_kernel<TI, TC>, grid, CS_THREADS, 0, (cudaStream_t)stream,  \
       (const TI*)in, ld_in, rows, cols, row_scale, fd, out_sum ? ws : nullptr, (TC*)cast_out, ld_cast, rpb, cx, out_sum)
   if (in_dtype == PMV_F32 && cast_dtype == PMV_F32) LAUNCH(float, float);
   else if (in_dtype == PMV_F32 && cast_dtype == PMV_BF16) LAUNCH(float, bf16);

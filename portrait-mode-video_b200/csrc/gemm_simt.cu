@@ -38,6 +38,7 @@ template <typename TIO, typename TOut>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const TIO* __restrict__ A, int64_t sam, int64_t sak,
                                                         const TIO* __restrict__ B, int64_t sbn, int64_t sbk,
                                                         int64_t M, int64_t N, int64_t K, int64_t k_per_split, EpiDev e) {
+  pdl_wait();
   __shared__ __align__(16) float As[BK][BM + PAD];
   __shared__ __align__(16) float Bs[BK][BN + PAD];
   const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
@@ -106,7 +107,7 @@ int gemm_simt_launch(int layout, const void* A, int64_t lda, const void* B, int6
   split_k = (int)ceil_div64(KK, kps);
   dim3 grid((unsigned)ceil_div64(NN, BN), (unsigned)ceil_div64(MM, BM), (unsigned)split_k);
 #define LAUNCH(TIO, TOUT)                                                                                  \
-  gemm_simt_kernel<TIO, TOUT><<<grid, 256, 0, stream>>>((const TIO*)A, sam, sak, (const TIO*)B, sbn, sbk, MM, NN, KK, kps, e)
+  pmv_launch(gemm_simt_kernel<TIO, TOUT>, grid, 256, 0, stream, (const TIO*)A, sam, sak, (const TIO*)B, sbn, sbk, MM, NN, KK, kps, e)
   if (io_dtype == PMV_F32 && out_dtype == PMV_F32) LAUNCH(float, float);
   else if (io_dtype == PMV_BF16 && out_dtype == PMV_BF16) LAUNCH(bf16, bf16);
   else if (io_dtype == PMV_BF16 && out_dtype == PMV_F32) LAUNCH(bf16, float);

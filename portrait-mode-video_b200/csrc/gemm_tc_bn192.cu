@@ -1,3 +1,4 @@
+#define PMV_PDL_FAMILY 4
 // gemm_tc_kernel instantiations for BN = 192 (one translation unit per tile width: they compile in parallel)
 #include "gemm_tc_kernel.cuh"
 

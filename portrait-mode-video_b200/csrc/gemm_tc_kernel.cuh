@@ -181,6 +181,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (PAIR) tc::cluster_sync_all(); else __syncthreads();  // PAIR: the peer's barriers must exist before anyone signals them
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlaps the tail of the previous kernel; nothing global has been touched yet
 
   const int64_t num_work = (int64_t)p.tiles_m * p.tiles_n * p.splits;
 
@@ -643,7 +644,7 @@ int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
     return PMV_OK;
   }
   unsigned grid = (unsigned)(work < num_sms ? work : num_sms);
-  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmD, p);
+  pmv_launch(kern, grid, NUM_THREADS, Cfg::SMEM_BYTES, stream, tmA, tmB, tmC, tmD, p);
   PMV_CHECK_LAUNCH();
   return PMV_OK;
 }

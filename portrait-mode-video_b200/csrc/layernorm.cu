@@ -1,3 +1,4 @@
+#define PMV_PDL_FAMILY 16
 // LayerNorm forward / backward over the channel axis of the fp32 residual stream.
 // Replaces native_layer_norm at attention.py:567,578 and video_model_builder.py:2163.
 // Memory-bound: 8 / 16 / 32 lanes per row, 16-byte loads, two-pass (mean, then centred variance) in fp32.
@@ -16,6 +17,7 @@ template <int LPR, int VPL, typename TOut>
 __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_fwd_kernel(
     const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
     TOut* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int64_t rows, float eps) {
+  pdl_wait();
   constexpr int C = 4 * LPR * VPL;
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
@@ -68,6 +70,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(
     const TDy* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
     const float* __restrict__ mean, const float* __restrict__ rstd, float* dx, const float* dx_base,
     float* __restrict__ partials, float* __restrict__ dgb, int64_t rows) {
+  pdl_wait();
   constexpr int C = 4 * LPR * VPL;
   constexpr int RPW = 32 / LPR;
   __shared__ float red[LN_WARPS][2 * C];
@@ -167,7 +170,7 @@ int launch_fwd(const float* x, const float* gamma, const float* beta, void* y, i
                float eps, cudaStream_t st) {
   int64_t blocks = ceil_div64(rows, LN_WARPS * (32 / LPR) * 2);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  PMV_DISPATCH_DTYPE(y_dtype, T, (layernorm_fwd_kernel<LPR, VPL, T><<<(unsigned)blocks, LN_WARPS * 32, 0, st>>>(
+  PMV_DISPATCH_DTYPE(y_dtype, T, (pmv_launch(layernorm_fwd_kernel<LPR, VPL, T>, (unsigned)blocks, LN_WARPS * 32, 0, st, 
                                      x, gamma, beta, (T*)y, mean, rstd, rows, eps)));
   PMV_CHECK_LAUNCH();
   return PMV_OK;
@@ -183,7 +186,7 @@ template <int LPR, int VPL>
 int launch_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma, const float* mean, const float* rstd, float* dx,
                const float* dx_base, float* ws, float* dgb, int64_t rows, cudaStream_t st) {
   const int64_t blocks = ln_bwd_blocks(rows);
-  PMV_DISPATCH_DTYPE(dy_dtype, T, (layernorm_bwd_kernel<LPR, VPL, T><<<(unsigned)blocks, LN_WARPS * 32, 0, st>>>(
+  PMV_DISPATCH_DTYPE(dy_dtype, T, (pmv_launch(layernorm_bwd_kernel<LPR, VPL, T>, (unsigned)blocks, LN_WARPS * 32, 0, st, 
                                       (const T*)dy, x, gamma, mean, rstd, dx, dx_base, ws, dgb, rows)));
   PMV_CHECK_LAUNCH();
   return PMV_OK;

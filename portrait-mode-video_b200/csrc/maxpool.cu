@@ -1,34 +1,35 @@
 // Residual-path MaxPool3d (1,3,3) / (1,2,2) / (0,1,1) on the fp32 token stream (attention.py:500-502, 558-564,
-// 571-573): channels-last, cls token copied; backward recomputes the arg-max (first maximum in scan order, like
-// ATen) and scatters with atomics (overlapping windows).
+// 571-573): channels-last, cls token copied.  The forward records, per output element, which of the nine window
+// positions won (first maximum in scan order, like ATen); the backward is a gather: every input element looks at the
+// <= 4 windows that contain it and sums the gradients of those it won.  No atomics, no zero fill of dx.
+// (The first version recomputed the arg-max and scattered with atomicAdd into a cleared buffer: 250 us at block 1.)
 #include "common.cuh"
 
 namespace {
 
-// ---------------------------------------------------------------------------------------------
-// skip-path max pool (fp32 residual stream), kernel (1,3,3) stride (1,2,2) pad (0,1,1)
-// ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) maxpool_skip_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
-                                                               int B, int T, int H, int W, int Ho, int Wo, int C) {
+                                                               uint8_t* __restrict__ win, int B, int T, int H, int W, int Ho, int Wo,
+                                                               int C) {
+  pdl_wait();
   const int C4 = C >> 2;
-  const int64_t Lo = (int64_t)T * Ho * Wo, Li = (int64_t)T * H * W;
+  const int Lo = T * Ho * Wo, Li = T * H * W;
   const int64_t total = (int64_t)B * (Lo + 1) * C4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c4 = (int)(i % C4);
-    int64_t r = i / C4;
-    const int64_t n = r % (Lo + 1);
-    const int64_t b = r / (Lo + 1);
-    const float* xb = x + b * (Li + 1) * C + c4 * 4;
+    const int r = (int)(i / C4);
+    const int n = r % (Lo + 1);
+    const int b = r / (Lo + 1);
+    const float* xb = x + (int64_t)b * (Li + 1) * C + c4 * 4;
     float m[4];
+    uchar4 a = make_uchar4(0, 0, 0, 0);
     if (n == 0) {
       load4(xb, m);
     } else {
-      int64_t l = n - 1;
-      const int wo = (int)(l % Wo); l /= Wo;
-      const int ho = (int)(l % Ho);
-      const int t = (int)(l / Ho);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) m[j] = -INFINITY;
+      int l = n - 1;
+      const int wo = l % Wo; l /= Wo;
+      const int ho = l % Ho;
+      const int t = l / Ho;
+      bool first = true;
 #pragma unroll
       for (int dh = 0; dh < 3; ++dh) {
         const int hi = ho * 2 + dh - 1;
@@ -38,51 +39,68 @@ __global__ void __launch_bounds__(256) maxpool_skip_fwd_kernel(const float* __re
           const int wi = wo * 2 + dw - 1;
           if (wi < 0 || wi >= W) continue;
           float v[4];
-          load4(xb + (1 + ((int64_t)t * H + hi) * W + wi) * C, v);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) m[j] = fmaxf(m[j], v[j]);
+          load4(xb + (int64_t)(1 + (t * H + hi) * W + wi) * C, v);
+          const uint8_t p = (uint8_t)(dh * 3 + dw);
+          if (first || v[0] > m[0] || v[0] != v[0]) { m[0] = v[0]; a.x = p; }  // NaN wins, like ATen
+          if (first || v[1] > m[1] || v[1] != v[1]) { m[1] = v[1]; a.y = p; }  // NaN wins, like ATen
+          if (first || v[2] > m[2] || v[2] != v[2]) { m[2] = v[2]; a.z = p; }  // NaN wins, like ATen
+          if (first || v[3] > m[3] || v[3] != v[3]) { m[3] = v[3]; a.w = p; }  // NaN wins, like ATen
+          first = false;
         }
       }
     }
-    store4(y + (b * (Lo + 1) + n) * C + c4 * 4, m);
+    const int64_t o = ((int64_t)b * (Lo + 1) + n) * C + c4 * 4;
+    store4(y + o, m);
+    if (win != nullptr) *reinterpret_cast<uchar4*>(win + o) = a;
   }
 }
 
-__global__ void __launch_bounds__(256) maxpool_skip_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                                               float* __restrict__ dx, int B, int T, int H, int W,
-                                                               int Ho, int Wo, int C) {
-  const int64_t Lo = (int64_t)T * Ho * Wo, Li = (int64_t)T * H * W;
-  const int64_t total = (int64_t)B * (Lo + 1) * C;
+__global__ void __launch_bounds__(256) maxpool_skip_bwd_kernel(const uint8_t* __restrict__ win, const float* __restrict__ dy,
+                                                               float* __restrict__ dx, int B, int T, int H, int W, int Ho, int Wo,
+                                                               int C) {
+  pdl_wait();
+  const int C4 = C >> 2;
+  const int Lo = T * Ho * Wo, Li = T * H * W;
+  const int64_t total = (int64_t)B * (Li + 1) * C4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    int64_t r = i / C;
-    const int64_t n = r % (Lo + 1);
-    const int64_t b = r / (Lo + 1);
-    const float g = dy[i];
-    const float* xb = x + b * (Li + 1) * C + c;
-    float* dxb = dx + b * (Li + 1) * C + c;
+    const int c4 = (int)(i % C4);
+    const int r = (int)(i / C4);
+    const int n = r % (Li + 1);
+    const int b = r / (Li + 1);
+    const int64_t ob = (int64_t)b * (Lo + 1) * C + c4 * 4;
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
     if (n == 0) {
-      atomicAdd(dxb, g);
-      continue;
-    }
-    int64_t l = n - 1;
-    const int wo = (int)(l % Wo); l /= Wo;
-    const int ho = (int)(l % Ho);
-    const int t = (int)(l / Ho);
-    float m = -INFINITY;
-    int64_t arg = -1;
-    for (int dh = 0; dh < 3; ++dh) {
-      const int hi = ho * 2 + dh - 1;
-      if (hi < 0 || hi >= H) continue;
-      for (int dw = 0; dw < 3; ++dw) {
-        const int wi = wo * 2 + dw - 1;
-        if (wi < 0 || wi >= W) continue;
-        const int64_t off = (1 + ((int64_t)t * H + hi) * W + wi) * C;
-        const float v = xb[off];
-        if (v > m || arg < 0) { m = v; arg = off; }  // first maximum in scan order (ATen max_pool3d)
+      load4(dy + ob, g);
+    } else {
+      int l = n - 1;
+      const int w = l % W; l /= W;
+      const int h = l % H;
+      const int t = l / H;
+      // windows containing row h: ho = h/2 with dh = 1 (h even), or ho = (h+1)/2 with dh = 0 and (h-1)/2 with dh = 2 (h odd)
+      const int nh = (h & 1) ? 2 : 1, nw = (w & 1) ? 2 : 1;
+      for (int a = 0; a < nh; ++a) {
+        const int ho = (h & 1) ? (a == 0 ? (h + 1) >> 1 : (h - 1) >> 1) : h >> 1;
+        const int dh = (h & 1) ? (a == 0 ? 0 : 2) : 1;
+        if (ho >= Ho) continue;
+        for (int c = 0; c < nw; ++c) {
+          const int wo = (w & 1) ? (c == 0 ? (w + 1) >> 1 : (w - 1) >> 1) : w >> 1;
+          const int dw = (w & 1) ? (c == 0 ? 0 : 2) : 1;
+          if (wo >= Wo) continue;
+          const int64_t o = ob + (int64_t)(1 + (t * Ho + ho) * Wo + wo) * C;
+          const uchar4 a4 = *reinterpret_cast<const uchar4*>(win + o);
+          const uint8_t p = (uint8_t)(dh * 3 + dw);
+          if (a4.x == p || a4.y == p || a4.z == p || a4.w == p) {
+            float d[4];
+            load4(dy + o, d);
+            if (a4.x == p) g[0] += d[0];
+            if (a4.y == p) g[1] += d[1];
+            if (a4.z == p) g[2] += d[2];
+            if (a4.w == p) g[3] += d[3];
+          }
+        }
       }
     }
-    atomicAdd(dxb + arg, g);
+    store4(dx + ((int64_t)b * (Li + 1) + n) * C + c4 * 4, g);
   }
 }
 
@@ -95,19 +113,24 @@ unsigned grid_for(int64_t items, int per_block, int max_blocks) {
 
 }  // namespace
 
-extern "C" int pmv_maxpool_skip_fwd(const float* x, float* y, int B, int T, int H, int W, int C, void* stream) {
+// `win` (uint8 [B, 1 + T*Ho*Wo, C], may be NULL for inference) receives the winning window position of every output.
+extern "C" int pmv_maxpool_skip_fwd(const float* x, float* y, uint8_t* win, int B, int T, int H, int W, int C, void* stream) {
   PMV_CHECK_ARG(C % 4 == 0, "maxpool: C must be a multiple of 4");
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const int64_t total = (int64_t)B * (1 + (int64_t)T * Ho * Wo) * (C / 4);
-  maxpool_skip_fwd_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(x, y, B, T, H, W, Ho, Wo, C);
+  PMV_CHECK_ARG((int64_t)B * (1 + (int64_t)T * H * W) < (1ll << 31), "maxpool: too many tokens");
+  pmv_launch(maxpool_skip_fwd_kernel, grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream, x, y, win, B, T, H, W, Ho, Wo, C);
   PMV_CHECK_LAUNCH();
   return PMV_OK;
 }
 
-extern "C" int pmv_maxpool_skip_bwd(const float* x, const float* dy, float* dx, int B, int T, int H, int W, int C, void* stream) {
+// dx is OVERWRITTEN (every input element is produced exactly once).
+extern "C" int pmv_maxpool_skip_bwd(const uint8_t* win, const float* dy, float* dx, int B, int T, int H, int W, int C, void* stream) {
+  PMV_CHECK_ARG(C % 4 == 0, "maxpool: C must be a multiple of 4");
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-  const int64_t total = (int64_t)B * (1 + (int64_t)T * Ho * Wo) * C;
-  maxpool_skip_bwd_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(x, dy, dx, B, T, H, W, Ho, Wo, C);
+  const int64_t total = (int64_t)B * (1 + (int64_t)T * H * W) * (C / 4);
+  PMV_CHECK_ARG((int64_t)B * (1 + (int64_t)T * H * W) < (1ll << 31), "maxpool: too many tokens");
+  pmv_launch(maxpool_skip_bwd_kernel, grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream, win, dy, dx, B, T, H, W, Ho, Wo, C);
   PMV_CHECK_LAUNCH();
   return PMV_OK;
 }

@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ c
                                                      int B, int Cin, int Tn, int H, int W, int To, int Ho, int Wo,
                                                      int kt, int kh, int kw, int st, int sh, int sw, int pt, int ph, int pw,
                                                      int span, int pitch) {
+  pdl_wait();
   extern __shared__ float rows_s[];  // [Cin*kt*kh][pitch]; element j of a row is input column j - pw
   const int K = Cin * kt * kh * kw;
   const int nrows = Cin * kt * kh;
@@ -81,7 +82,7 @@ extern "C" int pmv_patch_im2col(const float* clip, void* col, int64_t ld_col, in
       PMV_CHECK_CUDA(cudaFuncSetAttribute(im2col_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr_set = true;
     }
-    im2col_kernel<TT><<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(clip, (TT*)col, ld_col, B, Cin, T, H, W, To, Ho, Wo, kt,
+    pmv_launch(im2col_kernel<TT>, (unsigned)blocks, 256, smem, (cudaStream_t)stream, clip, (TT*)col, ld_col, B, Cin, T, H, W, To, Ho, Wo, kt,
                                                                              kh, kw, st, sh, sw, pt, ph, pw, span, pitch);
   });
   PMV_CHECK_LAUNCH();

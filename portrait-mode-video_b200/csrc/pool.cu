@@ -1,3 +1,4 @@
+#define PMV_PDL_FAMILY 32
 // attention_pool() with the depthwise 3x3x3 Conv3d (stride (1,s,s), pad 1, weights shared across heads) fused
 // with the LayerNorm(96) that follows it (attention.py:14-48, 241-282), forward and backward, for q, k and v
 // in ONE launch each.  Channels-last: the kernels read q / k / v straight out of the QKV GEMM output
@@ -115,6 +116,7 @@ __device__ __forceinline__ int find_job(const Launch& L) {
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T, bool BWD>
 __global__ void __launch_bounds__(THREADS, 2) pool_ln_march_kernel(const __grid_constant__ Launch L) {
+  pdl_wait();
   __shared__ __align__(16) float conv_s[2][CHUNK_TOK * HD];  // 18 KB; reused for the final partial reduction
   __shared__ float sgam[HD], sbet[HD];
   __shared__ int64_t row_out_s[ROWS];   // output token index of the row's first position (incl. cls slots)
@@ -371,6 +373,7 @@ __device__ __forceinline__ void dw_accum(float2 (&acc)[TAPS], const float2 (&xa)
 
 template <typename T>
 __global__ void __launch_bounds__(THREADS, 2) pool_ln_bwd_dw_kernel(const __grid_constant__ Launch L) {
+  pdl_wait();
   __shared__ float dws[NDW];
   int jj = 0;
   while (jj + 1 < L.njobs && (int)blockIdx.x >= L.job[jj + 1].blk_begin) ++jj;
@@ -463,6 +466,7 @@ __device__ __forceinline__ void tap_t(float2& acc, const T* __restrict__ p, cons
 
 template <typename T>
 __global__ void __launch_bounds__(THREADS, 2) pool_ln_bwd_input_kernel(const __grid_constant__ Launch L) {
+  pdl_wait();
   int jj = 0;
   while (jj + 1 < L.njobs && (int)blockIdx.x >= L.job[jj + 1].blk_begin) ++jj;
   const Job& J = L.job[jj];
@@ -567,6 +571,7 @@ constexpr int SV_THREADS = 256;
 constexpr int SV_TOK = SV_THREADS / LNL;  // 32 tokens per pass
 template <typename T>
 __global__ void __launch_bounds__(SV_THREADS) pool_ln_bwd_saved_kernel(const __grid_constant__ Launch L) {
+  pdl_wait();
   __shared__ float red[SV_TOK * 2 * HD];
   __shared__ float sgam[HD];
   const Job& J = L.job[find_job(L)];
@@ -579,6 +584,8 @@ __global__ void __launch_bounds__(SV_THREADS) pool_ln_bwd_saved_kernel(const __g
   const int64_t ntok = (int64_t)L.B * L.heads * (Lo + 1);
   const T* __restrict__ xhat = reinterpret_cast<const T*>(J.xhat);
   const T* __restrict__ dout = reinterpret_cast<const T*>(J.dout);
+  const float* __restrict__ dout32 = reinterpret_cast<const float*>(J.dout);
+  const bool f32 = J.dout_f32 != 0;
   float gm[CPL], adg[CPL], adb[CPL];
 #pragma unroll
   for (int j = 0; j < CPL; ++j) { gm[j] = sgam[sub * CPL + j]; adg[j] = 0.f; adb[j] = 0.f; }
@@ -588,7 +595,8 @@ __global__ void __launch_bounds__(SV_THREADS) pool_ln_bwd_saved_kernel(const __g
     const int64_t tk = ok ? tok : 0;
     float xh[CPL], dy[CPL];
     load12(xhat + tk * HD + sub * CPL, xh);
-    load12(dout + tk * J.dout_ld + sub * CPL, dy);
+    if (f32) load12(dout32 + tk * J.dout_ld + sub * CPL, dy);
+    else load12(dout + tk * J.dout_ld + sub * CPL, dy);
     const float rs = ok ? J.rstd[tk] : 0.f;
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -636,25 +644,37 @@ __global__ void __launch_bounds__(SV_THREADS) pool_ln_bwd_saved_kernel(const __g
   }
 }
 
-// grads_j[i] += sum over the job's partial vectors: dW from backward (ii), dgamma / dbeta from backward (i)
-// (grid.y = job, grid.z = slice of the partial vectors)
+// grads_j[i] = sum over the job's partial vectors: dW from backward (ii), dgamma / dbeta from backward (i).
+// Block = 32 gradient entries x 8 slices of the partial vectors, combined through shared memory: grads is
+// OVERWRITTEN (no zero fill by the caller, no atomics).  grid.y = job.
 constexpr int RED_SLICES = 8;
 __global__ void __launch_bounds__(256) reduce_jobs_kernel(const __grid_constant__ Launch L) {
+  pdl_wait();
+  __shared__ float part[RED_SLICES][32];
   const Job& J = L.job[blockIdx.y];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= NGRAD) return;
-  const bool is_dw = i < NDW;
-  const float* src = is_dw ? J.part_dw + i : J.part_ln + (i - NDW);
-  const int64_t stride = is_dw ? NDW : 2 * HD;
-  const int end = is_dw ? J.nblk_dw : J.nblk_ln;
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
   float s0 = 0.f, s1 = 0.f;
-  int b = blockIdx.z;
-  for (; b + RED_SLICES < end; b += 2 * RED_SLICES) {
-    s0 += src[(int64_t)b * stride];
-    s1 += src[(int64_t)(b + RED_SLICES) * stride];
+  if (i < NGRAD) {
+    const bool is_dw = i < NDW;
+    const float* src = is_dw ? J.part_dw + i : J.part_ln + (i - NDW);
+    const int64_t stride = is_dw ? NDW : 2 * HD;
+    const int end = is_dw ? J.nblk_dw : J.nblk_ln;
+    int b = slice;
+    for (; b + RED_SLICES < end; b += 2 * RED_SLICES) {
+      s0 += src[(int64_t)b * stride];
+      s1 += src[(int64_t)(b + RED_SLICES) * stride];
+    }
+    if (b < end) s0 += src[(int64_t)b * stride];
   }
-  if (b < end) s0 += src[(int64_t)b * stride];
-  atomicAdd(J.grads + i, s0 + s1);
+  part[slice][lane] = s0 + s1;
+  __syncthreads();
+  if (slice == 0 && i < NGRAD) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < RED_SLICES; ++k) s += part[k][lane];
+    J.grads[i] = s;
+  }
 }
 
 int nblocks_for(int64_t items, int max_blocks) {
@@ -699,7 +719,7 @@ int fill_jobs(Job* J, const void* qkv, int64_t ws_, const pmv_pool_job* jobs, in
     memset(&J[i], 0, sizeof(Job));
     J[i].in = reinterpret_cast<const char*>(qkv) + (int64_t)p.which * ws_ * esz;
     J[i].w = p.w; J[i].gamma = p.gamma; J[i].beta = p.beta; J[i].out = p.out; J[i].out_ld = p.out_ld;
-    J[i].dout = p.dout; J[i].dout_ld = p.dout_ld; J[i].grads = p.grads; J[i].xhat = p.xhat; J[i].rstd = p.rstd;
+    J[i].dout = p.dout; J[i].dout_ld = p.dout_ld; J[i].dout_f32 = p.dout_f32; J[i].grads = p.grads; J[i].xhat = p.xhat; J[i].rstd = p.rstd;
     J[i].s = p.stride_hw; J[i].Ho = out_hw(g.H, p.stride_hw); J[i].Wo = out_hw(g.W, p.stride_hw);
   }
   return PMV_OK;
@@ -768,10 +788,10 @@ int run_mode(int mode, Job* all, int njobs, const Geom& g, cudaStream_t st) {
       L.job[i] = J;
     }
     PMV_DISPATCH_DTYPE(g.dtype, TT, {
-      if (mode == 0) pool_ln_march_kernel<TT, false><<<(unsigned)total, THREADS, 0, st>>>(L);
-      else if (mode == 1) pool_ln_march_kernel<TT, true><<<(unsigned)total, THREADS, 0, st>>>(L);
-      else if (mode == 2) pool_ln_bwd_dw_kernel<TT><<<(unsigned)total, THREADS, 0, st>>>(L);
-      else pool_ln_bwd_input_kernel<TT><<<(unsigned)total, THREADS, 0, st>>>(L);
+      if (mode == 0) pmv_launch(pool_ln_march_kernel<TT, false>, (unsigned)total, THREADS, 0, st, L);
+      else if (mode == 1) pmv_launch(pool_ln_march_kernel<TT, true>, (unsigned)total, THREADS, 0, st, L);
+      else if (mode == 2) pmv_launch(pool_ln_bwd_dw_kernel<TT>, (unsigned)total, THREADS, 0, st, L);
+      else pmv_launch(pool_ln_bwd_input_kernel<TT>, (unsigned)total, THREADS, 0, st, L);
     });
     PMV_CHECK_LAUNCH();
   }
@@ -818,6 +838,8 @@ extern "C" int pmv_pool_ln_qkv_bwd(const void* qkv, int64_t batch_stride, int64_
   char* cursor = reinterpret_cast<char*>(ws);
   for (int i = 0; i < njobs; ++i) {
     PMV_CHECK_ARG(jobs[i].dout != nullptr && jobs[i].grads != nullptr && jobs[i].dout_ld % 4 == 0, "pool: bad backward job");
+    PMV_CHECK_ARG(!jobs[i].dout_f32 || (jobs[i].xhat != nullptr && jobs[i].rstd != nullptr),
+                  "pool: fp32 dout needs the saved-statistics backward (xhat / rstd)");
     J[i].din = reinterpret_cast<char*>(dqkv) + (int64_t)jobs[i].which * which_stride * esz;
     J[i].dconv = cursor;
     cursor += align16(ntok_conv(B, heads, T, H, W, J[i].s) * HD * 4);
@@ -850,7 +872,7 @@ extern "C" int pmv_pool_ln_qkv_bwd(const void* qkv, int64_t batch_stride, int64_
       }
     }
     if (LS.njobs > 0) {
-      PMV_DISPATCH_DTYPE(dtype, TT, (pool_ln_bwd_saved_kernel<TT><<<(unsigned)total, SV_THREADS, 0, st>>>(LS)));
+      PMV_DISPATCH_DTYPE(dtype, TT, (pmv_launch(pool_ln_bwd_saved_kernel<TT>, (unsigned)total, SV_THREADS, 0, st, LS)));
       PMV_CHECK_LAUNCH();
     }
     if (nr > 0) {
@@ -867,7 +889,7 @@ extern "C" int pmv_pool_ln_qkv_bwd(const void* qkv, int64_t batch_stride, int64_
   L.njobs = njobs; L.B = B; L.heads = heads; L.T = T; L.H = H; L.W = W;
   L.in_bs = batch_stride; L.in_ts = token_stride; L.in_hs = head_stride; L.eps = eps;
   for (int i = 0; i < njobs; ++i) L.job[i] = J[i];
-  reduce_jobs_kernel<<<dim3((NGRAD + 255) / 256, njobs, RED_SLICES), 256, 0, st>>>(L);
+  pmv_launch(reduce_jobs_kernel, dim3((NGRAD + 31) / 32, njobs), 256, 0, st, L);
   PMV_CHECK_LAUNCH();
   return PMV_OK;
 }

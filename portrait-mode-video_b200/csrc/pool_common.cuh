@@ -25,8 +25,9 @@ struct Job {
   int64_t out_ld;
   const void* dout;     // backward: gradient of `out`
   int64_t dout_ld;
+  int dout_f32;         // dout is fp32 whatever T is (saved-statistics backward only)
   void* din;            // backward: gradient wrt `in` (same strides)
-  float* grads;         // backward: [NGRAD] fp32, added to
+  float* grads;         // backward: [NGRAD] fp32, overwritten
   void* dconv;          // backward: pre-LN gradient [B*heads*Lo*96] in the compute dtype
   void* xhat;           // optional: normalised pre-affine tokens [B*heads*(1+Lo)][96] (forward writes, backward reads)
   float* rstd;          // optional: [B*heads*(1+Lo)]

@@ -1,3 +1,4 @@
+#define PMV_PDL_FAMILY 64
 // TMA-staged "t-march" version of the pooling stencils for stride 1 and 2 (attention.py:14-48, 241-282).
 //
 // A CTA owns a spatial tile of 4 output rows x 7 output columns of one (batch, head) and walks the T frames.
@@ -374,16 +375,17 @@ __global__ void __launch_bounds__(THREADS, 2) pool_tma_kernel(const __grid_const
   sm.conv = reinterpret_cast<float*>(base);
   sm.planes = base + 2 * TOK * HD * sizeof(float);
   sm.full = full_bar;
+  if (tid == 0) {
+    tc::tma_prefetch_desc(&L.tm[jj]);
+    for (int i = 0; i < NST; ++i) tc::mbar_init(&full_bar[i], 1);
+    tc::fence_barrier_init();
+  }
+  pdl_wait();  // nothing above reads or writes global memory
   if (MODE == M_FWD || MODE == M_BWD_LN) {
     if (tid < HD) {
       sgam[tid] = J.gamma[tid];
       sbet[tid] = MODE == M_FWD ? J.beta[tid] : 0.f;
     }
-  }
-  if (tid == 0) {
-    tc::tma_prefetch_desc(&L.tm[jj]);
-    for (int i = 0; i < NST; ++i) tc::mbar_init(&full_bar[i], 1);
-    tc::fence_barrier_init();
   }
   __syncthreads();
 
@@ -493,6 +495,7 @@ __global__ void __launch_bounds__(S2_THREADS, 3) pool_din_s2_kernel(const __grid
     for (int i = 0; i < S2_NST; ++i) tc::mbar_init(&full_bar[i], 1);
     tc::fence_barrier_init();
   }
+  pdl_wait();  // nothing above reads or writes global memory
   __syncthreads();
   float2 wr[TAPS];
   load_taps<false>(J.w, cp, wr);
@@ -575,6 +578,7 @@ __global__ void __launch_bounds__(S2_THREADS, 3) pool_din_s2_kernel(const __grid
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) pool_din_zero_kernel(const __grid_constant__ TLaunch L) {
+  pdl_wait();
   constexpr int PIECES = HD * sizeof(T) / 16;  // 16-byte pieces per (token, head)
   const Job& J = L.job[blockIdx.y];
   const int64_t ntok = (int64_t)L.T * L.H * L.W;
@@ -592,6 +596,7 @@ __global__ void __launch_bounds__(256) pool_din_zero_kernel(const __grid_constan
 
 template <typename T>
 __global__ void __launch_bounds__(S2_THREADS) pool_din_scatter_kernel(const __grid_constant__ TLaunch L) {
+  pdl_wait();
   int jj = 0;
   while (jj + 1 < L.njobs && (int)blockIdx.x >= L.job[jj + 1].blk_begin) ++jj;
   const Job& J = L.job[jj];
@@ -654,7 +659,7 @@ template <typename T, int MODE> int launch_mode(const TLaunch& L, int total_bloc
     PMV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  kern<<<(unsigned)total_blocks, THREADS, smem, st>>>(L);
+  pmv_launch(kern, (unsigned)total_blocks, THREADS, smem, st, L);
   PMV_CHECK_LAUNCH();
   return PMV_OK;
 }
@@ -702,7 +707,7 @@ int launch_din_strided(const Job* jobs, int njobs, TLaunch& L, int esz, cudaStre
       PMV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_set = true;
     }
-    kern<<<(unsigned)total, S2_THREADS, smem, st>>>(L2);
+    pmv_launch(kern, (unsigned)total, S2_THREADS, smem, st, L2);
     PMV_CHECK_LAUNCH();
   }
   // ---- stride >= 3
@@ -718,8 +723,8 @@ int launch_din_strided(const Job* jobs, int njobs, TLaunch& L, int esz, cudaStre
     L3.job[L3.njobs++] = J;
   }
   if (L3.njobs > 0) {
-    pool_din_zero_kernel<T><<<dim3(148 * 8, (unsigned)L3.njobs), 256, 0, st>>>(L3);
-    pool_din_scatter_kernel<T><<<(unsigned)total, S2_THREADS, 0, st>>>(L3);
+    pmv_launch(pool_din_zero_kernel<T>, dim3(148 * 8, (unsigned)L3.njobs), 256, 0, st, L3);
+    pmv_launch(pool_din_scatter_kernel<T>, (unsigned)total, S2_THREADS, 0, st, L3);
     PMV_CHECK_LAUNCH();
   }
   return PMV_OK;

@@ -7,6 +7,7 @@
 
 static __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, int nblocks, int n,
                                                                        int64_t stride, float* __restrict__ dst) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   // grid.y slices the partial rows; 4 independent accumulators keep 4 loads in flight per thread
@@ -28,5 +29,5 @@ static inline void launch_reduce_partials(const float* partials, int nblocks, in
   int slices = nblocks / 8;
   if (slices < 1) slices = 1;
   if (slices > 16) slices = 16;
-  reduce_partials_kernel<<<dim3((n + 255) / 256, slices), 256, 0, stream>>>(partials, nblocks, n, stride ? stride : n, dst);
+  pmv_launch(reduce_partials_kernel, dim3((n + 255) / 256, slices), 256, 0, stream, partials, nblocks, n, stride ? stride : n, dst);
 }

@@ -29,11 +29,19 @@ class Epilogue(C.Structure):
 
 class PoolJob(C.Structure):
     _fields_ = [("w", _p), ("gamma", _p), ("beta", _p), ("out", _p), ("out_ld", _i64), ("dout", _p), ("dout_ld", _i64),
-                ("grads", _p), ("stride_hw", _i), ("which", _i), ("xhat", _p), ("rstd", _p)]
+                ("grads", _p), ("stride_hw", _i), ("which", _i), ("xhat", _p), ("rstd", _p), ("dout_f32", _i)]
+
+
+class AdamWTensor(C.Structure):
+    _fields_ = [("param", _p), ("grad", _p), ("exp_avg", _p), ("exp_avg_sq", _p), ("shadow", _p), ("numel", _i64),
+                ("weight_decay", _f), ("lr_scale", _f)]
 
 
 _SIGS = {
     "pmv_version": (_i, []),
+    "pmv_set_pdl": (None, [_i]),
+    "pmv_adamw_workspace_bytes": (_i64, [_p, _i]),
+    "pmv_adamw_step": (_i, [_p, _i, _p, _f, _f, _f, _f, _p, _p, _p, _p]),
     "pmv_has_tcgen05": (_i, []),
     "pmv_layernorm_fwd": (_i, [_p, _p, _p, _p, _i, _p, _p, _i64, _i, _f, _p]),
     "pmv_layernorm_bwd_workspace_bytes": (_i64, [_i64, _i]),
@@ -47,7 +55,7 @@ _SIGS = {
     "pmv_pool_ln_qkv_fwd": (_i, [_p, _i64, _i64, _i64, _i64, C.POINTER(PoolJob), _i, _i, _i, _i, _i, _i, _f, _i, _p]),
     "pmv_pool_ln_qkv_bwd_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, C.POINTER(_i), _i]),
     "pmv_pool_ln_qkv_bwd": (_i, [_p, _i64, _i64, _i64, _i64, C.POINTER(PoolJob), _i, _p, _p, _i, _i, _i, _i, _i, _f, _i, _p]),
-    "pmv_maxpool_skip_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    "pmv_maxpool_skip_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "pmv_maxpool_skip_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "pmv_relpos_fwd_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, _i, _i]),
     "pmv_relpos_augment_q": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _p]),

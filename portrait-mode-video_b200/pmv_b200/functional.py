@@ -16,8 +16,12 @@ from . import ops
 
 
 def _cast(w: Optional[torch.Tensor], dtype):
+    """Operand copy of a weight in the compute dtype: the copy FusedAdamW keeps current (optim.py), else a cast."""
     if w is None or w.dtype == dtype:
         return w
+    sh = getattr(w, "_pmv_lp", None)
+    if sh is not None and sh.dtype == dtype and getattr(w, "_pmv_lp_version", -1) == w._version:
+        return sh
     return w.to(dtype)
 
 
@@ -175,16 +179,17 @@ class MaxPoolSkipFn(Function):
     @staticmethod
     def forward(ctx, x, thw):
         x = x.contiguous()
-        y = ops.maxpool_skip_fwd(x, thw)
-        if any(ctx.needs_input_grad):
-            ctx.save_for_backward(x)
         ctx.thw = tuple(thw)
+        if not any(ctx.needs_input_grad):
+            return ops.maxpool_skip_fwd(x, thw)
+        y, win = ops.maxpool_skip_fwd(x, thw, want_winner=True)  # 1 byte per output element instead of keeping x alive
+        ctx.save_for_backward(win)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        (x,) = ctx.saved_tensors
-        return ops.maxpool_skip_bwd(x, dy, ctx.thw), None
+        (win,) = ctx.saved_tensors
+        return ops.maxpool_skip_bwd(win, dy, ctx.thw), None
 
 
 def maxpool_skip(x, thw):
@@ -243,12 +248,13 @@ class PoolAttentionFn(Function):
         B, N = qkv5.shape[0], qkv5.shape[1]
         Nq, Nk = q_aug.shape[1], k_aug.shape[1]
         dq_aug, dk, dv = ops.attention_bwd(q_aug, k_aug, v, out, dout, lse, B, heads, ld, scale, residual=residual,
-                                           tc=int(tc_bwd and os.environ.get("PMV_TC_ATTENTION_BWD", "1") == "1"))
+                                           tc=int(tc_bwd and os.environ.get("PMV_TC_ATTENTION_BWD", "1") == "1"),
+                                           fp32_dkv=True)
         drh = drw = drt = None
         if has_rel:
             drh, drw, drt = ops.relpos_augment_q_bwd(dq_aug, q_aug, q_shape, k_shape, rel_h, rel_w, rel_t, 1.0 / scale)
         dqkv = torch.empty_like(qkv5)
-        g = torch.zeros(3, 96 * 27 + 192, dtype=torch.float32, device=qkv5.device)
+        g = torch.empty(3, 96 * 27 + 192, dtype=torch.float32, device=qkv5.device)
         ops.pool_ln_qkv_bwd(qkv5, heads, thw, [(0, sq, wq, gq, dq_aug.view(B, heads, Nq, ld), g[0]) + extra[0],
                                                (1, skv, wk, gk, dk.view(B, heads, Nk, 96), g[1]) + extra[1],
                                                (2, skv, wv, gv, dv.view(B, heads, Nk, 96), g[2]) + extra[2]], dqkv, eps)

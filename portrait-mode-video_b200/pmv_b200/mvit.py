@@ -114,6 +114,14 @@ class MViT(nn.Module):
         self.apply(self._init_weights)
         set_compute_dtype(self, compute_dtype)
 
+    def no_weight_decay(self):
+        """video_model_builder.py:2027-2049 (MVIT.ZERO_DECAY_POS_CLS; False in MVITv2_S_16x4.yaml:21): parameter-name
+        fragments the optimizer keeps out of weight decay.  This family has relative positions and a cls token only."""
+        names = []
+        if self.cfg.get("zero_decay_pos_cls", False):
+            names.extend(["rel_pos_h", "rel_pos_w", "rel_pos_hw", "rel_pos_t", "cls_token"])
+        return names
+
     @staticmethod
     def _init_weights(m):  # video_model_builder.py:2018-2025
         if isinstance(m, (nn.Linear, nn.Conv2d, nn.Conv3d)):

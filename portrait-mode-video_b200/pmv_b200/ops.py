@@ -175,7 +175,7 @@ def pool_ln_fwd(qkv: torch.Tensor, which: int, heads: int, thw: Sequence[int], s
 
 
 def pool_ln_bwd(qkv, which, heads, thw, stride_hw, w, gamma, dout, dqkv, grads, eps=LN_EPS):
-    """grads: fp32 [96*27 + 96 + 96] (Conv3d weight gradient, LayerNorm weight gradient, bias gradient), added to."""
+    """grads: fp32 [96*27 + 96 + 96] (Conv3d weight gradient, LayerNorm weight gradient, bias gradient), overwritten."""
     B = qkv.shape[0]
     T, H, W = thw
     ws = _ws(L.lib().pmv_pool_ln_bwd_workspace_bytes(B, heads, T, H, W, stride_hw), qkv.device)
@@ -204,7 +204,7 @@ def pool_ln_qkv_fwd(qkv, heads, thw, jobs, eps=LN_EPS):
 
 
 def pool_ln_qkv_bwd(qkv, heads, thw, jobs, dqkv, eps=LN_EPS):
-    """jobs: list of (which, stride_hw, w, gamma, dout, grads [, xhat, rstd]) — grads fp32 [96*27 + 192], added to.
+    """jobs: list of (which, stride_hw, w, gamma, dout, grads [, xhat, rstd]) — grads fp32 [96*27 + 192], overwritten.
     With xhat / rstd (saved by the forward) the LayerNorm backward skips the convolution recompute."""
     B, N = qkv.shape[0], qkv.shape[1]
     T, H, W = thw
@@ -215,7 +215,7 @@ def pool_ln_qkv_bwd(qkv, heads, thw, jobs, dqkv, eps=LN_EPS):
         which, s, w, gamma, dout, grads = job[:6]
         xhat, rstd = (job[6], job[7]) if len(job) > 6 else (None, None)
         arr[i] = L.PoolJob(L.ptr(w), L.ptr(gamma), None, None, 0, L.ptr(dout), dout.stride(2), L.ptr(grads), s, which,
-                           L.ptr(xhat), L.ptr(rstd))
+                           L.ptr(xhat), L.ptr(rstd), int(dout.dtype == torch.float32 and qkv.dtype != torch.float32))
         nbytes += (2 * B * N * heads * 96 + dout.shape[0] * dout.shape[1] * dout.shape[2] * 96) * qkv.element_size()
     ws = _ws(L.lib().pmv_pool_ln_qkv_bwd_workspace_bytes(B, heads, T, H, W, strides, len(jobs)), qkv.device)
     _run("pmv_pool_ln_qkv_bwd", 3, dict(bytes=nbytes, shape=(B, heads, T, H, W, [j[1] for j in jobs])), L.ptr(qkv), qkv.stride(0),
@@ -223,20 +223,23 @@ def pool_ln_qkv_bwd(qkv, heads, thw, jobs, dqkv, eps=LN_EPS):
          L.stream())
 
 
-def maxpool_skip_fwd(x, thw):
+def maxpool_skip_fwd(x, thw, want_winner=False):
+    """Returns y, or (y, win) with the uint8 winning-window-position map the backward gathers through."""
     B, N, Cdim = x.shape
     T, H, W = thw
     Lo = T * pooled_hw(H, 2) * pooled_hw(W, 2)
     y = torch.empty(B, 1 + Lo, Cdim, dtype=torch.float32, device=x.device)
-    _run("pmv_maxpool_skip_fwd", 1, dict(bytes=(x.numel() + y.numel()) * 4), L.ptr(x), L.ptr(y), B, T, H, W, Cdim, L.stream())
-    return y
+    win = torch.empty(B, 1 + Lo, Cdim, dtype=torch.uint8, device=x.device) if want_winner else None
+    _run("pmv_maxpool_skip_fwd", 1, dict(bytes=(x.numel() + y.numel()) * 4), L.ptr(x), L.ptr(y), L.ptr(win), B, T, H, W, Cdim, L.stream())
+    return (y, win) if want_winner else y
 
 
-def maxpool_skip_bwd(x, dy, thw, dx_accum=None):
-    B, N, Cdim = x.shape
+def maxpool_skip_bwd(win, dy, thw):
+    B, _, Cdim = dy.shape
     T, H, W = thw
-    dx = dx_accum if dx_accum is not None else torch.zeros_like(x)
-    _run("pmv_maxpool_skip_bwd", 1, dict(bytes=(2 * x.numel() + dy.numel()) * 4), L.ptr(x), L.ptr(dy.contiguous()), L.ptr(dx), B, T, H, W, Cdim, L.stream())
+    dx = torch.empty(B, 1 + T * H * W, Cdim, dtype=torch.float32, device=dy.device)
+    _run("pmv_maxpool_skip_bwd", 1, dict(bytes=dx.numel() * 4 + dy.numel() * 5), L.ptr(win), L.ptr(dy.contiguous()), L.ptr(dx), B, T, H, W, Cdim,
+         L.stream())
     return dx
 
 
@@ -316,18 +319,25 @@ def attention_fwd(q_aug, k_aug, v, B, heads, kd, scale, residual=True, want_lse=
     return out, (out_pre if out_pre is not None else (out if want_lse else None)), lse
 
 
-def attention_bwd(q_aug, k_aug, v, out, dout, lse, B, heads, kd, scale, residual=True, tc=None):
+def attention_bwd(q_aug, k_aug, v, out, dout, lse, B, heads, kd, scale, residual=True, tc=None, fp32_dkv=False):
     BH, Nq, ld = q_aug.shape
     Nk = k_aug.shape[1]
     use_tc = _tc_default(q_aug.dtype) if tc is None else int(tc)
     dq_aug = torch.empty_like(q_aug)
-    dk = torch.empty(BH, Nk, 96, dtype=q_aug.dtype, device=q_aug.device)
-    dv = torch.empty(BH, Nk, 96, dtype=q_aug.dtype, device=q_aug.device)
     ws = torch.empty(L.lib().pmv_attention_bwd_workspace_bytes(B, heads, Nq, Nk) // 4, dtype=torch.float32,
                      device=q_aug.device)
+    if use_tc and fp32_dkv:
+        # the tcgen05 path accumulates dk / dv in fp32 inside ws; hand those out instead of a bf16 copy
+        dk = dv = None
+    else:
+        dk = torch.empty(BH, Nk, 96, dtype=q_aug.dtype, device=q_aug.device)
+        dv = torch.empty(BH, Nk, 96, dtype=q_aug.dtype, device=q_aug.device)
     _run("pmv_attention_bwd", 4 if use_tc else 3, dict(flops=10 * BH * Nq * Nk * 96, tc=use_tc, shape=(BH, Nq, Nk, kd)), L.ptr(q_aug), L.ptr(k_aug), ld, kd, L.ptr(v), v.stride(1), L.ptr(out),
                                       L.ptr(dout.contiguous()), L.ptr(lse), L.ptr(dq_aug), L.ptr(dk), 96, L.ptr(dv), 96,
                                       L.ptr(ws), B, heads, Nq, Nk, scale, int(residual), L.dt(q_aug), use_tc, L.stream())
+    if dk is None:
+        n = BH * Nk * 96
+        dk, dv = ws[:n].view(BH, Nk, 96), ws[n:2 * n].view(BH, Nk, 96)
     return dq_aug, dk, dv
 
 

@@ -100,3 +100,24 @@ def test_checkpoint_loader_matches_reference_surgery(tmp_path):
     assert load_checkpoint({"model_state": params, "epoch": 7}, model224, epoch_reset=True) == -1
     for k, v in model224.state_dict().items():
         assert torch.equal(v, params[k]), k
+
+
+def test_param_groups_match_reference_construct_optimizer():
+    """Row f3 host logic: the zero-weight-decay grouping equals what the reference's construct_optimizer built for its own
+    MViTv2-S (fixture written by oracle/make_golden.py from models/optimizer.py:29-83)."""
+    from pmv_b200 import mvit
+    from pmv_b200.optim import param_groups
+    z = np.load(os.path.join(ROOT, "tests", "golden", "optimizer_reference.npz"))
+    model = mvit.MViT(mvit.MVITV2_S)
+    names = {id(p): n for n, p in model.named_parameters()}
+    groups = param_groups(model, 0.05, zero_wd_1d=True)
+    assert len(groups) == int(z["ngroups"])
+    for gi, g in enumerate(groups):
+        assert g["weight_decay"] == float(z[f"group{gi}_weight_decay"])
+        assert [names[id(p)] for p in g["params"]] == [str(n) for n in z[f"group{gi}_names"]]
+    # ZERO_DECAY_POS_CLS moves the relative-position tables and the cls token into the zero group (video_model_builder.py:2027-2049)
+    model.cfg = dict(model.cfg, zero_decay_pos_cls=True)
+    g2 = param_groups(model, 0.05, zero_wd_1d=True)
+    zero = {names[id(p)] for p in g2[-1]["params"]}
+    assert "cls_token" in zero and "blocks.0.attn.rel_pos_h" in zero and "blocks.3.attn.rel_pos_t" in zero
+    assert "blocks.0.attn.qkv.weight" not in zero

@@ -84,19 +84,20 @@ def test_pool_ln_fwd_bwd(dtype, B, heads, thw, s):
         assert nerr(dwg[2688:], br.grad) < TOL[dtype]
 
 
-@pytest.mark.parametrize("B,thw,C", [(2, (2, 8, 8), 192), (1, (2, 7, 5), 96), (2, (8, 14, 14), 768)])
+@pytest.mark.parametrize("B,thw,C", [(2, (2, 8, 8), 192), (1, (2, 7, 5), 96), (2, (8, 14, 14), 768), (1, (1, 1, 1), 32), (1, (2, 9, 16), 64)])
 def test_maxpool_skip(B, thw, C):
     from oracle import mvit_oracle as orc
     from pmv_b200 import ops
     T, H, W = thw
     x = randn(B, 1 + T * H * W, C, seed=11)
-    y = ops.maxpool_skip_fwd(x, thw)
+    y, win = ops.maxpool_skip_fwd(x, thw, want_winner=True)
+    assert torch.equal(ops.maxpool_skip_fwd(x, thw), y)
     xr = x.clone().requires_grad_(True)
     yr, _ = orc.max_pool_tokens(xr, thw, (1, 3, 3), (1, 2, 2), True)
     assert torch.equal(y, yr.detach())
     dy = randn(*y.shape, seed=12)
     yr.backward(dy)
-    dx = ops.maxpool_skip_bwd(x, dy, thw)
+    dx = ops.maxpool_skip_bwd(win, dy, thw)
     assert nerr(dx, xr.grad) < 1e-6
 
 
