@@ -181,6 +181,7 @@ def main():
                     help="mvitv2_s = MViTv2-S 16x4 (the BASELINE metric); mvitv2_b = MViTv2-B 32x3 (BASELINE config 5)")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="fused: pmv_b200.optim.FusedAdamW (reference grouping + clip 1.0); torch: torch.optim.AdamW(fused, capturable), no clip")
+    ap.add_argument("--unfused-head", action="store_true", help="final LN / head / cross entropy through torch ops instead of pmv_head_loss_*")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
@@ -249,7 +250,10 @@ def main():
     def step(c, l):
         if train:
             reducer.zero_grad()
-            loss = torch.nn.functional.cross_entropy(model([c]), l)
+            if args.unfused_head:
+                loss = torch.nn.functional.cross_entropy(model([c]), l)
+            else:
+                loss, _ = model.forward_loss([c], l)  # final LN + head + cross entropy as two launches each way (row f2)
             loss.backward()
             reducer.finish()
             opt.step()

@@ -235,6 +235,27 @@ int pmv_patch_im2col(const float* clip, void* col, int64_t ld_col, int B, int Ci
                      int kt, int kh, int kw, int st, int sh, int sw, int pt, int ph, int pw,
                      int dtype, void* stream);
 
+/* ---------------------------------------------------------------- head + loss (row f2) ----
+ * Tail of the step: final LayerNorm of the cls row (video_model_builder.py:2163-2165), TransformerBasicHead
+ * (head_helper.py:561-577: dropout -> Linear -> softmax in eval) and the soft-target cross entropy of
+ * losses.py:69-71 (mean over clips of sum_c -y_c log_softmax(logits)_c; integer `labels` = one-hot targets =
+ * nn.CrossEntropyLoss).  All fp32.
+ *   x: tokens [B, N, C] (row 0 of each clip is read), batch_stride = N*C.  keep_mask: optional uint8 [B, C] dropout
+ *   keep mask (kept values are scaled by 1/(1-dropout_p)); the caller owns the random numbers.
+ *   logits [B, classes] always; probs (optional) = softmax(logits); loss (optional device scalar, needs exactly one of
+ *   labels / soft_targets); xhat [B, C], rstd [B], xd [B, C] (optional): saved for the backward.
+ * Backward: dloss = device scalar gradient of the mean loss.  dx [B, N, C] is OVERWRITTEN (row 0 = gradient, other rows
+ * zero); dw [classes, C], dbias (optional), dgamma, dbeta are overwritten.  ws: pmv_head_loss_bwd_workspace_bytes(). */
+int pmv_head_loss_fwd(const float* x, int64_t batch_stride, const float* gamma, const float* beta, const float* w,
+                      const float* bias, const uint8_t* keep_mask, float dropout_p, const int64_t* labels,
+                      const float* soft_targets, float* logits, float* probs, float* loss, float* xhat,
+                      float* rstd, float* xd, int B, int C, int num_classes, float eps, void* stream);
+int64_t pmv_head_loss_bwd_workspace_bytes(int B, int C, int num_classes);
+int pmv_head_loss_bwd(const float* dloss, const float* logits, const int64_t* labels, const float* soft_targets,
+                      const float* w, const float* gamma, const uint8_t* keep_mask, float dropout_p, const float* xhat,
+                      const float* rstd, const float* xd, float* dx, int64_t batch_stride, int N, float* dw, float* dbias,
+                      float* dgamma, float* dbeta, float* ws, int B, int C, int num_classes, void* stream);
+
 /* Programmatic dependent launch for the library's kernels: bit mask of kernel families (1 attention fwd, 2 attention
  * bwd, 4 GEMM, 8 column sums, 16 LayerNorm, 32 | 64 pooling, 128 rel-pos, 256 others); 0 = off (default), -1 = all.
  * Also settable with the PMV_PDL environment variable before the first launch. */

@@ -392,6 +392,28 @@ def mvit_forward_pm(clip: torch.Tensor, pm: torch.Tensor, p: Params, cfg: dict, 
     return out
 
 
+def soft_target_cross_entropy(logits: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """losses.py:69-71 ``soft_cross_entropy`` = pytorchvideo.losses.SoftTargetCrossEntropyLoss(normalize_targets=False).
+    pytorchvideo is a third-party dependency that is not vendored under /root/reference (setup.py: pytorchvideo, unpinned;
+    the class has been stable since 0.1.3); its published algorithm: integer targets are converted to one-hot rows, then
+    ``loss = sum(-y * log_softmax(x, dim=-1), dim=-1)`` with reduction "mean" over the batch.  For one-hot rows this is
+    nn.CrossEntropyLoss (losses.py:66), which the test uses as the second anchor."""
+    if target.dtype in (torch.int64, torch.int32):
+        target = F.one_hot(target.long(), logits.shape[-1]).to(logits.dtype)
+    return torch.sum(-target * F.log_softmax(logits, dim=-1), dim=-1).mean()
+
+
+def head_loss(tokens: torch.Tensor, p: Params, target: torch.Tensor, keep_mask: torch.Tensor = None, dropout_p: float = 0.0):
+    """Final norm -> cls row (video_model_builder.py:2163-2165) -> TransformerBasicHead in training mode
+    (head_helper.py:561-566: dropout, projection; the dropout keep mask is an input so that the statement is
+    deterministic) -> loss.  Returns (loss, logits)."""
+    x = layer_norm(tokens, p["norm.weight"], p["norm.bias"])[:, 0]
+    if keep_mask is not None:
+        x = x * keep_mask.to(x.dtype) / (1.0 - dropout_p)
+    logits = F.linear(x, p["head.projection.weight"], p["head.projection.bias"])
+    return soft_target_cross_entropy(logits, target), logits
+
+
 def param_shapes(cfg: dict) -> Dict[str, Tuple[int, ...]]:
     """Shapes of every reference ``state_dict`` entry of ``MViT(cfg)``."""
     sh: Dict[str, Tuple[int, ...]] = {}

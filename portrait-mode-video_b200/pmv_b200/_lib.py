@@ -40,6 +40,9 @@ class AdamWTensor(C.Structure):
 _SIGS = {
     "pmv_version": (_i, []),
     "pmv_set_pdl": (None, [_i]),
+    "pmv_head_loss_fwd": (_i, [_p, _i64, _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p]),
+    "pmv_head_loss_bwd_workspace_bytes": (_i64, [_i, _i, _i]),
+    "pmv_head_loss_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _i64, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "pmv_adamw_workspace_bytes": (_i64, [_p, _i]),
     "pmv_adamw_step": (_i, [_p, _i, _p, _f, _f, _f, _f, _p, _p, _p, _p]),
     "pmv_has_tcgen05": (_i, []),

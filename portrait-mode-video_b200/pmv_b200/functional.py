@@ -271,6 +271,35 @@ def pool_attention(qkv, wq, wk, wv, gq, bq, gk, bk, gv, bv, rel_h, rel_w, rel_t,
                                  int(stride_q), int(stride_kv), float(scale), bool(residual), bool(use_tc_attn), float(eps))
 
 
+class HeadLossFn(Function):
+    """loss, logits = CE(Linear(dropout(LayerNorm(x)[:, 0])), target): video_model_builder.py:2163-2169,
+    head_helper.py:561-577, losses.py:69-71 in two launches each way (row f2).  The logits are returned for metrics
+    (top-k accuracy in train_net.py) and carry no gradient."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, w, bias, target, keep_mask, dropout_p, eps):
+        x = x.contiguous()
+        r = ops.head_loss_fwd(x, gamma, beta, w, bias, target=target, keep_mask=keep_mask, dropout_p=dropout_p,
+                              save=any(ctx.needs_input_grad), eps=eps)
+        ctx.save_for_backward(r["logits"], r["labels"], r["soft"], w, gamma, keep_mask, *r["saved"])
+        ctx.meta = (x.shape[1], float(dropout_p), bias is not None)
+        ctx.mark_non_differentiable(r["logits"])
+        return r["loss"], r["logits"]
+
+    @staticmethod
+    def backward(ctx, dloss, _dlogits):
+        logits, labels, soft, w, gamma, keep_mask, xhat, rstd, xd = ctx.saved_tensors
+        N, p, has_bias = ctx.meta
+        dloss = dloss.to(torch.float32).contiguous()
+        dx, dw, db, dgamma, dbeta = ops.head_loss_bwd(dloss, logits, labels, soft, w, gamma, keep_mask, p, (xhat, rstd, xd), N,
+                                                      has_bias=has_bias)
+        return dx, dgamma, dbeta, dw, db, None, None, None, None
+
+
+def head_loss(x, gamma, beta, w, bias, target, keep_mask=None, dropout_p=0.0, eps=1e-6):
+    return HeadLossFn.apply(x, gamma, beta, w, bias, target, keep_mask, float(dropout_p), float(eps))
+
+
 class PatchEmbedFn(Function):
     """PatchEmbed Conv3d + flatten/transpose + cls-token concat (stem_helper.py:320-325,
     video_model_builder.py:2115-2121) -> fp32 tokens [B, 1+L, 96]."""

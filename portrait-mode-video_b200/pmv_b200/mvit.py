@@ -140,6 +140,40 @@ class MViT(nn.Module):
         x = Fn.layer_norm(x, self.norm.weight, self.norm.bias, torch.float32, self.norm.eps)  # :2163
         return x[:, 0]                                                        # :2165
 
+    def forward_tokens(self, clip, thw_expected=None):
+        """The token stream before the final norm: [B, 1 + T*H*W / 64, 768] fp32."""
+        x, thw = self.patch_embed.forward_tokens(clip, self.cls_token)
+        assert tuple(thw) == tuple(thw_expected or (self.T, self.H, self.W)), thw
+        for blk in self.blocks:
+            x, thw = blk(x, thw)
+        return x
+
+    def _head_no_grad(self, tok):
+        """norm -> cls -> head in one launch (row f2 forward without a loss): logits, or softmax probabilities in eval
+        mode when the head has its activation (head_helper.py:568-570)."""
+        from . import ops
+        drop = self.training and hasattr(self.head, "dropout") and self.head.dropout.p > 0.0
+        if drop:  # training-mode forward without autograd: keep the module semantics, unfused
+            x = Fn.layer_norm(tok, self.norm.weight, self.norm.bias, torch.float32, self.norm.eps)
+            return self.head(x[:, 0])
+        probs = (not self.training) and self.head.act is not None
+        r = ops.head_loss_fwd(tok.contiguous(), self.norm.weight, self.norm.bias, self.head.projection.weight,
+                              self.head.projection.bias, want_probs=probs, eps=self.norm.eps)
+        return r["probs"] if probs else r["logits"]
+
+    def forward_loss(self, x, target):
+        """Training tail fused (row f2): returns (loss, logits) = what ``loss_fun(model(x), target)`` computes in
+        tools/train_net.py:172-186 with ``cross_entropy`` (int64 labels) or ``soft_cross_entropy`` (float [B, classes]
+        mixup targets, losses.py:69-71).  The head's dropout draws its keep mask from torch's generator."""
+        clip = x[0] if isinstance(x, (list, tuple)) else x
+        tok = self.forward_tokens(clip)
+        p = self.head.dropout.p if (self.training and hasattr(self.head, "dropout")) else 0.0
+        keep = None
+        if p > 0.0:
+            keep = (torch.rand(tok.shape[0], tok.shape[2], device=tok.device) >= p).to(torch.uint8)
+        return Fn.head_loss(tok, self.norm.weight, self.norm.bias, self.head.projection.weight, self.head.projection.bias,
+                            target, keep_mask=keep, dropout_p=p, eps=self.norm.eps)
+
     def forward(self, x, pm=None):
         """``x``: clip tensor or the reference's one-element list (:2099).  ``pm``: portrait-mode mask, a bool tensor
         [B] or the reference's list of per-loader-batch tensors (:2076-2077).  Portrait samples arrive transposed
@@ -150,6 +184,8 @@ class MViT(nn.Module):
         if pm is not None and isinstance(pm, (list, tuple)):
             pm = torch.cat(list(pm))
         if pm is None or int(pm.sum()) == 0:
+            if not torch.is_grad_enabled():
+                return self._head_no_grad(self.forward_tokens(clip))
             return self.head(self.forward_features(clip))
         assert len(pm) == clip.shape[0]
         pm = pm.to(device=clip.device, dtype=torch.bool)

@@ -341,6 +341,54 @@ def attention_bwd(q_aug, k_aug, v, out, dout, lse, B, heads, kd, scale, residual
     return dq_aug, dk, dv
 
 
+# ----------------------------------------------------------------------------- head + loss (row f2)
+def head_loss_fwd(x, gamma, beta, w, bias, target=None, keep_mask=None, dropout_p=0.0, want_probs=False, save=False, eps=LN_EPS):
+    """x [B, N, C] fp32 tokens.  target: int64 labels [B], float soft targets [B, classes] or None (no loss).
+    Returns dict(logits, probs, loss, saved) — saved = (xhat, rstd, xd) when ``save``."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 3
+    B, N, Cdim = x.shape
+    ncls = w.shape[0]
+    dev = x.device
+    logits = torch.empty(B, ncls, dtype=torch.float32, device=dev)
+    probs = torch.empty(B, ncls, dtype=torch.float32, device=dev) if want_probs else None
+    labels = soft = loss = None
+    if target is not None:
+        if target.dtype in (torch.int64, torch.int32):
+            labels = target.to(torch.int64).contiguous()
+        else:
+            soft = target.to(torch.float32).contiguous()
+            assert soft.shape == (B, ncls)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+    xhat = rstd = xd = None
+    if save:
+        xhat = torch.empty(B, Cdim, dtype=torch.float32, device=dev)
+        xd = torch.empty(B, Cdim, dtype=torch.float32, device=dev)
+        rstd = torch.empty(B, dtype=torch.float32, device=dev)
+    if keep_mask is not None:
+        assert keep_mask.dtype == torch.uint8 and keep_mask.shape == (B, Cdim) and keep_mask.is_contiguous()
+    _run("pmv_head_loss_fwd", 2 if (loss is not None or probs is not None) else 1, dict(bytes=(B * ncls * Cdim + B * Cdim) * 4), L.ptr(x), x.stride(0), L.ptr(gamma),
+         L.ptr(beta), L.ptr(w), L.ptr(bias), L.ptr(keep_mask), float(dropout_p), L.ptr(labels), L.ptr(soft), L.ptr(logits), L.ptr(probs),
+         L.ptr(loss), L.ptr(xhat), L.ptr(rstd), L.ptr(xd), B, Cdim, ncls, eps, L.stream())
+    return dict(logits=logits, probs=probs, loss=loss, labels=labels, soft=soft, saved=(xhat, rstd, xd))
+
+
+def head_loss_bwd(dloss, logits, labels, soft, w, gamma, keep_mask, dropout_p, saved, N, has_bias=True):
+    xhat, rstd, xd = saved
+    B, ncls = logits.shape
+    Cdim = w.shape[1]
+    dev = logits.device
+    dx = torch.empty(B, N, Cdim, dtype=torch.float32, device=dev)
+    dw = torch.empty(ncls, Cdim, dtype=torch.float32, device=dev)
+    db = torch.empty(ncls, dtype=torch.float32, device=dev) if has_bias else None
+    dgamma = torch.empty(Cdim, dtype=torch.float32, device=dev)
+    dbeta = torch.empty(Cdim, dtype=torch.float32, device=dev)
+    ws = _ws(L.lib().pmv_head_loss_bwd_workspace_bytes(B, Cdim, ncls), dev)
+    _run("pmv_head_loss_bwd", 4, dict(bytes=(2 * B * ncls * Cdim + B * N * Cdim) * 4), L.ptr(dloss), L.ptr(logits), L.ptr(labels), L.ptr(soft),
+         L.ptr(w), L.ptr(gamma), L.ptr(keep_mask), float(dropout_p), L.ptr(xhat), L.ptr(rstd), L.ptr(xd), L.ptr(dx), dx.stride(0), N,
+         L.ptr(dw), L.ptr(db), L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), B, Cdim, ncls, L.stream())
+    return dx, dw, db, dgamma, dbeta
+
+
 # ----------------------------------------------------------------------------- PatchEmbed
 def patch_im2col(clip, kernel, stride, padding, dtype):
     B, Cin, T, H, W = clip.shape

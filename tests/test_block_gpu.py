@@ -201,3 +201,40 @@ def test_pm_routing_matches_reference_fixture(dtype):
     assert (logits.argmax(1).cpu().numpy() == np.argmax(z["logits"], 1)).all()  # top-1 agrees per clip
     assert nerr(plain[1:2], z["logits"][1:2]) < OUT_TOL[dtype]                   # the landscape clip is unaffected
     assert float((plain[0] - logits[0]).abs().max()) > 1e-3                      # the routing really changes the portrait ones
+
+
+def test_forward_loss_matches_unfused_tail():
+    """Row f2 in the model: MViT.forward_loss (fused final LN / head / cross entropy) gives the loss and the gradients of
+    cross_entropy(model(x)) through the unfused tail, for integer labels and for soft (mixup) targets."""
+    from pmv_b200 import mvit
+    torch.manual_seed(5)
+    model = mvit.MViT(mvit.MVITV2_S, compute_dtype=torch.bfloat16).cuda().train()
+    model.head.dropout.p = 0.0
+    for blk in model.blocks:
+        blk.drop_path_prob = 0.0
+    clip = torch.randn(2, 3, 16, 224, 224, device="cuda")
+    labels = torch.tensor([3, 177], device="cuda")
+    soft = torch.zeros(2, 400, device="cuda")
+    soft[0, 3], soft[0, 9], soft[1, 177], soft[1, 2] = 0.7, 0.3, 0.4, 0.6
+    watch = ["head.projection.weight", "head.projection.bias", "norm.weight", "norm.bias", "blocks.15.mlp.fc2.weight",
+             "blocks.0.attn.qkv.weight", "cls_token"]
+    sd = dict(model.named_parameters())
+    for target in (labels, soft):
+        model.zero_grad(set_to_none=True)
+        logits = model([clip])
+        if target.dtype == torch.int64:
+            ref = torch.nn.functional.cross_entropy(logits, target)
+        else:
+            ref = torch.sum(-target * torch.log_softmax(logits, dim=-1), dim=-1).mean()
+        ref.backward()
+        g_ref = {n: sd[n].grad.clone() for n in watch}
+        model.zero_grad(set_to_none=True)
+        loss, logits2 = model.forward_loss([clip], target)
+        loss.backward()
+        assert nerr(logits2, logits.detach()) < 1e-5
+        assert abs(float(loss.detach()) - float(ref.detach())) < 1e-5 * max(1.0, abs(float(ref.detach())))
+        for n in watch:
+            # the tail itself is fp32 on both sides; below it the bf16 backward (and its atomics order) amplifies the
+            # last-bit differences of the incoming gradient
+            tol = 1e-4 if n.startswith(("head.", "norm.")) else 5e-2
+            assert nerr(sd[n].grad, g_ref[n]) < tol, n

@@ -335,3 +335,59 @@ def test_pool_ln_qkv_fused_launch(dtype):
             assert nerr(grads[i, :2592].view(96, 27), wr.grad.view(96, 27)) < TOL[dtype], (i, saved)
             assert nerr(grads[i, 2592:2688], gr.grad) < TOL[dtype], (i, saved)
             assert nerr(grads[i, 2688:], br.grad) < TOL[dtype], (i, saved)
+
+
+@pytest.mark.parametrize("B,N,C,ncls,target_kind,p", [(8, 393, 768, 400, "hard", 0.5), (3, 17, 768, 400, "soft", 0.0),
+                                                      (5, 2, 96, 10, "soft", 0.25), (2, 1, 100, 7, "hard", 0.0)])
+def test_head_loss_fused(B, N, C, ncls, target_kind, p):
+    """Row f2: final LN + cls select + head + (soft-target) cross entropy against the oracle, forward and backward."""
+    import torch.nn.functional as F
+    from oracle import mvit_oracle as orc
+    from pmv_b200 import functional as Fn
+    tok = randn(B, N, C, seed=31) * 1.5 + 0.2
+    prm = {"norm.weight": randn(C, seed=32) * 0.1 + 1, "norm.bias": randn(C, seed=33) * 0.1,
+           "head.projection.weight": randn(ncls, C, seed=34) * 0.05, "head.projection.bias": randn(ncls, seed=35) * 0.1}
+    g = torch.Generator(device="cpu").manual_seed(36)
+    if target_kind == "hard":
+        target = torch.randint(0, ncls, (B,), generator=g).cuda()
+    else:  # mixup-style rows: two classes share the mass, plus label smoothing
+        target = torch.full((B, ncls), 0.1 / ncls)
+        for b in range(B):
+            i, j = torch.randint(0, ncls, (2,), generator=g).tolist()
+            lam = float(torch.rand((), generator=g))
+            target[b, i] += 0.9 * lam
+            target[b, j] += 0.9 * (1 - lam)
+        target = target.cuda()
+    keep = (torch.rand(B, C, generator=g) >= p).to(torch.uint8).cuda() if p > 0 else None
+    ours = [t.clone().requires_grad_(True) for t in (tok, prm["norm.weight"], prm["norm.bias"], prm["head.projection.weight"],
+                                                     prm["head.projection.bias"])]
+    loss, logits = Fn.head_loss(ours[0], ours[1], ours[2], ours[3], ours[4], target, keep_mask=keep, dropout_p=p)
+    ref_in = {k: v.clone().requires_grad_(True) for k, v in prm.items()}
+    tok_r = tok.clone().requires_grad_(True)
+    loss_r, logits_r = orc.head_loss(tok_r, ref_in, target, keep, p)
+    assert nerr(logits, logits_r.detach()) < 1e-5
+    loss_v, loss_rv = float(loss.detach()), float(loss_r.detach())
+    assert abs(loss_v - loss_rv) < 1e-5 * max(1.0, abs(loss_rv))
+    if target_kind == "hard":  # second anchor: nn.CrossEntropyLoss (losses.py:66)
+        assert abs(loss_v - float(F.cross_entropy(logits_r.detach(), target))) < 1e-5 * max(1.0, abs(loss_rv))
+    (loss * 1.7).backward()
+    (loss_r * 1.7).backward()
+    refs = [tok_r, ref_in["norm.weight"], ref_in["norm.bias"], ref_in["head.projection.weight"], ref_in["head.projection.bias"]]
+    for a, b, name in zip(ours, refs, ["dx", "dgamma", "dbeta", "dW", "dbias"]):
+        assert nerr(a.grad, b.grad) < 1e-4, name
+    assert float(ours[0].grad[:, 1:].abs().max()) == 0.0 if N > 1 else True
+
+
+def test_head_eval_probabilities():
+    from oracle import mvit_oracle as orc
+    from pmv_b200 import ops
+    B, N, C, ncls = 4, 50, 768, 400
+    tok = randn(B, N, C, seed=41)
+    gm, bt = randn(C, seed=42) * 0.1 + 1, randn(C, seed=43) * 0.1
+    w, bias = randn(ncls, C, seed=44) * 0.05, randn(ncls, seed=45) * 0.1
+    r = ops.head_loss_fwd(tok, gm, bt, w, bias, want_probs=True)
+    x = orc.layer_norm(tok, gm, bt)[:, 0]
+    ref = torch.nn.functional.linear(x, w, bias)
+    assert nerr(r["logits"], ref) < 1e-5
+    assert nerr(r["probs"], ref.softmax(dim=1)) < 1e-5
+    assert r["loss"] is None
