@@ -112,7 +112,9 @@ __global__ void __launch_bounds__(CS_THREADS) colsum_cast_kernel(const TIn* __re
 // column quads per block (power-of-two-free: any cx <= 256), row slices
 static void colsum_grid(int64_t rows, int64_t cols, int* cx, unsigned* bx, int64_t* rpb, unsigned* by) {
   const int64_t col_threads = cols / 4;
-  *cx = col_threads < CS_THREADS ? (int)col_threads : CS_THREADS;
+  // one warp across 32 column quads (512 contiguous bytes of fp32 per row) whenever that tiles the columns exactly:
+  // min(col_threads, 256) left half of the second block idle at 1536 columns and a quarter of every block at 384
+  *cx = col_threads % 32 == 0 ? 32 : (col_threads < CS_THREADS ? (int)col_threads : CS_THREADS);
   *bx = (unsigned)ceil_div64(col_threads, *cx);
   const int ry = CS_THREADS / *cx;
   int64_t slices = ceil_div64(148 * 6, *bx);  // enough row slices to fill the machine

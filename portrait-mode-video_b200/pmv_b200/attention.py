@@ -190,7 +190,9 @@ class MultiScaleBlock(nn.Module):
                 raise NotImplementedError("pmv_b200.MultiScaleBlock: skip-path max-pool supports stride_q (1,2,2) only")
             self.pool_skip = nn.MaxPool3d([1, 3, 3], stride_q, [0, 1, 1], ceil_mode=False)  # parameter-free marker
 
-    def forward(self, x, thw_shape=None):
+    def forward(self, x, thw_shape=None, drop_scales=None):
+        """``drop_scales``: optional pre-drawn DropPath factors (attention branch, MLP branch), each [B] fp32 or None —
+        MViT draws the factors of all blocks with one set of launches; without it the block draws its own."""
         T = compute_dtype_of(self)
         B = x.shape[0]
         x = x.float() if x.dtype != torch.float32 else x
@@ -199,10 +201,14 @@ class MultiScaleBlock(nn.Module):
         if self.dim_mul_in_att and self.dim != self.dim_out:
             x = Fn.linear(x_norm, self.proj.weight, self.proj.bias, out_fp32=True)           # :569-570
         x_res = Fn.maxpool_skip(x, thw) if self.pool_skip is not None else x                  # :571-573
-        ds1 = drop_path_scale(B, self.drop_path_prob, self.training, x.device)
+        if drop_scales is not None:
+            ds1, ds2 = drop_scales
+        else:
+            ds1 = drop_path_scale(B, self.drop_path_prob, self.training, x.device)
         x, thw_new = self.attn(x_norm, thw, residual=x_res, row_scale=ds1)                    # :568,577
         x, x_norm2 = Fn.layer_norm_residual(x, self.norm2.weight, self.norm2.bias, T, self.norm2.eps)        # :578
-        ds2 = drop_path_scale(B, self.drop_path_prob, self.training, x.device)
+        if drop_scales is None:
+            ds2 = drop_path_scale(B, self.drop_path_prob, self.training, x.device)
         x = self.mlp(x_norm2, residual=x, row_scale=ds2, rows_per_scale=x.shape[1])           # :579,585
         if thw_shape:
             return x, thw_new

@@ -132,20 +132,31 @@ class MViT(nn.Module):
             nn.init.constant_(m.bias, 0)
             nn.init.constant_(m.weight, 1.0)
 
+    def _drop_path_scales(self, batch, device):
+        """DropPath factors mask / keep_prob (common.py:46-59) of every block and both residual branches, drawn with
+        one rand / add / floor / div instead of four small launches per branch (120 launches per MViTv2-S step)."""
+        if not self.training or all(blk.drop_path_prob == 0.0 for blk in self.blocks):
+            return [None] * len(self.blocks)
+        keep = getattr(self, "_dp_keep", None)
+        if keep is None or keep.device != device:
+            keep = torch.tensor([1.0 - blk.drop_path_prob for blk in self.blocks for _ in range(2)], dtype=torch.float32,
+                                device=device).unsqueeze(1)
+            self._dp_keep = keep
+        scales = (keep + torch.rand(keep.shape[0], batch, device=device)).floor_() / keep
+        return [None if blk.drop_path_prob == 0.0 else (scales[2 * i], scales[2 * i + 1]) for i, blk in enumerate(self.blocks)]
+
     def forward_features(self, clip, thw_expected=None):
-        x, thw = self.patch_embed.forward_tokens(clip, self.cls_token)        # :2100-2121
-        assert tuple(thw) == tuple(thw_expected or (self.T, self.H, self.W)), thw  # :2106
-        for blk in self.blocks:                                               # :2144-2146
-            x, thw = blk(x, thw)
+        x = self.forward_tokens(clip, thw_expected)
         x = Fn.layer_norm(x, self.norm.weight, self.norm.bias, torch.float32, self.norm.eps)  # :2163
         return x[:, 0]                                                        # :2165
 
     def forward_tokens(self, clip, thw_expected=None):
         """The token stream before the final norm: [B, 1 + T*H*W / 64, 768] fp32."""
-        x, thw = self.patch_embed.forward_tokens(clip, self.cls_token)
-        assert tuple(thw) == tuple(thw_expected or (self.T, self.H, self.W)), thw
-        for blk in self.blocks:
-            x, thw = blk(x, thw)
+        x, thw = self.patch_embed.forward_tokens(clip, self.cls_token)        # :2100-2121
+        assert tuple(thw) == tuple(thw_expected or (self.T, self.H, self.W)), thw  # :2106
+        scales = self._drop_path_scales(x.shape[0], x.device)
+        for blk, ds in zip(self.blocks, scales):                              # :2144-2146
+            x, thw = blk(x, thw, drop_scales=ds)
         return x
 
     def _head_no_grad(self, tok):
