@@ -23,12 +23,13 @@ clips = torch.randn(B, 3, 16, 224, 224, device=dev)
 labels = torch.randint(0, 400, (B,), device=dev)
 if mode == "train":
     model.train()
+    from pmv_b200.optim import FusedAdamW, param_groups
     reducer = GradAllReducer(model, bucket_mb=25.0)
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.05, fused=True, capturable=True)
+    opt = FusedAdamW(param_groups(model, 0.05, zero_wd_1d=True), lr=1e-4, max_grad_norm=1.0)  # as in bench.py
 
     def step(c, l):
         reducer.zero_grad()
-        loss = torch.nn.functional.cross_entropy(model([c]), l)
+        loss, _ = model.forward_loss([c], l)
         loss.backward()
         reducer.finish()
         opt.step()
