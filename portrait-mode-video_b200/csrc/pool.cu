@@ -654,20 +654,24 @@ __global__ void __launch_bounds__(256) reduce_jobs_kernel(const __grid_constant_
   const Job& J = L.job[blockIdx.y];
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + lane;
-  float s0 = 0.f, s1 = 0.f;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   if (i < NGRAD) {
     const bool is_dw = i < NDW;
     const float* src = is_dw ? J.part_dw + i : J.part_ln + (i - NDW);
     const int64_t stride = is_dw ? NDW : 2 * HD;
     const int end = is_dw ? J.nblk_dw : J.nblk_ln;
     int b = slice;
-    for (; b + RED_SLICES < end; b += 2 * RED_SLICES) {
-      s0 += src[(int64_t)b * stride];
-      s1 += src[(int64_t)(b + RED_SLICES) * stride];
+    // up to 1200 partial vectors: eight independent loads in flight per thread (two per iteration left the kernel
+    // waiting on one L2 round trip per pair: 14.6 us for 10 MB)
+    for (; b + 7 * RED_SLICES < end; b += 8 * RED_SLICES) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = src[(int64_t)(b + u * RED_SLICES) * stride];
+      s0 += v[0] + v[4]; s1 += v[1] + v[5]; s2 += v[2] + v[6]; s3 += v[3] + v[7];
     }
-    if (b < end) s0 += src[(int64_t)b * stride];
+    for (; b < end; b += RED_SLICES) s0 += src[(int64_t)b * stride];
   }
-  part[slice][lane] = s0 + s1;
+  part[slice][lane] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (slice == 0 && i < NGRAD) {
     float s = 0.f;

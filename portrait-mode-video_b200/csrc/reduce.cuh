@@ -14,6 +14,12 @@ static __global__ void __launch_bounds__(256) reduce_partials_kernel(const float
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   const int step = gridDim.y;
   int b = blockIdx.y;
+  for (; b + 7 * step < nblocks; b += 8 * step) {  // eight loads in flight
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = partials[(int64_t)(b + u * step) * stride + i];
+    s0 += v[0] + v[4]; s1 += v[1] + v[5]; s2 += v[2] + v[6]; s3 += v[3] + v[7];
+  }
   for (; b + 3 * step < nblocks; b += 4 * step) {
     s0 += partials[(int64_t)b * stride + i];
     s1 += partials[(int64_t)(b + step) * stride + i];
