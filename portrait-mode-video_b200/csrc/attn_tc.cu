@@ -23,6 +23,22 @@
 //   P      : tensor memory, bf16 pairs packed in 32-bit columns (column c = keys 2c, 2c+1).
 #include "tc_common.cuh"
 
+#ifdef PMV_ATTN_TRACE
+// Debug build only (scripts/attn_trace.py): per-CTA cycle stamps of the forward kernel's phases.
+constexpr int TRACE_CTAS = 1024, TRACE_SLOTS = 24;
+__device__ long long pmv_attn_trace_buf[TRACE_CTAS * TRACE_SLOTS];
+#define TRACE(slot)                                                                                                   \
+  do {                                                                                                                \
+    const int cta_ = blockIdx.y * gridDim.x + blockIdx.x;                                                             \
+    if (cta_ < TRACE_CTAS) pmv_attn_trace_buf[cta_ * TRACE_SLOTS + (slot)] = clock64();                               \
+  } while (0)
+extern "C" int pmv_debug_attn_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, pmv_attn_trace_buf, sizeof(long long) * TRACE_CTAS * TRACE_SLOTS) == cudaSuccess ? 0 : 1;
+}
+#else
+#define TRACE(slot) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int HD = PMV_HEAD_DIM;
@@ -67,6 +83,15 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int bh = blockIdx.y;
   const int q0 = blockIdx.x * BQ;
   const int ntiles = (g.Nk + BKV - 1) / BKV;
+#ifdef PMV_ATTN_TRACE
+  if (threadIdx.x == 0) {
+    TRACE(0);
+    unsigned smid; asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    const int cta_ = blockIdx.y * gridDim.x + blockIdx.x;
+    if (cta_ < TRACE_CTAS) { pmv_attn_trace_buf[cta_ * TRACE_SLOTS + 21] = smid; pmv_attn_trace_buf[cta_ * TRACE_SLOTS + 19] = (long long)gt; }
+  }
+#endif
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmQ);
@@ -92,6 +117,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base + 256;
+  if (threadIdx.x == 0) TRACE(1);
   pdl_wait();  // the prologue above overlaps the previous kernel's tail
 
   if (warp == 0) {
@@ -100,6 +126,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc::tma_load_3d(sQ, &tmQ, 0, q0, bh, q_full);
       tc::tma_load_3d(sQ + 16384, &tmQ, 64, q0, bh, q_full);
       if (KD == 160) tc::tma_load_3d(sQ + 32768, &tmQ2, 128, q0, bh, q_full);
+      TRACE(2);
       for (int j = 0; j < ntiles; ++j) {
         const int st = j & 1;
         tc::mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
@@ -120,6 +147,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int st = j & 1;
         tc::mbar_wait(&kv_full[st], (j >> 1) & 1);
         tc::tc_fence_after();
+        if (j < 4) TRACE(4 + j);
         const int nvalid = min(BKV, g.Nk - j * BKV);
         const uint32_t idesc = tc::make_idesc_bf16(BQ, (nvalid + 15) & ~15, false, false);
         const uint32_t sk_addr = tc::smem_u32(sStage + st * Cfg::STAGE_BYTES);
@@ -142,6 +170,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       };
       tc::mbar_wait(q_full, 0);
       tc::tc_fence_after();
+      TRACE(3);
       issue_s(0);
       const uint32_t idesc_pv = tc::make_idesc_bf16(BQ, HD, false, true);
       for (int j = 0; j < ntiles; ++j) {
@@ -171,6 +200,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int b = j & 1;
       tc::mbar_wait(&s_full[b], (j >> 1) & 1);
       tc::tc_fence_after();
+      if (warp == 4 && lane == 0 && j < 4) TRACE(8 + j);
       const int nvalid = min(BKV, g.Nk - j * BKV);
       const int nchunks = (nvalid + 31) >> 5;
       const uint32_t tmem_s = tmem_base + lane_addr + (uint32_t)b * 128;
@@ -180,15 +210,24 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (ch < nchunks) tc::tmem_ld32(tmem_s + ch * 32, s[ch]);
       tc::tmem_ld_wait();
       float mx = -INFINITY;
+      if (nvalid == BKV) {  // full tile (all but the last): no key masking, 1 instruction per score instead of 3
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        if (ch < nchunks) {
+        for (int ch = 0; ch < 4; ++ch)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float v = __uint_as_float(s[ch][i]);
-            if (ch * 32 + i >= nvalid) v = -INFINITY;
-            s[ch][i] = __float_as_uint(v);
-            mx = fmaxf(mx, v);
+          for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(s[ch][i]));
+        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      } else {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          if (ch < nchunks) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float v = __uint_as_float(s[ch][i]);
+              if (ch * 32 + i >= nvalid) v = -INFINITY;
+              s[ch][i] = __float_as_uint(v);
+              mx = fmaxf(mx, v);
+            }
           }
         }
       }
@@ -199,7 +238,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (__any_sync(0xffffffffu, grow)) {
           tc::mbar_wait(o_done, (j - 1) & 1);  // P_{j-1} V_{j-1} has landed in O
           tc::tc_fence_after();
-          const float alpha = grow ? exp2f((m_used - mx) * c) : 1.0f;
+          const float alpha = grow ? tc::fast_ex2((m_used - mx) * c) : 1.0f;
 #pragma unroll
           for (int ch = 0; ch < 3; ++ch) {
             uint32_t o[32];
@@ -222,8 +261,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float p0 = exp2f(fmaf(__uint_as_float(s[ch][2 * i]), c, -mc));
-            const float p1 = exp2f(fmaf(__uint_as_float(s[ch][2 * i + 1]), c, -mc));
+            const float p0 = tc::fast_ex2(fmaf(__uint_as_float(s[ch][2 * i]), c, -mc));
+            const float p1 = tc::fast_ex2(fmaf(__uint_as_float(s[ch][2 * i + 1]), c, -mc));
             sum += p0 + p1;
             __nv_bfloat162 pp = __floats2bfloat162_rn(p0, p1);
             pk[i] = *reinterpret_cast<uint32_t*>(&pp);
@@ -236,10 +275,12 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&p_full[b]);
+      if (warp == 4 && lane == 0 && j < 4) TRACE(12 + j);
     }
     // ---------------- epilogue: O / l (+ residual q), head-merged bf16 store, log-sum-exp
     tc::mbar_wait(o_final, 0);
     tc::tc_fence_after();
+    if (warp == 4 && lane == 0) TRACE(16);
     tc::mbar_wait(q_full, 0);
     const int n = q0 + row;
     const float inv = 1.0f / l_run;
@@ -287,6 +328,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
     if (lse != nullptr && n < g.Nq) lse[(int64_t)bh * g.Nq + n] = m_used * g.scale + logf(l_run);
+    if (warp == 4 && lane == 0) TRACE(17);
   }
 
   tc::tc_fence_before();
@@ -294,6 +336,14 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 2) {
     tc::tc_fence_after();
     tc::tmem_dealloc(tmem_base, 512);
+#ifdef PMV_ATTN_TRACE
+    if (lane == 0) {
+      TRACE(18);
+      unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+      const int cta_ = blockIdx.y * gridDim.x + blockIdx.x;
+      if (cta_ < TRACE_CTAS) pmv_attn_trace_buf[cta_ * TRACE_SLOTS + 20] = (long long)gt;
+    }
+#endif
   }
 }
 

@@ -264,7 +264,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int col = wh * 32 + 2 * i + h;
-              const float p = (rvalid && col < nv) ? exp2f(fmaf(__uint_as_float(s[2 * i + h]), c, -lse2)) : 0.f;
+              const float p = (rvalid && col < nv) ? tc::fast_ex2(fmaf(__uint_as_float(s[2 * i + h]), c, -lse2)) : 0.f;
               d[h] = p * (__uint_as_float(dp[2 * i + h]) - delta) * g.scale;
             }
             __nv_bfloat162 pp = __floats2bfloat162_rn(d[0], d[1]);
@@ -482,7 +482,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             for (int h = 0; h < 2; ++h) {
               const int cl = wh * 32 + 2 * e + h;        // query inside the half
               const int col = half * HK + cl;            // query inside the tile
-              p[h] = cl < nv ? exp2f(fmaf(__uint_as_float(s[2 * e + h]), c, -lse_t[col])) : 0.f;
+              p[h] = cl < nv ? tc::fast_ex2(fmaf(__uint_as_float(s[2 * e + h]), c, -lse_t[col])) : 0.f;
               d[h] = p[h] * (__uint_as_float(dp[2 * e + h]) - del_t[col]) * g.scale;
             }
             __nv_bfloat162 pp = __floats2bfloat162_rn(p[0], p[1]);

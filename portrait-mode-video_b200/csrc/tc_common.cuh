@@ -109,6 +109,15 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 
 // 32 lanes x 32 columns of 32-bit: thread t of the warp gets lane (base_lane + t), columns [col, col+32)
+// 2^x on the MUFU, one instruction.  exp2f() wraps the same MUFU.EX2 in a range fix-up for results below 2^-126
+// (FSETP + 2 predicated FMUL per call): three of the seven instructions per score element in the softmax loops,
+// which are issue-bound.  Flushing those results to zero is exact enough for probabilities.
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "

@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpmv_b200.so")
+LIB_PATH = os.environ.get("PMV_B200_LIB", os.path.join(_HERE, "libpmv_b200.so"))  # override: debug builds only
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_GELU, ACT_GELU_BWD = 0, 1, 2
