@@ -55,29 +55,35 @@ struct TcAttnGeom {
 template <int KD> struct ACfg {
   static constexpr int QK_BYTES = BQ * KD * 2;  // 32768 (kd 128) / 40960 (kd 160)
   static constexpr int STAGE_BYTES = QK_BYTES + V_BYTES;
-  static constexpr int SMEM_BYTES = QK_BYTES + 2 * STAGE_BYTES + 1024 + 256;
+  // K'/V ring depth: with two stages the load of tile j+2 can only start when P_j V_j has retired, and the softmax warps
+  // then wait ~0.4 us per tile for it (scripts/attn_trace.py); three stages fit for kd = 128 (205 KB), not for kd = 160
+  static constexpr int NST = KD == 128 ? 3 : 2;
+  static constexpr int SMEM_BYTES = QK_BYTES + NST * STAGE_BYTES + 1024 + 128 + 512;  // alignment slack, barriers, row scales
 };
 
 template <int KD>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQ2,
                    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmK2,
-                   const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ out, bf16* __restrict__ out_pre,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                   const __grid_constant__ CUtensorMap tmOpre, bf16* __restrict__ out, bf16* __restrict__ out_pre,
                    float* __restrict__ lse, TcAttnGeom g) {
   using Cfg = ACfg<KD>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
   uint8_t* sStage = smem + Cfg::QK_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::QK_BYTES + 2 * Cfg::STAGE_BYTES);
+  constexpr int NST = Cfg::NST;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::QK_BYTES + NST * Cfg::STAGE_BYTES);
   uint64_t* q_full = bars;         // [1]
-  uint64_t* kv_full = bars + 1;    // [2]
-  uint64_t* kv_empty = bars + 3;   // [2]
-  uint64_t* s_full = bars + 5;     // [2]
-  uint64_t* p_full = bars + 7;     // [2]
-  uint64_t* o_done = bars + 9;     // [1]  arrives after every P_j V_j
-  uint64_t* o_final = bars + 10;   // [1]  arrives once, after the last P V (unambiguous phase for the epilogue)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* kv_full = bars + 1;    // [NST <= 3]
+  uint64_t* kv_empty = bars + 4;   // [NST <= 3]
+  uint64_t* s_full = bars + 7;     // [2]
+  uint64_t* p_full = bars + 9;     // [2]
+  uint64_t* o_done = bars + 11;    // [1]  arrives after every P_j V_j
+  uint64_t* o_final = bars + 12;   // [1]  arrives once, after the last P V (unambiguous phase for the epilogue)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  float* s_inv = reinterpret_cast<float*>(bars + 16);  // [128] 1 / row sum, softmax warps -> epilogue
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
@@ -98,9 +104,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tc::tma_prefetch_desc(&tmK);
     tc::tma_prefetch_desc(&tmV);
     tc::mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NST; ++i) {
       tc::mbar_init(&kv_full[i], 1);
       tc::mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&s_full[i], 1);
       tc::mbar_init(&p_full[i], 4);
     }
@@ -128,8 +136,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (KD == 160) tc::tma_load_3d(sQ + 32768, &tmQ2, 128, q0, bh, q_full);
       TRACE(2);
       for (int j = 0; j < ntiles; ++j) {
-        const int st = j & 1;
-        tc::mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        const int st = j % NST;
+        tc::mbar_wait(&kv_empty[st], ((j / NST) & 1) ^ 1);
         uint8_t* sK = sStage + st * Cfg::STAGE_BYTES;
         uint8_t* sV = sK + Cfg::QK_BYTES;
         tc::mbar_expect_tx(&kv_full[st], Cfg::STAGE_BYTES);
@@ -144,10 +152,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (lane == 0) {
       const uint32_t sq_addr = tc::smem_u32(sQ);
       auto issue_s = [&](int j) {
-        const int st = j & 1;
-        tc::mbar_wait(&kv_full[st], (j >> 1) & 1);
+        const int st = j % NST;
+        tc::mbar_wait(&kv_full[st], (j / NST) & 1);
         tc::tc_fence_after();
-        if (j < 4) TRACE(4 + j);
+        if (j < 1) TRACE(4 + j);
         const int nvalid = min(BKV, g.Nk - j * BKV);
         const uint32_t idesc = tc::make_idesc_bf16(BQ, (nvalid + 15) & ~15, false, false);
         const uint32_t sk_addr = tc::smem_u32(sStage + st * Cfg::STAGE_BYTES);
@@ -179,13 +187,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc::tc_fence_after();
         const int nvalid = min(BKV, g.Nk - j * BKV);
         const int nks = (nvalid + 15) >> 4;
-        const uint32_t sv_addr = tc::smem_u32(sStage + (j & 1) * Cfg::STAGE_BYTES + Cfg::QK_BYTES);
+        const uint32_t sv_addr = tc::smem_u32(sStage + (j % NST) * Cfg::STAGE_BYTES + Cfg::QK_BYTES);
         const uint32_t tmem_p = tmem_base + (uint32_t)(j & 1) * 128;
         for (int ks = 0; ks < nks; ++ks) {
           const uint64_t db = tc::make_smem_desc(sv_addr + ks * 1024, 8192, 512, tc::SWIZZLE_64B);
           tc::umma_ts(tmem_o, tmem_p + ks * 8, db, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
         }
-        tc::umma_commit(&kv_empty[j & 1]);
+        tc::umma_commit(&kv_empty[j % NST]);
         tc::umma_commit(o_done);
         if (j == ntiles - 1) tc::umma_commit(o_final);
       }
@@ -209,6 +217,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int ch = 0; ch < 4; ++ch)
         if (ch < nchunks) tc::tmem_ld32(tmem_s + ch * 32, s[ch]);
       tc::tmem_ld_wait();
+      if (warp == 4 && lane == 0 && j == 1) TRACE(22);
       float mx = -INFINITY;
       if (nvalid == BKV) {  // full tile (all but the last): no key masking, 1 instruction per score instead of 3
         float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -259,76 +268,102 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int ch = 0; ch < 4; ++ch) {
         if (ch < nchunks) {
           uint32_t pk[16];
+          const float2 c2 = make_float2(c, c), nmc2 = make_float2(-mc, -mc);
+          float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = tc::fast_ex2(fmaf(__uint_as_float(s[ch][2 * i]), c, -mc));
-            const float p1 = tc::fast_ex2(fmaf(__uint_as_float(s[ch][2 * i + 1]), c, -mc));
-            sum += p0 + p1;
-            __nv_bfloat162 pp = __floats2bfloat162_rn(p0, p1);
-            pk[i] = *reinterpret_cast<uint32_t*>(&pp);
+          for (int i = 0; i < 16; ++i) {  // packed fp32 pairs: one FFMA2 + two MUFU + one FADD2 + one pack per two scores
+            const float2 t = __ffma2_rn(make_float2(__uint_as_float(s[ch][2 * i]), __uint_as_float(s[ch][2 * i + 1])), c2, nmc2);
+            const float2 pr = make_float2(tc::fast_ex2(t.x), tc::fast_ex2(t.y));
+            sum2 = __fadd2_rn(sum2, pr);
+            pk[i] = tc::pack_bf16x2_alu(pr.x, pr.y);
           }
+          sum += sum2.x + sum2.y;
           tc::tmem_st16(tmem_s + ch * 16, pk);
         }
       }
       l_run += sum;
+      if (warp == 4 && lane == 0 && j == 1) TRACE(23);
       tc::tmem_st_wait();
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&p_full[b]);
       if (warp == 4 && lane == 0 && j < 4) TRACE(12 + j);
     }
-    // ---------------- epilogue: O / l (+ residual q), head-merged bf16 store, log-sum-exp
+    // ---------------- hand the row scale to the epilogue (all eight warps), log-sum-exp
     tc::mbar_wait(o_final, 0);
     tc::tc_fence_after();
     if (warp == 4 && lane == 0) TRACE(16);
-    tc::mbar_wait(q_full, 0);
+    s_inv[row] = 1.0f / l_run;
+    if (lse != nullptr && q0 + row < g.Nq) lse[(int64_t)bh * g.Nq + q0 + row] = m_used * g.scale + logf(l_run);
+  }
+
+  // ---------------- epilogue: O / l (+ residual q), head-merged bf16 tiles, two bulk tensor stores.
+  // All eight warps take part (a warp reaches the TMEM lanes 32 (w % 4) .. + 31): warps 4..7 take channels [0, 48), the
+  // TMA / MMA / allocator warps, idle by now, channels [48, 96) - one warp per scheduler needed 1.5 us for the 96
+  // channels of its rows (scripts/attn_trace.py).  The rows are staged as dense [128][96] bf16 tiles in the idle K'/V
+  // ring; direct 16-byte stores from one thread per row touch 32 different lines per warp instruction.
+  tc::tc_fence_before();
+  __syncthreads();  // O complete (the softmax warps waited for o_final), s_inv written
+  tc::tc_fence_after();
+  {
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    const int c_base = warp >= 4 ? 0 : 48;
     const int n = q0 + row;
-    const float inv = 1.0f / l_run;
+    const float inv = s_inv[row];
     const int bidx = bh / g.heads, head = bh - bidx * g.heads;
-    const int64_t ooff = ((int64_t)bidx * g.Nq + n) * (g.heads * HD) + head * HD;
-    bf16* op = out + ooff;
     const bool add_q = g.residual && n >= 1;
+    uint8_t* sOut = sStage;
+    uint8_t* sPre = sStage + BQ * HD * 2;
+    uint32_t o32[32], o16[16];
+    tc::tmem_ld32(tmem_o + lane_addr + c_base, o32);
+    tc::tmem_ld16(tmem_o + lane_addr + c_base + 32, o16);
+    tc::tmem_ld_wait();
+    if (warp == 4 && lane == 0) TRACE(5);
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-      uint32_t o[32];
-      tc::tmem_ld32(tmem_o + lane_addr + ch * 32, o);
-      tc::tmem_ld_wait();
-      if (n < g.Nq) {
+    for (int v8 = 0; v8 < 6; ++v8) {  // 8 channels = one 16-byte chunk of the swizzled Q' row
+      const int col = c_base + v8 * 8;
+      float f[8];
 #pragma unroll
-        for (int v8 = 0; v8 < 4; ++v8) {  // 8 channels = one 16-byte chunk of the swizzled Q' row
-          const int col = ch * 32 + v8 * 8;
-          float f[8];
+      for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v8 < 4 ? o32[(v8 & 3) * 8 + i] : o16[(v8 & 1) * 8 + i]) * inv;
+      if (out_pre != nullptr) {  // pre-residual output, kept for backward (delta = rowsum(dO * O_attn))
+        uint4 pk;
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(f[0], f[1]), t1 = __floats2bfloat162_rn(f[2], f[3]);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(f[4], f[5]), t3 = __floats2bfloat162_rn(f[6], f[7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+        pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+        *reinterpret_cast<uint4*>(sPre + row * (HD * 2) + col * 2) = pk;
+      }
+      if (add_q) {
+        const int blk = col >> 6, cc = (col & 63) >> 3;
+        const uint4 qv = *reinterpret_cast<const uint4*>(sQ + blk * 16384 + row * 128 + ((cc ^ (row & 7)) << 4));
+        const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&qv);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[v8 * 8 + i]) * inv;
-          if (out_pre != nullptr) {  // pre-residual output, kept for backward (delta = rowsum(dO * O_attn))
-            uint4 pk;
-            __nv_bfloat162 t0 = __floats2bfloat162_rn(f[0], f[1]), t1 = __floats2bfloat162_rn(f[2], f[3]);
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(f[4], f[5]), t3 = __floats2bfloat162_rn(f[6], f[7]);
-            pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-            pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-            *reinterpret_cast<uint4*>(out_pre + ooff + col) = pk;
-          }
-          if (add_q) {
-            const int blk = col >> 6, cc = (col & 63) >> 3;
-            const uint4 qv = *reinterpret_cast<const uint4*>(sQ + blk * 16384 + row * 128 + ((cc ^ (row & 7)) << 4));
-            const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&qv);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              f[2 * i] += __low2float(q2[i]);
-              f[2 * i + 1] += __high2float(q2[i]);
-            }
-          }
-          uint4 pk;
-          __nv_bfloat162 t0 = __floats2bfloat162_rn(f[0], f[1]), t1 = __floats2bfloat162_rn(f[2], f[3]);
-          __nv_bfloat162 t2 = __floats2bfloat162_rn(f[4], f[5]), t3 = __floats2bfloat162_rn(f[6], f[7]);
-          pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-          pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-          *reinterpret_cast<uint4*>(op + col) = pk;
+        for (int i = 0; i < 4; ++i) {
+          f[2 * i] += __low2float(q2[i]);
+          f[2 * i + 1] += __high2float(q2[i]);
         }
       }
+      uint4 pk;
+      __nv_bfloat162 t0 = __floats2bfloat162_rn(f[0], f[1]), t1 = __floats2bfloat162_rn(f[2], f[3]);
+      __nv_bfloat162 t2 = __floats2bfloat162_rn(f[4], f[5]), t3 = __floats2bfloat162_rn(f[6], f[7]);
+      pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+      pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+      *reinterpret_cast<uint4*>(sOut + row * (HD * 2) + col * 2) = pk;
     }
-    if (lse != nullptr && n < g.Nq) lse[(int64_t)bh * g.Nq + n] = m_used * g.scale + logf(l_run);
-    if (warp == 4 && lane == 0) TRACE(17);
+    tc::fence_proxy_async();  // generic-proxy writes -> visible to the bulk stores
+    if (warp == 4 && lane == 0) TRACE(6);
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 4 && lane == 0) {
+      tc::tma_store_3d(&tmO, sOut, head * HD, q0, bidx);
+      if (out_pre != nullptr) tc::tma_store_3d(&tmOpre, sPre, head * HD, q0, bidx);
+      tc::bulk_commit_group();
+      TRACE(7);
+      tc::bulk_wait_group_read0();  // shared memory is released when the CTA exits
+      TRACE(17);
+    }
   }
 
   tc::tc_fence_before();
@@ -359,6 +394,12 @@ int launch(const void* q_aug, const void* k_aug, int64_t ld_qk, const void* v, i
   if ((rc = pmv_make_tensor_map_3d(&tmQ2, q_aug, 2, KD, g.Nq, BH, ld_qk, (uint64_t)g.Nq * ld_qk, 32, BQ, 1, 64))) return rc;
   if ((rc = pmv_make_tensor_map_3d(&tmK2, k_aug, 2, KD, g.Nk, BH, ld_qk, (uint64_t)g.Nk * ld_qk, 32, BKV, 1, 64))) return rc;
   if ((rc = pmv_make_tensor_map_3d(&tmV, v, 2, HD, g.Nk, BH, ld_v, (uint64_t)g.Nk * ld_v, 32, BKV, 1, 64))) return rc;
+  CUtensorMap tmO, tmOpre;
+  const uint64_t ld_o = (uint64_t)g.heads * HD;
+  if ((rc = pmv_make_tensor_map_3d(&tmO, out, 2, ld_o, g.Nq, (uint64_t)g.B, ld_o, (uint64_t)g.Nq * ld_o, HD, BQ, 1, 0))) return rc;
+  if ((rc = pmv_make_tensor_map_3d(&tmOpre, out_pre != nullptr ? out_pre : out, 2, ld_o, g.Nq, (uint64_t)g.B, ld_o, (uint64_t)g.Nq * ld_o, HD,
+                                   BQ, 1, 0)))
+    return rc;
   auto kern = attn_tc_fwd_kernel<KD>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -366,7 +407,7 @@ int launch(const void* q_aug, const void* k_aug, int64_t ld_qk, const void* v, i
     attr_set = true;
   }
   dim3 grid((unsigned)((g.Nq + BQ - 1) / BQ), (unsigned)BH);
-  pmv_launch(kern, grid, THREADS, Cfg::SMEM_BYTES, stream, tmQ, tmQ2, tmK, tmK2, tmV, (bf16*)out, (bf16*)out_pre, lse, g);
+  pmv_launch(kern, grid, THREADS, Cfg::SMEM_BYTES, stream, tmQ, tmQ2, tmK, tmK2, tmV, tmO, tmOpre, (bf16*)out, (bf16*)out_pre, lse, g);
   PMV_CHECK_LAUNCH();
   return PMV_OK;
 }

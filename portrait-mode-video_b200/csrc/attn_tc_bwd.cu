@@ -267,8 +267,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               const float p = (rvalid && col < nv) ? tc::fast_ex2(fmaf(__uint_as_float(s[2 * i + h]), c, -lse2)) : 0.f;
               d[h] = p * (__uint_as_float(dp[2 * i + h]) - delta) * g.scale;
             }
-            __nv_bfloat162 pp = __floats2bfloat162_rn(d[0], d[1]);
-            pk[i] = *reinterpret_cast<uint32_t*>(&pp);
+            pk[i] = tc::pack_bf16x2_alu(d[0], d[1]);
           }
           tc::tmem_st16(tmem_s + lane_addr + b * HK + wh * 32, pk);
           tc::tmem_st_wait();
@@ -485,10 +484,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               p[h] = cl < nv ? tc::fast_ex2(fmaf(__uint_as_float(s[2 * e + h]), c, -lse_t[col])) : 0.f;
               d[h] = p[h] * (__uint_as_float(dp[2 * e + h]) - del_t[col]) * g.scale;
             }
-            __nv_bfloat162 pp = __floats2bfloat162_rn(p[0], p[1]);
-            __nv_bfloat162 dd = __floats2bfloat162_rn(d[0], d[1]);
-            pk[e] = *reinterpret_cast<uint32_t*>(&pp);
-            dk[e] = *reinterpret_cast<uint32_t*>(&dd);
+            pk[e] = tc::pack_bf16x2_alu(p[0], p[1]);
+            dk[e] = tc::pack_bf16x2_alu(d[0], d[1]);
           }
           tc::tmem_st16(tmem_st + lane_addr + b * HK + wh * 32, pk);
           tc::tmem_st16(tmem_dpt + lane_addr + b * HK + wh * 32, dk);

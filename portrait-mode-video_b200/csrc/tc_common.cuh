@@ -109,6 +109,23 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 
 // 32 lanes x 32 columns of 32-bit: thread t of the warp gets lane (base_lane + t), columns [col, col+32)
+// bulk tensor store shared -> global (3-D map); rows / columns outside the tensor are clipped by the hardware
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// Two fp32 -> one packed bf16 pair on the integer ALU (round half away from zero: +0x8000 on the magnitude, keep the high
+// halves).  cvt.rn.bf16x2.f32 shares the quarter-rate unit with MUFU.EX2; the softmax loops issue one or two packs per
+// exponential, so they were bound by that unit.  Differs from round-to-nearest-even only on exact ties.
+__device__ __forceinline__ uint32_t pack_bf16x2_alu(float lo, float hi) {
+  const uint32_t a = __float_as_uint(lo) + 0x8000u, b = __float_as_uint(hi) + 0x8000u;
+  return __byte_perm(a, b, 0x7632);
+}
+
 // 2^x on the MUFU, one instruction.  exp2f() wraps the same MUFU.EX2 in a range fix-up for results below 2^-126
 // (FSETP + 2 predicated FMUL per call): three of the seven instructions per score element in the softmax loops,
 // which are issue-bound.  Flushing those results to zero is exact enough for probabilities.

@@ -25,11 +25,11 @@ assert handle.pmv_debug_attn_trace(buf) == 0
 t = np.frombuffer(buf, dtype=np.int64).reshape(CTAS, SLOTS)[:416].astype(np.float64)
 ghz = 1.965
 names = {1: "prologue done (barriers, TMEM alloc, sync)", 2: "TMA: Q + first K/V requested", 3: "MMA: Q landed", 4: "MMA: K0/V0 landed",
-         8: "softmax: S0 ready", 12: "softmax: P0 written", 5: "MMA: K1 landed", 9: "softmax: S1 ready", 13: "softmax: P1 written",
-         6: "MMA: K2 landed", 10: "softmax: S2 ready", 14: "softmax: P2 written", 7: "MMA: K3 landed", 11: "softmax: S3 ready",
-         15: "softmax: P3 written", 16: "softmax: O final", 17: "epilogue stores done", 18: "TMEM freed (CTA end)"}
+         8: "softmax: S0 ready", 12: "softmax: P0 written", 5: "epilogue: O in registers", 9: "softmax: S1 ready", 13: "softmax: P1 written",
+         6: "epilogue: tiles staged in smem", 10: "softmax: S2 ready", 14: "softmax: P2 written", 7: "epilogue: bulk stores issued", 11: "softmax: S3 ready",
+         15: "softmax: P3 written", 22: "softmax: S1 in registers", 23: "softmax: exp loop 1 issued", 16: "softmax: O final", 17: "epilogue stores done", 18: "TMEM freed (CTA end)"}
 print(f"{'phase':48s} {'median us':>10s} {'p10':>8s} {'p90':>8s}")
-for slot in [1, 2, 3, 4, 8, 12, 5, 9, 13, 6, 10, 14, 7, 11, 15, 16, 17, 18]:
+for slot in [1, 2, 3, 4, 8, 12, 9, 22, 23, 13, 10, 14, 11, 15, 16, 5, 6, 7, 17, 18]:
     d = (t[:, slot] - t[:, 0]) / ghz / 1e3
     print(f"{names[slot]:48s} {np.median(d):10.2f} {np.percentile(d, 10):8.2f} {np.percentile(d, 90):8.2f}")
 g0 = t[:, 19].min()
