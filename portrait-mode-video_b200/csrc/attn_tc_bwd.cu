@@ -239,9 +239,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int64_t ooff = ((int64_t)bidx * g.Nq + n) * ld_o + head * HD;
     // delta = rowsum(dO * O_pre) comes from attn_delta_kernel (coalesced; it was 18 % of this kernel when every thread
     // fetched its own two 192-byte rows)
-    float delta = 0.f, lse2 = 0.f;
+    float delta_s = 0.f, lse2 = 0.f;  // delta * scale, lse * log2(e)
     if (rvalid) {
-      delta = delta_in[(int64_t)bh * g.Nq + n];
+      delta_s = delta_in[(int64_t)bh * g.Nq + n] * g.scale;
       lse2 = lse[(int64_t)bh * g.Nq + n] * 1.4426950408889634f;
     }
     int hh = 0;
@@ -258,14 +258,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tc::tmem_ld32(tmem_s + lane_addr + b * HK + wh * 32, s);
           tc::tmem_ld32(tmem_dp + lane_addr + b * HK + wh * 32, dp);
           tc::tmem_ld_wait();
+          // No masking of keys >= Nk or queries >= Nq: TMA zero-fills those rows of K', V, Q' and dO, so a stray dS column
+          // multiplies a zero K' row in dQ' += dS K', and a stray query row has S = dP = delta = 0 (its dQ' is not stored).
+          // 4 instructions per score: FFMA, MUFU.EX2, FFMA, FMUL (+ the pack on the integer ALU).
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             float d[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              const int col = wh * 32 + 2 * i + h;
-              const float p = (rvalid && col < nv) ? tc::fast_ex2(fmaf(__uint_as_float(s[2 * i + h]), c, -lse2)) : 0.f;
-              d[h] = p * (__uint_as_float(dp[2 * i + h]) - delta) * g.scale;
+              const float p = tc::fast_ex2(fmaf(__uint_as_float(s[2 * i + h]), c, -lse2));
+              d[h] = p * fmaf(__uint_as_float(dp[2 * i + h]), g.scale, -delta_s);
             }
             pk[i] = tc::pack_bf16x2_alu(d[0], d[1]);
           }
@@ -460,7 +462,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int n = q0 + tid128;
         const bool ok = n < g.Nq;
         lse_t[tid128] = ok ? lse[(int64_t)bh * g.Nq + n] * 1.4426950408889634f : 0.f;
-        del_t[tid128] = ok ? delta[(int64_t)bh * g.Nq + n] : 0.f;
+        del_t[tid128] = ok ? delta[(int64_t)bh * g.Nq + n] * g.scale : 0.f;  // delta * scale
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight softmax warps only
       for (int half = 0; half < 2; ++half) {
@@ -477,12 +479,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
             float p[2], d[2];
+            // no masking of queries >= Nq: their Q' and dO rows are zero-filled by TMA, so P^T dO and dS^T Q' gain nothing
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              const int cl = wh * 32 + 2 * e + h;        // query inside the half
-              const int col = half * HK + cl;            // query inside the tile
-              p[h] = cl < nv ? tc::fast_ex2(fmaf(__uint_as_float(s[2 * e + h]), c, -lse_t[col])) : 0.f;
-              d[h] = p[h] * (__uint_as_float(dp[2 * e + h]) - del_t[col]) * g.scale;
+              const int col = half * HK + wh * 32 + 2 * e + h;  // query inside the tile
+              p[h] = tc::fast_ex2(fmaf(__uint_as_float(s[2 * e + h]), c, -lse_t[col]));
+              d[h] = p[h] * fmaf(__uint_as_float(dp[2 * e + h]), g.scale, -del_t[col]);
             }
             pk[e] = tc::pack_bf16x2_alu(p[0], p[1]);
             dk[e] = tc::pack_bf16x2_alu(d[0], d[1]);
