@@ -23,6 +23,22 @@
 // through the matrix descriptor only (layouts pinned by tests/test_tcgen05_probe.py).
 #include "tc_common.cuh"
 
+#ifdef PMV_ATTN_TRACE
+// Debug build only (scripts/attn_trace.py bwd): per-CTA cycle stamps of the dQ kernel's phases.
+constexpr int BTRACE_CTAS = 1024, BTRACE_SLOTS = 24;
+__device__ long long pmv_attn_bwd_trace_buf[BTRACE_CTAS * BTRACE_SLOTS];
+#define BTRACE(slot)                                                                                                  \
+  do {                                                                                                                \
+    const int cta_ = blockIdx.y * gridDim.x + blockIdx.x;                                                             \
+    if (cta_ < BTRACE_CTAS) pmv_attn_bwd_trace_buf[cta_ * BTRACE_SLOTS + (slot)] = clock64();                         \
+  } while (0)
+extern "C" int pmv_debug_attn_bwd_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, pmv_attn_bwd_trace_buf, sizeof(long long) * BTRACE_CTAS * BTRACE_SLOTS) == cudaSuccess ? 0 : 1;
+}
+#else
+#define BTRACE(slot) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int HD = PMV_HEAD_DIM;
@@ -47,11 +63,36 @@ template <int KD> struct BCfg {
 
 // K-major descriptor of k-step ks (16 columns) inside a [rows x KD] tile, starting `half` * 64 rows into the tile
 // (128B-swizzle blocks: 64 rows = 8192 B; the 64B-swizzle block of the bias columns: 64 rows = 4096 B)
-template <int KD> __device__ __forceinline__ uint64_t kmajor_desc(uint32_t base, int ks, int half = 0) {
-  if (ks < 8)
-    return tc::make_smem_desc(base + (uint32_t)(ks >> 2) * 16384 + (uint32_t)half * 8192 + (uint32_t)(ks & 3) * 32, 16, 1024, tc::SWIZZLE_128B);
-  return tc::make_smem_desc(base + 32768 + (uint32_t)half * 4096 + (uint32_t)(ks - 8) * 32, 16, 512, tc::SWIZZLE_64B);
+// ONE thread issues every MMA of a CTA (18 - 26 per half-tile here), and building two 64-bit descriptors from a byte
+// address per MMA (shift, mask, or, for both words) made that thread the bottleneck of both kernels: the softmax warps
+// waited 0.55 us per half for it (scripts/attn_trace_bwd.py).  The high word of a descriptor depends only on the layout
+// and the low word is (address >> 4) | (LBO >> 4) << 16, which is additive in the address: a tile's low words are made
+// once and each MMA adds a constant.
+struct KDesc { uint32_t lo128, lo64; };  // K-major [rows x KD] tile: 128B-swizzle blocks / the 64B-swizzle bias block
+__device__ __forceinline__ uint32_t desc_lo(uint64_t d) { return (uint32_t)d; }
+__device__ __forceinline__ uint32_t desc_hi(uint64_t d) { return (uint32_t)(d >> 32); }
+__device__ __forceinline__ uint64_t desc_join(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+__device__ __forceinline__ KDesc kdesc(uint32_t base) {
+  KDesc d;
+  d.lo128 = desc_lo(tc::make_smem_desc(base, 16, 1024, tc::SWIZZLE_128B));
+  d.lo64 = desc_lo(tc::make_smem_desc(base + 32768, 16, 512, tc::SWIZZLE_64B));
+  return d;
 }
+template <int KD> __device__ __forceinline__ uint64_t kmajor_desc(KDesc d, int ks, int half = 0) {
+  if (ks < 8)
+    return desc_join(d.lo128 + (uint32_t)((ks >> 2) * 1024 + half * 512 + (ks & 3) * 2), desc_hi(tc::make_smem_desc(0, 16, 1024, tc::SWIZZLE_128B)));
+  return desc_join(d.lo64 + (uint32_t)(half * 256 + (ks - 8) * 2), desc_hi(tc::make_smem_desc(0, 16, 512, tc::SWIZZLE_64B)));
+}
+// MN-major reads of the same tiles (B operand of the "retire" products): 16-row k-steps are 2048 B (1024 B) apart
+struct MDesc { uint32_t lo128, lo64; };
+__device__ __forceinline__ MDesc mdesc(uint32_t base) {
+  MDesc d;
+  d.lo128 = desc_lo(tc::make_smem_desc(base, 16384, 1024, tc::SWIZZLE_128B));
+  d.lo64 = desc_lo(tc::make_smem_desc(base + 32768, 8192, 512, tc::SWIZZLE_64B));
+  return d;
+}
+__device__ __forceinline__ uint64_t mn128_desc(MDesc d, int kk) { return desc_join(d.lo128 + (uint32_t)kk * 128, desc_hi(tc::make_smem_desc(0, 16384, 1024, tc::SWIZZLE_128B))); }
+__device__ __forceinline__ uint64_t mn64_desc(MDesc d, int kk) { return desc_join(d.lo64 + (uint32_t)kk * 64, desc_hi(tc::make_smem_desc(0, 8192, 512, tc::SWIZZLE_64B))); }
 
 __device__ __forceinline__ void load_tile_qk(uint8_t* dst, const CUtensorMap* m128, const CUtensorMap* m64, int kd, int row0,
                                              int bh, uint64_t* bar) {
@@ -130,6 +171,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) BTRACE(0);
   const int bh = blockIdx.y;
   const int bidx = bh / g.heads, head = bh - bidx * g.heads;
   const int q0 = blockIdx.x * BT;
@@ -153,6 +195,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dq = tmem_base + 256;  // S / dP: buffer b at + 64 b
   pdl_wait();  // the prologue above overlaps the previous kernel's tail
+  if (threadIdx.x == 0) BTRACE(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -173,7 +216,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t sq_addr = tc::smem_u32(sQ), sdo_addr = tc::smem_u32(sdO);
+      const KDesc dQt = kdesc(tc::smem_u32(sQ)), ddO = kdesc(tc::smem_u32(sdO));
       const uint32_t idesc_128 = tc::make_idesc_bf16(BT, 128, false, true);
       const uint32_t idesc_32 = tc::make_idesc_bf16(BT, 32, false, true);
       tc::mbar_wait(q_full, 0);
@@ -182,7 +225,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       bool have_prev = false, first_dq = true;
       int p_b = 0, p_hh = 0, p_nks = 0, p_half = 0, p_st = 0;
       bool p_last = false;
-      uint32_t p_sk = 0;
+      MDesc p_sk{0, 0};
       // dQ' += dS K' for the half recorded in p_*: A = dS (TMEM, packed bf16), B = K' rows of that half read MN-major
       auto retire = [&]() {
         tc::mbar_wait(&ds_full[p_b], (uint32_t)((p_hh >> 1) & 1));
@@ -192,8 +235,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           first_dq = false;
           const uint32_t a = tmem_s + p_b * HK + packed_col(ks);
           const int kk = 4 * p_half + ks;
-          tc::umma_ts(tmem_dq, a, tc::make_smem_desc(p_sk + kk * 2048, 16384, 1024, tc::SWIZZLE_128B), idesc_128, acc);
-          if (KD == 160) tc::umma_ts(tmem_dq + 128, a, tc::make_smem_desc(p_sk + 32768 + kk * 1024, 8192, 512, tc::SWIZZLE_64B), idesc_32, acc);
+          tc::umma_ts(tmem_dq, a, mn128_desc(p_sk, kk), idesc_128, acc);
+          if (KD == 160) tc::umma_ts(tmem_dq + 128, a, mn64_desc(p_sk, kk), idesc_32, acc);
         }
         if (p_last) tc::umma_commit(&kv_empty[p_st]);
       };
@@ -203,7 +246,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc::tc_fence_after();
         const int nvalid = min(BT, g.Nk - j * BT);
         const uint32_t sk_addr = tc::smem_u32(sStage + st * Cfg::STAGE_BYTES);
-        const uint32_t sv_addr = sk_addr + Cfg::QK_BYTES;
+        const KDesc dK = kdesc(sk_addr), dV = kdesc(sk_addr + Cfg::QK_BYTES);
+        const MDesc mK = mdesc(sk_addr);
         for (int half = 0; half < 2; ++half) {
           const int nv = min(HK, nvalid - HK * half);
           if (nv <= 0) break;
@@ -212,14 +256,14 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const uint32_t idesc_s = tc::make_idesc_bf16(BT, n16, false, false);
 #pragma unroll
           for (int ks = 0; ks < KD / 16; ++ks)  // S = Q' K'^T (keys of this half)
-            tc::umma_ss(tmem_s + b * HK, kmajor_desc<KD>(sq_addr, ks), kmajor_desc<KD>(sk_addr, ks, half), idesc_s, ks > 0);
+            tc::umma_ss(tmem_s + b * HK, kmajor_desc<KD>(dQt, ks), kmajor_desc<KD>(dK, ks, half), idesc_s, ks > 0);
 #pragma unroll
           for (int ks = 0; ks < HD / 16; ++ks)  // dP = dO V^T
-            tc::umma_ss(tmem_dp + b * HK, kmajor_desc<128>(sdo_addr, ks), kmajor_desc<128>(sv_addr, ks, half), idesc_s, ks > 0);
+            tc::umma_ss(tmem_dp + b * HK, kmajor_desc<128>(ddO, ks), kmajor_desc<128>(dV, ks, half), idesc_s, ks > 0);
           tc::umma_commit(&sdp_full[b]);
           if (have_prev) retire();
           have_prev = true;
-          p_b = b; p_hh = hh; p_nks = n16 >> 4; p_half = half; p_st = st; p_sk = sk_addr;
+          p_b = b; p_hh = hh; p_nks = n16 >> 4; p_half = half; p_st = st; p_sk = mK;
           p_last = (half == 1) || (nvalid <= HK);
           ++hh;
         }
@@ -253,6 +297,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int b = hh & 1;
         tc::mbar_wait(&sdp_full[b], (uint32_t)((hh >> 1) & 1));
         tc::tc_fence_after();
+        if (warp == 4 && lane == 0 && hh < 8) BTRACE(2 + 2 * hh);
         if (wh * 32 < nv) {
           uint32_t s[32], dp[32], pk[16];
           tc::tmem_ld32(tmem_s + lane_addr + b * HK + wh * 32, s);
@@ -277,12 +322,14 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&ds_full[b]);
+        if (warp == 4 && lane == 0 && hh < 8) BTRACE(3 + 2 * hh);
         ++hh;
       }
     }
     // epilogue: dQ' (+ dO on the first 96 columns for rows >= 1: residual pooling) -> bf16
     tc::mbar_wait(dq_final, 0);
     tc::tc_fence_after();
+    if (warp == 4 && lane == 0) BTRACE(18);
     bf16* dqp = dq_aug + ((int64_t)bh * g.Nq + n) * g.ld_qk;
     const bool add_do = g.residual && n >= 1;
 #pragma unroll 1
@@ -313,10 +360,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
       }
     }
+    if (warp == 4 && lane == 0) BTRACE(19);
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 2) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 512); }
+  if (warp == 2) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 512); if (lane == 0) BTRACE(20); }
 }
 
 // ================================================================================================ dK / dV kernel
@@ -392,7 +440,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t sk_addr = tc::smem_u32(sK), sv_addr = tc::smem_u32(sV);
+      const KDesc dKt = kdesc(tc::smem_u32(sK)), dVt = kdesc(tc::smem_u32(sV));
       tc::mbar_wait(k_full, 0);
       tc::tc_fence_after();
       const uint32_t idesc_o = tc::make_idesc_bf16(BT, HD, false, true);  // N = 96 channels, B read MN-major
@@ -400,7 +448,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       bool have_prev = false, first_acc = true;
       int p_b = 0, p_hh = 0, p_nks = 0, p_half = 0, p_st = 0;
       bool p_last = false;
-      uint32_t p_sq = 0, p_sdo = 0;
+      MDesc p_sq{0, 0}, p_sdo{0, 0};
       // dV += P^T dO ; dK += dS^T Q'[:, :96] for the recorded half (B tiles read MN-major: 16-query steps are 2048 B apart)
       auto retire = [&]() {
         tc::mbar_wait(&pds_full[p_b], (uint32_t)((p_hh >> 1) & 1));
@@ -409,8 +457,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const uint32_t acc = first_acc ? 0u : 1u;
           first_acc = false;
           const int kk = 4 * p_half + ks;
-          tc::umma_ts(tmem_dv, tmem_st + p_b * HK + packed_col(ks), tc::make_smem_desc(p_sdo + kk * 2048, 16384, 1024, tc::SWIZZLE_128B), idesc_o, acc);
-          tc::umma_ts(tmem_dk, tmem_dpt + p_b * HK + packed_col(ks), tc::make_smem_desc(p_sq + kk * 2048, 16384, 1024, tc::SWIZZLE_128B), idesc_o, acc);
+          tc::umma_ts(tmem_dv, tmem_st + p_b * HK + packed_col(ks), mn128_desc(p_sdo, kk), idesc_o, acc);
+          tc::umma_ts(tmem_dk, tmem_dpt + p_b * HK + packed_col(ks), mn128_desc(p_sq, kk), idesc_o, acc);
         }
         if (p_last) tc::umma_commit(&q_empty[p_st]);
       };
@@ -421,7 +469,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tc::tc_fence_after();
         const int nqv = min(BT, g.Nq - q0);
         const uint32_t sq_addr = tc::smem_u32(sStage + st * Cfg::STAGE_BYTES);
-        const uint32_t sdo_addr = sq_addr + Cfg::QK_BYTES;
+        const KDesc dQs = kdesc(sq_addr), dOs = kdesc(sq_addr + Cfg::QK_BYTES);
+        const MDesc mQ = mdesc(sq_addr), mdO = mdesc(sq_addr + Cfg::QK_BYTES);
         for (int half = 0; half < 2; ++half) {
           const int nv = min(HK, nqv - HK * half);
           if (nv <= 0) break;
@@ -430,14 +479,14 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const uint32_t idesc_s = tc::make_idesc_bf16(BT, n16, false, false);
 #pragma unroll
           for (int ks = 0; ks < KD / 16; ++ks)  // S^T = K' Q'^T (queries of this half)
-            tc::umma_ss(tmem_st + b * HK, kmajor_desc<KD>(sk_addr, ks), kmajor_desc<KD>(sq_addr, ks, half), idesc_s, ks > 0);
+            tc::umma_ss(tmem_st + b * HK, kmajor_desc<KD>(dKt, ks), kmajor_desc<KD>(dQs, ks, half), idesc_s, ks > 0);
 #pragma unroll
           for (int ks = 0; ks < HD / 16; ++ks)  // dP^T = V dO^T
-            tc::umma_ss(tmem_dpt + b * HK, kmajor_desc<128>(sv_addr, ks), kmajor_desc<128>(sdo_addr, ks, half), idesc_s, ks > 0);
+            tc::umma_ss(tmem_dpt + b * HK, kmajor_desc<128>(dVt, ks), kmajor_desc<128>(dOs, ks, half), idesc_s, ks > 0);
           tc::umma_commit(&sdp_full[b]);
           if (have_prev) retire();
           have_prev = true;
-          p_b = b; p_hh = hh; p_nks = n16 >> 4; p_half = half; p_st = st; p_sq = sq_addr; p_sdo = sdo_addr;
+          p_b = b; p_hh = hh; p_nks = n16 >> 4; p_half = half; p_st = st; p_sq = mQ; p_sdo = mdO;
           p_last = (half == 1) || (nqv <= HK);
           ++hh;
         }
