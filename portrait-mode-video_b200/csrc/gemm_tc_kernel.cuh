@@ -232,6 +232,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0 && leader) {
       const uint32_t idesc = tc::make_idesc_bf16(BM_TILE, BN, A_MN, B_MN);
+      // One thread issues every MMA; at BN = 96 an MMA is ~48 tensor cycles, so the issue loop itself must be short.
+      // A descriptor's high word depends only on the layout and its low word is additive in the address: both operands'
+      // low words are made once for stage 0, a stage adds STAGE_BYTES >> 4 and a 16-wide k-step 2 (K-major) or 128
+      // (MN-major: 2048 B).
+      const uint64_t proto_a = A_MN ? tc::make_smem_desc(tc::smem_u32(smem), 8192, 1024, tc::SWIZZLE_128B)
+                                    : tc::make_smem_desc(tc::smem_u32(smem), 16, 1024, tc::SWIZZLE_128B);
+      const uint64_t proto_b = B_MN ? tc::make_smem_desc(tc::smem_u32(smem) + Cfg::A_BYTES, 8192, 1024, tc::SWIZZLE_128B)
+                                    : tc::make_smem_desc(tc::smem_u32(smem) + Cfg::A_BYTES, 16, 1024, tc::SWIZZLE_128B);
+      const uint32_t hi_a = (uint32_t)(proto_a >> 32), hi_b = (uint32_t)(proto_b >> 32);
+      const uint32_t lo_a0 = (uint32_t)proto_a, lo_b0 = (uint32_t)proto_b;
+      constexpr uint32_t STEP_A = A_MN ? 128u : 2u, STEP_B = B_MN ? 128u : 2u, STAGE16 = (uint32_t)Cfg::STAGE_BYTES >> 4;
+      auto mma = [&](uint32_t tmem_d, uint32_t lo_a, uint32_t lo_b, uint32_t accumulate) {
+        const uint64_t da = ((uint64_t)hi_a << 32) | lo_a, db = ((uint64_t)hi_b << 32) | lo_b;
+        if (PAIR) tc::umma_ss2(tmem_d, da, db, idesc, accumulate);
+        else tc::umma_ss(tmem_d, da, db, idesc, accumulate);
+      };
       int stage = 0;
       uint32_t phase = 0;
       int64_t it = 0;
@@ -244,21 +260,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc::mbar_wait(&acc_empty[as], aphase ^ 1);
         tc::tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * Cfg::ACC_COLS;
-        for (int64_t kb = kbeg; kb < kend; kb += BK) {
+        const int nkb = (int)((kend - kbeg + BK - 1) / BK);
+        const int tail = (int)(kend - kbeg) - (nkb - 1) * BK;  // reduction length of the last block (1..BK)
+        for (int kbi = 0; kbi < nkb; ++kbi) {
           tc::mbar_wait(&full_bar[stage], phase);
           tc::tc_fence_after();
-          const uint32_t sa = tc::smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t sb = sa + Cfg::A_BYTES;
-          const int64_t rem = kend - kb;
-          const int nk = rem >= BK ? BK / 16 : (int)((rem + 15) / 16);
-#pragma unroll 4
-          for (int k = 0; k < nk; ++k) {
-            const uint64_t da = A_MN ? tc::make_smem_desc(sa + k * 2048, 8192, 1024, tc::SWIZZLE_128B)
-                                     : tc::make_smem_desc(sa + k * 32, 16, 1024, tc::SWIZZLE_128B);
-            const uint64_t db = B_MN ? tc::make_smem_desc(sb + k * 2048, 8192, 1024, tc::SWIZZLE_128B)
-                                     : tc::make_smem_desc(sb + k * 32, 16, 1024, tc::SWIZZLE_128B);
-            if (PAIR) tc::umma_ss2(tmem_d, da, db, idesc, (kb > kbeg || k > 0) ? 1u : 0u);
-            else tc::umma_ss(tmem_d, da, db, idesc, (kb > kbeg || k > 0) ? 1u : 0u);
+          const uint32_t lo_a = lo_a0 + (uint32_t)stage * STAGE16, lo_b = lo_b0 + (uint32_t)stage * STAGE16;
+          if (kbi + 1 < nkb || tail == BK) {
+            mma(tmem_d, lo_a, lo_b, kbi > 0 ? 1u : 0u);
+            mma(tmem_d, lo_a + STEP_A, lo_b + STEP_B, 1u);
+            mma(tmem_d, lo_a + 2 * STEP_A, lo_b + 2 * STEP_B, 1u);
+            mma(tmem_d, lo_a + 3 * STEP_A, lo_b + 3 * STEP_B, 1u);
+          } else {
+            const int nk = (tail + 15) / 16;
+            for (int k = 0; k < nk; ++k) mma(tmem_d, lo_a + k * STEP_A, lo_b + k * STEP_B, (kbi > 0 || k > 0) ? 1u : 0u);
           }
           // frees the smem stage (PAIR: in both CTAs) once these MMAs have read it
           if (PAIR) tc::umma_commit2_mc(&empty_bar[stage], 3); else tc::umma_commit(&empty_bar[stage]);
