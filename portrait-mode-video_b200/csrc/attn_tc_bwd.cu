@@ -230,14 +230,23 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       auto retire = [&]() {
         tc::mbar_wait(&ds_full[p_b], (uint32_t)((p_hh >> 1) & 1));
         tc::tc_fence_after();
-        for (int ks = 0; ks < p_nks; ++ks) {
-          const uint32_t acc = first_dq ? 0u : 1u;
-          first_dq = false;
-          const uint32_t a = tmem_s + p_b * HK + packed_col(ks);
-          const int kk = 4 * p_half + ks;
-          tc::umma_ts(tmem_dq, a, mn128_desc(p_sk, kk), idesc_128, acc);
-          if (KD == 160) tc::umma_ts(tmem_dq + 128, a, mn64_desc(p_sk, kk), idesc_32, acc);
+        const uint32_t a0 = tmem_s + p_b * HK;
+        MDesc d = p_sk;  // advanced to the half's first k-step: a k-step is 128 (64) descriptor units
+        d.lo128 += (uint32_t)(4 * p_half) * 128;
+        d.lo64 += (uint32_t)(4 * p_half) * 64;
+        auto one = [&](int ks, uint32_t acc) {
+          tc::umma_ts(tmem_dq, a0 + packed_col(ks), mn128_desc(d, ks), idesc_128, acc);
+          if (KD == 160) tc::umma_ts(tmem_dq + 128, a0 + packed_col(ks), mn64_desc(d, ks), idesc_32, acc);
+        };
+        if (p_nks == 4) {  // full half: straight-line issue (the loop form cost ~80 ns per MMA on the single issuing thread)
+          one(0, first_dq ? 0u : 1u);
+          one(1, 1u);
+          one(2, 1u);
+          one(3, 1u);
+        } else {
+          for (int ks = 0; ks < p_nks; ++ks) one(ks, (first_dq && ks == 0) ? 0u : 1u);
         }
+        first_dq = false;
         if (p_last) tc::umma_commit(&kv_empty[p_st]);
       };
       for (int j = 0; j < ntiles; ++j) {
@@ -254,6 +263,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const int n16 = (nv + 15) & ~15;
           const int b = hh & 1;
           const uint32_t idesc_s = tc::make_idesc_bf16(BT, n16, false, false);
+          if (hh == 2) BTRACE(21);
 #pragma unroll
           for (int ks = 0; ks < KD / 16; ++ks)  // S = Q' K'^T (keys of this half)
             tc::umma_ss(tmem_s + b * HK, kmajor_desc<KD>(dQt, ks), kmajor_desc<KD>(dK, ks, half), idesc_s, ks > 0);
@@ -261,7 +271,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (int ks = 0; ks < HD / 16; ++ks)  // dP = dO V^T
             tc::umma_ss(tmem_dp + b * HK, kmajor_desc<128>(ddO, ks), kmajor_desc<128>(dV, ks, half), idesc_s, ks > 0);
           tc::umma_commit(&sdp_full[b]);
+          if (hh == 2) BTRACE(22);
           if (have_prev) retire();
+          if (hh == 2) BTRACE(23);
           have_prev = true;
           p_b = b; p_hh = hh; p_nks = n16 >> 4; p_half = half; p_st = st; p_sk = mK;
           p_last = (half == 1) || (nvalid <= HK);
@@ -453,13 +465,23 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       auto retire = [&]() {
         tc::mbar_wait(&pds_full[p_b], (uint32_t)((p_hh >> 1) & 1));
         tc::tc_fence_after();
-        for (int ks = 0; ks < p_nks; ++ks) {
-          const uint32_t acc = first_acc ? 0u : 1u;
-          first_acc = false;
-          const int kk = 4 * p_half + ks;
-          tc::umma_ts(tmem_dv, tmem_st + p_b * HK + packed_col(ks), mn128_desc(p_sdo, kk), idesc_o, acc);
-          tc::umma_ts(tmem_dk, tmem_dpt + p_b * HK + packed_col(ks), mn128_desc(p_sq, kk), idesc_o, acc);
+        const uint32_t ap = tmem_st + p_b * HK, ad = tmem_dpt + p_b * HK;
+        MDesc d_do = p_sdo, d_q = p_sq;
+        d_do.lo128 += (uint32_t)(4 * p_half) * 128;
+        d_q.lo128 += (uint32_t)(4 * p_half) * 128;
+        auto one = [&](int ks, uint32_t acc) {
+          tc::umma_ts(tmem_dv, ap + packed_col(ks), mn128_desc(d_do, ks), idesc_o, acc);
+          tc::umma_ts(tmem_dk, ad + packed_col(ks), mn128_desc(d_q, ks), idesc_o, acc);
+        };
+        if (p_nks == 4) {  // full half: straight-line issue
+          one(0, first_acc ? 0u : 1u);
+          one(1, 1u);
+          one(2, 1u);
+          one(3, 1u);
+        } else {
+          for (int ks = 0; ks < p_nks; ++ks) one(ks, (first_acc && ks == 0) ? 0u : 1u);
         }
+        first_acc = false;
         if (p_last) tc::umma_commit(&q_empty[p_st]);
       };
       for (int i = 0; i < nq_tiles; ++i) {

@@ -28,8 +28,8 @@ order = [1]
 for hh in range(7):
     names[2 + 2 * hh] = f"softmax: S/dP of half {hh} ready"; names[3 + 2 * hh] = f"softmax: dS of half {hh} written"
     order += [2 + 2 * hh, 3 + 2 * hh]
-names.update({18: "softmax: dQ final", 19: "epilogue stores issued", 20: "TMEM freed (CTA end)"})
-order += [18, 19, 20]
+names.update({21: "MMA thread: starts issuing S/dP of half 2", 22: "MMA thread: S/dP of half 2 issued + committed", 23: "MMA thread: dQ += dS K of half 1 issued", 18: "softmax: dQ final", 19: "epilogue stores issued", 20: "TMEM freed (CTA end)"})
+order += [21, 22, 23, 18, 19, 20]
 print(f"{'phase':40s} {'median us':>10s} {'p10':>8s} {'p90':>8s}")
 for slot in order:
     d = (t[:, slot] - t[:, 0]) / ghz / 1e3
