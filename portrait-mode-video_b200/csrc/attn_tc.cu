@@ -151,6 +151,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t sq_addr = tc::smem_u32(sQ);
+      const uint32_t hi128 = (uint32_t)(tc::make_smem_desc(0, 16, 1024, tc::SWIZZLE_128B) >> 32);
+      const uint32_t hi64 = (uint32_t)(tc::make_smem_desc(0, 16, 512, tc::SWIZZLE_64B) >> 32);
+      const uint32_t lq128 = (uint32_t)tc::make_smem_desc(sq_addr, 16, 1024, tc::SWIZZLE_128B);
+      const uint32_t lq64 = (uint32_t)tc::make_smem_desc(sq_addr + 32768, 16, 512, tc::SWIZZLE_64B);
       auto issue_s = [&](int j) {
         const int st = j % NST;
         tc::mbar_wait(&kv_full[st], (j / NST) & 1);
@@ -160,17 +164,21 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const uint32_t idesc = tc::make_idesc_bf16(BQ, (nvalid + 15) & ~15, false, false);
         const uint32_t sk_addr = tc::smem_u32(sStage + st * Cfg::STAGE_BYTES);
         const uint32_t tmem_s = tmem_base + (uint32_t)(j & 1) * 128;
+        // descriptor low words are additive in the address (>> 4): one per tile, a constant per MMA (the single issuing
+        // thread is on the critical path of the first score tile and of the last P V)
+        const uint32_t lk128 = (uint32_t)tc::make_smem_desc(sk_addr, 16, 1024, tc::SWIZZLE_128B);
+        const uint32_t lk64 = (uint32_t)tc::make_smem_desc(sk_addr + 32768, 16, 512, tc::SWIZZLE_64B);
 #pragma unroll
         for (int ks = 0; ks < KD / 16; ++ks) {
           uint64_t da, db;
           if (ks < 8) {
-            const uint32_t off = (uint32_t)(ks >> 2) * 16384 + (uint32_t)(ks & 3) * 32;
-            da = tc::make_smem_desc(sq_addr + off, 16, 1024, tc::SWIZZLE_128B);
-            db = tc::make_smem_desc(sk_addr + off, 16, 1024, tc::SWIZZLE_128B);
+            const uint32_t off = (uint32_t)(ks >> 2) * 1024 + (uint32_t)(ks & 3) * 2;
+            da = ((uint64_t)hi128 << 32) | (lq128 + off);
+            db = ((uint64_t)hi128 << 32) | (lk128 + off);
           } else {
-            const uint32_t off = 32768 + (uint32_t)(ks - 8) * 32;
-            da = tc::make_smem_desc(sq_addr + off, 16, 512, tc::SWIZZLE_64B);
-            db = tc::make_smem_desc(sk_addr + off, 16, 512, tc::SWIZZLE_64B);
+            const uint32_t off = (uint32_t)(ks - 8) * 2;
+            da = ((uint64_t)hi64 << 32) | (lq64 + off);
+            db = ((uint64_t)hi64 << 32) | (lk64 + off);
           }
           tc::umma_ss(tmem_s, da, db, idesc, ks > 0);
         }
@@ -189,9 +197,12 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int nks = (nvalid + 15) >> 4;
         const uint32_t sv_addr = tc::smem_u32(sStage + (j % NST) * Cfg::STAGE_BYTES + Cfg::QK_BYTES);
         const uint32_t tmem_p = tmem_base + (uint32_t)(j & 1) * 128;
-        for (int ks = 0; ks < nks; ++ks) {
-          const uint64_t db = tc::make_smem_desc(sv_addr + ks * 1024, 8192, 512, tc::SWIZZLE_64B);
-          tc::umma_ts(tmem_o, tmem_p + ks * 8, db, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
+        const uint64_t dv0 = tc::make_smem_desc(sv_addr, 8192, 512, tc::SWIZZLE_64B);  // + 64 per 16-key step (1024 B)
+        if (nks == 8) {  // full tile: straight-line issue
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) tc::umma_ts(tmem_o, tmem_p + ks * 8, dv0 + (uint64_t)(ks * 64), idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
+        } else {
+          for (int ks = 0; ks < nks; ++ks) tc::umma_ts(tmem_o, tmem_p + ks * 8, dv0 + (uint64_t)(ks * 64), idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
         }
         tc::umma_commit(&kv_empty[j % NST]);
         tc::umma_commit(o_done);
