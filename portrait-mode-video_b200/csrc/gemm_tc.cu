@@ -37,18 +37,31 @@ static int pick_kind(const EpiDev& e) {
   return scale ? EK_GENERIC : EK_PLAIN;
 }
 
-static int pick_bn(int64_t M, int64_t N, int splits) {
-  // wave-quantisation model: cost = waves over 148 SMs x (tile width + fixed per-tile overhead in columns);
-  // ties go to the wider tile (better operand reuse per byte staged)
+static int pick_bn(int64_t M, int64_t N, int64_t K, int splits) {
+  // Cost model in SM cycles, max of two rates plus a per-wave constant:
+  //   tensor : waves over 148 SMs x k-blocks x 4 MMAs x BN / 2 cycles (a 128 x BN x 16 MMA)
+  //   L2     : every column tile re-reads A, every row tile re-reads B; the GEMMs of this model saturate at ~9 TB/s of
+  //            L2 -> SM traffic (4580 B per cycle): 128 x 96 tiles of the K = 1152 / 1536 dgrad and fc2 GEMMs measured exactly
+  //            bytes / 9 TB/s (22 and 30 us), which the wave count alone (the previous model) could not see.
+  // Ties go to the wider tile.
   const int cands[4] = {256, 192, 128, 96};
   int best = 96;
   double best_cost = -1.0;
   const int64_t tiles_m = ceil_div64(M, BM);
+  const int64_t kb = ceil_div64(ceil_div64(K, splits), BK);
   for (int i = 0; i < 4; ++i) {
-    const int64_t tiles = tiles_m * ceil_div64(N, cands[i]) * splits;
+    const int64_t tiles_n = ceil_div64(N, cands[i]);
+    const int64_t tiles = tiles_m * tiles_n * splits;
     const int64_t waves = ceil_div64(tiles, 148);
-    const double cost = (double)waves * (cands[i] + 48);
+    const double tensor = (double)waves * (double)kb * 4.0 * (cands[i] / 2.0);
+    const double bytes = 2.0 * (double)K * ((double)tiles_n * (double)M + (double)tiles_m * (double)N);
+    const double l2 = bytes / 4580.0;
+    const double cost = (tensor > l2 ? tensor : l2) + (double)waves * (cands[i] * 6.0 + 600.0);
     if (best_cost < 0 || cost < best_cost - 1e-9) { best_cost = cost; best = cands[i]; }
+  }
+  if (const char* ev = std::getenv("PMV_GEMM_BN")) {  // experiments: force a tile width
+    const int f = atoi(ev);
+    if (f == 96 || f == 128 || f == 192 || f == 256) best = f;
   }
   return best;
 }
@@ -63,7 +76,7 @@ int gemm_tc_launch(int layout, const void* A, int64_t lda, const void* B, int64_
   PMV_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "gemm(tc): operands must be 16-byte aligned");
   PMV_CHECK_ARG(layout != PMV_GEMM_NT_REDUCE_M || out_dtype == PMV_F32, "gemm(tc): wgrad output must be fp32");
   if (split_k < 1) split_k = 1;
-  const int BN = pick_bn(MM, NN, split_k);
+  const int BN = pick_bn(MM, NN, KK, split_k);
   CUtensorMap tmA, tmB;
   int rc;
   if (layout == PMV_GEMM_TN) {
