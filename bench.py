@@ -358,6 +358,9 @@ def main():
     # per-kernel CUDA-event times over two more passes of the same step (events on the launching stream)
     with ops.record_kernels() as rec:
         for _ in range(2):
+            # hold the GPU back while the host enqueues the eager step (~30 ms of Python for ~15 ms of kernels): otherwise an
+            # event pair also times the wait for the next launch to arrive and every kernel looks ~20 % slower than it is
+            torch.cuda._sleep(int(0.08 * 1.9e9))
             eager_step(clips, labels)
         torch.cuda.synchronize()
         roof, shares, detail = summarize_kernels(rec, peaks)
