@@ -190,8 +190,8 @@ int pmv_relpos_augment_q(void* q_aug, int64_t ld, const float* rel_h, const floa
                          int BH, int qt, int qh, int qw, int kt, int kh, int kw,
                          float inv_scale, int dtype, int tc, void* stream);
 int pmv_relpos_augment_k(void* k_aug, int64_t ld, int BH, int kt, int kh, int kw, int dtype, void* stream);
-/* Backward of augment_q: given dQ' (same layout), adds the table gradients into d_rel (fp32
- * [rows_h + rows_w + rows_t][96]: the three tables stacked in that order) and adds the bias path's
+/* Backward of augment_q: given dQ' (same layout), writes the table gradients to d_rel (fp32
+ * [rows_h + rows_w + rows_t][96]: the three tables stacked in that order; OVERWRITTEN) and adds the bias path's
  * contribution to dq in place (columns [0,96) of dq_aug, non-cls rows).
  * ws: workspace of pmv_relpos_bwd_workspace_bytes() bytes (stacked tables, their gradient, the dense dRQ;
  * both products run through pmv_gemm). */

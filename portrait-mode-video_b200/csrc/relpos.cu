@@ -123,32 +123,35 @@ __global__ void __launch_bounds__(SC_WARPS * 32) relpos_scatter_kernel(const T* 
   }
 }
 
-// d_rel[i] += inv_scale * dcat[i]
+// d_rel[i] = inv_scale * dcat[i]
 __global__ void __launch_bounds__(256) relpos_dtab_kernel(float* __restrict__ d_rel, const float* __restrict__ dcat, int n, float inv_scale) {
   pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) d_rel[i] += inv_scale * dcat[i];
+  if (i < n) d_rel[i] = inv_scale * dcat[i];
 }
 
+// K'[row, 96 + j] = 1 where j is the key's h, KH + w or KH + KW + t coordinate, else 0 (zero row for the cls key).
+// One warp per key row, lanes = the augmented columns (the element-per-thread form paid a 64-bit div / mod per element:
+// 7 us for 0.4 M elements).
 template <typename T>
 __global__ void __launch_bounds__(256) relpos_augment_k_kernel(T* __restrict__ k_aug, int64_t ld, int64_t BH, int kt, int kh, int kw) {
   pdl_wait();
   const int aug = (int)ld - HD;
   const int Nk = kt * kh * kw + 1;
-  const int64_t total = BH * Nk * aug;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int j = (int)(i % aug);
-    const int64_t row = i / aug;
-    const int n = (int)(row % Nk);
-    float v = 0.f;
+  const int rows = (int)(BH * Nk);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
+    const int n = row % Nk;
+    int c0 = -1, c1 = -1, c2 = -1;
     if (n > 0) {
       int l = n - 1;
       const int iw = l % kw; l /= kw;
       const int ih = l % kh;
       const int it = l / kh;
-      v = (j == ih || j == kh + iw || j == kh + kw + it) ? 1.f : 0.f;
+      c0 = ih; c1 = kh + iw; c2 = kh + kw + it;
     }
-    k_aug[row * ld + HD + j] = from_f32<T>(v);
+    T* dst = k_aug + (int64_t)row * ld + HD;
+    for (int j = lane; j < aug; j += 32) dst[j] = from_f32<T>((j == c0 || j == c1 || j == c2) ? 1.f : 0.f);
   }
 }
 
@@ -200,8 +203,9 @@ extern "C" int pmv_relpos_augment_q(void* q_aug, int64_t ld, const float* rel_h,
 extern "C" int pmv_relpos_augment_k(void* k_aug, int64_t ld, int BH, int kt, int kh, int kw, int dtype, void* stream) {
   PMV_CHECK_ARG(ld >= HD + kh + kw + kt, "relpos: ld too small");
   if (ld == HD) return PMV_OK;
-  const int64_t total = (int64_t)BH * (kt * kh * kw + 1) * (ld - HD);
-  int64_t blocks = ceil_div64(total, 256);
+  const int64_t rows = (int64_t)BH * (kt * kh * kw + 1);
+  PMV_CHECK_ARG(rows < (1ll << 31), "relpos: too many key rows");
+  int64_t blocks = ceil_div64(rows, 8);
   if (blocks > 148 * 8) blocks = 148 * 8;
   PMV_DISPATCH_DTYPE(dtype, T, (pmv_launch(relpos_augment_k_kernel<T>, (unsigned)blocks, 256, 0, (cudaStream_t)stream, (T*)k_aug, ld, BH, kt, kh, kw)));
   PMV_CHECK_LAUNCH();
@@ -215,7 +219,7 @@ extern "C" int64_t pmv_relpos_bwd_workspace_bytes(int BH, int qt, int qh, int qw
   return 2 * align256(np * HD * 4) + align256(M * np * 4);
 }
 
-/* d_rel: [rows_h + rows_w + rows_t][96] fp32 (the three tables stacked), added to. */
+/* d_rel: [rows_h + rows_w + rows_t][96] fp32 (the three tables stacked), OVERWRITTEN. */
 extern "C" int pmv_relpos_augment_q_bwd(void* dq_aug, const void* q_aug, int64_t ld, const float* rel_h, const float* rel_w,
                                         const float* rel_t, const int32_t* idx_h, const int32_t* idx_w, const int32_t* idx_t,
                                         float* d_rel, float* ws,

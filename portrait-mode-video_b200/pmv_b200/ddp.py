@@ -73,6 +73,9 @@ class GradAllReducer:
         return len(self.buckets)
 
     def zero_grad(self):
+        if self.device.type == "cuda":
+            from . import ops
+            ops.ZERO_ARENA.reset(self.device)  # one fill for all split-K weight gradients of the coming step
         for b in self.buckets:
             for p in b.params:
                 p.grad = None

@@ -136,13 +136,50 @@ def _pick_split(rows: int, n1: int, n2: int) -> int:
     return max(1, min(want, rows // 512 if rows >= 512 else 1))
 
 
+class ZeroArena:
+    """Pre-zeroed fp32 memory for the split-K weight gradients of one step.  ``reset()`` (called from
+    GradAllReducer.zero_grad at the start of a step) clears the whole arena with ONE fill and rewinds it; ``take(n)`` hands
+    out the next n zeroed floats, or None once the arena is used up - it never hands out memory that was not cleared since
+    the last reset, so forgetting reset() only costs the fallback (a torch.zeros per gradient: ~80 fill launches per
+    MViTv2-S step).  The arena sizes itself from the demand of the previous step."""
+
+    def __init__(self):
+        self.buf = None
+        self.used = 0
+        self.demand = 0
+
+    def reset(self, device):
+        want = self.demand
+        if want > 0 and (self.buf is None or self.buf.numel() < want or self.buf.device != device):
+            self.buf = torch.empty(int(want * 1.05) + 1024, dtype=torch.float32, device=device)
+        if self.buf is not None:
+            self.buf.zero_()
+        self.used = 0
+        self.demand = 0
+
+    def take(self, n, device):
+        n_al = (n + 63) // 64 * 64  # 256-byte granules: TMA / vector alignment of every gradient
+        self.demand += n_al
+        if self.buf is None or self.buf.device != device or self.used + n_al > self.buf.numel() or self.used < 0:
+            return None
+        out = self.buf[self.used:self.used + n]
+        self.used += n_al
+        return out
+
+
+ZERO_ARENA = ZeroArena()
+
+
 def linear_wgrad(dy2d, x2d, tc=None):
     """dW[N,K] = dy[M,N]^T @ x[M,K] in fp32 (split over the token rows, fp32 atomics)."""
     M, N = dy2d.shape
     K = x2d.shape[1]
     split = _pick_split(M, N, K)
-    out = torch.zeros(N, K, dtype=torch.float32, device=dy2d.device) if split > 1 else \
-        torch.empty(N, K, dtype=torch.float32, device=dy2d.device)
+    if split > 1:
+        flat = ZERO_ARENA.take(N * K, dy2d.device)
+        out = flat.view(N, K) if flat is not None else torch.zeros(N, K, dtype=torch.float32, device=dy2d.device)
+    else:
+        out = torch.empty(N, K, dtype=torch.float32, device=dy2d.device)
     return gemm(L.GEMM_NT_REDUCE_M, dy2d, x2d, M, N, K, out, split_k=split, tc=tc)
 
 
@@ -295,7 +332,7 @@ def relpos_augment_q_bwd(dq_aug, q_aug, q_shape, k_shape, rel_h, rel_w, rel_t, i
                   rel_index_table(q_shape[0], k_shape[0], dev))
     nh, nw, nt = rel_h.shape[0], rel_w.shape[0], rel_t.shape[0]
     ncat = nh + nw + nt
-    d_rel = torch.zeros(ncat, 96, dtype=torch.float32, device=dev)
+    d_rel = torch.empty(ncat, 96, dtype=torch.float32, device=dev)
     ws = _ws(L.lib().pmv_relpos_bwd_workspace_bytes(BH, *q_shape, *k_shape), dev)
     use_tc = _tc_default(q_aug.dtype) if tc is None else int(tc)
     e = q_aug.element_size()

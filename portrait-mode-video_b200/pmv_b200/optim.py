@@ -110,6 +110,7 @@ class FusedAdamW:
         self.lr.fill_(float(lr))
 
     def zero_grad(self, set_to_none: bool = True):
+        ops.ZERO_ARENA.reset(self.device)  # one fill for all split-K weight gradients of the coming step
         for p, _ in self._flat:
             if set_to_none:
                 p.grad = None
