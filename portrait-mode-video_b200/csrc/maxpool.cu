@@ -14,9 +14,10 @@ __global__ void __launch_bounds__(256) maxpool_skip_fwd_kernel(const float* __re
   const int C4 = C >> 2;
   const int Lo = T * Ho * Wo, Li = T * H * W;
   const int64_t total = (int64_t)B * (Lo + 1) * C4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % C4);
-    const int r = (int)(i / C4);
+  // 32-bit index arithmetic (the host checks total < 2^31): the two 64-bit divisions per element were most of the kernel
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (uint32_t)total; i += gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % (uint32_t)C4);
+    const int r = (int)(i / (uint32_t)C4);
     const int n = r % (Lo + 1);
     const int b = r / (Lo + 1);
     const float* xb = x + (int64_t)b * (Li + 1) * C + c4 * 4;
@@ -62,9 +63,10 @@ __global__ void __launch_bounds__(256) maxpool_skip_bwd_kernel(const uint8_t* __
   const int C4 = C >> 2;
   const int Lo = T * Ho * Wo, Li = T * H * W;
   const int64_t total = (int64_t)B * (Li + 1) * C4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % C4);
-    const int r = (int)(i / C4);
+  // 32-bit index arithmetic (the host checks total < 2^31): the two 64-bit divisions per element were most of the kernel
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (uint32_t)total; i += gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % (uint32_t)C4);
+    const int r = (int)(i / (uint32_t)C4);
     const int n = r % (Li + 1);
     const int b = r / (Li + 1);
     const int64_t ob = (int64_t)b * (Lo + 1) * C + c4 * 4;
@@ -76,27 +78,36 @@ __global__ void __launch_bounds__(256) maxpool_skip_bwd_kernel(const uint8_t* __
       const int w = l % W; l /= W;
       const int h = l % H;
       const int t = l / H;
-      // windows containing row h: ho = h/2 with dh = 1 (h even), or ho = (h+1)/2 with dh = 0 and (h-1)/2 with dh = 2 (h odd)
-      const int nh = (h & 1) ? 2 : 1, nw = (w & 1) ? 2 : 1;
-      for (int a = 0; a < nh; ++a) {
-        const int ho = (h & 1) ? (a == 0 ? (h + 1) >> 1 : (h - 1) >> 1) : h >> 1;
-        const int dh = (h & 1) ? (a == 0 ? 0 : 2) : 1;
-        if (ho >= Ho) continue;
-        for (int c = 0; c < nw; ++c) {
-          const int wo = (w & 1) ? (c == 0 ? (w + 1) >> 1 : (w - 1) >> 1) : w >> 1;
-          const int dw = (w & 1) ? (c == 0 ? 0 : 2) : 1;
-          if (wo >= Wo) continue;
-          const int64_t o = ob + (int64_t)(1 + (t * Ho + ho) * Wo + wo) * C;
-          const uchar4 a4 = *reinterpret_cast<const uchar4*>(win + o);
-          const uint8_t p = (uint8_t)(dh * 3 + dw);
-          if (a4.x == p || a4.y == p || a4.z == p || a4.w == p) {
-            float d[4];
-            load4(dy + o, d);
-            if (a4.x == p) g[0] += d[0];
-            if (a4.y == p) g[1] += d[1];
-            if (a4.z == p) g[2] += d[2];
-            if (a4.w == p) g[3] += d[3];
-          }
+      // windows containing row h: ho = h/2 with dh = 1 (h even), or ho = (h+1)/2 with dh = 0 and (h-1)/2 with dh = 2 (h odd).
+      // All (up to four) winner words are requested before any is inspected, then the gradients of the windows this input
+      // won: two dependent round trips per element instead of two per window.
+      int ho2[2], dh2[2], wo2[2], dw2[2];
+      ho2[0] = (h & 1) ? (h + 1) >> 1 : h >> 1; dh2[0] = (h & 1) ? 0 : 1;
+      ho2[1] = (h - 1) >> 1;                    dh2[1] = 2;
+      wo2[0] = (w & 1) ? (w + 1) >> 1 : w >> 1; dw2[0] = (w & 1) ? 0 : 1;
+      wo2[1] = (w - 1) >> 1;                    dw2[1] = 2;
+      const bool hv[2] = {ho2[0] < Ho, (h & 1) != 0};   // the second candidate exists only for odd coordinates
+      const bool wv[2] = {wo2[0] < Wo, (w & 1) != 0};
+      uchar4 a4[4];
+      int64_t off[4];
+      bool live[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int a = k >> 1, c = k & 1;
+        live[k] = hv[a] && wv[c];
+        off[k] = ob + (int64_t)(1 + (t * Ho + ho2[a]) * Wo + wo2[c]) * C;
+        a4[k] = live[k] ? *reinterpret_cast<const uchar4*>(win + off[k]) : make_uchar4(255, 255, 255, 255);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint8_t p = (uint8_t)(dh2[k >> 1] * 3 + dw2[k & 1]);
+        if (a4[k].x == p || a4[k].y == p || a4[k].z == p || a4[k].w == p) {
+          float d[4];
+          load4(dy + off[k], d);
+          if (a4[k].x == p) g[0] += d[0];
+          if (a4[k].y == p) g[1] += d[1];
+          if (a4[k].z == p) g[2] += d[2];
+          if (a4[k].w == p) g[3] += d[3];
         }
       }
     }
@@ -118,7 +129,7 @@ extern "C" int pmv_maxpool_skip_fwd(const float* x, float* y, uint8_t* win, int 
   PMV_CHECK_ARG(C % 4 == 0, "maxpool: C must be a multiple of 4");
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const int64_t total = (int64_t)B * (1 + (int64_t)T * Ho * Wo) * (C / 4);
-  PMV_CHECK_ARG((int64_t)B * (1 + (int64_t)T * H * W) < (1ll << 31), "maxpool: too many tokens");
+  PMV_CHECK_ARG((int64_t)B * (1 + (int64_t)T * H * W) * (C / 4) < (1ll << 31), "maxpool: too many elements");
   pmv_launch(maxpool_skip_fwd_kernel, grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream, x, y, win, B, T, H, W, Ho, Wo, C);
   PMV_CHECK_LAUNCH();
   return PMV_OK;
@@ -129,7 +140,7 @@ extern "C" int pmv_maxpool_skip_bwd(const uint8_t* win, const float* dy, float* 
   PMV_CHECK_ARG(C % 4 == 0, "maxpool: C must be a multiple of 4");
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const int64_t total = (int64_t)B * (1 + (int64_t)T * H * W) * (C / 4);
-  PMV_CHECK_ARG((int64_t)B * (1 + (int64_t)T * H * W) < (1ll << 31), "maxpool: too many tokens");
+  PMV_CHECK_ARG((int64_t)B * (1 + (int64_t)T * H * W) * (C / 4) < (1ll << 31), "maxpool: too many elements");
   pmv_launch(maxpool_skip_bwd_kernel, grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream, win, dy, dx, B, T, H, W, Ho, Wo, C);
   PMV_CHECK_LAUNCH();
   return PMV_OK;

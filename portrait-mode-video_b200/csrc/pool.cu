@@ -589,25 +589,29 @@ __global__ void __launch_bounds__(SV_THREADS) pool_ln_bwd_saved_kernel(const __g
   float gm[CPL], adg[CPL], adb[CPL];
 #pragma unroll
   for (int j = 0; j < CPL; ++j) { gm[j] = sgam[sub * CPL + j]; adg[j] = 0.f; adb[j] = 0.f; }
-  for (int64_t t0 = (int64_t)lb * SV_TOK; t0 < ntok; t0 += (int64_t)J.nblk * SV_TOK) {
-    const int64_t tok = t0 + g;
-    const bool ok = tok < ntok;
-    const int64_t tk = ok ? tok : 0;
-    float xh[CPL], dy[CPL];
-    load12(xhat + tk * HD + sub * CPL, xh);
-    if (f32) load12(dout32 + tk * J.dout_ld + sub * CPL, dy);
-    else load12(dout + tk * J.dout_ld + sub * CPL, dy);
-    const float rs = ok ? J.rstd[tk] : 0.f;
+  // two tokens per lane group in flight: the loads of both are issued before either is reduced (one token per iteration
+  // left the kernel at a third of the HBM rate: a DRAM round trip per token per group)
+  struct Tok { float xh[CPL], dy[CPL]; float rs; int64_t tok; bool ok; };
+  auto fetch = [&](int64_t t0, Tok& t) {
+    t.tok = t0 + g;
+    t.ok = t.tok < ntok;
+    const int64_t tk = t.ok ? t.tok : 0;
+    load12(xhat + tk * HD + sub * CPL, t.xh);
+    if (f32) load12(dout32 + tk * J.dout_ld + sub * CPL, t.dy);
+    else load12(dout + tk * J.dout_ld + sub * CPL, t.dy);
+    t.rs = t.ok ? J.rstd[tk] : 0.f;
+  };
+  auto consume = [&](Tok& t) {
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
-      if (!ok) dy[j] = 0.f;
-      const float gg = dy[j] * gm[j];
+      if (!t.ok) t.dy[j] = 0.f;
+      const float gg = t.dy[j] * gm[j];
       s1 += gg;
-      s2 += gg * xh[j];
-      adg[j] += dy[j] * xh[j];
-      adb[j] += dy[j];
-      dy[j] = gg;
+      s2 += gg * t.xh[j];
+      adg[j] += t.dy[j] * t.xh[j];
+      adb[j] += t.dy[j];
+      t.dy[j] = gg;
     }
 #pragma unroll
     for (int o = LNL / 2; o > 0; o >>= 1) {
@@ -616,12 +620,12 @@ __global__ void __launch_bounds__(SV_THREADS) pool_ln_bwd_saved_kernel(const __g
     }
     s1 *= (1.0f / HD);
     s2 *= (1.0f / HD);
-    if (!ok) continue;
+    if (!t.ok) return;
     float dc[CPL];
 #pragma unroll
-    for (int j = 0; j < CPL; ++j) dc[j] = rs * (dy[j] - s1 - xh[j] * s2);
-    const int64_t bh = tok / (Lo + 1);
-    const int n = (int)(tok - bh * (Lo + 1));
+    for (int j = 0; j < CPL; ++j) dc[j] = t.rs * (t.dy[j] - s1 - t.xh[j] * s2);
+    const int64_t bh = t.tok / (Lo + 1);
+    const int n = (int)(t.tok - bh * (Lo + 1));
     if (n == 0) {
       const int head = (int)(bh % L.heads);
       const int64_t b = bh / L.heads;
@@ -629,6 +633,15 @@ __global__ void __launch_bounds__(SV_THREADS) pool_ln_bwd_saved_kernel(const __g
     } else {
       store12(reinterpret_cast<T*>(J.dconv) + (bh * Lo + (n - 1)) * HD + sub * CPL, dc);
     }
+  };
+  const int64_t tstep = (int64_t)J.nblk * SV_TOK;
+  for (int64_t t0 = (int64_t)lb * SV_TOK; t0 < ntok; t0 += 2 * tstep) {
+    Tok A, B;
+    fetch(t0, A);
+    const bool has_b = t0 + tstep < ntok;
+    if (has_b) fetch(t0 + tstep, B);
+    consume(A);
+    if (has_b) consume(B);
   }
 #pragma unroll
   for (int j = 0; j < CPL; ++j) {
