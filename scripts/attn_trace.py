@@ -1,6 +1,5 @@
 """Phase timeline inside the attention forward CTAs (debug build with -DPMV_ATTN_TRACE, see the TRACE() points in
-csrc/attn_tc.cu).  Build the traced library first (every csrc/*.cu with -DPMV_ATTN_TRACE into
-scripts/bin/libpmv_b200_trace.so), then:  PMV_B200_LIB=scripts/bin/libpmv_b200_trace.so python scripts/attn_trace.py
+csrc/attn_tc.cu).  Build the traced library first (python scripts/build_trace_lib.py), then:  PMV_B200_LIB=scripts/bin/libpmv_b200_trace.so python scripts/attn_trace.py
 Prints, per phase, the median / p90 time since CTA start over all CTAs, and the CTA start offsets per SM."""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -1,5 +1,5 @@
 """Phase timeline inside the attention backward dQ CTAs (debug build with -DPMV_ATTN_TRACE; BTRACE() points in
-csrc/attn_tc_bwd.cu).  PMV_B200_LIB=scripts/bin/libpmv_b200_trace.so python scripts/attn_trace_bwd.py"""
+csrc/attn_tc_bwd.cu).  python scripts/build_trace_lib.py, then PMV_B200_LIB=scripts/bin/libpmv_b200_trace.so python scripts/attn_trace_bwd.py"""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "portrait-mode-video_b200"))
