@@ -101,6 +101,7 @@ int gemm_tc_launch(int layout, const void* A, int64_t lda, const void* B, int64_
   p.k_per_split = ceil_div64(ceil_div64(KK, split_k), BK) * BK;
   p.splits = (int)ceil_div64(KK, p.k_per_split);
   p.e = e;
+  PMV_CHECK_ARG((int64_t)p.tiles_m * p.tiles_n * p.splits < (1ll << 31), "gemm(tc): too many tiles");
   if (p.splits > 1) {
     PMV_CHECK_ARG(out_dtype == PMV_F32 && e.atomic, "gemm(tc): split-K needs the atomic fp32 epilogue");
   }

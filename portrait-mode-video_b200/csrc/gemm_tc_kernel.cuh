@@ -147,8 +147,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t cta_rank = PAIR ? tc::cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   constexpr int BM_TILE = PAIR ? 2 * BM : BM;                 // rows of a work item
-  const int64_t work0 = PAIR ? (blockIdx.x >> 1) : blockIdx.x;  // first work item / stride of this CTA (pair)
-  const int64_t work_step = PAIR ? (gridDim.x >> 1) : gridDim.x;
+  // work items are indexed in 32 bits (the host checks the count): the tile decode runs once per 32-column chunk in
+  // every epilogue thread and once per tile in the single TMA / MMA threads - 64-bit div / mod there cost more than
+  // the chunk's own arithmetic
+  const uint32_t work0 = PAIR ? (blockIdx.x >> 1) : blockIdx.x;  // first work item / stride of this CTA (pair)
+  const uint32_t work_step = PAIR ? (gridDim.x >> 1) : gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmA);
@@ -183,7 +186,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // everything above overlaps the tail of the previous kernel; nothing global has been touched yet
 
-  const int64_t num_work = (int64_t)p.tiles_m * p.tiles_n * p.splits;
+  const uint32_t num_work = (uint32_t)p.tiles_m * (uint32_t)p.tiles_n * (uint32_t)p.splits;
+  const uint32_t tiles_n = (uint32_t)p.tiles_n, tiles_m = (uint32_t)p.tiles_m, tiles_mn = tiles_n * tiles_m;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -191,10 +195,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t full_bar0_cl = PAIR ? tc::mapa_u32(&full_bar[0], 0) : 0u;  // the leader's full barriers
-      for (int64_t wi = work0; wi < num_work; wi += work_step) {
-        const int tn = (int)(wi % p.tiles_n);
-        const int tm = (int)((wi / p.tiles_n) % p.tiles_m);
-        const int sp = (int)(wi / ((int64_t)p.tiles_n * p.tiles_m));
+      for (uint32_t wi = work0; wi < num_work; wi += work_step) {
+        const int tn = (int)(wi % tiles_n);
+        const int tm = (int)((wi / tiles_n) % tiles_m);
+        const int sp = (int)(wi / tiles_mn);
         const int m0 = tm * BM_TILE + (int)cta_rank * BM, n0 = tn * BN;
         const int64_t kbeg = (int64_t)sp * p.k_per_split;
         const int64_t kend = kbeg + p.k_per_split < p.K ? kbeg + p.k_per_split : p.K;
@@ -251,8 +255,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int64_t it = 0;
-      for (int64_t wi = work0; wi < num_work; wi += work_step, ++it) {
-        const int sp = (int)(wi / ((int64_t)p.tiles_n * p.tiles_m));
+      for (uint32_t wi = work0; wi < num_work; wi += work_step, ++it) {
+        const int sp = (int)(wi / tiles_mn);
         const int64_t kbeg = (int64_t)sp * p.k_per_split;
         const int64_t kend = kbeg + p.k_per_split < p.K ? kbeg + p.k_per_split : p.K;
         const int as = (int)(it & 1);
@@ -305,7 +309,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto sw16_bf = [&](int j) -> int { return row * 64 + ((j ^ ((row >> 1) & 3)) << 4); };
 
     struct Cursor {
-      int64_t wi, it;
+      uint32_t wi, it;
       int c;
     };
     auto valid = [&](const Cursor& cu) { return cu.wi < num_work; };
@@ -314,8 +318,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (cu.c >= BN) { cu.c = half * 32; cu.wi += work_step; ++cu.it; }
     };
     auto coords = [&](const Cursor& cu, int& row0, int& col0) {
-      const int tn = (int)(cu.wi % p.tiles_n);
-      const int tm = (int)((cu.wi / p.tiles_n) % p.tiles_m);
+      const int tn = (int)(cu.wi % tiles_n);
+      const int tm = (int)((cu.wi / tiles_n) % tiles_m);
       row0 = tm * BM_TILE + (int)cta_rank * BM + q * 32;
       col0 = tn * BN + cu.c;
     };
@@ -463,7 +467,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool has_scale = (KIND == EK_RES || KIND == EK_GENERIC) && e.row_scale != nullptr;
 
     struct Cursor {
-      int64_t wi, it;
+      uint32_t wi, it;
       int c;
     };
     struct Pre {     // operands of one chunk fetched ahead: fp32 residual (16 B) or bf16 pre-activation (8 B) per itr
@@ -476,8 +480,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (cu.c >= BN) { cu.c = half * 32; cu.wi += work_step; ++cu.it; }
     };
     auto coords = [&](const Cursor& cu, int64_t& row0, int64_t& col) {
-      const int tn = (int)(cu.wi % p.tiles_n);
-      const int tm = (int)((cu.wi / p.tiles_n) % p.tiles_m);
+      const int tn = (int)(cu.wi % tiles_n);
+      const int tm = (int)((cu.wi / tiles_n) % tiles_m);
       row0 = (int64_t)tm * BM_TILE + (int64_t)cta_rank * BM + q * 32 + lr;
       col = (int64_t)tn * BN + cu.c + lc * 4;
     };
