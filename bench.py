@@ -242,10 +242,6 @@ def main():
     else:
         model.eval()
         model.head.act = None
-        # programmatic dependent launch: +1.8 % on the inference graph, -3 % on the training graph (runtime.cu), so only here
-        if "PMV_PDL" not in os.environ:
-            from pmv_b200 import _lib
-            _lib.lib().pmv_set_pdl(-1)
 
     def step(c, l):
         if train:

@@ -257,7 +257,7 @@ int pmv_head_loss_bwd(const float* dloss, const float* logits, const int64_t* la
                       float* dgamma, float* dbeta, float* ws, int B, int C, int num_classes, void* stream);
 
 /* Programmatic dependent launch for the library's kernels: bit mask of kernel families (1 attention fwd, 2 attention
- * bwd, 4 GEMM, 8 column sums, 16 LayerNorm, 32 | 64 pooling, 128 rel-pos, 256 others); 0 = off (default), -1 = all.
+ * bwd, 4 GEMM, 8 column sums, 16 LayerNorm, 32 | 64 pooling, 128 rel-pos, 256 others); -1 = all (default), 0 = off.
  * Also settable with the PMV_PDL environment variable before the first launch. */
 void pmv_set_pdl(int family_mask);
 

@@ -42,7 +42,7 @@ void pmv_set_error(const char* fmt, ...);
 
 // ---------------------------------------------------------------------------
 // launches.  Every kernel of the library is launched through pmv_launch and calls pdl_wait() before it touches global
-// memory.  With programmatic dependent launch enabled for its family (runtime.cu: pmv_set_pdl / PMV_PDL, default off)
+// memory.  With programmatic dependent launch enabled for its family (runtime.cu: pmv_set_pdl / PMV_PDL, default on)
 // the CTAs of kernel N+1 are scheduled while kernel N drains - their prologue (barrier init, TMEM allocation,
 // descriptor prefetch) overlaps its tail - and griddepcontrol.wait blocks until kernel N has completed and flushed;
 // without the launch attribute the instruction is a no-op.  scripts/pdl_probe.cu measures the edge cost.
