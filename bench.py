@@ -242,6 +242,9 @@ def main():
     else:
         model.eval()
         model.head.act = None
+        if T == torch.bfloat16:
+            from pmv_b200.attention import cache_low_precision_weights
+            cache_low_precision_weights(model)  # constant weights: no fp32 -> bf16 cast kernels in the forward
 
     def step(c, l):
         if train:

@@ -238,3 +238,26 @@ def test_forward_loss_matches_unfused_tail():
             # last-bit differences of the incoming gradient
             tol = 1e-4 if n.startswith(("head.", "norm.")) else 5e-2
             assert nerr(sd[n].grad, g_ref[n]) < tol, n
+
+
+def test_cached_low_precision_weights_change_nothing():
+    """Inference with cache_low_precision_weights gives bit-identical logits, and a weight update invalidates the copies."""
+    from pmv_b200 import mvit
+    from pmv_b200.attention import cache_low_precision_weights
+    torch.manual_seed(7)
+    model = mvit.MViT(mvit.MVITV2_S, compute_dtype=torch.bfloat16).cuda().eval()
+    model.head.act = None
+    clip = torch.randn(1, 3, 16, 224, 224, device="cuda")
+    with torch.no_grad():
+        ref = model([clip])
+        assert cache_low_precision_weights(model) > 60
+        got = model([clip])
+        assert torch.equal(ref, got)
+        w = model.blocks[5].mlp.fc1.weight
+        w.mul_(1.5)  # bumps the version: the stale copy must not be used
+        changed = model([clip])
+        fresh = mvit.MViT(mvit.MVITV2_S, compute_dtype=torch.bfloat16).cuda().eval()
+        fresh.head.act = None
+        fresh.load_state_dict(model.state_dict())
+        assert torch.equal(changed, fresh([clip]))
+        assert not torch.equal(changed, ref)
