@@ -36,6 +36,8 @@ if mode == "train":
         return loss
 else:
     model.eval(); model.head.act = None
+    from pmv_b200.attention import cache_low_precision_weights
+    cache_low_precision_weights(model)  # as in bench.py
 
     def step(c, l):
         with torch.no_grad():
