@@ -121,3 +121,27 @@ def test_param_groups_match_reference_construct_optimizer():
     zero = {names[id(p)] for p in g2[-1]["params"]}
     assert "cls_token" in zero and "blocks.0.attn.rel_pos_h" in zero and "blocks.3.attn.rel_pos_t" in zero
     assert "blocks.0.attn.qkv.weight" not in zero
+
+
+def test_zero_arena_never_hands_out_uncleared_memory():
+    """Host logic of the split-K weight-gradient arena (ops.ZeroArena): sizes itself from the previous step's demand, hands out
+    zeroed, 256-byte aligned slices after reset(), and returns None (fallback to torch.zeros) when it was not reset."""
+    from pmv_b200.ops import ZeroArena
+    dev = torch.device("cpu")
+    a = ZeroArena()
+    a.reset(dev)
+    assert a.take(1000, dev) is None and a.take(70, dev) is None        # first step: nothing allocated yet, demand recorded
+    a.reset(dev)                                                         # second step: sized for 1024 + 128 floats
+    x, y = a.take(1000, dev), a.take(70, dev)
+    assert x is not None and y is not None and x.numel() == 1000 and y.numel() == 70
+    assert float(x.abs().sum()) == 0.0 and float(y.abs().sum()) == 0.0
+    assert (y.data_ptr() - x.data_ptr()) % 256 == 0 and y.data_ptr() - x.data_ptr() >= 4000
+    x.fill_(3.0); y.fill_(5.0)                                            # gradients of this step
+    # a second backward without reset(): the arena must not hand the dirty memory out again
+    z = a.take(1000, dev)
+    assert z is None or float(z.abs().sum()) == 0.0
+    if z is not None:
+        assert z.data_ptr() >= y.data_ptr() + 70 * 4
+    a.reset(dev)                                                         # next step: everything cleared again
+    x2 = a.take(1000, dev)
+    assert x2 is not None and float(x2.abs().sum()) == 0.0
