@@ -17,10 +17,29 @@
 // The direct-load kernels of pool.cu remain for strides >= 3 (mostly-zero gathers) and for backward (iii) at
 // stride 2.  Before this file the register-window kernels were latency-bound on L2 (9 dependent 4-byte loads per
 // output, 12 warps per SM): 0.2-0.8 TB/s (profiles/r01_kernels_before.txt).
+#include <cstdlib>
 #include "pool_common.cuh"
 #include "tc_common.cuh"
 
 namespace pool {
+#ifdef PMV_ATTN_TRACE
+// debug builds only (scripts/build_trace_lib.py): per-step phase stamps of thread 0 of the first 1024 CTAs
+constexpr int PTRACE_CTAS = 1024, PTRACE_SLOTS = 64;
+__device__ long long pmv_pool_trace_buf[4 * PTRACE_CTAS * PTRACE_SLOTS];  // [MODE][cta][slot]
+#define PTRACE(slot)                                                                                              \
+  do {                                                                                                            \
+    if (threadIdx.x == 0 && blockIdx.x < PTRACE_CTAS && (slot) < PTRACE_SLOTS)                                    \
+      pmv_pool_trace_buf[(MODE * PTRACE_CTAS + blockIdx.x) * PTRACE_SLOTS + (slot)] = clock64();                                         \
+  } while (0)
+#define WTRACE(cond, slot)                                                                                        \
+  do {                                                                                                            \
+    if ((cond) && blockIdx.x < PTRACE_CTAS && (slot) < PTRACE_SLOTS)                                              \
+      pmv_pool_trace_buf[(1 * PTRACE_CTAS + blockIdx.x) * PTRACE_SLOTS + (slot)] = clock64();                     \
+  } while (0)
+#else
+#define PTRACE(slot) do { } while (0)
+#define WTRACE(cond, slot) do { } while (0)
+#endif
 namespace {
 
 constexpr int CW = 7;                 // output columns per tile (56, 28, 14, 7 are multiples)
@@ -28,6 +47,8 @@ constexpr int TOK = ROWS * CW;        // 28 tokens per LayerNorm phase
 constexpr int THREADS = TOK * LNL;    // 224: conv phase uses the first 192 (4 rows x 48 channel pairs)
 constexpr int NST = 3;                // plane ring depth
 constexpr int CLS_WARPS = THREADS / 32;
+// the dW and stride-1 input-gradient marches have no LayerNorm phase: 192 threads, so 2 CTAs per SM get 168 registers
+constexpr int threads_for(int mode) { return (mode == 2 || mode == 3) ? ROWS * NCP : THREADS; }
 enum { M_FWD = 0, M_BWD_LN = 1, M_BWD_DW = 2, M_BWD_IN = 3 };
 
 struct TLaunch {
@@ -62,11 +83,25 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_5d_a(uint32_t smem_dst, const CUtensorMap* m, int c0, int c1, int c2, int c3, int c4, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+          smem_dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
 __device__ __forceinline__ float2 lds2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 __device__ __forceinline__ float2 lds2(const bf16* p) {
   const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
   return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
+
+__device__ const uint32_t pool_zero_words[4] = {0u, 0u, 0u, 0u};
+__device__ __forceinline__ uint32_t ld_raw(const bf16* p) { return __ldg(reinterpret_cast<const unsigned int*>(p)); }
+__device__ __forceinline__ float2 ld_raw(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+__device__ __forceinline__ float2 raw_to_f2(uint32_t u) { return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
+__device__ __forceinline__ float2 raw_to_f2(float2 v) { return v; }
 
 struct Smem {
   uint8_t* planes;   // NST x plane bytes
@@ -94,6 +129,7 @@ __device__ __forceinline__ void march(const TLaunch& L, const Job& J, const CUte
   // LayerNorm-phase role
   const int g = tid >> 3, sub = tid & 7;
   const int g_row = g / CW, g_w = g - g_row * CW;
+  using Raw = typename std::conditional<std::is_same<T, bf16>::value, uint32_t, float2>::type;
 
   auto decode = [&](int item, int& b, int& head, int& th, int& tw) {
     const int bh = item / per_bh;
@@ -164,12 +200,24 @@ __device__ __forceinline__ void march(const TLaunch& L, const Job& J, const CUte
         dst[j] = ok ? ld2(dc + j * HD) : make_float2(0.f, 0.f);
       }
     };
-    // M_BWD_DW: step tin needs the pre-LN gradient of frames tin-1, tin, tin+1.  Frame tin+2 is requested at the END of
-    // step tin, into the register slot frame tin-1 just vacated, so the loads fly during the barrier and the wait for the
-    // next plane (they used to be consumed right after issue: 37 % of the samples, profiles/r01_pool_ncu.md)
+    // M_BWD_DW: step tin needs the pre-LN gradient of frames tin-1, tin, tin+1.  The phase stamps of round 2
+    // (profiles/r02_pool_trace.md) showed 0.7-1.5 us per step between the FFMA2 section and the barrier: `ok ? load : 0`
+    // and the bf16 unpack consume the loaded word right after the request, so the warp sat out a full L2 / DRAM round trip
+    // every step.  Now the raw words of frame tin+3 are requested at the end of step tin (out-of-range positions read a
+    // zero word instead of being selected afterwards) and unpacked one step later, into the slot frame tin-1 vacated.
+    Raw raw[MODE == M_BWD_DW ? CW : 1];
+    auto fetch_dc = [&](int tout) {
+      const T* dc = reinterpret_cast<const T*>(J.dconv) + ((bh * Lo + (int64_t)(tout * Ho + row) * Wo + col0) * HD + 2 * cp);
+#pragma unroll
+      for (int j = 0; j < CW; ++j) {
+        const bool ok = row_ok && tout >= 0 && tout < Tn && col0 + j < Wo;
+        raw[j] = ld_raw(ok ? dc + j * HD : reinterpret_cast<const T*>(pool_zero_words));
+      }
+    };
     if constexpr (MODE == M_BWD_DW) {
       load_dc(acc[0], 0);
       load_dc(acc[1], 1);
+      fetch_dc(2);
     }
 
     auto step = [&](auto ptag, int tin) {
@@ -177,8 +225,10 @@ __device__ __forceinline__ void march(const TLaunch& L, const Job& J, const CUte
       constexpr int SLOT_M1 = (P + 2) % 3, SLOT_0 = P, SLOT_P1 = (P + 1) % 3;  // output frames tin-1, tin, tin+1
       if (tin > Tn) return;
       const int k = i * Tn + tin;
+      if (i == 0) PTRACE(8 + 6 * tin);
       if (tin < Tn) {
         tc::mbar_wait(&sm.full[k % NST], (uint32_t)((k / NST) & 1));
+        if (i == 0) PTRACE(8 + 6 * tin + 1);
         if (conv_thread) {
           const T* plane = reinterpret_cast<const T*>(sm.planes + (size_t)(k % NST) * PLANE_STRIDE) + 2 * cp;
 #pragma unroll
@@ -215,9 +265,15 @@ __device__ __forceinline__ void march(const TLaunch& L, const Job& J, const CUte
         }
       }
       const int tout = tin - 1;
+      if (i == 0) PTRACE(8 + 6 * tin + 2);
       if constexpr (MODE == M_BWD_DW) {
-        if (tin < Tn) load_dc(acc[SLOT_M1], tin + 2);
+        if (tin < Tn) {
+#pragma unroll
+          for (int j = 0; j < CW; ++j) acc[SLOT_M1][j] = raw_to_f2(raw[j]);  // frame tin + 2, requested a step ago
+          fetch_dc(tin + 3);
+        }
         __syncthreads();  // everyone is done with plane k: its ring slot may be refilled
+        if (i == 0) PTRACE(8 + 6 * tin + 3);
         if (tid == 0 && tin < Tn && k + NST < total) issue(k + NST);
         return;
       }
@@ -314,6 +370,7 @@ __device__ __forceinline__ void march(const TLaunch& L, const Job& J, const CUte
         }
       }
       buf ^= 1;
+      if (i == 0) PTRACE(8 + 6 * tin + 4);
     };
 
     for (int t3 = 0; t3 <= Tn; t3 += 3) {
@@ -343,7 +400,7 @@ __device__ __forceinline__ void march(const TLaunch& L, const Job& J, const CUte
   if (MODE == M_BWD_DW) {
     __syncthreads();
     float* dws = sm.conv;  // NDW = 2592 floats
-    for (int q = tid; q < NDW; q += THREADS) dws[q] = 0.f;
+    for (int q = tid; q < NDW; q += threads_for(MODE)) dws[q] = 0.f;
     __syncthreads();
 #pragma unroll 1
     for (int rr = 0; rr < ROWS; ++rr) {
@@ -356,12 +413,12 @@ __device__ __forceinline__ void march(const TLaunch& L, const Job& J, const CUte
       }
       __syncthreads();
     }
-    for (int q = tid; q < NDW; q += THREADS) partial_out[q] = dws[q];
+    for (int q = tid; q < NDW; q += threads_for(MODE)) partial_out[q] = dws[q];
   }
 }
 
 template <typename T, int MODE>
-__global__ void __launch_bounds__(THREADS, 2) pool_tma_kernel(const __grid_constant__ TLaunch L) {
+__global__ void __launch_bounds__(threads_for(MODE), 2) pool_tma_kernel(const __grid_constant__ TLaunch L) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   __shared__ float sgam[HD], sbet[HD];
@@ -371,6 +428,17 @@ __global__ void __launch_bounds__(THREADS, 2) pool_tma_kernel(const __grid_const
   const Job& J = L.job[jj];
   const int tid = threadIdx.x;
   const int lb = blockIdx.x - J.blk_begin;
+#ifdef PMV_ATTN_TRACE
+  if (tid == 0 && blockIdx.x < PTRACE_CTAS) {
+    PTRACE(0);
+    unsigned smid; unsigned long long gt;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    pmv_pool_trace_buf[(MODE * PTRACE_CTAS + blockIdx.x) * PTRACE_SLOTS + 1] = smid;
+    pmv_pool_trace_buf[(MODE * PTRACE_CTAS + blockIdx.x) * PTRACE_SLOTS + 2] = (long long)gt;
+    pmv_pool_trace_buf[(MODE * PTRACE_CTAS + blockIdx.x) * PTRACE_SLOTS + 4] = J.s * 10000 + jj * 1000 + (lb >= J.nblk ? 999 : 0);
+  }
+#endif
   Smem sm;
   sm.conv = reinterpret_cast<float*>(base);
   sm.planes = base + 2 * TOK * HD * sizeof(float);
@@ -459,11 +527,460 @@ __global__ void __launch_bounds__(THREADS, 2) pool_tma_kernel(const __grid_const
   float* partial = nullptr;
   if (MODE == M_BWD_LN) partial = J.part_ln + (int64_t)lb * 2 * HD;
   if (MODE == M_BWD_DW) partial = J.part_dw + (int64_t)lb * NDW;
+  PTRACE(5);
   if (J.s == 1) march<T, MODE, 1>(L, J, &L.tm[jj], sm, lb, J.nblk, sgam, sbet, partial);
   else if (MODE != M_BWD_IN && J.s == 2) march<T, MODE, 2>(L, J, &L.tm[jj], sm, lb, J.nblk, sgam, sbet, partial);
   else if (MODE != M_BWD_IN) march<T, MODE, 0>(L, J, &L.tm[jj], sm, lb, J.nblk, sgam, sbet, partial);
+#ifdef PMV_ATTN_TRACE
+  if (tid == 0 && blockIdx.x < PTRACE_CTAS) {
+    PTRACE(6);
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    pmv_pool_trace_buf[(MODE * PTRACE_CTAS + blockIdx.x) * PTRACE_SLOTS + 3] = (long long)gt;
+  }
+#endif
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Forward, warp-specialised (round 2).  The phase stamps of the kernel above (scripts/pool_trace.py,
+// profiles/r02_pool_trace.md) showed where a frame step of 1.7-1.9 us went: 0.1 us waiting for the plane, 0.55-0.7 us in
+// the FFMA2 section (= the FMA-pipe rate of the 12 conv warps of an SM) and 1.1 us in park -> __syncthreads -> LayerNorm
+// -> stores, during which the FMA pipe idles because all warps of the CTA move through the phases together.
+// Here the two halves run as a producer / consumer pipeline inside the CTA, with no CTA-wide barrier in the march:
+//   warps 0-5  (192 threads = 4 rows x 48 channel pairs): wait full[k] -> 27 LDS + 189 FFMA2 -> arrive empty[k] -> park
+//              the completed frame in a 2-deep ring (wait cfree / arrive parked) -> next plane;
+//   warps 6-7  LayerNorm + stores of the parked frames: 4 lanes per token x 24 channels, 14 tokens per warp in two
+//              interleaved passes, packed fp32 math, 16-byte stores; warp 6 also refills the plane ring (all lanes wait
+//              on empty[k], lane 0 issues the TMA request) as soon as every conv warp released a slot.
+// All hand-offs are mbarriers (one elected arrive per warp after __syncwarp).  Lessons of the first versions (same trace
+// file): (a) the role branch must use a provably warp-uniform warp index and the wait loops must not be lane-divergent,
+// otherwise every __shfl_xor_sync / __syncwarp compiles to its WARPSYNC.COLLECTIVE form and a LayerNorm pass takes 3.5-5.5
+// us; (b) doing the LayerNorm in the conv warps themselves one frame later ("deferred", no role split) keeps all warps in
+// phase through the shared barriers - 0.5 us FFMA2 + 0.75 us LayerNorm per step, no overlap; (c) shared loads / stores
+// are explicit ld.shared / st.shared (the pointer-in-struct form above compiled to generic LD / ST).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int WS_THREADS = 256;
+constexpr int WS_CONV_WARPS = 6, WS_LN_WARPS = 2;
+constexpr int NCB = 2;          // parked-frame ring depth
+constexpr int LN4 = 4;          // lanes per token in the LayerNorm warps
+constexpr int CPL4 = HD / LN4;  // 24 channels per lane
+constexpr int TPW = TOK / WS_LN_WARPS;  // 14 tokens per LayerNorm warp and frame: two passes of 8 lane groups
+static_assert(WS_CONV_WARPS * 32 == ROWS * NCP && TPW * WS_LN_WARPS == TOK && TPW <= 16, "role mapping");
+
+__device__ __forceinline__ float2 lds_pair(uint32_t addr, const bf16*) {
+  uint32_t u;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(addr));
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+__device__ __forceinline__ float2 lds_pair(uint32_t addr, const float*) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f2(uint32_t addr, float2 v) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t pack2(float2 v) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// 8 consecutive channels: one 16-byte store (bf16) / two (fp32)
+__device__ __forceinline__ void store8(bf16* p, float2 a, float2 b, float2 c, float2 d) {
+  uint4 t;
+  t.x = pack2(a); t.y = pack2(b); t.z = pack2(c); t.w = pack2(d);
+  *reinterpret_cast<uint4*>(p) = t;
+}
+__device__ __forceinline__ void store8(float* p, float2 a, float2 b, float2 c, float2 d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a.x, a.y, b.x, b.y);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(c.x, c.y, d.x, d.y);
+}
+
+// Pin a kernel-parameter field in a register.  Fields of the job table are addressed with a run-time index, so every use
+// compiles to an indexed constant load (LDC / LDCU c[0x0][R + off]) that the compiler prefers to re-issue rather than
+// keep in a register; in the store section of the LayerNorm warps those loads sat in front of every predicate and
+// address (profiles/r02_pool_trace.md: 1.2 us for ~150 instructions).
+template <typename P> __device__ __forceinline__ P* pin(P* p) {
+  asm volatile("" : "+l"(p));
+  return p;
+}
+__device__ __forceinline__ int pin(int v) {
+  asm volatile("" : "+r"(v));
+  return v;
+}
+__device__ __forceinline__ int64_t pin(int64_t v) {
+  asm volatile("" : "+l"(v));
+  return v;
+}
+__device__ __forceinline__ float pin(float v) {
+  asm volatile("" : "+f"(v));
+  return v;
+}
+
+struct WsBars {
+  uint64_t full[NST], empty[NST], parked[NCB], cfree[NCB];
+};
+
+struct WsItem {
+  int b, head, th, tw;
+};
+__device__ __forceinline__ WsItem ws_decode(int item, int per_bh, int n_tw, int heads) {
+  WsItem it;
+  const int bh = item / per_bh;
+  const int rem = item - bh * per_bh;
+  it.th = rem / n_tw;
+  it.tw = rem - it.th * n_tw;
+  it.b = bh / heads;
+  it.head = bh - it.b * heads;
+  return it;
+}
+
+// ---- conv warps -----------------------------------------------------------------------------------------------------
+template <typename T, int S>
+__device__ __forceinline__ void ws_conv(const TLaunch& L, const Job& J, uint32_t planes_a, uint32_t cbuf_a, WsBars* bars, int n_my,
+                                        int tid /* 0..191: conv thread index (compact over the conv warps) */) {
+  using G = Geo<S>;
+  constexpr uint32_t PLANE_BYTES = G::PLANE_ELEMS * sizeof(T);
+  constexpr uint32_t PLANE_STRIDE = (PLANE_BYTES + 127u) & ~127u;
+  constexpr uint32_t ESZ = sizeof(T);
+  const int lane = tid & 31;
+  const int cp = tid % NCP, r = tid / NCP;
+  const int Tn = pin(L.T);
+  float2 wr[TAPS];
+  load_taps<false>(J.w, cp, wr);
+  const uint32_t park_off = (uint32_t)((r * CW) * HD + 2 * cp) * 4u;
+  int f = 0;  // parked frames so far
+  auto park = [&](float2 (&a)[CW]) {
+    const int slot = f % NCB;
+    tc::mbar_wait(&bars->cfree[slot], (uint32_t)(((f / NCB) & 1) ^ 1));
+    const uint32_t dst = cbuf_a + (uint32_t)slot * (TOK * HD * 4u) + park_off;
+#pragma unroll
+    for (int j = 0; j < CW; ++j) {
+      sts_f2(dst + (uint32_t)j * (HD * 4u), a[j]);
+      a[j] = make_float2(0.f, 0.f);
+    }
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(&bars->parked[slot]);
+    ++f;
+  };
+  for (int i = 0; i < n_my; ++i) {
+    float2 acc[3][CW];
+#pragma unroll
+    for (int s3 = 0; s3 < 3; ++s3)
+#pragma unroll
+      for (int j = 0; j < CW; ++j) acc[s3][j] = make_float2(0.f, 0.f);
+    auto step = [&](auto ptag, int tin) {
+      constexpr int P = decltype(ptag)::value;
+      constexpr int SLOT_M1 = (P + 2) % 3, SLOT_0 = P, SLOT_P1 = (P + 1) % 3;  // output frames tin-1, tin, tin+1
+      if (tin >= Tn) return;
+      const int k = i * Tn + tin;
+      WTRACE(tid == 0 && i == 0, 8 + 4 * tin);
+      tc::mbar_wait(&bars->full[k % NST], (uint32_t)((k / NST) & 1));
+      WTRACE(tid == 0 && i == 0, 8 + 4 * tin + 1);
+      const uint32_t plane = planes_a + (uint32_t)(k % NST) * PLANE_STRIDE + (uint32_t)(2 * cp) * ESZ;
+#pragma unroll
+      for (int dh = 0; dh < 3; ++dh) {
+        constexpr int NX = S == 0 ? 3 * CW : G::BW;
+        float2 x[NX];
+        if constexpr (S == 0) {  // tap tiles (dh, dw): [ROWS][CW] tokens each
+#pragma unroll
+          for (int dw = 0; dw < 3; ++dw)
+#pragma unroll
+            for (int j = 0; j < CW; ++j)
+              x[dw * CW + j] = lds_pair(plane + (uint32_t)((((dh * 3 + dw) * ROWS + r) * CW + j) * HD) * ESZ, (const T*)nullptr);
+        } else {
+          const uint32_t prow = plane + (uint32_t)((r * S + dh) * (G::BW * HD)) * ESZ;
+#pragma unroll
+          for (int c = 0; c < G::BW; ++c) x[c] = lds_pair(prow + (uint32_t)(c * HD) * ESZ, (const T*)nullptr);
+        }
+#pragma unroll
+        for (int dw = 0; dw < 3; ++dw)
+#pragma unroll
+          for (int j = 0; j < CW; ++j) {
+            const float2 xv = S == 0 ? x[dw * CW + j] : x[j * S + dw];
+            acc[SLOT_P1][j] = __ffma2_rn(xv, wr[0 * 9 + dh * 3 + dw], acc[SLOT_P1][j]);
+            acc[SLOT_0][j] = __ffma2_rn(xv, wr[1 * 9 + dh * 3 + dw], acc[SLOT_0][j]);
+            acc[SLOT_M1][j] = __ffma2_rn(xv, wr[2 * 9 + dh * 3 + dw], acc[SLOT_M1][j]);
+          }
+      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bars->empty[k % NST]);  // this warp is done with plane k
+      WTRACE(tid == 0 && i == 0, 8 + 4 * tin + 2);
+      if (tin >= 1) {
+        park(acc[SLOT_M1]);
+      } else {  // what plane 0 contributed to "frame -1" is discarded; the slot becomes frame 2 in the next step
+#pragma unroll
+        for (int j = 0; j < CW; ++j) acc[SLOT_M1][j] = make_float2(0.f, 0.f);
+      }
+      if (tin == Tn - 1) park(acc[SLOT_0]);  // frame Tn would be zero padding: the last frame is complete as well
+      WTRACE(tid == 0 && i == 0, 8 + 4 * tin + 3);
+    };
+    for (int t3 = 0; t3 < Tn; t3 += 3) {
+      step(std::integral_constant<int, 0>{}, t3);
+      step(std::integral_constant<int, 1>{}, t3 + 1);
+      step(std::integral_constant<int, 2>{}, t3 + 2);
+    }
+  }
+}
+
+// ---- LayerNorm warps (+ the TMA producer in the first one) -----------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void ws_ln(const TLaunch& L, const Job& J, const CUtensorMap* tm, uint32_t planes_a, uint32_t cbuf_a,
+                                      WsBars* bars, const float* sgam, const float* sbet, int w, int lb, int nblk, int n_my,
+                                      int per_bh, int n_tw) {
+  // one instance for all strides (the plane geometry only matters to the TMA requests): keeps the kernel's code small
+  const int S = pin(J.s);
+  const uint32_t PLANE_BYTES = (uint32_t)(S == 1 ? Geo<1>::PLANE_ELEMS : S == 2 ? Geo<2>::PLANE_ELEMS : Geo<0>::PLANE_ELEMS) * sizeof(T);
+  const uint32_t PLANE_STRIDE = (PLANE_BYTES + 127u) & ~127u;
+  const int lane = threadIdx.x & 31;
+  const int g8 = lane >> 2, sub = lane & (LN4 - 1);  // lane group (token) 0..7, channel quarter
+  const int Tn = pin(L.T), Ho = pin(J.Ho), Wo = pin(J.Wo), heads = pin(L.heads);
+  const int Lo = Tn * Ho * Wo;
+  const int total = n_my * Tn;
+  // ---- producer state (warp 0): next plane to request = (item index pi, frame pt), decoded tile of that item.  (Moving
+  // the requests into conv warp 0 was tried: it then waits for the slowest conv warp every step, 0.3-0.5 us.)
+  int pk = 0, pi = 0, pt = 0;
+  WsItem pit = ws_decode(lb, per_bh, n_tw, heads);
+  auto issue_next = [&]() {  // all lanes keep the bookkeeping, lane 0 talks to the TMA unit
+    if (lane == 0) {
+      uint64_t* bar = &bars->full[pk % NST];
+      tc::mbar_expect_tx(bar, PLANE_BYTES);
+      const uint32_t dst = planes_a + (uint32_t)(pk % NST) * PLANE_STRIDE;
+      if (S >= 3) {
+        constexpr uint32_t TILE_BYTES = Geo<0>::TILE_ELEMS * sizeof(T);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap)
+          tma_load_5d_a(dst + tap * TILE_BYTES, tm, pit.head * HD, pit.tw * CW * S + tap % 3 - 1, pit.th * ROWS * S + tap / 3 - 1, pt,
+                        pit.b, bar);
+      } else {
+        tma_load_5d_a(dst, tm, pit.head * HD, pit.tw * CW * S - 1, pit.th * ROWS * S - 1, pt, pit.b, bar);
+      }
+    }
+    ++pk;
+    if (++pt == Tn) {
+      pt = 0;
+      ++pi;
+      pit = ws_decode(lb + pi * nblk, per_bh, n_tw, heads);
+    }
+  };
+  if (w == 0) {
+    while (pk < NST && pk < total) issue_next();
+    __syncwarp();
+  }
+  int kr = 0;  // planes released so far (warp 0)
+  // gamma / beta of this lane's 24 channels come from shared memory (two LDS.128 per 8 channels): 48 registers less
+  const uint32_t gam_a = tc::smem_u32(sgam) + (uint32_t)(sub * CPL4) * 4u, bet_a = tc::smem_u32(sbet) + (uint32_t)(sub * CPL4) * 4u;
+  T* const outp = pin(reinterpret_cast<T*>(J.out));
+  T* const xhp = pin(reinterpret_cast<T*>(J.xhat));
+  float* const rsp = pin(J.rstd);
+  const int64_t out_ld = pin(J.out_ld);
+  const float eps = pin(L.eps);
+  // this lane's two tokens of a frame (pass 0: all 8 groups, pass 1: groups 0..5)
+  int trow[2], tcol[2];
+  uint32_t toff[2];
+  bool tlane[2];
+#pragma unroll
+  for (int p2 = 0; p2 < 2; ++p2) {
+    const int tw_ = p2 * 8 + g8;
+    tlane[p2] = tw_ < TPW;
+    const int tok = w * TPW + (tlane[p2] ? tw_ : TPW - 1);
+    trow[p2] = tok / CW;
+    tcol[p2] = tok - trow[p2] * CW;
+    toff[p2] = (uint32_t)(tok * HD + sub * CPL4) * 4u;
+  }
+  int i = 0, tout = 0;
+  WsItem it = ws_decode(lb, per_bh, n_tw, heads);
+  for (int f = 0; f < total; ++f) {
+    WTRACE(w == 0 && lane == 0 && i == 0 && tout < 4, 40 + 6 * tout);
+    if (w == 0) {  // refill the plane ring: every plane the conv warps have finished by the time frame f is parked
+      int target = i * Tn + tout + 2;
+      if (target > (i + 1) * Tn) target = (i + 1) * Tn;
+      for (; kr < target; ++kr) {
+        tc::mbar_wait(&bars->empty[kr % NST], (uint32_t)((kr / NST) & 1));
+        if (pk < total) issue_next();  // plane kr + NST
+      }
+      __syncwarp();
+    }
+    const int slot = f % NCB;
+    tc::mbar_wait(&bars->parked[slot], (uint32_t)((f / NCB) & 1));
+    WTRACE(w == 0 && lane == 0 && i == 0 && tout < 4, 40 + 6 * tout + 1);
+    const uint32_t src = cbuf_a + (uint32_t)slot * (TOK * HD * 4u);
+    float2 v[2][CPL4 / 2];
+#pragma unroll
+    for (int p2 = 0; p2 < 2; ++p2)
+#pragma unroll
+      for (int q4 = 0; q4 < CPL4 / 4; ++q4) {
+        const float4 t4 = lds_f4(src + toff[p2] + 16u * q4);
+        v[p2][2 * q4] = make_float2(t4.x, t4.y);
+        v[p2][2 * q4 + 1] = make_float2(t4.z, t4.w);
+      }
+    float mu[2], var[2];
+#pragma unroll
+    for (int p2 = 0; p2 < 2; ++p2) {
+      float2 s2 = __fadd2_rn(v[p2][0], v[p2][1]), s3 = __fadd2_rn(v[p2][2], v[p2][3]);
+#pragma unroll
+      for (int j = 4; j < CPL4 / 2; j += 2) { s2 = __fadd2_rn(s2, v[p2][j]); s3 = __fadd2_rn(s3, v[p2][j + 1]); }
+      s2 = __fadd2_rn(s2, s3);
+      mu[p2] = s2.x + s2.y;
+    }
+    // every value of the frame has gone into the sums above, so the loads have landed: release the slot
+    WTRACE(w == 0 && lane == 0 && i == 0 && tout < 4 && mu[0] != 12345.f, 40 + 6 * tout + 2);
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(&bars->cfree[slot]);
+#pragma unroll
+    for (int o = 1; o < LN4; o <<= 1)
+#pragma unroll
+      for (int p2 = 0; p2 < 2; ++p2) mu[p2] += __shfl_xor_sync(0xffffffffu, mu[p2], o);
+    WTRACE(w == 0 && lane == 0 && i == 0 && tout < 4 && mu[0] != 12345.f, 40 + 6 * tout + 3);
+#pragma unroll
+    for (int p2 = 0; p2 < 2; ++p2) {
+      mu[p2] *= (1.0f / HD);
+      const float2 nm = make_float2(-mu[p2], -mu[p2]);
+      float2 q2 = make_float2(0.f, 0.f), q3 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < CPL4 / 2; j += 2) {
+        v[p2][j] = __fadd2_rn(v[p2][j], nm);
+        v[p2][j + 1] = __fadd2_rn(v[p2][j + 1], nm);
+        q2 = __ffma2_rn(v[p2][j], v[p2][j], q2);
+        q3 = __ffma2_rn(v[p2][j + 1], v[p2][j + 1], q3);
+      }
+      q2 = __fadd2_rn(q2, q3);
+      var[p2] = q2.x + q2.y;
+    }
+#pragma unroll
+    for (int o = 1; o < LN4; o <<= 1)
+#pragma unroll
+      for (int p2 = 0; p2 < 2; ++p2) var[p2] += __shfl_xor_sync(0xffffffffu, var[p2], o);
+    WTRACE(w == 0 && lane == 0 && i == 0 && tout < 4 && var[0] != 12345.f, 40 + 6 * tout + 4);
+    const int64_t tok0 = ((int64_t)it.b * heads + it.head) * (Lo + 1) + 1 + (int64_t)tout * Ho * Wo;
+#pragma unroll
+    for (int p2 = 0; p2 < 2; ++p2) {
+      const float rs = rsqrtf(var[p2] * (1.0f / HD) + eps);
+      const float2 r2 = make_float2(rs, rs);
+      const int orow = it.th * ROWS + trow[p2], ocol = it.tw * CW + tcol[p2];
+      const bool tvalid = tlane[p2] && orow < Ho && ocol < Wo;
+      const int64_t otok = tok0 + orow * Wo + ocol;
+      T* const op = outp + otok * out_ld + sub * CPL4;
+      T* const xp = xhp + otok * HD + sub * CPL4;
+#pragma unroll
+      for (int q8 = 0; q8 < CPL4 / 8; ++q8) {
+        float2 o[4];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float4 g4 = lds_f4(gam_a + 32u * q8 + 16u * e), b4 = lds_f4(bet_a + 32u * q8 + 16u * e);
+          v[p2][4 * q8 + 2 * e] = __fmul2_rn(v[p2][4 * q8 + 2 * e], r2);
+          v[p2][4 * q8 + 2 * e + 1] = __fmul2_rn(v[p2][4 * q8 + 2 * e + 1], r2);
+          o[2 * e] = __ffma2_rn(v[p2][4 * q8 + 2 * e], make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
+          o[2 * e + 1] = __ffma2_rn(v[p2][4 * q8 + 2 * e + 1], make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
+        }
+        if (tvalid) {
+          store8(op + 8 * q8, o[0], o[1], o[2], o[3]);
+          if (xhp) store8(xp + 8 * q8, v[p2][4 * q8], v[p2][4 * q8 + 1], v[p2][4 * q8 + 2], v[p2][4 * q8 + 3]);
+        }
+      }
+      if (tvalid && xhp && sub == 0) rsp[otok] = rs;
+    }
+    WTRACE(w == 0 && lane == 0 && i == 0 && tout < 4, 40 + 6 * tout + 5);
+    if (++tout == Tn) {
+      tout = 0;
+      ++i;
+      it = ws_decode(lb + i * nblk, per_bh, n_tw, heads);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(WS_THREADS, 2) pool_ws_fwd_kernel(const __grid_constant__ TLaunch L) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(16) float sgam[HD];
+  __shared__ __align__(16) float sbet[HD];
+  __shared__ __align__(8) WsBars bars;
+  int jj = 0;
+  while (jj + 1 < L.njobs && (int)blockIdx.x >= L.job[jj + 1].blk_begin) ++jj;
+  const Job& J = L.job[jj];
+  const int tid = threadIdx.x;
+  const int lb = blockIdx.x - J.blk_begin;
+  const uint32_t base_a = (tc::smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t cbuf_a = base_a, planes_a = base_a + NCB * TOK * HD * 4u;
+#ifdef PMV_ATTN_TRACE
+  if (tid == 0 && blockIdx.x < PTRACE_CTAS) {
+    long long* tb = pmv_pool_trace_buf + (1 * PTRACE_CTAS + blockIdx.x) * PTRACE_SLOTS;
+    unsigned smid; unsigned long long gt;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    tb[0] = clock64(); tb[1] = smid; tb[2] = (long long)gt; tb[4] = J.s * 10000 + jj * 1000 + (lb >= J.nblk ? 999 : 0);
+  }
+#endif
+  if (tid == 0) {
+    tc::tma_prefetch_desc(&L.tm[jj]);
+    for (int i = 0; i < NST; ++i) { tc::mbar_init(&bars.full[i], 1); tc::mbar_init(&bars.empty[i], WS_CONV_WARPS); }
+    for (int i = 0; i < NCB; ++i) { tc::mbar_init(&bars.parked[i], WS_CONV_WARPS); tc::mbar_init(&bars.cfree[i], WS_LN_WARPS); }
+    tc::fence_barrier_init();
+  }
+  pdl_wait();  // nothing above reads or writes global memory
+  if (tid < HD) { sgam[tid] = J.gamma[tid]; sbet[tid] = J.beta[tid]; }
+  __syncthreads();  // barrier initialisation, gamma / beta visible to every warp
+  if (lb >= J.nblk) {
+    // ---------------------------------------------------------------- cls tokens: LayerNorm only, one warp per token
+    const T* __restrict__ in = reinterpret_cast<const T*>(J.in);
+    const int Lo = L.T * J.Ho * J.Wo;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int ncls = L.B * L.heads;
+    for (int bh = (lb - J.nblk) * (WS_THREADS / 32) + warp; bh < ncls; bh += J.ncls_blk * (WS_THREADS / 32)) {
+      const int head = bh % L.heads, b = bh / L.heads;
+      const int64_t in_off = (int64_t)b * L.in_bs + (int64_t)head * L.in_hs + lane;
+      const int64_t tok = (int64_t)bh * (Lo + 1);
+      float v[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) v[j] = to_f32(in[in_off + 32 * j]);
+      const float mu = warp_sum(v[0] + v[1] + v[2]) * (1.0f / HD);
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { const float d = v[j] - mu; q += d * d; }
+      const float rs = rsqrtf(warp_sum(q) * (1.0f / HD) + L.eps);
+      T* o = reinterpret_cast<T*>(J.out) + tok * J.out_ld + lane;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) o[32 * j] = from_f32<T>((v[j] - mu) * rs * sgam[lane + 32 * j] + sbet[lane + 32 * j]);
+      if (J.xhat) {
+        T* xo = reinterpret_cast<T*>(J.xhat) + tok * HD + lane;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) xo[32 * j] = from_f32<T>((v[j] - mu) * rs);
+        if (lane == 0) J.rstd[tok] = rs;
+      }
+    }
+    return;
+  }
+  const int n_th = (J.Ho + ROWS - 1) / ROWS, n_tw = (J.Wo + CW - 1) / CW;
+  const int per_bh = n_th * n_tw;
+  const int nitems = L.B * L.heads * per_bh;
+  const int n_my = lb < nitems ? (nitems - lb + J.nblk - 1) / J.nblk : 0;
+  // warp index through a shuffle: provably warp-uniform, so the role branch below is not treated as divergent
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  // roles by warp: 3 and 7 are the LayerNorm warps, so that they sit together on one scheduler (warp id mod 4) instead
+  // of sharing schedulers with FFMA2-saturated conv warps (profiles/r02_pool_trace.md: their ~350 instructions per frame
+  // took 1800 cycles there); the conv warps 0,1,2,4,5,6 fill the other three schedulers evenly
+  if ((warp_u & 3) != 3) {
+    const int ctid = (warp_u - (warp_u >> 2)) * 32 + (tid & 31);
+    if (J.s == 1) ws_conv<T, 1>(L, J, planes_a, cbuf_a, &bars, n_my, ctid);
+    else if (J.s == 2) ws_conv<T, 2>(L, J, planes_a, cbuf_a, &bars, n_my, ctid);
+    else ws_conv<T, 0>(L, J, planes_a, cbuf_a, &bars, n_my, ctid);
+  } else {
+    ws_ln<T>(L, J, &L.tm[jj], planes_a, cbuf_a, &bars, sgam, sbet, warp_u >> 2, lb, J.nblk, n_my, per_bh, n_tw);
+  }
+#ifdef PMV_ATTN_TRACE
+  if (tid == 0 && blockIdx.x < PTRACE_CTAS) {
+    long long* tb = pmv_pool_trace_buf + (1 * PTRACE_CTAS + blockIdx.x) * PTRACE_SLOTS;
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    tb[6] = clock64(); tb[3] = (long long)gt;
+  }
+#endif
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // backward (iii), stride 2: gather form over an INPUT tile of 8 rows x 14 columns (= the 4 x 7 output tile it feeds,
@@ -651,7 +1168,27 @@ int make_map(CUtensorMap* tm, const void* base, int esz, int64_t dims[5], int64_
                                 (uint32_t)walk);
 }
 
+template <typename T> int launch_ws_fwd(const TLaunch& L, int total_blocks, size_t max_plane, cudaStream_t st) {
+  const size_t smem = 128 + NCB * TOK * HD * sizeof(float) + NST * ((max_plane + 127) / 128 * 128);
+  auto kern = pool_ws_fwd_kernel<T>;
+  static size_t attr = 0;
+  if (smem > attr) {
+    PMV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  pmv_launch(kern, (unsigned)total_blocks, WS_THREADS, smem, st, L);
+  PMV_CHECK_LAUNCH();
+  return PMV_OK;
+}
+
+// PMV_POOL_WS=0 selects the forward kernel of round 1 (kept as the A/B reference of the warp-specialised one)
+bool ws_enabled() {
+  static const bool on = [] { const char* e = std::getenv("PMV_POOL_WS"); return e == nullptr || e[0] != '0'; }();
+  return on;
+}
+
 template <typename T, int MODE> int launch_mode(const TLaunch& L, int total_blocks, size_t max_plane, cudaStream_t st) {
+  if (MODE == M_FWD && ws_enabled()) return launch_ws_fwd<T>(L, total_blocks, max_plane, st);
   const size_t smem = smem_bytes(max_plane);
   auto kern = pool_tma_kernel<T, MODE>;
   static size_t attr = 0;
@@ -659,7 +1196,7 @@ template <typename T, int MODE> int launch_mode(const TLaunch& L, int total_bloc
     PMV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  pmv_launch(kern, (unsigned)total_blocks, THREADS, smem, st, L);
+  pmv_launch(kern, (unsigned)total_blocks, threads_for(MODE), smem, st, L);
   PMV_CHECK_LAUNCH();
   return PMV_OK;
 }
@@ -802,3 +1339,9 @@ int tma_launch(int mode, const Job* jobs, int njobs, int B, int heads, int T, in
 }
 
 }  // namespace pool
+
+#ifdef PMV_ATTN_TRACE
+extern "C" int pmv_debug_pool_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, pool::pmv_pool_trace_buf, sizeof(long long) * 4 * pool::PTRACE_CTAS * pool::PTRACE_SLOTS) == cudaSuccess ? 0 : 1;
+}
+#endif

@@ -56,11 +56,14 @@ def load_checkpoint(path_or_state: Union[str, dict], model: torch.nn.Module, opt
     missing, unexpected = module.load_state_dict(matched, strict=False)
     load_checkpoint.last_report = dict(not_loaded=[k for k in model_dict if k not in matched], not_used=not_used,
                                        missing=list(missing), unexpected=list(unexpected))
+    epoch = -1
     if "epoch" in ckpt and not epoch_reset:
         if optimizer is not None and "optimizer_state" in ckpt:
             optimizer.load_state_dict(ckpt["optimizer_state"])
-        return int(ckpt["epoch"])
-    return -1
+        epoch = int(ckpt["epoch"])
+    if optimizer is not None and hasattr(optimizer, "sync_low_precision"):
+        optimizer.sync_low_precision()  # the weights changed under the optimizer's bf16 operand copies (fine-tuning too)
+    return epoch
 
 
 load_checkpoint.last_report = None

@@ -12,6 +12,7 @@ Inference needs no collective (pure batch partitioning, tools/test_net.py:131-13
 """
 from __future__ import annotations
 
+import contextlib
 from typing import List
 
 import torch
@@ -44,13 +45,27 @@ class GradAllReducer:
     buffer with one multi-tensor copy on the communication stream and all-reduced there; ``finish()`` re-points
     ``p.grad`` at the reduced flat views.  With one rank nothing is copied at all."""
 
-    def __init__(self, module: torch.nn.Module, bucket_mb: float = 25.0, compress_dtype=None, process_group=None):
+    def __init__(self, module: torch.nn.Module, bucket_mb: float = 25.0, compress_dtype=None, process_group=None,
+                 broadcast_init: bool = True):
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         params = [p for p in module.parameters() if p.requires_grad]
         assert params, "no trainable parameters"
         self.params = params
         self.device = params[0].device
+        if self.world > 1 and broadcast_init:
+            # DistributedDataParallel broadcasts rank 0's parameters and buffers at construction (build.py:71-79 relies on
+            # it: only rank 0 loads the checkpoint / draws the initial weights that count)
+            with torch.no_grad():
+                for t in list(module.parameters()) + list(module.buffers()):
+                    dist.broadcast(t.data, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0,
+                                   group=process_group)
+        self._sync = True
+        if self.device.type == "cuda":
+            from . import ops
+            self.arena = ops.attach_arena(params)
+        else:
+            self.arena = None
         self.stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
         self.buckets: List[_Bucket] = []
         cur, cur_bytes, limit = [], 0, int(bucket_mb * 2 ** 20)
@@ -73,16 +88,31 @@ class GradAllReducer:
         return len(self.buckets)
 
     def zero_grad(self):
-        if self.device.type == "cuda":
-            from . import ops
-            ops.ZERO_ARENA.reset(self.device)  # one fill for all split-K weight gradients of the coming step
+        if self.arena is not None:
+            self.arena.reset(self.device)  # one fill for all split-K weight gradients of the coming step
         for b in self.buckets:
             for p in b.params:
                 p.grad = None
+        self._rearm()
+
+    def _rearm(self):
+        for b in self.buckets:
             b.pending = len(b.params)
             b.work = None
 
+    @contextlib.contextmanager
+    def no_sync(self):
+        """Gradient accumulation (DistributedDataParallel.no_sync): backward passes inside the context only accumulate
+        into ``p.grad``; the first backward outside it reduces the accumulated gradients."""
+        prev, self._sync = self._sync, False
+        try:
+            yield
+        finally:
+            self._sync = prev
+
     def _hook(self, p):
+        if not self._sync:
+            return
         b = self._owner[p]
         b.pending -= 1
         if b.pending == 0 and self.world > 1:
@@ -110,6 +140,7 @@ class GradAllReducer:
     def finish(self):
         """Call after backward(): waits for every bucket reduction; gradients are then the mean over ranks."""
         if self.world == 1:
+            self._rearm()
             return
         for b in self.buckets:
             assert b.pending == 0, "a parameter received no gradient (find_unused_parameters=False semantics)"
@@ -128,3 +159,4 @@ class GradAllReducer:
                 p.grad = v
         if self.stream is not None:
             torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        self._rearm()  # a further backward before zero_grad() (accumulation) counts the buckets down again

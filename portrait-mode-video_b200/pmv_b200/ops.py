@@ -137,46 +137,73 @@ def _pick_split(rows: int, n1: int, n2: int) -> int:
 
 
 class ZeroArena:
-    """Pre-zeroed fp32 memory for the split-K weight gradients of one step.  ``reset()`` (called from
-    GradAllReducer.zero_grad at the start of a step) clears the whole arena with ONE fill and rewinds it; ``take(n)`` hands
-    out the next n zeroed floats, or None once the arena is used up - it never hands out memory that was not cleared since
-    the last reset, so forgetting reset() only costs the fallback (a torch.zeros per gradient: ~80 fill launches per
-    MViTv2-S step).  The arena sizes itself from the demand of the previous step."""
+    """Pre-zeroed fp32 memory for the split-K weight gradients of one step of ONE model.  Owned by that model's
+    GradAllReducer / FusedAdamW and attached to its parameters (``p._pmv_arena``, ``attach_arena``): the autograd functions
+    take the arena of the weight they differentiate, so two models in one process (teacher / student, a second reducer)
+    never share memory.  ``reset()`` (from the owner's ``zero_grad``, i.e. when last step's gradients are dead) clears the
+    whole arena with ONE fill and rewinds it; ``take(n)`` hands out the next n zeroed floats, or None once the arena is used
+    up — it never hands out memory that was not cleared since the last reset, so forgetting reset() only costs the fallback
+    (a torch.zeros per gradient: ~80 fill launches per MViTv2-S step).  ``exhaust()`` (``zero_grad(set_to_none=False)``:
+    the gradients stay alive inside the arena) makes take() return None until the next reset.  The arena sizes itself from
+    the demand of the previous step; once a reset()/take() ran under CUDA-graph capture the buffer is frozen (a captured
+    graph keeps writing to its addresses, so it is never reallocated afterwards)."""
 
     def __init__(self):
         self.buf = None
         self.used = 0
         self.demand = 0
+        self.frozen = False
+
+    @staticmethod
+    def _capturing(device) -> bool:
+        return device.type == "cuda" and torch.cuda.is_current_stream_capturing()
 
     def reset(self, device):
         want = self.demand
-        if want > 0 and (self.buf is None or self.buf.numel() < want or self.buf.device != device):
+        if self._capturing(device):
+            self.frozen = True
+        if want > 0 and not self.frozen and (self.buf is None or self.buf.numel() < want or self.buf.device != device):
             self.buf = torch.empty(int(want * 1.05) + 1024, dtype=torch.float32, device=device)
         if self.buf is not None:
             self.buf.zero_()
         self.used = 0
         self.demand = 0
 
+    def exhaust(self):
+        """Nothing more is handed out until the next reset() (the slices given out so far stay valid)."""
+        self.used = -1
+
     def take(self, n, device):
         n_al = (n + 63) // 64 * 64  # 256-byte granules: TMA / vector alignment of every gradient
         self.demand += n_al
-        if self.buf is None or self.buf.device != device or self.used + n_al > self.buf.numel() or self.used < 0:
+        if self.buf is None or self.buf.device != device or self.used < 0 or self.used + n_al > self.buf.numel():
             return None
+        if self._capturing(device):
+            self.frozen = True
         out = self.buf[self.used:self.used + n]
         self.used += n_al
         return out
 
 
-ZERO_ARENA = ZeroArena()
+def attach_arena(params, arena: Optional["ZeroArena"] = None) -> "ZeroArena":
+    """Binds one arena to the parameters of a model (re-uses the one already attached to the first parameter, so a
+    reducer and an optimizer over the same model share it)."""
+    params = list(params)
+    if arena is None:
+        arena = next((getattr(p, "_pmv_arena") for p in params if getattr(p, "_pmv_arena", None) is not None), None) or ZeroArena()
+    for p in params:
+        p._pmv_arena = arena
+    return arena
 
 
-def linear_wgrad(dy2d, x2d, tc=None):
-    """dW[N,K] = dy[M,N]^T @ x[M,K] in fp32 (split over the token rows, fp32 atomics)."""
+def linear_wgrad(dy2d, x2d, tc=None, arena: Optional[ZeroArena] = None):
+    """dW[N,K] = dy[M,N]^T @ x[M,K] in fp32 (split over the token rows, fp32 atomics into zeroed memory: a slice of the
+    owning model's ``arena`` when there is one, else a fresh torch.zeros)."""
     M, N = dy2d.shape
     K = x2d.shape[1]
     split = _pick_split(M, N, K)
     if split > 1:
-        flat = ZERO_ARENA.take(N * K, dy2d.device)
+        flat = arena.take(N * K, dy2d.device) if arena is not None else None
         out = flat.view(N, K) if flat is not None else torch.zeros(N, K, dtype=torch.float32, device=dy2d.device)
     else:
         out = torch.empty(N, K, dtype=torch.float32, device=dy2d.device)

@@ -103,6 +103,7 @@ class FusedAdamW:
         nbytes = L.lib().pmv_adamw_workspace_bytes(self._arr, len(self._flat))
         self._ws = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
         self._numel = sum(p.numel() for p, _ in self._flat)
+        self.arena = ops.attach_arena([p for p, _ in self._flat])  # split-K weight-gradient memory of THIS model
 
     # ------------------------------------------------------------------ schedule
     def set_lr(self, lr: float):
@@ -110,7 +111,10 @@ class FusedAdamW:
         self.lr.fill_(float(lr))
 
     def zero_grad(self, set_to_none: bool = True):
-        ops.ZERO_ARENA.reset(self.device)  # one fill for all split-K weight gradients of the coming step
+        if set_to_none:
+            self.arena.reset(self.device)  # last step's gradients are dead: one fill for all split-K weight gradients
+        else:
+            self.arena.exhaust()  # the gradients stay alive (some inside the arena): hand nothing out until they are dropped
         for p, _ in self._flat:
             if set_to_none:
                 p.grad = None
@@ -137,17 +141,65 @@ class FusedAdamW:
         nlaunch = 1 + (-(-n // 320)) * 2  # prep + (norm, update) per 320 tensors (+ a 4-byte copy node for grad_norm)
         ops._run("pmv_adamw_step", nlaunch, dict(bytes=self._numel * 34), self._arr, n, L.ptr(self.lr), self.betas[0], self.betas[1],
                  self.eps, self.max_grad_norm, L.ptr(self.step_count), L.ptr(self.grad_norm), L.ptr(self._ws), L.stream())
+        for p, _ in self._flat:  # the kernel regenerated every operand copy from p: they are current whatever happened before
+            if "lp" in self.state[p]:
+                p._pmv_lp_version = p._version
 
-    # ------------------------------------------------------------------ checkpointing (same layout idea as torch.optim)
+    # ------------------------------------------------------------------ checkpointing: torch.optim.AdamW's layout
     def state_dict(self):
-        return dict(step=int(self.step_count.item()), lr=float(self.lr.item()),
-                    state=[dict(exp_avg=self.state[p]["exp_avg"].clone(), exp_avg_sq=self.state[p]["exp_avg_sq"].clone())
-                           for p, _ in self._flat])
+        """``torch.optim.AdamW.state_dict()`` layout — ``{"state": {idx: {step, exp_avg, exp_avg_sq}}, "param_groups":
+        [{lr, betas, eps, weight_decay, ..., params: [idx, ...]}]}`` with idx running over the groups in order — so that a
+        checkpoint written here resumes in the reference (utils/checkpoint.py:130-160 saves ``optimizer.state_dict()``) and
+        the reference's ``optimizer_state`` resumes here (:547-553)."""
+        step = float(self.step_count.item())
+        lr = float(self.lr.item())
+        state, groups, idx = {}, [], 0
+        for g in self.param_groups:
+            ids = []
+            for p in g["params"]:
+                if not p.requires_grad:
+                    continue
+                st = self.state[p]
+                state[idx] = dict(step=torch.tensor(step), exp_avg=st["exp_avg"].clone(), exp_avg_sq=st["exp_avg_sq"].clone())
+                ids.append(idx)
+                idx += 1
+            groups.append(dict(lr=lr * float(g["lr_scale"]), betas=self.betas, eps=self.eps, weight_decay=float(g["weight_decay"]),
+                               amsgrad=False, maximize=False, foreach=None, capturable=False, differentiable=False, fused=None,
+                               lr_scale=float(g["lr_scale"]), params=ids))
+        return dict(state=state, param_groups=groups)
 
     def load_state_dict(self, sd):
-        self.step_count.fill_(int(sd["step"]))
-        self.lr.fill_(float(sd["lr"]))
-        for (p, _), s in zip(self._flat, sd["state"]):
-            self.state[p]["exp_avg"].copy_(s["exp_avg"])
-            self.state[p]["exp_avg_sq"].copy_(s["exp_avg_sq"])
+        """Accepts the torch.optim layout (above; what a reference ``.pyth`` checkpoint carries) and the private layout
+        of round 1 (``{"step", "lr", "state": [...]}``).  Moments are matched by position: the reference numbers the
+        parameters group by group in ``construct_optimizer`` order, which ``param_groups()`` reproduces."""
+        if "param_groups" in sd:  # torch.optim layout
+            groups = sd["param_groups"]
+            ids = [i for g in groups for i in g["params"]]
+            if len(ids) != len(self._flat):
+                raise ValueError(f"optimizer state has {len(ids)} parameters, this optimizer {len(self._flat)}")
+            steps = set()
+            for (p, _), i in zip(self._flat, ids):
+                st = sd["state"].get(i, sd["state"].get(str(i)))
+                if st is None:  # torch keeps no state for a parameter that was never stepped
+                    self.state[p]["exp_avg"].zero_()
+                    self.state[p]["exp_avg_sq"].zero_()
+                    continue
+                if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                    raise ValueError(f"optimizer state {i}: shape {tuple(st['exp_avg'].shape)} vs parameter {tuple(p.shape)}")
+                self.state[p]["exp_avg"].copy_(st["exp_avg"])
+                self.state[p]["exp_avg_sq"].copy_(st["exp_avg_sq"])
+                steps.add(int(float(st["step"])))
+            if len(steps) > 1:
+                raise ValueError(f"per-parameter step counts differ ({sorted(steps)}): one shared step count is kept")
+            self.step_count.fill_(steps.pop() if steps else 0)
+            # one learning rate + a scale per group: take the group with scale 1 (or the first) as the base
+            base = next((float(g["lr"]) / float(g.get("lr_scale", 1.0)) for g in groups if float(g.get("lr_scale", 1.0)) != 0.0), None)
+            if base is not None:
+                self.lr.fill_(base)
+        else:
+            self.step_count.fill_(int(sd["step"]))
+            self.lr.fill_(float(sd["lr"]))
+            for (p, _), s_ in zip(self._flat, sd["state"]):
+                self.state[p]["exp_avg"].copy_(s_["exp_avg"])
+                self.state[p]["exp_avg_sq"].copy_(s_["exp_avg_sq"])
         self.sync_low_precision()
