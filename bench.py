@@ -83,8 +83,34 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def summarize_kernels(rec, peaks):
-    """Per-family CUDA-event time from ops.record_kernels(); roofline of the dominant family."""
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` captures
+# (profiles/r02_ncu_traffic.json: kernel family -> MB per launch at the shape the family spends most time in); null
+# where no capture exists.
+def load_traffic():
+    path = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    try:
+        return json.load(open(path))
+    except Exception:  # noqa: BLE001
+        return {}
+
+
+def family_roofline(name, f, peaks, traffic):
+    """Roofline object of one kernel family: achieved = algorithmic work / CUDA-event time (all launches of one step)."""
+    if f["flops"] > 0:
+        ach = f["flops"] / (f["ms"] * 1e-3) / 1e12
+        peak, unit, bound, src = peaks["bf16_sustained"], "TFLOP/s", "tensor", "bf16_tflops_sustained"
+    else:
+        ach = f["bytes"] / (f["ms"] * 1e-3) / 1e9
+        peak, unit, bound, src = peaks["hbm_gbs"], "GB/s", "hbm", "hbm_gbs"
+    return dict(bound=bound, kernel=name, achieved=round(ach, 2), peak=peak, unit=unit, frac=round(ach / peak, 4),
+                traffic=traffic.get(name), peak_source=f"MEASURED_PEAKS.json {src} ({peaks['source']})",
+                avg_launch_us=round(f["ms"] * 1e3 / max(f["launches"], 1), 2), launches_per_step=f["launches"],
+                ms_per_step=round(f["ms"], 3))
+
+
+def summarize_kernels(rec, peaks, passes):
+    """Per-family CUDA-event time from ops.record_kernels() over `passes` recorded steps, reported PER STEP; roofline of
+    the dominant family and of the two families the BASELINE metric names (attention, pooling)."""
     fam = {}
     for name, meta, e0, e1 in rec:
         ms = e0.elapsed_time(e1)
@@ -110,22 +136,31 @@ def summarize_kernels(rec, peaks):
         with open(dump, "w") as f:
             for k, a in rows:
                 rate = (a["flops"] / a["ms"] / 1e9) if a["flops"] else (a["bytes"] / a["ms"] / 1e6)
-                f.write(f"{a['ms']:9.3f} ms  n={a['n']:3d}  {rate:9.1f} {'TFLOP/s' if a['flops'] else 'GB/s'}  {k}\n")
+                f.write(f"{a['ms'] / passes:9.3f} ms/step  n={a['n'] // passes:3d}  {rate:9.1f} {'TFLOP/s' if a['flops'] else 'GB/s'}  {k}\n")
+    for f in fam.values():  # per step
+        f["ms"] /= passes; f["flops"] /= passes; f["bytes"] /= passes
+        f["launches"] = f["launches"] // passes
+    traffic = load_traffic()
     total = sum(f["ms"] for f in fam.values()) or 1.0
     shares = {k: round(f["ms"] / total, 4) for k, f in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
     dom = max(fam, key=lambda k: fam[k]["ms"])
-    d = fam[dom]
-    if d["flops"] > 0:
-        ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
-        roof = dict(bound="tensor", kernel=dom, achieved=round(ach, 2), peak=peaks["bf16_sustained"], unit="TFLOP/s",
-                    frac=round(ach / peaks["bf16_sustained"], 4), traffic=None,
-                    peak_source=f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
-                    avg_launch_us=round(d["ms"] * 1e3 / d["launches"], 2), launches_per_pass=d["launches"])
-    else:
-        ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
-        roof = dict(bound="hbm", kernel=dom, achieved=round(ach, 1), peak=peaks["hbm_gbs"], unit="GB/s",
-                    frac=round(ach / peaks["hbm_gbs"], 4), traffic=None, peak_source=f"MEASURED_PEAKS.json hbm_gbs ({peaks['source']})",
-                    avg_launch_us=round(d["ms"] * 1e3 / d["launches"], 2), launches_per_pass=d["launches"])
+    roof = family_roofline(dom, fam[dom], peaks, traffic)
+    named = {}
+
+    def merged(keys, label):
+        m = dict(ms=0.0, launches=0, flops=0.0, bytes=0.0)
+        for k in keys:
+            if k in fam:
+                for a in m:
+                    m[a] += fam[k][a]
+        if m["launches"]:
+            named[label] = family_roofline(label, m, peaks, traffic)
+
+    for k in ("attention_fwd_tcgen05", "attention_bwd_tcgen05", "pool_ln_qkv_fwd", "pool_ln_qkv_bwd"):
+        if k in fam:
+            named[k] = family_roofline(k, fam[k], peaks, traffic)
+    merged(("attention_fwd_tcgen05", "attention_bwd_tcgen05"), "attention")
+    merged(("pool_ln_qkv_fwd", "pool_ln_qkv_bwd"), "pool")
     detail = {}
     for k, f in fam.items():
         e = dict(ms=round(f["ms"], 3), launches=f["launches"])
@@ -134,7 +169,7 @@ def summarize_kernels(rec, peaks):
         elif f["bytes"]:
             e["gbs"] = round(f["bytes"] / (f["ms"] * 1e-3) / 1e9, 1)
         detail[k] = e
-    return roof, shares, detail
+    return roof, shares, detail, named
 
 
 # ---------------------------------------------------------------------------------------------- CPU reference arm
@@ -183,6 +218,7 @@ def main():
                     help="fused: pmv_b200.optim.FusedAdamW (reference grouping + clip 1.0); torch: torch.optim.AdamW(fused, capturable), no clip")
     ap.add_argument("--unfused-head", action="store_true", help="final LN / head / cross entropy through torch ops instead of pmv_head_loss_*")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-infer", action="store_true", help="train mode: skip the inference measurement reported under `infer`")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -221,7 +257,9 @@ def main():
     peaks = load_peaks()
     T = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     torch.manual_seed(1234)
-    model = mvit.MViT(mvit.MVITV2_B if big else mvit.MVITV2_S, compute_dtype=T).to(dev)
+    # droppath_batched: the DropPath factors of all 32 residual branches come from one torch.rand instead of one per branch
+    # (same distribution; the default draws branch by branch in the reference's generator order, 120 more launches)
+    model = mvit.MViT(dict(mvit.MVITV2_B if big else mvit.MVITV2_S, droppath_batched=True), compute_dtype=T).to(dev)
     B = args.batch
     g = torch.Generator(device="cpu").manual_seed(100 + rank)
     host_clips = torch.randn((B,) + clip_shape, generator=g).pin_memory()
@@ -246,136 +284,164 @@ def main():
             from pmv_b200.attention import cache_low_precision_weights
             cache_low_precision_weights(model)  # constant weights: no fp32 -> bf16 cast kernels in the forward
 
-    def step(c, l):
-        if train:
-            reducer.zero_grad()
-            if args.unfused_head:
-                loss = torch.nn.functional.cross_entropy(model([c]), l)
-            else:
-                loss, _ = model.forward_loss([c], l)  # final LN + head + cross entropy as two launches each way (row f2)
-            loss.backward()
-            reducer.finish()
-            opt.step()
-            return loss
+    def train_step(c, l):
+        reducer.zero_grad()
+        if args.unfused_head:
+            loss = torch.nn.functional.cross_entropy(model([c]), l)
+        else:
+            loss, _ = model.forward_loss([c], l)  # final LN + head + cross entropy as two launches each way (row f2)
+        loss.backward()
+        reducer.finish()
+        opt.step()
+        return loss
+
+    def infer_step(c, l):
         with torch.no_grad():
             return model([c])
-
-    eager_step = step
-    graphed = None
-    for _ in range(max(args.warmup, 3)):
-        eager_step(clips, labels)
-    if not args.no_graph:
-        # the whole step (forward [+ backward + bucketed all-reduce + AdamW]) as one CUDA graph: ~750 launches per
-        # step issued from Python were the bottleneck (host-bound), see pmv_b200/graphs.py
-        try:
-            from pmv_b200.graphs import GraphedStep
-            graphed = GraphedStep(eager_step, [clips, labels])
-            step = graphed
-        except Exception as exc:  # noqa: BLE001  (capture is an optimisation: fall back to eager launches, say so)
-            print(f"[bench] CUDA-graph capture failed ({type(exc).__name__}: {exc}); running eager", file=sys.stderr)
-            torch.cuda.synchronize()
-            graphed = None
-
-    # End-to-end loop: every step's clips travel pinned host -> device inside the timed region and the step's result is
-    # read back.  The copy of step i+1 is issued on a copy stream while step i computes (what a data loader with a
-    # prefetch queue does); two staging buffers, events both ways.
-    copy_stream = torch.cuda.Stream()
-    stage_c = [torch.empty_like(clips) for _ in range(2)]
-    stage_l = [torch.empty_like(labels) for _ in range(2)]
-    ev_ready = [torch.cuda.Event() for _ in range(2)]
-    ev_free = [torch.cuda.Event() for _ in range(2)]
-
-    def e2e_loop(n):
-        cur = torch.cuda.current_stream()
-
-        def prefetch(i):
-            b = i & 1
-            with torch.cuda.stream(copy_stream):
-                if i >= 2:
-                    copy_stream.wait_event(ev_free[b])  # the step that used this staging buffer has consumed it
-                stage_c[b].copy_(host_clips, non_blocking=True)
-                stage_l[b].copy_(host_labels, non_blocking=True)
-                ev_ready[b].record(copy_stream)
-
-        prefetch(0)
-        out = None
-        for i in range(n):
-            b = i & 1
-            cur.wait_event(ev_ready[b])
-            if i + 1 < n:
-                prefetch(i + 1)
-            if graphed is not None:  # device-to-device into the graph's static inputs (77 MB, ~25 us), then replay
-                graphed.static_inputs[0].copy_(stage_c[b], non_blocking=True)
-                graphed.static_inputs[1].copy_(stage_l[b], non_blocking=True)
-                ev_free[b].record(cur)
-                res = graphed(graphed.static_inputs[0], graphed.static_inputs[1])
-            else:
-                res = step(stage_c[b], stage_l[b])
-                ev_free[b].record(cur)
-            out = res.float().cpu()  # D2H read of the loss (train) / logits (infer): synchronises the step
-        return out
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, n):
+    copy_stream = torch.cuda.Stream()
+    stage_c = [torch.empty_like(clips) for _ in range(2)]
+    stage_l = [torch.empty_like(labels) for _ in range(2)]
+    keep_alive = []  # captured graphs (they hold NCCL kernels: released before the process group is torn down)
+
+    def measure(eager_step, n_steps, with_clocks):
+        """Device-timed `value` (inputs resident in HBM) and end-to-end value (pinned host -> device copies and the result
+        read-back inside the timed region) of one kind of step; CUDA events, max over ranks."""
+        graphed = None
+        for _ in range(max(args.warmup, 3)):
+            eager_step(clips, labels)
+        step = eager_step
+        if not args.no_graph:
+            # the whole step (forward [+ backward + bucketed all-reduce + AdamW]) as one CUDA graph: ~750 launches per
+            # step issued from Python were the bottleneck (host-bound), see pmv_b200/graphs.py
+            try:
+                from pmv_b200.graphs import GraphedStep
+                graphed = GraphedStep(eager_step, [clips, labels])
+                step = graphed
+                keep_alive.append(graphed)
+            except Exception as exc:  # noqa: BLE001  (capture is an optimisation: fall back to eager launches, say so)
+                print(f"[bench] CUDA-graph capture failed ({type(exc).__name__}: {exc}); running eager", file=sys.stderr)
+                torch.cuda.synchronize()
+                graphed = None
+
+        # End-to-end loop: every step's clips travel pinned host -> device inside the timed region and the step's result is
+        # read back.  The copy of step i+1 is issued on a copy stream while step i computes (what a data loader with a
+        # prefetch queue does); two staging buffers, events both ways.
+        ev_ready = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
+
+        def e2e_loop(n):
+            cur = torch.cuda.current_stream()
+
+            def prefetch(i):
+                b = i & 1
+                with torch.cuda.stream(copy_stream):
+                    if i >= 2:
+                        copy_stream.wait_event(ev_free[b])  # the step that used this staging buffer has consumed it
+                    stage_c[b].copy_(host_clips, non_blocking=True)
+                    stage_l[b].copy_(host_labels, non_blocking=True)
+                    ev_ready[b].record(copy_stream)
+
+            prefetch(0)
+            out = None
+            for i in range(n):
+                b = i & 1
+                cur.wait_event(ev_ready[b])
+                if i + 1 < n:
+                    prefetch(i + 1)
+                if graphed is not None:  # device-to-device into the graph's static inputs (77 MB, ~25 us), then replay
+                    graphed.static_inputs[0].copy_(stage_c[b], non_blocking=True)
+                    graphed.static_inputs[1].copy_(stage_l[b], non_blocking=True)
+                    ev_free[b].record(cur)
+                    res = graphed(graphed.static_inputs[0], graphed.static_inputs[1])
+                else:
+                    res = step(stage_c[b], stage_l[b])
+                    ev_free[b].record(cur)
+                out = res.float().cpu()  # D2H read of the loss (train) / logits (infer): synchronises the step
+            return out
+
+        def timed(fn, n):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            barrier()
+            ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            return float(ms) / n
+
+        for _ in range(max(args.warmup, 3)):
+            step(clips, labels)
+        sampler = ClockSampler(local) if with_clocks else None
+        if sampler is not None and rank == 0:
+            sampler.start()
+        ms_dev = timed(lambda: step(clips, labels), n_steps)
+        l0 = ops.LAUNCHES
+        eager_step(clips, labels)  # launch count of one step (the graph replays exactly these launches)
+        launches = ops.LAUNCHES - l0
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(n):
-            fn()
+        e2e_loop(n_steps)
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        ms_t = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms) / n
+            dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+        clocks = sampler.stop() if (sampler is not None and rank == 0) else None
+        return dict(ms_dev=ms_dev, ms_e2e=float(ms_t) / n_steps, launches=int(launches), clocks=clocks, graphed=graphed is not None)
 
-    for _ in range(max(args.warmup, 3)):
-        step(clips, labels)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ms_dev = timed(lambda: step(clips, labels), args.steps)
-    l0 = ops.LAUNCHES
-    eager_step(clips, labels)  # launch count of one step (the graph replays exactly these launches)
-    launches = ops.LAUNCHES - l0
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    e2e_loop(args.steps)
-    e1.record()
-    barrier()
-    ms_t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-    ms_e2e = float(ms_t) / args.steps
-    clocks = sampler.stop() if rank == 0 else None
+    eager_step = train_step if train else infer_step
+    m = measure(eager_step, args.steps, True)
+    ms_dev, ms_e2e, launches, clocks = m["ms_dev"], m["ms_e2e"], m["launches"], m["clocks"]
 
-    # per-kernel CUDA-event times over two more passes of the same step (events on the launching stream)
+    # per-kernel CUDA-event times over two more passes of the same step (events on the launching stream), reported per step
+    PASSES = 2
     with ops.record_kernels() as rec:
-        for _ in range(2):
+        for _ in range(PASSES):
             # hold the GPU back while the host enqueues the eager step (~30 ms of Python for ~15 ms of kernels): otherwise an
             # event pair also times the wait for the next launch to arrive and every kernel looks ~20 % slower than it is
             torch.cuda._sleep(int(0.08 * 1.9e9))
             eager_step(clips, labels)
         torch.cuda.synchronize()
-        roof, shares, detail = summarize_kernels(rec, peaks)
+        roof, shares, detail, named = summarize_kernels(rec, peaks, PASSES)
+
+    # the other half of the BASELINE metric in the same line: inference clips/s of the same model (config 3) after a
+    # training run, with the weights the optimizer just produced (bf16 operand copies cached: no cast kernels)
+    infer = None
+    if train and not args.no_infer:
+        model.eval()
+        act, model.head.act = model.head.act, None
+        if T == torch.bfloat16:
+            from pmv_b200.attention import cache_low_precision_weights
+            cache_low_precision_weights(model)
+        mi = measure(infer_step, args.steps, False)
+        model.head.act = act
+        model.train()
+        infer = {"metric": f"{model_name} infer clips/sec", "value": round(B * world / (mi["ms_dev"] * 1e-3), 2), "unit": "clips/s",
+                 "ms_per_step": round(mi["ms_dev"], 3), "gpu_launches": mi["launches"], "per_gpu_batch": B,
+                 "e2e": {"value": round(B * world / (mi["ms_e2e"] * 1e-3), 2), "unit": "clips/s",
+                         "h2d_bytes_per_step": host_clips.numel() * 4 + host_labels.numel() * 8, "d2h_bytes_per_step": B * 400 * 4,
+                         "ms_per_step": round(mi["ms_e2e"], 3)}}
 
     def shutdown():
         """Leave the process group without hanging: the captured graph holds NCCL kernels, so release it first; a
         watchdog ends the process if the communicator teardown still blocks (the result line is already out)."""
-        nonlocal graphed, step
         if world == 1:
             return
         sys.stdout.flush()
         import gc
         import threading
         threading.Timer(30.0, lambda: os._exit(0)).start()
-        step = eager_step
-        graphed = None
+        keep_alive.clear()
         gc.collect()
         torch.cuda.synchronize()
         dist.barrier()
@@ -396,12 +462,18 @@ def main():
         "config": {"workload": workload, "per_gpu_batch": B, "global_batch": total_clips, "mode": args.mode,
                    "parallelism": f"dp{world} (batch-sharded; {'bucketed NCCL grad all-reduce overlapped with backward' if train else 'no collective'})",
                    "l2": "no explicit flush: per-step activations (>2 GB) exceed the 126 MB L2",
-                   "launch": "one CUDA graph per step" if graphed is not None else "eager (one Python call per kernel)",
+                   "droppath": "factors of all branches drawn by one torch.rand (droppath_batched)",
+                   "launch": "one CUDA graph per step" if m["graphed"] else "eager (one Python call per kernel)",
                    "model_tflops_per_gpu": round(flop_per_clip * B / (ms_dev * 1e-3) / 1e3, 1)},
         "e2e": {"value": round(e2e_v, 2), "unit": "clips/s", "h2d_bytes_per_step": host_clips.numel() * 4 + host_labels.numel() * 8,
                 "d2h_bytes_per_step": 4 if train else B * 400 * 4, "ms_per_step": round(ms_e2e, 3)},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernel_time_share": shares, "kernels": detail,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+        "roofline_attention": named.get("attention"), "roofline_pool": named.get("pool"),
+        "roofline_families": {k: v for k, v in named.items() if k not in ("attention", "pool")},
+        "kernel_time_share": shares, "kernels": detail,
     }
+    if infer is not None:
+        line["infer"] = infer
     if not args.no_cpu_baseline and world == 1:
         v, ms = cpu_reference(args.mode, 2 if train else 3, 1, threads)
         line["cpu_baseline"] = {"value": round(v, 4), "unit": "clips/s", "cores": threads, "kind": "port",

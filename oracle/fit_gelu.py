@@ -5,7 +5,8 @@ The GELU / GELU' epilogues of csrc/gemm_tc_kernel.cuh (``phi2``) evaluate the no
 
     Phi(x) = 0.5 + xc * Q(xc^2),   xc = clamp(x, -3 sqrt 2, +3 sqrt 2),   Q = degree-8 polynomial.
 
-``fit()`` re-derives the coefficients (Chebyshev-node least squares of (Phi(x) - 0.5) / x in x^2, float64);
+``fit()`` re-derives a table of the same quality (near-minimax: Lawson-reweighted least squares of Phi(x) - 0.5 =
+x Q(x^2) on Chebyshev nodes, float64);
 ``COEFFS`` are the constants compiled into the kernel (highest degree first, Horner order); ``sweep()`` evaluates the
 float32 Horner form exactly as the kernel does and returns the worst |Phi| and |gelu| errors over [-8, 8].
 
@@ -27,18 +28,26 @@ def _phi(x: np.ndarray) -> np.ndarray:
     return 0.5 * (1.0 + np.vectorize(math.erf)(x / math.sqrt(2.0)))
 
 
-def fit(degree: int = 8, nodes: int = 4001) -> np.ndarray:
-    """Least-squares fit of (Phi(x) - 0.5) / x as a polynomial in s = x^2 on Chebyshev nodes of (0, Z]."""
+def fit(degree: int = 8, nodes: int = 4001, lawson_iters: int = 60) -> np.ndarray:
+    """Near-minimax fit of Phi(x) - 0.5 = x * Q(x^2) on (0, Z]: weighted least squares on Chebyshev nodes with Lawson's
+    reweighting (weights grow where the error is largest), which is how the compiled table was obtained."""
     k = np.arange(nodes)
     x = 0.5 * Z * (1.0 + np.cos(np.pi * (k + 0.5) / nodes))
     x = x[x > 1e-6]
-    y = (_phi(x) - 0.5) / x
-    s = x * x
-    # scale s to [0, 1] for conditioning, then undo the scaling on the coefficients
+    y = _phi(x) - 0.5
     smax = Z * Z
-    V = np.vander(s / smax, degree + 1)  # highest degree first
-    c, *_ = np.linalg.lstsq(V, y, rcond=None)
-    return c / smax ** np.arange(degree, -1, -1)
+    V = np.vander(x * x / smax, degree + 1) * x[:, None]  # columns: x * (s / smax)^p, highest degree first
+    w = np.ones_like(x)
+    best, best_err = None, np.inf
+    for _ in range(lawson_iters):
+        sw = np.sqrt(w)
+        c, *_ = np.linalg.lstsq(V * sw[:, None], y * sw, rcond=None)
+        err = np.abs(V @ c - y)
+        if err.max() < best_err:
+            best, best_err = c, err.max()
+        w = w * (err / err.max() + 1e-3)
+        w /= w.sum()
+    return best / smax ** np.arange(degree, -1, -1)
 
 
 def phi_poly_f32(x: np.ndarray, coeffs=COEFFS) -> np.ndarray:
@@ -63,7 +72,7 @@ def sweep(lo: float = -8.0, hi: float = 8.0, n: int = 400001, coeffs=COEFFS):
 
 if __name__ == "__main__":
     c = fit()
-    print("fitted (float64 least squares) vs compiled:")
+    print("fitted (float64, Lawson-reweighted least squares) vs compiled:")
     for a, b in zip(c, COEFFS):
         print(f"  {a: .10e}   {b: .10e}")
     pe, ge = sweep()

@@ -97,6 +97,27 @@ __device__ __forceinline__ float2 lds2(const bf16* p) {
   return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 
+// Pin a kernel-parameter field in a register.  Fields of the job table are addressed with a run-time index, so every use
+// compiles to an indexed constant load (LDC / LDCU c[0x0][R + off]) that the compiler prefers to re-issue rather than
+// keep in a register; in the store section of the LayerNorm warps those loads sat in front of every predicate and
+// address (profiles/r02_pool_trace.md: 1.2 us for ~150 instructions).
+template <typename P> __device__ __forceinline__ P* pin(P* p) {
+  asm volatile("" : "+l"(p));
+  return p;
+}
+__device__ __forceinline__ int pin(int v) {
+  asm volatile("" : "+r"(v));
+  return v;
+}
+__device__ __forceinline__ int64_t pin(int64_t v) {
+  asm volatile("" : "+l"(v));
+  return v;
+}
+__device__ __forceinline__ float pin(float v) {
+  asm volatile("" : "+f"(v));
+  return v;
+}
+
 __device__ const uint32_t pool_zero_words[4] = {0u, 0u, 0u, 0u};
 __device__ __forceinline__ uint32_t ld_raw(const bf16* p) { return __ldg(reinterpret_cast<const unsigned int*>(p)); }
 __device__ __forceinline__ float2 ld_raw(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
@@ -119,7 +140,13 @@ __device__ __forceinline__ void march(const TLaunch& L, const Job& J, const CUte
   const int tid = threadIdx.x;
   const bool conv_thread = tid < ROWS * NCP;
   const int cp = tid % NCP, r = conv_thread ? tid / NCP : 0;
-  const int Ho = J.Ho, Wo = J.Wo, Tn = L.T;
+  // job-table fields used inside the frame loop are pinned in registers for the dW / input-gradient marches (indexed
+  // constant loads otherwise, see pin()); the forward / recompute modes of this kernel are fallbacks and short of registers
+  constexpr bool PIN = MODE == M_BWD_DW || MODE == M_BWD_IN;
+  const int Ho = PIN ? pin(J.Ho) : J.Ho, Wo = PIN ? pin(J.Wo) : J.Wo, Tn = PIN ? pin(L.T) : L.T;
+  T* const dinp = PIN ? pin(reinterpret_cast<T*>(J.din)) : reinterpret_cast<T*>(J.din);
+  const T* const dconvp = PIN ? pin(reinterpret_cast<const T*>(J.dconv)) : reinterpret_cast<const T*>(J.dconv);
+  const int64_t in_bs = PIN ? pin(L.in_bs) : L.in_bs, in_ts = PIN ? pin(L.in_ts) : L.in_ts, in_hs = PIN ? pin(L.in_hs) : L.in_hs;
   const int Lo = Tn * Ho * Wo;
   const int n_th = (Ho + ROWS - 1) / ROWS, n_tw = (Wo + CW - 1) / CW;
   const int per_bh = n_th * n_tw;
@@ -193,7 +220,7 @@ __device__ __forceinline__ void march(const TLaunch& L, const Job& J, const CUte
       for (int j = 0; j < CW; ++j) acc[s3][j] = make_float2(0.f, 0.f);
 
     auto load_dc = [&](float2 (&dst)[CW], int tout) {  // M_BWD_DW
-      const T* dc = reinterpret_cast<const T*>(J.dconv) + ((bh * Lo + (int64_t)(tout * Ho + row) * Wo + col0) * HD + 2 * cp);
+      const T* dc = dconvp + ((bh * Lo + (int64_t)(tout * Ho + row) * Wo + col0) * HD + 2 * cp);
 #pragma unroll
       for (int j = 0; j < CW; ++j) {
         const bool ok = row_ok && tout >= 0 && tout < Tn && col0 + j < Wo;
@@ -207,7 +234,7 @@ __device__ __forceinline__ void march(const TLaunch& L, const Job& J, const CUte
     // zero word instead of being selected afterwards) and unpacked one step later, into the slot frame tin-1 vacated.
     Raw raw[MODE == M_BWD_DW ? CW : 1];
     auto fetch_dc = [&](int tout) {
-      const T* dc = reinterpret_cast<const T*>(J.dconv) + ((bh * Lo + (int64_t)(tout * Ho + row) * Wo + col0) * HD + 2 * cp);
+      const T* dc = dconvp + ((bh * Lo + (int64_t)(tout * Ho + row) * Wo + col0) * HD + 2 * cp);
 #pragma unroll
       for (int j = 0; j < CW; ++j) {
         const bool ok = row_ok && tout >= 0 && tout < Tn && col0 + j < Wo;
@@ -279,11 +306,10 @@ __device__ __forceinline__ void march(const TLaunch& L, const Job& J, const CUte
       }
       if (MODE == M_BWD_IN) {
         if (tout >= 0 && row_ok) {
-          T* drow = reinterpret_cast<T*>(J.din) + ((int64_t)b * L.in_bs + (int64_t)head * L.in_hs +
-                                                   (int64_t)(1 + (tout * Ho + row) * Wo + col0) * L.in_ts + 2 * cp);
+          T* drow = dinp + ((int64_t)b * in_bs + (int64_t)head * in_hs + (int64_t)(1 + (tout * Ho + row) * Wo + col0) * in_ts + 2 * cp);
 #pragma unroll
           for (int j = 0; j < CW; ++j)
-            if (col0 + j < Wo) st2(drow + (int64_t)j * L.in_ts, acc[SLOT_M1][j]);
+            if (col0 + j < Wo) st2(drow + (int64_t)j * in_ts, acc[SLOT_M1][j]);
         }
 #pragma unroll
         for (int j = 0; j < CW; ++j) acc[SLOT_M1][j] = make_float2(0.f, 0.f);
@@ -599,27 +625,6 @@ __device__ __forceinline__ void store8(bf16* p, float2 a, float2 b, float2 c, fl
 __device__ __forceinline__ void store8(float* p, float2 a, float2 b, float2 c, float2 d) {
   *reinterpret_cast<float4*>(p) = make_float4(a.x, a.y, b.x, b.y);
   *reinterpret_cast<float4*>(p + 4) = make_float4(c.x, c.y, d.x, d.y);
-}
-
-// Pin a kernel-parameter field in a register.  Fields of the job table are addressed with a run-time index, so every use
-// compiles to an indexed constant load (LDC / LDCU c[0x0][R + off]) that the compiler prefers to re-issue rather than
-// keep in a register; in the store section of the LayerNorm warps those loads sat in front of every predicate and
-// address (profiles/r02_pool_trace.md: 1.2 us for ~150 instructions).
-template <typename P> __device__ __forceinline__ P* pin(P* p) {
-  asm volatile("" : "+l"(p));
-  return p;
-}
-__device__ __forceinline__ int pin(int v) {
-  asm volatile("" : "+r"(v));
-  return v;
-}
-__device__ __forceinline__ int64_t pin(int64_t v) {
-  asm volatile("" : "+l"(v));
-  return v;
-}
-__device__ __forceinline__ float pin(float v) {
-  asm volatile("" : "+f"(v));
-  return v;
 }
 
 struct WsBars {
@@ -1006,7 +1011,8 @@ __global__ void __launch_bounds__(S2_THREADS, 3) pool_din_s2_kernel(const __grid
   const int tid = threadIdx.x;
   const int lb = blockIdx.x - J.blk_begin;
   const int cp = tid % NCP, r = tid / NCP;
-  const int Tn = L.T, Ho = J.Ho, Wo = J.Wo;
+  const int Tn = pin(L.T), Ho = pin(J.Ho), Wo = pin(J.Wo), LH = pin(L.H), LW = pin(L.W);
+  const int64_t in_ts = pin(L.in_ts);
   if (tid == 0) {
     tc::tma_prefetch_desc(tm);
     for (int i = 0; i < S2_NST; ++i) tc::mbar_init(&full_bar[i], 1);
@@ -1054,11 +1060,11 @@ __global__ void __launch_bounds__(S2_THREADS, 3) pool_din_s2_kernel(const __grid
 #pragma unroll
       for (int par = 0; par < 2; ++par) {
         const int hi = hi0 + par;
-        if (hi >= L.H) continue;
-        T* drow = dbase + (int64_t)(1 + (ti * L.H + hi) * L.W + tw * 2 * CW) * L.in_ts;
+        if (hi >= LH) continue;
+        T* drow = dbase + (int64_t)(1 + (ti * LH + hi) * LW + tw * 2 * CW) * in_ts;
 #pragma unroll
         for (int c = 0; c < 2 * CW; ++c) {
-          if (tw * 2 * CW + c >= L.W) continue;
+          if (tw * 2 * CW + c >= LW) continue;
           float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
           for (int dt = 0; dt < 3; ++dt) {
@@ -1077,7 +1083,7 @@ __global__ void __launch_bounds__(S2_THREADS, 3) pool_din_s2_kernel(const __grid
               }
             }
           }
-          st2(drow + (int64_t)c * L.in_ts, acc);
+          st2(drow + (int64_t)c * in_ts, acc);
         }
       }
       __syncthreads();  // frame ti-1 is no longer needed: its ring slot takes frame ti+2

@@ -223,7 +223,11 @@ def cache_low_precision_weights(module: nn.Module, dtype: torch.dtype = torch.bf
     n = 0
     for p in module.parameters():
         if p.dim() >= 2 and p.dtype != dtype:
-            p._pmv_lp = p.detach().to(dtype)
+            lp = getattr(p, "_pmv_lp", None)
+            if lp is not None and lp.dtype == dtype and lp.shape == p.shape and lp.device == p.device:
+                lp.copy_(p.detach())  # in place: FusedAdamW (and a captured graph of its step) keep writing to this tensor
+            else:
+                p._pmv_lp = p.detach().to(dtype)
             p._pmv_lp_version = p._version
             n += 1
     return n

@@ -137,6 +137,11 @@ class MViT(nn.Module):
         one rand / add / floor / div instead of four small launches per branch (120 launches per MViTv2-S step)."""
         if not self.training or all(blk.drop_path_prob == 0.0 for blk in self.blocks):
             return [None] * len(self.blocks)
+        if not self.cfg.get("droppath_batched", False):
+            # default: every block draws its own factors, branch by branch, in the reference's order and with the
+            # reference's call pattern (one torch.rand of B values per DropPath call, common.py:46-59), so a seeded run
+            # consumes the generator exactly like the reference model does
+            return [None] * len(self.blocks)
         keep = getattr(self, "_dp_keep", None)
         if keep is None or keep.device != device:
             keep = torch.tensor([1.0 - blk.drop_path_prob for blk in self.blocks for _ in range(2)], dtype=torch.float32,
@@ -155,8 +160,15 @@ class MViT(nn.Module):
         x, thw = self.patch_embed.forward_tokens(clip, self.cls_token)        # :2100-2121
         assert tuple(thw) == tuple(thw_expected or (self.T, self.H, self.W)), thw  # :2106
         scales = self._drop_path_scales(x.shape[0], x.device)
+        ckpt = self.cfg.get("act_checkpoint", False) and torch.is_grad_enabled()
         for blk, ds in zip(self.blocks, scales):                              # :2144-2146
-            x, thw = blk(x, thw, drop_scales=ds)
+            if ckpt:
+                # MODEL.ACT_CHECKPOINT (video_model_builder.py:1958-1959 wraps every block in fairscale's
+                # checkpoint_wrapper): the block's activations are dropped after the forward and recomputed in backward
+                from torch.utils.checkpoint import checkpoint
+                x, thw = checkpoint(blk, x, thw, ds, use_reentrant=False, preserve_rng_state=True)
+            else:
+                x, thw = blk(x, thw, drop_scales=ds)
         return x
 
     def _head_no_grad(self, tok):

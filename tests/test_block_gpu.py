@@ -3,7 +3,7 @@
   * against the golden fixtures the UNMODIFIED reference produced (tests/golden/),
   * against the oracle on the real MViTv2-S stage shapes, forward + backward.
 Tolerances (normalised max error): fp32 mode 1e-4, bf16 mode 1e-2 on outputs (north star); bf16 gradients
-3e-2 (one extra bf16 rounding per backward operand)."""
+3e-2 (one extra bf16 rounding per backward operand) for every block, see grad_ok."""
 import glob
 import json
 import os
@@ -32,16 +32,12 @@ def l2err(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-def grad_ok(a, b, dtype, has_maxpool):
-    """Gradient parity.  fp32 mode: normalised max error <= 1e-4.  bf16 mode: <= 3e-2, except downstream of the
-    skip-path MaxPool3d, whose backward is discontinuous in its input: a bf16-rounded activation can move an
-    arg-max to the neighbouring window element (the reference under autocast behaves the same way), which moves
-    single gradient entries by O(1).  There the check is the relative L2 error (robust to isolated flips)."""
-    if dtype == torch.float32:
-        return nerr(a, b) < 1e-4
-    if has_maxpool:
-        return l2err(a, b) < 0.12
-    return nerr(a, b) < 3e-2
+def grad_ok(a, b, dtype):
+    """Gradient parity, normalised max error: fp32 mode <= 1e-4, bf16 mode <= 3e-2 — for every block.  Downstream of the
+    skip-path MaxPool3d the bf16 comparison side is the oracle with its max-pool forced to the winners the kernel chose
+    (tests/test_parity2_gpu.py::forced_max_pool): a bf16-rounded activation can move an arg-max to a neighbouring,
+    nearly equal window element, which moves single gradient entries by O(1) without being an error of the backward."""
+    return nerr(a, b) < GRAD_TOL[dtype]
 
 
 def make_block(cfg, dtype):
@@ -68,16 +64,34 @@ def test_block_matches_reference_fixture(path, dtype):
     blk.load_state_dict(params, strict=True)  # the reference's own state_dict keys
     N = 1 + int(np.prod(cfg["thw"]))
     x = detgen.det_normal((cfg["B"], N, cfg["dim"]), cfg["seed"], name + ".x").cuda().requires_grad_(True)
-    y, thw = blk(x, cfg["thw"])
+    from test_parity2_gpu import capture_maxpool_winners, forced_max_pool
+    with capture_maxpool_winners() as cap:
+        y, thw = blk(x, cfg["thw"])
     assert list(thw) == cfg["thw_out"]
     assert nerr(y.detach(), z["y"]) < OUT_TOL[dtype]
     dy = detgen.det_normal(tuple(y.shape), cfg["seed"], name + ".dy").cuda()
     y.backward(dy)
     gt = GRAD_TOL[dtype]
     mp = blk.pool_skip is not None and cfg["dim"] != cfg["dim_out"]
-    assert grad_ok(x.grad, z["dx"], dtype, mp)
     if mp and dtype == torch.bfloat16:
-        gt = 0.15  # arg-max flips also perturb norm1 / skip-proj parameter gradients (see grad_ok)
+        # gradients against the (reference-pinned) oracle routed through the kernel's own max-pool winners, at the plain
+        # bf16 bound; the fixture's gradients belong to the fp32 arg-maxes and are checked in fp32 mode
+        po = {k: v.cuda().clone().requires_grad_(True) for k, v in params.items()}
+        xo = x.detach().clone().requires_grad_(True)
+        saved = orc.max_pool_tokens
+        orc.max_pool_tokens = forced_max_pool(cap.wins[0])
+        try:
+            yo, _ = orc.multiscale_block(xo, cfg["thw"], po, "", cfg["num_heads"], cfg["stride_q"], cfg["stride_kv"],
+                                         hw_switch_auto=cfg.get("hw_switch_auto", False))
+        finally:
+            orc.max_pool_tokens = saved
+        yo.backward(dy)
+        assert grad_ok(x.grad, xo.grad, dtype)
+        for k, p in blk.named_parameters():
+            if not k.endswith("norm_k.bias"):
+                assert grad_ok(p.grad, po[k].grad, dtype), k
+        return
+    assert grad_ok(x.grad, z["dx"], dtype)
     for k, p in blk.named_parameters():
         g = p.grad.reshape(-1).double().cpu()
         if f"g::{k}::full" in z.files:
@@ -106,30 +120,8 @@ STAGES = [  # dim, dim_out, heads, thw, stride_q, stride_kv  (SURVEY.md Appendix
 def test_stage_shapes_fwd_bwd_vs_oracle(stage, dtype):
     """BASELINE config 2: one MultiScaleBlock at every MViTv2-S stage shape, fwd + bwd, B = 1, against the
     oracle evaluated on the GPU in fp32."""
-    from oracle import detgen, mvit_oracle as orc
-    dim, dim_out, heads, thw, sq, skv = STAGES[stage]
-    cfg = dict(dim=dim, dim_out=dim_out, num_heads=heads, thw=thw, stride_q=[1, sq, sq], stride_kv=[1, skv, skv], seed=100 + stage)
-    shapes = orc.block_param_shapes("", dim, dim_out, heads, thw, cfg["stride_q"], cfg["stride_kv"])
-    params = {k: v.cuda() for k, v in detgen.det_params(shapes, cfg["seed"]).items()}
-    blk = make_block(cfg, dtype)
-    blk.load_state_dict(params, strict=True)
-    N = 1 + int(np.prod(thw))
-    x = detgen.det_normal((1, N, dim), cfg["seed"], "x").cuda().requires_grad_(True)
-    y, thw_new = blk(x, thw)
-    po = {k: v.clone().requires_grad_(True) for k, v in params.items()}
-    xo = x.detach().clone().requires_grad_(True)
-    yo, thw_o = orc.multiscale_block(xo, thw, po, "", heads, cfg["stride_q"], cfg["stride_kv"])
-    assert list(thw_new) == list(thw_o)
-    assert nerr(y.detach(), yo.detach()) < OUT_TOL[dtype]
-    dy = detgen.det_normal(tuple(y.shape), cfg["seed"], "dy").cuda()
-    y.backward(dy)
-    yo.backward(dy)
-    mp = blk.pool_skip is not None and dim != dim_out
-    assert grad_ok(x.grad, xo.grad, dtype, mp)
-    for k, p in blk.named_parameters():
-        if k.endswith("norm_k.bias"):
-            continue
-        assert grad_ok(p.grad, po[k].grad, dtype, mp), k
+    from test_parity2_gpu import _stage_case
+    _stage_case(STAGES[stage], dtype, 1, 100 + stage)
 
 
 def test_droppath_training_mode_matches_oracle():

@@ -145,3 +145,107 @@ def test_zero_arena_never_hands_out_uncleared_memory():
     a.reset(dev)                                                         # next step: everything cleared again
     x2 = a.take(1000, dev)
     assert x2 is not None and float(x2.abs().sum()) == 0.0
+
+
+def test_gelu_polynomial_of_the_gemm_epilogue():
+    """The degree-8 erf-GELU polynomial compiled into csrc/gemm_tc_kernel.cuh (phi2): coefficients in the source equal
+    oracle/fit_gelu.py's table, and the float32 Horner form stays within 1.1e-5 (Phi) / 5e-5 (gelu, on [-8, 8]) of the exact erf form
+    the reference uses (common.py:13,21 nn.GELU())."""
+    from oracle import fit_gelu
+    src = open(os.path.join(ROOT, "portrait-mode-video_b200", "csrc", "gemm_tc_kernel.cuh")).read()
+    body = src[src.index("float2 phi2(float2 x)"):src.index("float2 gelu2(float2 x)")]
+    found = [float(v) for v in re.findall(r"make_float2\((-?\d\.\d+e[+-]\d+)f,", body)]
+    assert found == list(fit_gelu.COEFFS), found
+    phi_err, gelu_err = fit_gelu.sweep()
+    assert phi_err < 1.1e-5 and gelu_err < 5e-5, (phi_err, gelu_err)
+    # the committed fit script reproduces a table of the same quality, and the two polynomials agree as functions
+    refit = tuple(fit_gelu.fit())
+    phi_err2, _ = fit_gelu.sweep(coeffs=refit)
+    assert phi_err2 < 1.5e-5, phi_err2
+    xs = np.linspace(-6, 6, 20001)
+    assert np.max(np.abs(fit_gelu.phi_poly_f32(xs, refit) - fit_gelu.phi_poly_f32(xs))) < 2.5e-5
+
+
+def test_zero_arena_is_per_owner_and_safe_with_live_gradients():
+    """the split-K weight-gradient arena must not be shared between models, must not hand out memory while
+    gradients of zero_grad(set_to_none=False) live in it, and must not be reallocated once a graph captured it."""
+    from pmv_b200 import ops
+    dev = torch.device("cpu")
+    pa = [torch.nn.Parameter(torch.zeros(4, 4)) for _ in range(2)]
+    pb = [torch.nn.Parameter(torch.zeros(4, 4))]
+    a, b = ops.attach_arena(pa), ops.attach_arena(pb)
+    assert a is not b and pa[0]._pmv_arena is a and pa[1]._pmv_arena is a and pb[0]._pmv_arena is b
+    assert ops.attach_arena(pa) is a  # an optimizer over the same model shares the reducer's arena
+    for arena in (a, b):
+        arena.reset(dev); arena.take(100, dev); arena.reset(dev)
+    ga = a.take(100, dev); ga.fill_(1.0)
+    b.reset(dev)                                   # the other model's zero_grad
+    gb = b.take(100, dev)
+    assert float(ga.sum()) == 100.0 and float(gb.sum()) == 0.0 and ga.data_ptr() != gb.data_ptr()
+    # zero_grad(set_to_none=False): gradients stay alive in the arena -> nothing more is handed out until the next reset
+    a.exhaust()
+    assert a.take(10, dev) is None and float(ga.sum()) == 100.0
+    a.reset(dev)
+    assert a.take(10, dev) is not None
+    # frozen after capture: a larger demand must not replace the buffer a captured graph writes to
+    a.frozen = True
+    ptr = a.buf.data_ptr()
+    a.take(10 ** 6, dev)
+    a.reset(dev)
+    assert a.buf.data_ptr() == ptr
+
+
+def test_drop_path_consumes_rng_like_the_reference():
+    """common.py:46-59: one torch.rand of B values per DropPath call.  pmv_b200.common.drop_path_scale (what the blocks
+    call branch by branch in the default mode) must leave the generator in the same state and give the same masks."""
+    from oracle import ref_loader
+    if not ref_loader.reference_available():
+        pytest.skip("reference tree not present")
+    ref_common = __import__("sys").modules.get("slowfast.models.common") or (ref_loader.load_attention() and __import__("sys").modules["slowfast.models.common"])
+    from pmv_b200.common import drop_path_scale
+    x = torch.ones(8, 5, 3)
+    rates = [0.0, 0.1, 0.1, 0.2]
+    torch.manual_seed(7)
+    want = [ref_common.drop_path(x, r, True) for r in rates]
+    tail_ref = torch.rand(3)
+    torch.manual_seed(7)
+    got = []
+    for r in rates:
+        s = drop_path_scale(8, r, True, x.device)
+        got.append(x if s is None else x * s.view(8, 1, 1))
+    tail = torch.rand(3)
+    for a_, b_ in zip(want, got):
+        assert torch.equal(a_, b_)
+    assert torch.equal(tail, tail_ref)
+
+
+def test_reference_mvit_builds_with_the_block_swapped():
+    """The drop-in seam: the reference's own video_model_builder.MViT constructed with
+    ``MultiScaleBlock`` replaced by pmv_b200's has the reference's state_dict (397 tensors, same shapes) and loads the
+    reference's weights strictly.  Runs in a subprocess: the full-model loader stubs third-party imports process-wide."""
+    from oracle import ref_loader
+    if not ref_loader.reference_available():
+        pytest.skip("reference tree not present")
+    import subprocess
+    import sys
+    code = r"""
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import torch
+from oracle import ref_loader
+ref, cfg = ref_loader.load_full_model()
+vmb = sys.modules["slowfast.models.video_model_builder"]
+import pmv_b200.attention as ours
+vmb.MultiScaleBlock = ours.MultiScaleBlock            # the three-line patch of INTEGRATION.md
+swapped = vmb.MViT(cfg)
+a = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+b = {k: tuple(v.shape) for k, v in swapped.state_dict().items()}
+assert a == b, sorted(set(a) ^ set(b))[:5]
+assert len(a) == 397 and sum(p.numel() for p in swapped.parameters()) == 34537744
+swapped.load_state_dict(ref.state_dict(), strict=True)
+assert all(type(blk) is ours.MultiScaleBlock for blk in swapped.blocks)
+assert [blk.dim_out for blk in swapped.blocks] == [blk.dim_out for blk in ref.blocks]
+print("SWAP_OK", len(a))
+""" % (ROOT, os.path.join(ROOT, "portrait-mode-video_b200"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "SWAP_OK 397" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
