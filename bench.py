@@ -268,7 +268,7 @@ def main():
     train = args.mode == "train"
     if train:
         model.train()
-        reducer = GradAllReducer(model, bucket_mb=25.0)
+        reducer = GradAllReducer(model, bucket_mb=25.0, last_bucket_mb=2.0)
         if args.optimizer == "fused":
             # the reference recipe (MVITv2_S_16x4.yaml:62-75): AdamW, WEIGHT_DECAY 0.05 with zero decay for 1-D parameters,
             # global-norm clipping at 1.0 — one multi-tensor pass that also refreshes the bf16 weights (pmv_b200/optim.py)

@@ -20,9 +20,13 @@ import torch.distributed as dist
 
 
 class _Bucket:
+    ALIGN = 64  # floats: every slot starts on a 256-byte boundary (the wgrad kernels write their slot with 16-byte vector
+                # reductions / bulk tensor stores when it is the parameter's gradient home)
+
     def __init__(self, params, device, compress_dtype, need_flat):
         self.params = params
-        n = sum(p.numel() for p in params)
+        A = self.ALIGN
+        n = sum((p.numel() + A - 1) // A * A for p in params)
         # flat fp32 staging buffer of the bucket (only needed when there is something to reduce)
         self.flat = torch.zeros(n, dtype=torch.float32, device=device) if need_flat else None
         self.views = []
@@ -30,7 +34,7 @@ class _Bucket:
             off = 0
             for p in params:
                 self.views.append(self.flat[off:off + p.numel()].view_as(p))
-                off += p.numel()
+                off += (p.numel() + A - 1) // A * A
         self.pending = len(params)
         self.work = None
         self.avg_done = False
@@ -46,7 +50,7 @@ class GradAllReducer:
     ``p.grad`` at the reduced flat views.  With one rank nothing is copied at all."""
 
     def __init__(self, module: torch.nn.Module, bucket_mb: float = 25.0, compress_dtype=None, process_group=None,
-                 broadcast_init: bool = True):
+                 broadcast_init: bool = True, last_bucket_mb: float = None):
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         params = [p for p in module.parameters() if p.requires_grad]
@@ -68,8 +72,18 @@ class GradAllReducer:
             self.arena = None
         self.stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
         self.buckets: List[_Bucket] = []
+        # Buckets in backward order.  ``last_bucket_mb``: the gradients of the FIRST layers arrive last and nothing is left
+        # to hide their all-reduce behind, so they get a small bucket of their own (its reduction is what the step
+        # waits for after backward; profiles/r02_ddp_timeline.md)
+        order = list(reversed(params))
+        tail = []
+        if last_bucket_mb is not None and last_bucket_mb > 0:
+            tb = 0
+            while order and tb + order[-1].numel() * 4 <= int(last_bucket_mb * 2 ** 20):
+                tb += order[-1].numel() * 4
+                tail.insert(0, order.pop())
         cur, cur_bytes, limit = [], 0, int(bucket_mb * 2 ** 20)
-        for p in reversed(params):
+        for p in order:
             cur.append(p)
             cur_bytes += p.numel() * 4
             if cur_bytes >= limit:
@@ -77,11 +91,18 @@ class GradAllReducer:
                 cur, cur_bytes = [], 0
         if cur:
             self.buckets.append(_Bucket(cur, self.device, compress_dtype, self.world > 1))
+        if tail:
+            self.buckets.append(_Bucket(tail, self.device, compress_dtype, self.world > 1))
         self._owner = {}
         for b in self.buckets:
-            for p in b.params:
+            for i, p in enumerate(b.params):
                 self._owner[p] = b
                 p.register_post_accumulate_grad_hook(self._hook)
+                if b.views and self.device.type == "cuda" and p.dim() == 2:
+                    # matrix weights (99 % of the bytes): the split-K wgrad kernels write straight into the bucket, so the
+                    # pack copy below only moves the small tensors (the timeline of round 2 showed 0.23 ms of pack kernels
+                    # per step, profiles/r02_ddp_timeline.md)
+                    p._pmv_grad_home = b.views[i]
 
     @property
     def num_buckets(self):
@@ -93,6 +114,8 @@ class GradAllReducer:
         for b in self.buckets:
             for p in b.params:
                 p.grad = None
+            if b.flat is not None and self.device.type == "cuda":
+                b.flat.zero_()  # the gradient homes accumulate split-K partial products
         self._rearm()
 
     def _rearm(self):
@@ -128,7 +151,14 @@ class GradAllReducer:
             self._reduce(b)
 
     def _reduce(self, b: _Bucket):
-        torch._foreach_copy_(b.views, [p.grad for p in b.params])  # pack: one multi-tensor copy
+        # pack: one multi-tensor copy of the gradients that were not written into the bucket by their producer
+        dst, src = [], []
+        for v, p in zip(b.views, b.params):
+            if p.grad.data_ptr() != v.data_ptr():
+                dst.append(v)
+                src.append(p.grad)
+        if dst:
+            torch._foreach_copy_(dst, src)
         buf = b.flat
         if b.compressed is not None:
             b.compressed.copy_(b.flat)

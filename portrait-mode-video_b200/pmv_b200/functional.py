@@ -102,6 +102,7 @@ class LinearFn(Function):
             ctx.save_for_backward(x2, w, row_scale)
         ctx.meta = (x.shape, rows_per_scale, bias is not None, residual is not None, T)
         ctx.arena = getattr(weight, "_pmv_arena", None)
+        ctx.param = weight  # the nn.Parameter (not its bf16 copy): where its gradient may be written directly
         return y.view(*x.shape[:-1], N)
 
     @staticmethod
@@ -118,7 +119,7 @@ class LinearFn(Function):
             dyT = dy2
             db = ops.colsum_cast(dy2, None, want_sum=True)[0] if has_bias else None
         dx = ops.linear_dgrad(dyT, w, T).view(xshape) if ctx.needs_input_grad[0] else None
-        dw = ops.linear_wgrad(dyT, x2, arena=ctx.arena)
+        dw = ops.linear_wgrad(dyT, x2, arena=ctx.arena, home=ops.grad_home(ctx.param))
         return dx, dw, db, (dy if has_res else None), None, None, None
 
 
@@ -148,6 +149,7 @@ class MlpFn(Function):
             ctx.save_for_backward(x2, w1c, w2c, u, h, row_scale)
         ctx.meta = (x.shape, rows_per_scale, residual is not None, T)
         ctx.arenas = (getattr(w1, "_pmv_arena", None), getattr(w2, "_pmv_arena", None))
+        ctx.params = (w1, w2)
         return y.view(*x.shape[:-1], N)
 
     @staticmethod
@@ -163,10 +165,10 @@ class MlpFn(Function):
         else:
             dyT = dy2
             db2 = ops.colsum_cast(dy2, None)[0]
-        dw2 = ops.linear_wgrad(dyT, h, arena=ctx.arenas[1])
+        dw2 = ops.linear_wgrad(dyT, h, arena=ctx.arenas[1], home=ops.grad_home(ctx.params[1]))
         du = ops.linear_dgrad(dyT, w2c, T, act=L.ACT_GELU_BWD, aux_in=u)
         db1 = ops.colsum_cast(du, None)[0]
-        dw1 = ops.linear_wgrad(du, x2, arena=ctx.arenas[0])
+        dw1 = ops.linear_wgrad(du, x2, arena=ctx.arenas[0], home=ops.grad_home(ctx.params[0]))
         dx = ops.linear_dgrad(du, w1c, T).view(xshape)
         return dx, dw1, db1, dw2, db2, (dy if has_res else None), None, None
 

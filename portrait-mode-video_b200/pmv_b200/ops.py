@@ -196,12 +196,24 @@ def attach_arena(params, arena: Optional["ZeroArena"] = None) -> "ZeroArena":
     return arena
 
 
-def linear_wgrad(dy2d, x2d, tc=None, arena: Optional[ZeroArena] = None):
-    """dW[N,K] = dy[M,N]^T @ x[M,K] in fp32 (split over the token rows, fp32 atomics into zeroed memory: a slice of the
-    owning model's ``arena`` when there is one, else a fresh torch.zeros)."""
+def grad_home(param) -> Optional[torch.Tensor]:
+    """The place a weight gradient should be written to directly: the parameter's slot in its all-reduce bucket
+    (GradAllReducer sets ``_pmv_grad_home``; zeroed by its zero_grad).  Only while the parameter holds no gradient yet —
+    with gradient accumulation autograd adds the new gradient to the old one, which must then be a different tensor."""
+    home = getattr(param, "_pmv_grad_home", None)
+    if home is None or param.grad is not None:
+        return None
+    return home
+
+
+def linear_wgrad(dy2d, x2d, tc=None, arena: Optional[ZeroArena] = None, home: Optional[torch.Tensor] = None):
+    """dW[N,K] = dy[M,N]^T @ x[M,K] in fp32 (split over the token rows, fp32 atomics into zeroed memory: the parameter's
+    slot in its all-reduce bucket (``home``), else a slice of the owning model's ``arena``, else a fresh torch.zeros)."""
     M, N = dy2d.shape
     K = x2d.shape[1]
     split = _pick_split(M, N, K)
+    if home is not None and tuple(home.shape) == (N, K) and home.is_contiguous():
+        return gemm(L.GEMM_NT_REDUCE_M, dy2d, x2d, M, N, K, home, split_k=split, tc=tc)
     if split > 1:
         flat = arena.take(N * K, dy2d.device) if arena is not None else None
         out = flat.view(N, K) if flat is not None else torch.zeros(N, K, dtype=torch.float32, device=dy2d.device)

@@ -381,6 +381,14 @@ def test_fused_adamw_state_dict_round_trips_with_torch_adamw():
 
 
 def _ddp_worker(rank, world, port, compress, q):
+    try:
+        _ddp_worker_body(rank, world, port, compress, q)
+    except Exception:  # noqa: BLE001  (report instead of leaving the parent to time out)
+        import traceback
+        q.put((rank, float("inf"), traceback.format_exc()))
+
+
+def _ddp_worker_body(rank, world, port, compress, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     torch.cuda.set_device(rank)
@@ -427,8 +435,13 @@ def test_nccl_ddp_gradients_equal_single_process(compress):
     procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, compress, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=300) for _ in procs]
-    for p in procs:
-        p.join(120)
-        assert p.exitcode == 0
+    try:
+        res = [q.get(timeout=150) for _ in procs]
+    finally:
+        for p in procs:
+            p.join(30)
+            if p.is_alive():
+                p.kill()
+    for _, err, tol in res:
+        assert not isinstance(tol, str), tol  # a worker's traceback
     assert all(err < tol for _, err, tol in res), res
