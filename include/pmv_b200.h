@@ -156,6 +156,9 @@ typedef struct {
   float* rstd;         /* optional [B, heads, 1+T*Ho*Wo]: ... and 1/sigma; backward then skips the convolution recompute */
   int dout_f32;        /* backward, saved-statistics path only: dout is fp32 whatever the compute dtype (e.g. the fp32
                         * dk / dv accumulators pmv_attention_bwd leaves in its workspace when dk == dv == NULL) */
+  int onehot;          /* forward: also fill columns [96, out_ld) of `out` with the one-hot key coordinates of every token
+                        * (zeros for the cls row) — what pmv_relpos_augment_k writes into K'; the pooling kernel knows the
+                        * (t, h, w) of the token it normalises, so the separate launch disappears */
 } pmv_pool_job;
 int pmv_pool_ln_qkv_fwd(const void* qkv, int64_t batch_stride, int64_t token_stride, int64_t which_stride, int64_t head_stride,
                         const pmv_pool_job* jobs, int njobs, int B, int heads, int T, int H, int W, float eps, int dtype,

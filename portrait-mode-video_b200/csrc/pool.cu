@@ -736,7 +736,7 @@ int fill_jobs(Job* J, const void* qkv, int64_t ws_, const pmv_pool_job* jobs, in
     memset(&J[i], 0, sizeof(Job));
     J[i].in = reinterpret_cast<const char*>(qkv) + (int64_t)p.which * ws_ * esz;
     J[i].w = p.w; J[i].gamma = p.gamma; J[i].beta = p.beta; J[i].out = p.out; J[i].out_ld = p.out_ld;
-    J[i].dout = p.dout; J[i].dout_ld = p.dout_ld; J[i].dout_f32 = p.dout_f32; J[i].grads = p.grads; J[i].xhat = p.xhat; J[i].rstd = p.rstd;
+    J[i].dout = p.dout; J[i].dout_ld = p.dout_ld; J[i].dout_f32 = p.dout_f32; J[i].onehot = p.onehot; J[i].grads = p.grads; J[i].xhat = p.xhat; J[i].rstd = p.rstd;
     J[i].s = p.stride_hw; J[i].Ho = out_hw(g.H, p.stride_hw); J[i].Wo = out_hw(g.W, p.stride_hw);
   }
   return PMV_OK;
@@ -830,7 +830,24 @@ extern "C" int pmv_pool_ln_qkv_fwd(const void* qkv, int64_t batch_stride, int64_
   if (rc) return rc;
   for (int i = 0; i < njobs; ++i)
     PMV_CHECK_ARG(jobs[i].out != nullptr && jobs[i].out_ld % 4 == 0 && jobs[i].out_ld >= HD, "pool: bad output");
-  return run_mode(0, J, njobs, g, (cudaStream_t)stream);
+  // one-hot key-coordinate columns: written by the warp-specialised forward kernel itself; every other path (direct
+  // kernels, PMV_POOL_WS=0) gets the separate launch
+  const bool tma_ok = pmv_has_tcgen05() && std::getenv("PMV_POOL_DIRECT") == nullptr;
+  bool fused[MAX_JOBS];
+  for (int i = 0; i < njobs; ++i) {
+    fused[i] = J[i].onehot && tma_ok && tma_eligible(J[i].s, 0, dtype == PMV_BF16 ? 2 : 4) && tma_fwd_writes_onehot() &&
+               (J[i].out_ld - HD) % 32 == 0;
+    if (!fused[i]) J[i].onehot = 0;
+  }
+  rc = run_mode(0, J, njobs, g, (cudaStream_t)stream);
+  if (rc) return rc;
+  for (int i = 0; i < njobs; ++i) {
+    if (jobs[i].onehot && !fused[i]) {
+      rc = pmv_relpos_augment_k(jobs[i].out, jobs[i].out_ld, B * heads, T, J[i].Ho, J[i].Wo, dtype, stream);
+      if (rc) return rc;
+    }
+  }
+  return PMV_OK;
 }
 
 extern "C" int64_t pmv_pool_ln_qkv_bwd_workspace_bytes(int B, int heads, int T, int H, int W, const int* strides_hw, int njobs) {

@@ -26,6 +26,7 @@ struct Job {
   const void* dout;     // backward: gradient of `out`
   int64_t dout_ld;
   int dout_f32;         // dout is fp32 whatever T is (saved-statistics backward only)
+  int onehot;           // forward: fill columns [96, out_ld) with the one-hot key coordinates (K' of the rel-pos scheme)
   void* din;            // backward: gradient wrt `in` (same strides)
   float* grads;         // backward: [NGRAD] fp32, overwritten
   void* dconv;          // backward: pre-LN gradient [B*heads*Lo*96] in the compute dtype
@@ -78,6 +79,7 @@ template <bool FLIP> __device__ __forceinline__ void load_taps(const float* __re
 // pool_tma.cu
 int tma_items(int B, int heads, int Ho, int Wo);
 bool tma_eligible(int stride_hw, int mode, int elem_bytes);
+bool tma_fwd_writes_onehot();  // the warp-specialised forward kernel is in use (it fills Job::onehot columns itself)
 int tma_launch(int mode, const Job* jobs, int njobs, int B, int heads, int T, int H, int W, int64_t bs, int64_t ts, int64_t hs,
                float eps, int dtype, cudaStream_t st);
 

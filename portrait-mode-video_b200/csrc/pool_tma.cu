@@ -785,6 +785,8 @@ __device__ __forceinline__ void ws_ln(const TLaunch& L, const Job& J, const CUte
   float* const rsp = pin(J.rstd);
   const int64_t out_ld = pin(J.out_ld);
   const float eps = pin(L.eps);
+  const int onehot = pin(J.onehot);
+  const int aug4 = ((int)out_ld - HD) / LN4;  // one-hot columns per lane (a multiple of 8 when J.onehot is set)
   // this lane's two tokens of a frame (pass 0: all 8 groups, pass 1: groups 0..5)
   int trow[2], tcol[2];
   uint32_t toff[2];
@@ -889,6 +891,22 @@ __device__ __forceinline__ void ws_ln(const TLaunch& L, const Job& J, const CUte
         }
       }
       if (tvalid && xhp && sub == 0) rsp[otok] = rs;
+      if (onehot && tvalid) {
+        // K' of the rel-pos scheme: columns [96, ld) = onehot(k_h) | onehot(k_w) | onehot(k_t) (csrc/relpos.cu); this lane
+        // writes its quarter of them
+        const int c0 = orow, c1 = Ho + ocol, c2 = Ho + Wo + tout;
+        T* const ap = outp + otok * out_ld + HD + sub * aug4;
+        for (int e = 0; e < aug4; e += 8) {
+          float2 h[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = sub * aug4 + e + 2 * u;
+            h[u].x = (j == c0 || j == c1 || j == c2) ? 1.f : 0.f;
+            h[u].y = (j + 1 == c0 || j + 1 == c1 || j + 1 == c2) ? 1.f : 0.f;
+          }
+          store8(ap + e, h[0], h[1], h[2], h[3]);
+        }
+      }
     }
     WTRACE(w == 0 && lane == 0 && i == 0 && tout < 4, 40 + 6 * tout + 5);
     if (++tout == Tn) {
@@ -951,6 +969,9 @@ __global__ void __launch_bounds__(WS_THREADS, 2) pool_ws_fwd_kernel(const __grid
       T* o = reinterpret_cast<T*>(J.out) + tok * J.out_ld + lane;
 #pragma unroll
       for (int j = 0; j < 3; ++j) o[32 * j] = from_f32<T>((v[j] - mu) * rs * sgam[lane + 32 * j] + sbet[lane + 32 * j]);
+      if (J.onehot) {  // the cls key carries no coordinates
+        for (int j = HD + lane; j < (int)J.out_ld; j += 32) o[j - lane] = from_f32<T>(0.f);
+      }
       if (J.xhat) {
         T* xo = reinterpret_cast<T*>(J.xhat) + tok * HD + lane;
 #pragma unroll
@@ -1208,6 +1229,8 @@ template <typename T, int MODE> int launch_mode(const TLaunch& L, int total_bloc
 }
 
 }  // namespace
+
+bool tma_fwd_writes_onehot() { return ws_enabled(); }
 
 int tma_items(int B, int heads, int Ho, int Wo) { return B * heads * ((Ho + ROWS - 1) / ROWS) * ((Wo + CW - 1) / CW); }
 

@@ -19,7 +19,12 @@
 //     dRcat       = dRQ^T x Q / scale         (wgrad GEMM, split over the query rows)
 // The dense detour costs (rows_h + rows_w + rows_t) instead of (k_h + k_w + k_t) columns per query, all of it on
 // the tensor cores; the previous CUDA-core kernels (one warp per query, 96-long dot products out of shared
-// memory) ran at 3 TFLOP/s and were 10 % of the training step (profiles/r01_kernels_before.txt).
+// memory) ran at 3 TFLOP/s and were 10 % of the training step (profiles/r01_kernels_before.txt).  Round 2 retried a
+// CUDA-core version that computes only the k_h + k_w + k_t products a query needs in ONE launch (tables in shared memory, 8
+// lanes per query, halving-butterfly reduction, no intermediate in HBM): correct, but 131 / 42 us against 101 / 34 us of this
+// detour at block 0 / the mid-stage blocks (profiles/r02_relpos_fused_rejected.txt) — every query re-reads 22-36 table rows
+// (4-7 KB) from shared memory, i.e. 1.4 MB per SM at the mid-stage: shared-memory bandwidth again.  The products are a
+// small GEMM and stay on the tensor cores.
 #include "common.cuh"
 
 namespace {

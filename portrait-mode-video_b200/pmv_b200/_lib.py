@@ -29,7 +29,7 @@ class Epilogue(C.Structure):
 
 class PoolJob(C.Structure):
     _fields_ = [("w", _p), ("gamma", _p), ("beta", _p), ("out", _p), ("out_ld", _i64), ("dout", _p), ("dout_ld", _i64),
-                ("grads", _p), ("stride_hw", _i), ("which", _i), ("xhat", _p), ("rstd", _p), ("dout_f32", _i)]
+                ("grads", _p), ("stride_hw", _i), ("which", _i), ("xhat", _p), ("rstd", _p), ("dout_f32", _i), ("onehot", _i)]
 
 
 class AdamWTensor(C.Structure):

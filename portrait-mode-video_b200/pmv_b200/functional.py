@@ -232,10 +232,10 @@ class PoolAttentionFn(Function):
         extra = [tuple(saved[2 * i:2 * i + 2]) for i in range(3)] if need else [(), (), ()]
         ops.pool_ln_qkv_fwd(qkv5, heads, thw, [(0, stride_q, wq, gq, bq, q_aug.view(B, heads, Nq, ld)) + extra[0],
                                                (1, stride_kv, wk, gk, bk, k_aug.view(B, heads, Nk, ld)) + extra[1],
-                                               (2, stride_kv, wv, gv, bv, v.view(B, heads, Nk, 96)) + extra[2]], eps)
+                                               (2, stride_kv, wv, gv, bv, v.view(B, heads, Nk, 96)) + extra[2]], eps,
+                            onehot_jobs=(1,) if has_rel else ())  # K' one-hot coordinate columns come with the pooling
         if has_rel:
             ops.relpos_augment_q(q_aug, q_shape, k_shape, rel_h, rel_w, rel_t, 1.0 / scale)
-            ops.relpos_augment_k(k_aug, k_shape)
         out, out_pre, lse = ops.attention_fwd(q_aug, k_aug, v, B, heads, ld, scale, residual=residual, want_lse=need,
                                      tc=(1 if (use_tc_attn and T == torch.bfloat16) else 0))
         if need:

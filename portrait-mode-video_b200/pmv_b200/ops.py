@@ -261,10 +261,11 @@ def pool_ln_bwd(qkv, which, heads, thw, stride_hw, w, gamma, dout, dqkv, grads, 
          L.dt(qkv), L.stream())
 
 
-def pool_ln_qkv_fwd(qkv, heads, thw, jobs, eps=LN_EPS):
+def pool_ln_qkv_fwd(qkv, heads, thw, jobs, eps=LN_EPS, onehot_jobs=()):
     """q / k / v pooled in one launch.  qkv: [B, N, 3, heads, 96]; jobs: list of (which, stride_hw, w, gamma, beta, out
     [, xhat, rstd]) with out [B, heads, 1+L', ld]; xhat [B, heads, 1+L', 96] / rstd [B, heads, 1+L'] (optional) receive the
-    normalised pre-affine tokens and 1/sigma for the backward pass."""
+    normalised pre-affine tokens and 1/sigma for the backward pass.  ``onehot_jobs``: indices of jobs whose columns
+    [96, ld) are also filled with the one-hot key coordinates (K' of the rel-pos scheme; replaces relpos_augment_k)."""
     B, N = qkv.shape[0], qkv.shape[1]
     T, H, W = thw
     arr = (L.PoolJob * len(jobs))()
@@ -273,7 +274,7 @@ def pool_ln_qkv_fwd(qkv, heads, thw, jobs, eps=LN_EPS):
         which, s, w, gamma, beta, out = job[:6]
         xhat, rstd = (job[6], job[7]) if len(job) > 6 else (None, None)
         arr[i] = L.PoolJob(L.ptr(w), L.ptr(gamma), L.ptr(beta), L.ptr(out), out.stride(2), None, 0, None, s, which,
-                           L.ptr(xhat), L.ptr(rstd))
+                           L.ptr(xhat), L.ptr(rstd), 0, int(i in onehot_jobs))
         nbytes += (B * N * heads * 96 + out.shape[0] * out.shape[1] * out.shape[2] * 96) * qkv.element_size()
     _run("pmv_pool_ln_qkv_fwd", 1, dict(bytes=nbytes, shape=(B, heads, T, H, W, [j[1] for j in jobs])), L.ptr(qkv), qkv.stride(0),
          qkv.stride(1), qkv.stride(2), qkv.stride(3), arr, len(jobs), B, heads, T, H, W, eps, L.dt(qkv), L.stream())
