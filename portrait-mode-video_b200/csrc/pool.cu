@@ -580,12 +580,18 @@ __global__ void __launch_bounds__(SV_THREADS) pool_ln_bwd_saved_kernel(const __g
   if (tid < HD) sgam[tid] = J.gamma[tid];
   __syncthreads();
   const int g = tid >> 3, sub = tid & 7;
-  const int Lo = L.T * J.Ho * J.Wo;
-  const int64_t ntok = (int64_t)L.B * L.heads * (Lo + 1);
-  const T* __restrict__ xhat = reinterpret_cast<const T*>(J.xhat);
-  const T* __restrict__ dout = reinterpret_cast<const T*>(J.dout);
-  const float* __restrict__ dout32 = reinterpret_cast<const float*>(J.dout);
+  // job-table fields of the token loop pinned in registers (indexed constant loads otherwise, see pin())
+  const int heads = pin(L.heads);
+  const int Lo = pin(L.T * J.Ho * J.Wo);
+  const int64_t ntok = (int64_t)L.B * heads * (Lo + 1);
+  const T* __restrict__ xhat = pin(reinterpret_cast<const T*>(J.xhat));
+  const T* __restrict__ dout = pin(reinterpret_cast<const T*>(J.dout));
+  const float* __restrict__ dout32 = reinterpret_cast<const float*>(dout);
   const bool f32 = J.dout_f32 != 0;
+  const int64_t dout_ld = pin(J.dout_ld), in_bs = pin(L.in_bs), in_hs = pin(L.in_hs);
+  const float* const rstdp = pin(J.rstd);
+  T* const dinp = pin(reinterpret_cast<T*>(J.din));
+  T* const dconvp = pin(reinterpret_cast<T*>(J.dconv));
   float gm[CPL], adg[CPL], adb[CPL];
 #pragma unroll
   for (int j = 0; j < CPL; ++j) { gm[j] = sgam[sub * CPL + j]; adg[j] = 0.f; adb[j] = 0.f; }
@@ -597,9 +603,9 @@ __global__ void __launch_bounds__(SV_THREADS) pool_ln_bwd_saved_kernel(const __g
     t.ok = t.tok < ntok;
     const int64_t tk = t.ok ? t.tok : 0;
     load12(xhat + tk * HD + sub * CPL, t.xh);
-    if (f32) load12(dout32 + tk * J.dout_ld + sub * CPL, t.dy);
-    else load12(dout + tk * J.dout_ld + sub * CPL, t.dy);
-    t.rs = t.ok ? J.rstd[tk] : 0.f;
+    if (f32) load12(dout32 + tk * dout_ld + sub * CPL, t.dy);
+    else load12(dout + tk * dout_ld + sub * CPL, t.dy);
+    t.rs = t.ok ? rstdp[tk] : 0.f;
   };
   auto consume = [&](Tok& t) {
     float s1 = 0.f, s2 = 0.f;
@@ -627,11 +633,11 @@ __global__ void __launch_bounds__(SV_THREADS) pool_ln_bwd_saved_kernel(const __g
     const int64_t bh = t.tok / (Lo + 1);
     const int n = (int)(t.tok - bh * (Lo + 1));
     if (n == 0) {
-      const int head = (int)(bh % L.heads);
-      const int64_t b = bh / L.heads;
-      store12(reinterpret_cast<T*>(J.din) + b * L.in_bs + head * L.in_hs + sub * CPL, dc);
+      const int head = (int)(bh % heads);
+      const int64_t b = bh / heads;
+      store12(dinp + b * in_bs + head * in_hs + sub * CPL, dc);
     } else {
-      store12(reinterpret_cast<T*>(J.dconv) + (bh * Lo + (n - 1)) * HD + sub * CPL, dc);
+      store12(dconvp + (bh * Lo + (n - 1)) * HD + sub * CPL, dc);
     }
   };
   const int64_t tstep = (int64_t)J.nblk * SV_TOK;

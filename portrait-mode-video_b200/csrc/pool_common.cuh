@@ -39,6 +39,27 @@ struct Job {
   int nblk_ln, nblk_dw;           // number of partial vectors behind part_ln / part_dw (for the reduce kernel)
 };
 
+// Pin a kernel-parameter field in a register.  Fields of the job table are addressed with a run-time index, so every use
+// compiles to an indexed constant load (LDC / LDCU c[0x0][R + off]) that the compiler prefers to re-issue rather than
+// keep in a register; in the store section of the LayerNorm warps those loads sat in front of every predicate and
+// address (profiles/r02_pool_trace.md: 1.2 us for ~150 instructions).
+template <typename P> __device__ __forceinline__ P* pin(P* p) {
+  asm volatile("" : "+l"(p));
+  return p;
+}
+__device__ __forceinline__ int pin(int v) {
+  asm volatile("" : "+r"(v));
+  return v;
+}
+__device__ __forceinline__ int64_t pin(int64_t v) {
+  asm volatile("" : "+l"(v));
+  return v;
+}
+__device__ __forceinline__ float pin(float v) {
+  asm volatile("" : "+f"(v));
+  return v;
+}
+
 // ---- 2-channel loads / stores ---------------------------------------------------------------------------------
 __device__ __forceinline__ float2 ld2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 __device__ __forceinline__ float2 ld2(const bf16* p) {

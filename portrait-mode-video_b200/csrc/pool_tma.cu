@@ -97,27 +97,6 @@ __device__ __forceinline__ float2 lds2(const bf16* p) {
   return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 
-// Pin a kernel-parameter field in a register.  Fields of the job table are addressed with a run-time index, so every use
-// compiles to an indexed constant load (LDC / LDCU c[0x0][R + off]) that the compiler prefers to re-issue rather than
-// keep in a register; in the store section of the LayerNorm warps those loads sat in front of every predicate and
-// address (profiles/r02_pool_trace.md: 1.2 us for ~150 instructions).
-template <typename P> __device__ __forceinline__ P* pin(P* p) {
-  asm volatile("" : "+l"(p));
-  return p;
-}
-__device__ __forceinline__ int pin(int v) {
-  asm volatile("" : "+r"(v));
-  return v;
-}
-__device__ __forceinline__ int64_t pin(int64_t v) {
-  asm volatile("" : "+l"(v));
-  return v;
-}
-__device__ __forceinline__ float pin(float v) {
-  asm volatile("" : "+f"(v));
-  return v;
-}
-
 __device__ const uint32_t pool_zero_words[4] = {0u, 0u, 0u, 0u};
 __device__ __forceinline__ uint32_t ld_raw(const bf16* p) { return __ldg(reinterpret_cast<const unsigned int*>(p)); }
 __device__ __forceinline__ float2 ld_raw(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
