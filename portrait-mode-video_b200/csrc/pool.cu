@@ -750,7 +750,8 @@ int fill_jobs(Job* J, const void* qkv, int64_t ws_, const pmv_pool_job* jobs, in
 
 // Runs one mode over the jobs: those the TMA t-march can take go to pool_tma.cu, the rest to the direct kernels here.
 // mode 0 forward, 1 backward (i), 2 backward (ii), 3 backward (iii).
-int run_mode(int mode, Job* all, int njobs, const Geom& g, cudaStream_t st) {
+int run_mode(int mode, Job* all, int njobs, const Geom& g, cudaStream_t st, cudaStream_t st_b) {
+  // st_b: stream of the second job class of the launch (tap tiles; mode 3: the strided input-gradient kernels)
   Job tj[MAX_JOBS], dj[MAX_JOBS];
   int ti[MAX_JOBS], di[MAX_JOBS];
   int nt = 0, nd = 0;
@@ -790,7 +791,8 @@ int run_mode(int mode, Job* all, int njobs, const Geom& g, cudaStream_t st) {
         if (mode == 1) all[ci[i]].nblk_ln = cj[i].nblk + cj[i].ncls_blk;
         if (mode == 2) all[ci[i]].nblk_dw = cj[i].nblk;
       }
-      int rc = tma_launch(mode, cj, nc, g.B, g.heads, g.T, g.H, g.W, g.bs, g.ts, g.hs, g.eps, g.dtype, st);
+      int rc = tma_launch(mode, cj, nc, g.B, g.heads, g.T, g.H, g.W, g.bs, g.ts, g.hs, g.eps, g.dtype,
+                          (mode != 3 && cls == 1) ? st_b : st, st_b);
       if (rc) return rc;
     }
   }
@@ -822,6 +824,61 @@ int run_mode(int mode, Job* all, int njobs, const Geom& g, cudaStream_t st) {
 }
 
 }  // namespace
+
+namespace {
+struct AuxStreams {
+  cudaStream_t s[2];
+  cudaEvent_t fork, join[2];
+  int state;  // 0 = not created, 1 = ready, -1 = unavailable
+};
+AuxStreams g_aux[64];
+bool streams_enabled() {
+  static const bool on = [] { const char* e = std::getenv("PMV_POOL_STREAMS"); return e == nullptr || e[0] != '0'; }();
+  return on;
+}
+AuxStreams* aux_for_device() {
+  int dev = 0;
+  if (!streams_enabled() || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  AuxStreams& a = g_aux[dev];
+  if (a.state == 0) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    // creating streams / events is legal during capture, but keep the first use outside of it simple: any failure
+    // disables the fork for this device
+    bool ok = cudaStreamCreateWithFlags(&a.s[0], cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&a.s[1], cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&a.join[0], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&a.join[1], cudaEventDisableTiming) == cudaSuccess;
+    (void)cs;
+    a.state = ok ? 1 : -1;
+    if (!ok) cudaGetLastError();
+  }
+  return a.state == 1 ? &a : nullptr;
+}
+}  // namespace
+
+PoolFork pool_fork(cudaStream_t main) {
+  PoolFork f;
+  f.main = main; f.side[0] = main; f.side[1] = main; f.on = false;
+  AuxStreams* a = aux_for_device();
+  if (a == nullptr) return f;
+  if (cudaEventRecord(a->fork, main) != cudaSuccess || cudaStreamWaitEvent(a->s[0], a->fork, 0) != cudaSuccess ||
+      cudaStreamWaitEvent(a->s[1], a->fork, 0) != cudaSuccess) {
+    cudaGetLastError();
+    return f;
+  }
+  f.side[0] = a->s[0]; f.side[1] = a->s[1]; f.on = true;
+  return f;
+}
+
+void pool_join(const PoolFork& f) {
+  if (!f.on) return;
+  AuxStreams* a = aux_for_device();
+  for (int i = 0; i < 2; ++i) {
+    cudaEventRecord(a->join[i], f.side[i]);
+    cudaStreamWaitEvent(f.main, a->join[i], 0);
+  }
+}
 }  // namespace pool
 
 using namespace pool;
@@ -845,7 +902,15 @@ extern "C" int pmv_pool_ln_qkv_fwd(const void* qkv, int64_t batch_stride, int64_
                (J[i].out_ld - HD) % 32 == 0;
     if (!fused[i]) J[i].onehot = 0;
   }
-  rc = run_mode(0, J, njobs, g, (cudaStream_t)stream);
+  {
+    // dense-plane jobs on the caller's stream, tap-tile jobs (stride >= 3: 32-64 CTAs) beside them
+    bool two_classes = false, has_dense = false, has_tap = false;
+    for (int i = 0; i < njobs; ++i) (J[i].s <= 2 ? has_dense : has_tap) = true;
+    two_classes = has_dense && has_tap && tma_ok;
+    PoolFork fk = two_classes ? pool_fork((cudaStream_t)stream) : PoolFork{(cudaStream_t)stream, {(cudaStream_t)stream, (cudaStream_t)stream}, false};
+    rc = run_mode(0, J, njobs, g, (cudaStream_t)stream, fk.side[0]);
+    pool_join(fk);
+  }
   if (rc) return rc;
   for (int i = 0; i < njobs; ++i) {
     if (jobs[i].onehot && !fused[i]) {
@@ -916,13 +981,18 @@ extern "C" int pmv_pool_ln_qkv_bwd(const void* qkv, int64_t batch_stride, int64_
       PMV_CHECK_LAUNCH();
     }
     if (nr > 0) {
-      rc = run_mode(1, rj, nr, g, st);
+      rc = run_mode(1, rj, nr, g, st, st);
       if (rc) return rc;
       for (int k = 0; k < nr; ++k) J[ri[k]].nblk_ln = rj[k].nblk_ln;
     }
   }
-  for (int mode = 2; mode <= 3; ++mode) {
-    rc = run_mode(mode, J, njobs, g, st);
+  // dW (caller's stream; its tap-tile class on side stream 1), the stride-1 input gradient (side stream 0) and the strided
+  // input-gradient kernels (side stream 1) only depend on the pre-LN gradient written above
+  {
+    PoolFork fk = pool_fork(st);
+    rc = run_mode(2, J, njobs, g, st, fk.side[1]);
+    if (!rc) rc = run_mode(3, J, njobs, g, fk.side[0], fk.side[1]);
+    pool_join(fk);
     if (rc) return rc;
   }
   Launch L;

@@ -102,6 +102,18 @@ int tma_items(int B, int heads, int Ho, int Wo);
 bool tma_eligible(int stride_hw, int mode, int elem_bytes);
 bool tma_fwd_writes_onehot();  // the warp-specialised forward kernel is in use (it fills Job::onehot columns itself)
 int tma_launch(int mode, const Job* jobs, int njobs, int B, int heads, int T, int H, int W, int64_t bs, int64_t ts, int64_t hs,
-               float eps, int dtype, cudaStream_t st);
+               float eps, int dtype, cudaStream_t st, cudaStream_t st_strided);
+
+// Fork / join of the independent pooling launches (pool.cu).  The kernels of one pooling call each fill 0.2-0.9 waves of the
+// machine (profiles/r02_pool_ncu.md) and several of them do not depend on one another (dW vs the input-gradient kernels,
+// dense-plane vs tap-tile job classes), so they are issued on two lazily created side streams between an event fork and
+// an event join on the caller's stream: inside a captured CUDA graph these become parallel branches.  PMV_POOL_STREAMS=0
+// keeps everything on the caller's stream.
+struct PoolFork {
+  cudaStream_t main, side[2];
+  bool on;
+};
+PoolFork pool_fork(cudaStream_t main);
+void pool_join(const PoolFork& f);
 
 }  // namespace pool

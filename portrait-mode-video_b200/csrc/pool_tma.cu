@@ -1279,7 +1279,7 @@ int launch_din_strided(const Job* jobs, int njobs, TLaunch& L, int esz, cudaStre
 // mode: 0 forward, 1 backward (i), 2 backward (ii), 3 backward (iii).  `jobs` hold their block ranges for this launch
 // (blk_begin / nblk / ncls_blk) and, for the backward modes, part_ln / part_dw / dconv / din.
 int tma_launch(int mode, const Job* jobs, int njobs, int B, int heads, int T, int H, int W, int64_t bs, int64_t ts, int64_t hs,
-               float eps, int dtype, cudaStream_t st) {
+               float eps, int dtype, cudaStream_t st, cudaStream_t st_strided) {
   TLaunch L;
   memset(&L, 0, sizeof(L));
   L.njobs = njobs; L.B = B; L.heads = heads; L.T = T; L.H = H; L.W = W;
@@ -1300,11 +1300,12 @@ int tma_launch(int mode, const Job* jobs, int njobs, int B, int heads, int T, in
       }
     }
     if (nother > 0) {
-      int rc = dtype == PMV_BF16 ? launch_din_strided<bf16>(jobs, njobs, L, esz, st) : launch_din_strided<float>(jobs, njobs, L, esz, st);
+      int rc = dtype == PMV_BF16 ? launch_din_strided<bf16>(jobs, njobs, L, esz, st_strided)
+                                 : launch_din_strided<float>(jobs, njobs, L, esz, st_strided);
       if (rc) return rc;
     }
     if (n1 == 0) return PMV_OK;
-    if (n1 < njobs) return tma_launch(3, s1, n1, B, heads, T, H, W, bs, ts, hs, eps, dtype, st);
+    if (n1 < njobs) return tma_launch(3, s1, n1, B, heads, T, H, W, bs, ts, hs, eps, dtype, st, st);
   }
   int total = 0;
   size_t max_plane = 0;

@@ -113,13 +113,18 @@ class LinearFn(Function):
         dy2 = dy.reshape(-1, N)
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
+        join = None
         if dy2.dtype != T or row_scale is not None:
             db, dyT = ops.colsum_cast(dy2, T, row_scale, rps, want_sum=has_bias)
         else:
             dyT = dy2
-            db = ops.colsum_cast(dy2, None, want_sum=True)[0] if has_bias else None
+            db = None
+            if has_bias:  # sum only: runs beside the two GEMMs below
+                db, join = ops.colsum_beside(dy2)
         dx = ops.linear_dgrad(dyT, w, T).view(xshape) if ctx.needs_input_grad[0] else None
         dw = ops.linear_wgrad(dyT, x2, arena=ctx.arena, home=ops.grad_home(ctx.param))
+        if join is not None:
+            join()
         return dx, dw, db, (dy if has_res else None), None, None, None
 
 
@@ -167,9 +172,10 @@ class MlpFn(Function):
             db2 = ops.colsum_cast(dy2, None)[0]
         dw2 = ops.linear_wgrad(dyT, h, arena=ctx.arenas[1], home=ops.grad_home(ctx.params[1]))
         du = ops.linear_dgrad(dyT, w2c, T, act=L.ACT_GELU_BWD, aux_in=u)
-        db1 = ops.colsum_cast(du, None)[0]
+        db1, join = ops.colsum_beside(du)  # the fc1 bias gradient, beside the two GEMMs that also read du
         dw1 = ops.linear_wgrad(du, x2, arena=ctx.arenas[0], home=ops.grad_home(ctx.params[0]))
         dx = ops.linear_dgrad(du, w1c, T).view(xshape)
+        join()
         return dx, dw1, db1, dw2, db2, (dy if has_res else None), None, None
 
 

@@ -233,6 +233,65 @@ def colsum_cast(x2d, cast_dtype=None, row_scale=None, rows_per_scale=1, want_sum
     return s, c
 
 
+class _SideStream:
+    """One side stream per device for work that only has to finish before the calling autograd node returns: the
+    bias-gradient column sums, which are memory-bound 256-thread CTAs without shared memory and fit beside the persistent
+    GEMM CTAs of the same backward node.  fork(): the side stream waits for everything issued so far on the current
+    stream; join(): the current stream waits for the side stream.  Inside a captured CUDA graph the side work becomes a
+    parallel branch.  PMV_SIDE_STREAM=0 disables it (everything on the current stream)."""
+
+    _by_device = {}
+
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device=device)
+        self.fork_ev = torch.cuda.Event()
+        self.join_ev = torch.cuda.Event()
+
+    @classmethod
+    def get(cls, device):
+        import os
+        if os.environ.get("PMV_SIDE_STREAM", "1") == "0" or device.type != "cuda":
+            return None
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        st = cls._by_device.get(key)
+        if st is None:
+            st = cls._by_device[key] = cls(device)
+        return st
+
+    def fork(self):
+        self.fork_ev.record(torch.cuda.current_stream())
+        self.stream.wait_event(self.fork_ev)
+
+    def join(self):
+        self.join_ev.record(self.stream)
+        torch.cuda.current_stream().wait_event(self.join_ev)
+
+
+def colsum_beside(x2d):
+    """Column sums of x2d (a bias gradient) launched on the side stream: returns (sum, join) — call join() before the sum
+    is handed to anything else.  The output and the workspace are allocated on the CURRENT stream (the caching allocator
+    keys blocks by the allocating stream; the join orders every later use after the side kernels)."""
+    side = _SideStream.get(x2d.device)
+    if side is None or _RECORDER is not None:  # per-kernel timing (bench.py) measures on the current stream only
+        return colsum_cast(x2d, None)[0], (lambda: None)
+    global LAUNCHES
+    rows, cols = x2d.shape
+    s = torch.empty(cols, dtype=torch.float32, device=x2d.device)
+    ws = _ws(L.lib().pmv_colsum_workspace_bytes(rows, cols), x2d.device)
+    side.fork()
+    LAUNCHES += 2
+    L.check(L.lib().pmv_colsum_cast(L.ptr(x2d), L.dt(x2d), x2d.stride(0), rows, cols, None, 1, L.ptr(s), L.ptr(ws), None, 0, 0,
+                                    C.c_void_p(side.stream.cuda_stream)), "pmv_colsum_cast")
+
+    def join(keep=(ws, x2d)):
+        # `ws` must stay allocated until the current stream has been ordered after the side kernels: freed earlier, the
+        # caching allocator (which only knows the allocating stream) hands the block to the next allocation of the current
+        # stream while the side stream still writes its partial sums into it (seen as a corrupted fc1 weight gradient)
+        side.join()
+
+    return s, join
+
+
 # ----------------------------------------------------------------------------- pooling
 def pooled_hw(n: int, s: int) -> int:
     return (n - 1) // s + 1
