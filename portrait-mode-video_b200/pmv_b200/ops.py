@@ -208,13 +208,15 @@ def grad_home(param) -> Optional[torch.Tensor]:
 
 def linear_wgrad(dy2d, x2d, tc=None, arena: Optional[ZeroArena] = None, home: Optional[torch.Tensor] = None):
     """dW[N,K] = dy[M,N]^T @ x[M,K] in fp32 (split over the token rows, fp32 atomics into zeroed memory: the parameter's
-    slot in its all-reduce bucket (``home``), else a slice of the owning model's ``arena``, else a fresh torch.zeros)."""
+    slot in its all-reduce bucket (``home``), else a slice of the owning model's ``arena``, else a fresh torch.zeros).
+    (Launching it on the side stream beside the dgrad GEMM of the same layer was measured: 14.11 ms per step against
+    14.21 / 13.96 / 14.22 without — two persistent 148-CTA GEMMs do not share SMs, nothing to gain.)"""
     M, N = dy2d.shape
     K = x2d.shape[1]
     split = _pick_split(M, N, K)
     if home is not None and tuple(home.shape) == (N, K) and home.is_contiguous():
-        return gemm(L.GEMM_NT_REDUCE_M, dy2d, x2d, M, N, K, home, split_k=split, tc=tc)
-    if split > 1:
+        out = home
+    elif split > 1:
         flat = arena.take(N * K, dy2d.device) if arena is not None else None
         out = flat.view(N, K) if flat is not None else torch.zeros(N, K, dtype=torch.float32, device=dy2d.device)
     else:
