@@ -9,7 +9,12 @@
  * Conventions
  *   - All pointers are DEVICE pointers unless named `*_host`.  No allocation happens
  *     inside the library; temporaries are caller-provided workspaces.
- *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Every kernel of a call is ordered on that
+ *     stream as seen by the caller.  The pooling entry points may run launches that do not depend on one another on
+ *     two library-owned side streams (created lazily per device, cudaStreamNonBlocking) between an event fork and an
+ *     event join on `stream` — parallel branches when the call is captured into a CUDA graph; PMV_POOL_STREAMS=0 in the
+ *     environment keeps everything on `stream`.  This and the tensor maps / function attributes created on first use
+ *     are the only state the library keeps.
  *   - Every function returns 0 on success or a PMV_ERR_* code; pmv_last_error() returns a
  *     thread-local description of the last failure.
  *   - dtype arguments take PMV_F32 or PMV_BF16 ("fp32 mode" / "bf16 mode" of the path:
