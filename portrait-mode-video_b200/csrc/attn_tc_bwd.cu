@@ -35,8 +35,26 @@ __device__ long long pmv_attn_bwd_trace_buf[BTRACE_CTAS * BTRACE_SLOTS];
 extern "C" int pmv_debug_attn_bwd_trace(long long* host_out) {
   return cudaMemcpyFromSymbol(host_out, pmv_attn_bwd_trace_buf, sizeof(long long) * BTRACE_CTAS * BTRACE_SLOTS) == cudaSuccess ? 0 : 1;
 }
+// dK/dV kernel: 4096 CTAs x 32 slots (scripts/attn_trace_dkv.py)
+constexpr int KTRACE_CTAS = 4096, KTRACE_SLOTS = 32;
+__device__ long long pmv_attn_dkv_trace_buf[KTRACE_CTAS * KTRACE_SLOTS];
+#define KTRACE(slot)                                                                                                  \
+  do {                                                                                                                \
+    const int cta_ = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;                                  \
+    if (cta_ < KTRACE_CTAS) pmv_attn_dkv_trace_buf[cta_ * KTRACE_SLOTS + (slot)] = clock64();                         \
+  } while (0)
+#define KTRACE_VAL(slot, val)                                                                                         \
+  do {                                                                                                                \
+    const int cta_ = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;                                  \
+    if (cta_ < KTRACE_CTAS) pmv_attn_dkv_trace_buf[cta_ * KTRACE_SLOTS + (slot)] = (long long)(val);                  \
+  } while (0)
+extern "C" int pmv_debug_attn_dkv_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, pmv_attn_dkv_trace_buf, sizeof(long long) * KTRACE_CTAS * KTRACE_SLOTS) == cudaSuccess ? 0 : 1;
+}
 #else
 #define BTRACE(slot) do { } while (0)
+#define KTRACE(slot) do { } while (0)
+#define KTRACE_VAL(slot, val) do { } while (0)
 #endif
 
 namespace {
@@ -52,7 +70,7 @@ struct BwdGeom {
   float scale;
   int residual;
   int64_t ld_qk;
-  int q_tiles_per_chunk;
+  int chunks;  // dK/dV kernel: the query tiles are split evenly over gridDim.z = chunks CTAs per (key tile, batch, head)
 };
 
 template <int KD> struct BCfg {
@@ -409,9 +427,17 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int bidx = bh / g.heads, head = bh - bidx * g.heads;
   const int k0 = blockIdx.x * BT;
   const int total_qt = (g.Nq + BT - 1) / BT;
-  const int qt_begin = blockIdx.z * g.q_tiles_per_chunk;
-  const int qt_end = min(total_qt, qt_begin + g.q_tiles_per_chunk);
-  const int nq_tiles = qt_end - qt_begin;  // >= 1 by construction of the grid
+  const int qt_begin = (int)(((int64_t)blockIdx.z * total_qt) / g.chunks);
+  const int qt_end = (int)(((int64_t)(blockIdx.z + 1) * total_qt) / g.chunks);
+  const int nq_tiles = qt_end - qt_begin;  // >= 1: chunks <= total_qt
+#ifdef PMV_ATTN_TRACE
+  if (threadIdx.x == 0) {
+    KTRACE(0);
+    unsigned smid; asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    KTRACE_VAL(29, smid); KTRACE_VAL(30, gt);
+  }
+#endif
 
   if (warp == 0 && lane == 0) {
     tc::mbar_init(k_full, 1);
@@ -430,6 +456,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_st = tmem_base, tmem_dpt = tmem_base + 128, tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 384;
+  if (threadIdx.x == 0) KTRACE(1);
   pdl_wait();  // the prologue above overlaps the previous kernel's tail
 
   if (warp == 0) {
@@ -455,6 +482,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const KDesc dKt = kdesc(tc::smem_u32(sK)), dVt = kdesc(tc::smem_u32(sV));
       tc::mbar_wait(k_full, 0);
       tc::tc_fence_after();
+      KTRACE(2);
       const uint32_t idesc_o = tc::make_idesc_bf16(BT, HD, false, true);  // N = 96 channels, B read MN-major
       int hh = 0;
       bool have_prev = false, first_acc = true;
@@ -489,6 +517,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int q0 = (qt_begin + i) * BT;
         tc::mbar_wait(&q_full[st], (i >> 1) & 1);
         tc::tc_fence_after();
+        if (i < 3) KTRACE(3 + i);
         const int nqv = min(BT, g.Nq - q0);
         const uint32_t sq_addr = tc::smem_u32(sStage + st * Cfg::STAGE_BYTES);
         const KDesc dQs = kdesc(sq_addr), dOs = kdesc(sq_addr + Cfg::QK_BYTES);
@@ -499,6 +528,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const int n16 = (nv + 15) & ~15;
           const int b = hh & 1;
           const uint32_t idesc_s = tc::make_idesc_bf16(BT, n16, false, false);
+          if (hh == 2) KTRACE(6);
 #pragma unroll
           for (int ks = 0; ks < KD / 16; ++ks)  // S^T = K' Q'^T (queries of this half)
             tc::umma_ss(tmem_st + b * HK, kmajor_desc<KD>(dKt, ks), kmajor_desc<KD>(dQs, ks, half), idesc_s, ks > 0);
@@ -506,7 +536,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           for (int ks = 0; ks < HD / 16; ++ks)  // dP^T = V dO^T
             tc::umma_ss(tmem_dpt + b * HK, kmajor_desc<128>(dVt, ks), kmajor_desc<128>(dOs, ks, half), idesc_s, ks > 0);
           tc::umma_commit(&sdp_full[b]);
+          if (hh == 2) KTRACE(7);
           if (have_prev) retire();
+          if (hh == 2) KTRACE(8);
           have_prev = true;
           p_b = b; p_hh = hh; p_nks = n16 >> 4; p_half = half; p_st = st; p_sq = mQ; p_sdo = mdO;
           p_last = (half == 1) || (nqv <= HK);
@@ -542,6 +574,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int b = hh & 1;
         tc::mbar_wait(&sdp_full[b], (uint32_t)((hh >> 1) & 1));
         tc::tc_fence_after();
+        if (warp == 4 && lane == 0 && hh < 8) KTRACE(9 + 2 * hh);
         if (wh * 32 < nv) {
           uint32_t s[32], dp[32], pk[16], dk[16];
           tc::tmem_ld32(tmem_st + lane_addr + b * HK + wh * 32, s);
@@ -567,11 +600,14 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&pds_full[b]);
+        if (warp == 4 && lane == 0 && hh < 8) KTRACE(10 + 2 * hh);
         ++hh;
       }
     }
+    if (warp == 4 && lane == 0) KTRACE(25);
     tc::mbar_wait(final_bar, 0);
     tc::tc_fence_after();
+    if (warp == 4 && lane == 0) KTRACE(26);
     const int key = k0 + row;
     float* dkp = dk_ws + ((int64_t)bh * g.Nk + key) * HD;
     float* dvp = dv_ws + ((int64_t)bh * g.Nk + key) * HD;
@@ -581,7 +617,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tc::tmem_ld32(tmem_dv + lane_addr + ch * 32, a);
       tc::tmem_ld32(tmem_dk + lane_addr + ch * 32, b);
       tc::tmem_ld_wait();
-      if (key < g.Nk) {
+      if (key < g.Nk && g.chunks == 1) {  // the only contribution to these rows: plain stores into an un-cleared workspace
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          *reinterpret_cast<uint4*>(dvp + ch * 32 + e) = make_uint4(a[e], a[e + 1], a[e + 2], a[e + 3]);
+          *reinterpret_cast<uint4*>(dkp + ch * 32 + e) = make_uint4(b[e], b[e + 1], b[e + 2], b[e + 3]);
+        }
+      } else if (key < g.Nk) {
 #pragma unroll
         for (int e = 0; e < 32; e += 4) {  // 16-byte vector reductions (rows are 384-byte aligned)
           asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dvp + ch * 32 + e), "f"(__uint_as_float(a[e])),
@@ -592,9 +634,20 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
     }
   }
+  if (warp == 4 && lane == 0) KTRACE(27);
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 2) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 512); }
+  if (warp == 2) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, 512);
+#ifdef PMV_ATTN_TRACE
+    if (lane == 0) {
+      KTRACE(28);
+      unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+      KTRACE_VAL(31, gt);
+    }
+#endif
+  }
 }
 
 template <typename T>
@@ -608,6 +661,31 @@ __global__ void __launch_bounds__(256) cast_rows96_kernel(const float* __restric
     load4(src + r * HD + c4 * 4, v);
     store4(dst + r * ld + c4 * 4, v);
   }
+}
+
+// How many CTAs share the query tiles of one (key tile, batch, head) in the dK/dV kernel.  Cycle stamps
+// (scripts/attn_trace_dkv.py, profiles/r02_attn_dkv_trace.md): a CTA pays ~2 us until its first S^T / dP^T is ready and
+// ~3.5 us at the end (final commit, 98 KB of red.global.add per CTA, TMEM release) around ~2.05 us (kd = 128) / ~2.3 us
+// (kd = 160) per 128-query tile, one CTA per SM at a time.  The first version aimed at >= 3 CTAs per SM and paid that fixed
+// cost 3 - 6 times per SM (mid-stage: 512 CTAs of 4 query tiles, 49 us; one chunk: 128 CTAs of 13 tiles).  Pick the chunk count
+// that minimises  rounds x (fixed + tiles per chunk x per-tile).
+int dkv_chunks(int q_tiles, int64_t base_ctas, int kd) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* ev = getenv("PMV_ATTN_DKV_CHUNKS");
+    forced = ev != nullptr ? atoi(ev) : 0;
+  }
+  if (forced > 0) return forced < q_tiles ? forced : q_tiles;
+  const double per_tile = kd == 128 ? 2.05 : 2.3;
+  double best = 1e30;
+  int best_c = 1;
+  for (int c = 1; c <= q_tiles && c <= 64; ++c) {
+    const int64_t rounds = (base_ctas * c + 147) / 148;
+    const double fixed = c == 1 ? 4.5 : 5.8;  // plain stores instead of reductions
+    const double t = (double)rounds * (fixed + (double)((q_tiles + c - 1) / c) * per_tile);
+    if (t < best - 1e-9) { best = t; best_c = c; }
+  }
+  return best_c;
 }
 
 template <int KD>
@@ -630,7 +708,6 @@ int launch_bwd(const void* q_aug, const void* k_aug, int64_t ld_qk, const void* 
   float* dk_ws = ws;
   float* dv_ws = ws + krows * HD;
   float* delta = ws + 2 * krows * HD;
-  PMV_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)(2 * krows * HD) * sizeof(float), stream));
 
   auto kq = attn_bwd_dq_kernel<KD>;
   auto kkv = attn_bwd_dkv_kernel<KD>;
@@ -650,12 +727,11 @@ int launch_bwd(const void* q_aug, const void* k_aug, int64_t ld_qk, const void* 
   }
   pmv_launch(kq, dim3((unsigned)q_tiles, (unsigned)BH), THREADS, Cfg::SMEM_BYTES, stream, 
       tmQ, tmQ2, tmK, tmK2, tmV, tmdO, (const bf16*)dout, lse, delta, (bf16*)dq_aug, g);
-  // split the query tiles so that about 3 CTAs per SM exist
-  int chunks = (int)((148 * 3 + (int64_t)k_tiles * BH - 1) / ((int64_t)k_tiles * BH));
-  if (chunks < 1) chunks = 1;
-  if (chunks > q_tiles) chunks = q_tiles;
-  g.q_tiles_per_chunk = (q_tiles + chunks - 1) / chunks;
-  chunks = (q_tiles + g.q_tiles_per_chunk - 1) / g.q_tiles_per_chunk;
+  const int chunks = dkv_chunks(q_tiles, (int64_t)k_tiles * (int64_t)BH, KD);
+  g.chunks = chunks;
+  // several chunks add their partial dK / dV into the workspace (cleared here, between the two kernels' launches: the dQ
+  // kernel does not touch it); a single chunk stores
+  if (chunks > 1) PMV_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)(2 * krows * HD) * sizeof(float), stream));
   pmv_launch(kkv, dim3((unsigned)k_tiles, (unsigned)BH, (unsigned)chunks), THREADS, Cfg::SMEM_BYTES, stream, 
       tmQ, tmQ2, tmK, tmK2, tmV, tmdO, lse, delta, dk_ws, dv_ws, g);
   int64_t cblocks = ceil_div64(krows * (HD / 4), 256);
