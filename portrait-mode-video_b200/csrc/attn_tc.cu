@@ -129,7 +129,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   pdl_wait();  // the prologue above overlaps the previous kernel's tail
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       tc::mbar_expect_tx(q_full, Cfg::QK_BYTES);
       tc::tma_load_3d(sQ, &tmQ, 0, q0, bh, q_full);
       tc::tma_load_3d(sQ + 16384, &tmQ, 64, q0, bh, q_full);
@@ -149,7 +149,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       const uint32_t sq_addr = tc::smem_u32(sQ);
       const uint32_t hi128 = (uint32_t)(tc::make_smem_desc(0, 16, 1024, tc::SWIZZLE_128B) >> 32);
       const uint32_t hi64 = (uint32_t)(tc::make_smem_desc(0, 16, 512, tc::SWIZZLE_64B) >> 32);
@@ -367,7 +367,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (warp == 4 && lane == 0) TRACE(6);
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 4 && lane == 0) {
+    if (warp == 4 && tc::elect_one()) {
       tc::tma_store_3d(&tmO, sOut, head * HD, q0, bidx);
       if (out_pre != nullptr) tc::tma_store_3d(&tmOpre, sPre, head * HD, q0, bidx);
       tc::bulk_commit_group();

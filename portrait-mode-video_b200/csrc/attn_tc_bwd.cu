@@ -216,7 +216,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (threadIdx.x == 0) BTRACE(1);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       tc::mbar_expect_tx(q_full, Cfg::STAGE_BYTES);
       load_tile_qk(sQ, &tmQ, &tmQ2, KD, q0, bh, q_full);
       tc::tma_load_3d(sdO, &tmdO, head * HD, q0, bidx, q_full);
@@ -233,7 +233,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       const KDesc dQt = kdesc(tc::smem_u32(sQ)), ddO = kdesc(tc::smem_u32(sdO));
       const uint32_t idesc_128 = tc::make_idesc_bf16(BT, 128, false, true);
       const uint32_t idesc_32 = tc::make_idesc_bf16(BT, 32, false, true);
@@ -403,8 +403,8 @@ __global__ void __launch_bounds__(THREADS, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQ2,
                     const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmK2,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
-                    const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dk_ws,
-                    float* __restrict__ dv_ws, BwdGeom g) {
+                    const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV,
+                    const float* __restrict__ lse, const float* __restrict__ delta, BwdGeom g) {
   using Cfg = BCfg<KD>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -460,7 +460,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   pdl_wait();  // the prologue above overlaps the previous kernel's tail
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       tc::mbar_expect_tx(k_full, Cfg::STAGE_BYTES);
       load_tile_qk(sK, &tmK, &tmK2, KD, k0, bh, k_full);
       tc::tma_load_3d(sV, &tmV, 0, k0, bh, k_full);
@@ -478,7 +478,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       const KDesc dKt = kdesc(tc::smem_u32(sK)), dVt = kdesc(tc::smem_u32(sV));
       tc::mbar_wait(k_full, 0);
       tc::tc_fence_after();
@@ -580,18 +580,24 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tc::tmem_ld32(tmem_st + lane_addr + b * HK + wh * 32, s);
           tc::tmem_ld32(tmem_dpt + lane_addr + b * HK + wh * 32, dp);
           tc::tmem_ld_wait();
+          // lse / delta of the 32 queries of this warp half: 16-byte broadcast loads (one per four scores, not two per score)
+          const float4* l4 = reinterpret_cast<const float4*>(lse_t + half * HK + wh * 32);
+          const float4* d4 = reinterpret_cast<const float4*>(del_t + half * HK + wh * 32);
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            float p[2], d[2];
+          for (int e4 = 0; e4 < 8; ++e4) {
+            const float4 lv = l4[e4], dv = d4[e4];
+            const float ls[4] = {lv.x, lv.y, lv.z, lv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w};
+            float p[4], d[4];
             // no masking of queries >= Nq: their Q' and dO rows are zero-filled by TMA, so P^T dO and dS^T Q' gain nothing
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int col = half * HK + wh * 32 + 2 * e + h;  // query inside the tile
-              p[h] = tc::fast_ex2(fmaf(__uint_as_float(s[2 * e + h]), c, -lse_t[col]));
-              d[h] = p[h] * fmaf(__uint_as_float(dp[2 * e + h]), g.scale, -del_t[col]);
+            for (int h = 0; h < 4; ++h) {
+              p[h] = tc::fast_ex2(fmaf(__uint_as_float(s[4 * e4 + h]), c, -ls[h]));
+              d[h] = p[h] * fmaf(__uint_as_float(dp[4 * e4 + h]), g.scale, -ds[h]);
             }
-            pk[e] = tc::pack_bf16x2_alu(p[0], p[1]);
-            dk[e] = tc::pack_bf16x2_alu(d[0], d[1]);
+            pk[2 * e4] = tc::pack_bf16x2_alu(p[0], p[1]);
+            pk[2 * e4 + 1] = tc::pack_bf16x2_alu(p[2], p[3]);
+            dk[2 * e4] = tc::pack_bf16x2_alu(d[0], d[1]);
+            dk[2 * e4 + 1] = tc::pack_bf16x2_alu(d[2], d[3]);
           }
           tc::tmem_st16(tmem_st + lane_addr + b * HK + wh * 32, pk);
           tc::tmem_st16(tmem_dpt + lane_addr + b * HK + wh * 32, dk);
@@ -608,30 +614,42 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tc::mbar_wait(final_bar, 0);
     tc::tc_fence_after();
     if (warp == 4 && lane == 0) KTRACE(26);
-    const int key = k0 + row;
-    float* dkp = dk_ws + ((int64_t)bh * g.Nk + key) * HD;
-    float* dvp = dv_ws + ((int64_t)bh * g.Nk + key) * HD;
+    // dV / dK tiles leave through shared memory: [128 keys x 32 channels] fp32 boxes in the 128B-swizzle layout (a thread
+    // owns a key row; 16-byte chunk j of row r sits at chunk j ^ (r & 7), so the eight lanes of a quarter warp hit eight
+    // different bank groups), then one bulk tensor reduce-add (several chunks) or store (one chunk) per box.  Per-thread
+    // red.global.add.v4 / st.global.v4 with a 384-byte stride between lanes cost 3.2 / 5.5 us per CTA: every warp
+    // instruction is 32 separate line requests (scripts/attn_trace_dkv.py).  Keys >= Nk are clipped by the tensor map.
+    uint8_t* sOut = sStage;  // the Q' / dO ring is idle: every MMA has retired
 #pragma unroll 1
     for (int ch = wh; ch < 3; ch += 2) {
       uint32_t a[32], b[32];
       tc::tmem_ld32(tmem_dv + lane_addr + ch * 32, a);
       tc::tmem_ld32(tmem_dk + lane_addr + ch * 32, b);
       tc::tmem_ld_wait();
-      if (key < g.Nk && g.chunks == 1) {  // the only contribution to these rows: plain stores into an un-cleared workspace
+      uint8_t* rv = sOut + ch * 16384 + row * 128;
+      uint8_t* rk = sOut + (3 + ch) * 16384 + row * 128;
 #pragma unroll
-        for (int e = 0; e < 32; e += 4) {
-          *reinterpret_cast<uint4*>(dvp + ch * 32 + e) = make_uint4(a[e], a[e + 1], a[e + 2], a[e + 3]);
-          *reinterpret_cast<uint4*>(dkp + ch * 32 + e) = make_uint4(b[e], b[e + 1], b[e + 2], b[e + 3]);
-        }
-      } else if (key < g.Nk) {
+      for (int j = 0; j < 8; ++j) {
+        const int off = (j ^ (row & 7)) << 4;
+        *reinterpret_cast<uint4*>(rv + off) = make_uint4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
+        *reinterpret_cast<uint4*>(rk + off) = make_uint4(b[4 * j], b[4 * j + 1], b[4 * j + 2], b[4 * j + 3]);
+      }
+    }
+    tc::fence_proxy_async();  // generic-proxy writes -> visible to the bulk operations
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (warp == 4 && tc::elect_one()) {
 #pragma unroll
-        for (int e = 0; e < 32; e += 4) {  // 16-byte vector reductions (rows are 384-byte aligned)
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dvp + ch * 32 + e), "f"(__uint_as_float(a[e])),
-                       "f"(__uint_as_float(a[e + 1])), "f"(__uint_as_float(a[e + 2])), "f"(__uint_as_float(a[e + 3])) : "memory");
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dkp + ch * 32 + e), "f"(__uint_as_float(b[e])),
-                       "f"(__uint_as_float(b[e + 1])), "f"(__uint_as_float(b[e + 2])), "f"(__uint_as_float(b[e + 3])) : "memory");
+      for (int ch = 0; ch < 3; ++ch) {
+        if (g.chunks == 1) {
+          tc::tma_store_3d(&tmDV, sOut + ch * 16384, ch * 32, k0, bh);
+          tc::tma_store_3d(&tmDK, sOut + (3 + ch) * 16384, ch * 32, k0, bh);
+        } else {
+          tc::tma_reduce_add_3d(&tmDV, sOut + ch * 16384, ch * 32, k0, bh);
+          tc::tma_reduce_add_3d(&tmDK, sOut + (3 + ch) * 16384, ch * 32, k0, bh);
         }
       }
+      tc::bulk_commit_group();
+      tc::bulk_wait_group_read0();  // shared memory is released when the CTA exits
     }
   }
   if (warp == 4 && lane == 0) KTRACE(27);
@@ -708,6 +726,9 @@ int launch_bwd(const void* q_aug, const void* k_aug, int64_t ld_qk, const void* 
   float* dk_ws = ws;
   float* dv_ws = ws + krows * HD;
   float* delta = ws + 2 * krows * HD;
+  CUtensorMap tmDK, tmDV;  // fp32 accumulators [BH][Nk][96] as [128 keys x 32 channels] boxes
+  if ((rc = pmv_make_tensor_map_3d(&tmDK, dk_ws, 4, HD, g.Nk, BH, HD, (uint64_t)g.Nk * HD, 32, BT, 1, 128))) return rc;
+  if ((rc = pmv_make_tensor_map_3d(&tmDV, dv_ws, 4, HD, g.Nk, BH, HD, (uint64_t)g.Nk * HD, 32, BT, 1, 128))) return rc;
 
   auto kq = attn_bwd_dq_kernel<KD>;
   auto kkv = attn_bwd_dkv_kernel<KD>;
@@ -733,7 +754,7 @@ int launch_bwd(const void* q_aug, const void* k_aug, int64_t ld_qk, const void* 
   // kernel does not touch it); a single chunk stores
   if (chunks > 1) PMV_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)(2 * krows * HD) * sizeof(float), stream));
   pmv_launch(kkv, dim3((unsigned)k_tiles, (unsigned)BH, (unsigned)chunks), THREADS, Cfg::SMEM_BYTES, stream, 
-      tmQ, tmQ2, tmK, tmK2, tmV, tmdO, lse, delta, dk_ws, dv_ws, g);
+      tmQ, tmQ2, tmK, tmK2, tmV, tmdO, tmDK, tmDV, lse, delta, g);
   int64_t cblocks = ceil_div64(krows * (HD / 4), 256);
   if (cblocks > 148 * 8) cblocks = 148 * 8;
   if (dk != nullptr) pmv_launch(cast_rows96_kernel<bf16>, (unsigned)cblocks, 256, 0, stream, dk_ws, (bf16*)dk, krows, ld_dk);

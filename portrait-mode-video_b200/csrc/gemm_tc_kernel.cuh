@@ -191,7 +191,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (tc::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t full_bar0_cl = PAIR ? tc::mapa_u32(&full_bar[0], 0) : 0u;  // the leader's full barriers
@@ -234,7 +234,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0 && leader) {
+    if (leader && tc::elect_one()) {
       const uint32_t idesc = tc::make_idesc_bf16(BM_TILE, BN, A_MN, B_MN);
       // One thread issues every MMA; at BN = 96 an MMA is ~48 tensor cycles, so the issue loop itself must be short.
       // A descriptor's high word depends only on the layout and its low word is additive in the address: both operands'
