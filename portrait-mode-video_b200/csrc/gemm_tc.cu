@@ -4,6 +4,19 @@
 
 #include "gemm_tc_kernel.cuh"
 
+#ifdef PMV_ATTN_TRACE
+// Debug build only (scripts/gemm_trace.py): per-CTA, per-work-item cycle stamps of the tcgen05 GEMM (GTRACE points).
+static long long* g_gemm_trace = nullptr;
+extern "C" int pmv_debug_gemm_trace(long long* host_out, int reset) {
+  const size_t n = (size_t)gemm_tc::GT_CTAS * gemm_tc::GT_ITEMS * gemm_tc::GT_SLOTS * sizeof(long long);
+  if (g_gemm_trace == nullptr && cudaMalloc(&g_gemm_trace, n) != cudaSuccess) return 1;
+  if (host_out != nullptr && cudaMemcpy(host_out, g_gemm_trace, n, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+  if (reset && cudaMemset(g_gemm_trace, 0, n) != cudaSuccess) return 1;
+  return 0;
+}
+#endif
+
+
 using namespace gemm_tc;
 
 int gemm_tc_launch_bn96(int, int, int, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
@@ -101,6 +114,9 @@ int gemm_tc_launch(int layout, const void* A, int64_t lda, const void* B, int64_
   p.k_per_split = ceil_div64(ceil_div64(KK, split_k), BK) * BK;
   p.splits = (int)ceil_div64(KK, p.k_per_split);
   p.e = e;
+#ifdef PMV_ATTN_TRACE
+  p.trace = g_gemm_trace;
+#endif
   PMV_CHECK_ARG((int64_t)p.tiles_m * p.tiles_n * p.splits < (1ll << 31), "gemm(tc): too many tiles");
   if (p.splits > 1) {
     PMV_CHECK_ARG(out_dtype == PMV_F32 && e.atomic, "gemm(tc): split-K needs the atomic fp32 epilogue");

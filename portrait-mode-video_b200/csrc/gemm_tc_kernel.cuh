@@ -43,7 +43,20 @@ struct TcParams {
   int tiles_m, tiles_n, splits;
   int64_t k_per_split;      // multiple of BK
   EpiDev e;
+#ifdef PMV_ATTN_TRACE
+  long long* trace;  // debug build (scripts/gemm_trace.py): [CTA][GT_ITEMS][GT_SLOTS] clock64 stamps
+#endif
 };
+#ifdef PMV_ATTN_TRACE
+constexpr int GT_CTAS = 148, GT_ITEMS = 12, GT_SLOTS = 8;
+#define GTRACE(item, slot)                                                                                             \
+  do {                                                                                                                 \
+    if (p.trace != nullptr && (item) < GT_ITEMS && blockIdx.x < GT_CTAS)                                               \
+      p.trace[((int64_t)blockIdx.x * GT_ITEMS + (item)) * GT_SLOTS + (slot)] = clock64();                              \
+  } while (0)
+#else
+#define GTRACE(item, slot) do { } while (0)
+#endif
 
 // kinds whose epilogue goes registers -> swizzled smem tile -> TMA store (thread = accumulator row)
 __host__ __device__ constexpr bool kind_tma(int kind) { return kind == EK_PLAIN || kind == EK_GELU || kind == EK_GELU_BWD || kind == EK_ACCUM; }
@@ -204,6 +217,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int64_t kend = kbeg + p.k_per_split < p.K ? kbeg + p.k_per_split : p.K;
         for (int64_t kb = kbeg; kb < kend; kb += BK) {
           tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (kb == kbeg) GTRACE((wi - work0) / work_step, 3);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           if constexpr (PAIR) {
@@ -230,6 +244,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        GTRACE((wi - work0) / work_step, 4);
       }
     }
   } else if (warp == 1) {
@@ -263,12 +278,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t aphase = (uint32_t)((it >> 1) & 1);
         tc::mbar_wait(&acc_empty[as], aphase ^ 1);
         tc::tc_fence_after();
+        GTRACE(it, 0);
         const uint32_t tmem_d = tmem_base + as * Cfg::ACC_COLS;
         const int nkb = (int)((kend - kbeg + BK - 1) / BK);
         const int tail = (int)(kend - kbeg) - (nkb - 1) * BK;  // reduction length of the last block (1..BK)
         for (int kbi = 0; kbi < nkb; ++kbi) {
           tc::mbar_wait(&full_bar[stage], phase);
           tc::tc_fence_after();
+          if (kbi == 0) GTRACE(it, 1);
           const uint32_t lo_a = lo_a0 + (uint32_t)stage * STAGE16, lo_b = lo_b0 + (uint32_t)stage * STAGE16;
           if (kbi + 1 < nkb || tail == BK) {
             mma(tmem_d, lo_a, lo_b, kbi > 0 ? 1u : 0u);
@@ -284,6 +301,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (PAIR) tc::umma_commit2_mc(&acc_full[as], 3); else tc::umma_commit(&acc_full[as]);  // accumulator complete -> epilogue(s)
+        GTRACE(it, 2);
       }
     }
   } else if constexpr (kind_tma(KIND)) {
@@ -308,20 +326,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     };
     auto sw16_bf = [&](int j) -> int { return row * 64 + ((j ^ ((row >> 1) & 3)) << 4); };
 
+    // the tile decode (two 32-bit divisions) runs once per tile, not once per 32-column chunk
     struct Cursor {
       uint32_t wi, it;
       int c;
+      int row0, colt;  // first row of this warp's slab, first column of the tile
     };
     auto valid = [&](const Cursor& cu) { return cu.wi < num_work; };
-    auto advance = [&](Cursor& cu) {
-      cu.c += 64;
-      if (cu.c >= BN) { cu.c = half * 32; cu.wi += work_step; ++cu.it; }
-    };
-    auto coords = [&](const Cursor& cu, int& row0, int& col0) {
+    auto decode = [&](Cursor& cu) {
       const int tn = (int)(cu.wi % tiles_n);
       const int tm = (int)((cu.wi / tiles_n) % tiles_m);
-      row0 = tm * BM_TILE + (int)cta_rank * BM + q * 32;
-      col0 = tn * BN + cu.c;
+      cu.row0 = tm * BM_TILE + (int)cta_rank * BM + q * 32;
+      cu.colt = tn * BN;
+    };
+    auto advance = [&](Cursor& cu) {
+      cu.c += 64;
+      if (cu.c >= BN) { cu.c = half * 32; cu.wi += work_step; ++cu.it; decode(cu); }
+    };
+    auto coords = [&](const Cursor& cu, int& row0, int& col0) {
+      row0 = cu.row0;
+      col0 = cu.colt + cu.c;
     };
     const uint32_t acc_empty0_cl = PAIR ? tc::mapa_u32(&acc_empty[0], 0) : 0u;
     auto release_acc = [&](int as) {  // lane 0: this warp has its part of accumulator stage `as` in registers
@@ -333,14 +357,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int row0, col0;
       coords(cu, row0, col0);
       if (col0 >= p.N || row0 >= p.M) return;
-      if (lane == 0) {
+      if (tc::elect_one()) {
         tc::mbar_expect_tx(&my_aux_bar[n_loaded & 1], 2048);
         tc::tma_load_2d(wbuf + 4096 + (n_loaded & 1) * 2048, &tmD, col0, row0, &my_aux_bar[n_loaded & 1]);
       }
       ++n_loaded;
     };
 
-    Cursor cur{work0, 0, half * 32};
+    Cursor cur{work0, 0, half * 32, 0, 0};
+    decode(cur);
+    const bool has_bias = KIND != EK_GELU_BWD && KIND != EK_ACCUM && e.bias != nullptr;
+    float4 bq[8];
+    auto load_bias = [&](const Cursor& cu) {
+      const int col0 = cu.colt + cu.c;
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        bq[g] = (col0 + 4 * g < p.N) ? __ldg(reinterpret_cast<const float4*>(e.bias + col0 + 4 * g)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    if (has_bias && cur.c < BN && valid(cur)) load_bias(cur);
     if (cur.c < BN) {
       if ((KIND == EK_GELU_BWD || KIND == EK_ACCUM) && valid(cur)) load_aux(cur);
       while (valid(cur)) {
@@ -355,28 +389,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();  // everyone has consumed the aux buffer the next request overwrites (two requests back)
           if (valid(nxt)) load_aux(nxt);
         }
-        // the chunk's bias slice is requested before the accumulator wait (it used to be consumed right after issue: the
-        // FADD2 behind it carried most of the long-scoreboard samples of the epilogue, profiles/r01_gemm_ncu_full_summary.txt)
-        float4 bq[8];
-        const bool use_bias = KIND != EK_GELU_BWD && KIND != EK_ACCUM && e.bias != nullptr && live;
-        if (use_bias) {
-#pragma unroll
-          for (int g = 0; g < 8; ++g)
-            bq[g] = (col0 + 4 * g < p.N) ? __ldg(reinterpret_cast<const float4*>(e.bias + col0 + 4 * g)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        // the chunk's bias slice was requested one chunk ago, right after the previous slice had been consumed (requested
+        // next to its use, the FADD2 behind it waited ~0.1 us per chunk: scripts/gemm_trace.py)
+        const bool use_bias = has_bias && live;
         if (first_chunk) {
           tc::mbar_wait(&acc_full[as], (uint32_t)((cur.it >> 1) & 1));
           tc::tc_fence_after();
+          if (warp == 2 && lane == 0) GTRACE(cur.it, 5);
         }
         uint32_t r[32];
+#ifdef PMV_ATTN_TRACE
+        const bool fine = warp == 2 && lane == 0 && cur.it == 1 && cur.c < 128;
+        const int fitem = 8 + (cur.c >> 6);
+        if (fine) GTRACE(fitem, 0);
+#endif
         if (live) {
           tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * Cfg::ACC_COLS + cur.c, r);
           tc::tmem_ld_wait();
         }
+#ifdef PMV_ATTN_TRACE
+        if (fine) GTRACE(fitem, 1);
+#endif
         if (last_chunk) {  // the accumulator stage is in registers: hand it back to the MMA warp
           tc::tc_fence_before();
           __syncwarp();
           if (lane == 0) release_acc(as);
+          if (warp == 2 && lane == 0) GTRACE(cur.it, 6);
         }
         if (live) {
           float2 v[16];
@@ -389,11 +427,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               v[2 * g + 1] = __fadd2_rn(v[2 * g + 1], make_float2(bq[g].z, bq[g].w));
             }
           }
+          if (has_bias && valid(nxt)) load_bias(nxt);
           const int ob = n_item % OUT_BUFS;
           uint8_t* otile = wbuf + ob * OUT_TILE;
           // the bulk store that last read this buffer must be done with it
-          if (lane == 0) bulk_wait_read<OUT_BUFS - 1>();
+#ifdef PMV_ATTN_TRACE
+          if (fine) GTRACE(fitem, 2);
+#endif
+          if (tc::elect_one()) bulk_wait_read<OUT_BUFS - 1>();
           __syncwarp();
+#ifdef PMV_ATTN_TRACE
+          if (fine) GTRACE(fitem, 3);
+#endif
           if (KIND == EK_GELU && e.aux_out) {
             uint8_t* atile = wbuf + 4096 + ob * 2048;
 #pragma unroll
@@ -439,18 +484,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 8; ++j)
               *reinterpret_cast<float4*>(otile + sw16(j)) = make_float4(v[2 * j].x, v[2 * j].y, v[2 * j + 1].x, v[2 * j + 1].y);
           }
+#ifdef PMV_ATTN_TRACE
+          if (fine) GTRACE(fitem, 4);
+#endif
           tc::fence_proxy_async();  // generic-proxy writes -> visible to the bulk store
           __syncwarp();
-          if (lane == 0) {
+#ifdef PMV_ATTN_TRACE
+          if (fine) GTRACE(fitem, 5);
+#endif
+          if (tc::elect_one()) {
             tma_store_2d(&tmC, otile, col0, row0);
             if (KIND == EK_GELU && e.aux_out) tma_store_2d(&tmD, wbuf + 4096 + ob * 2048, col0, row0);
             bulk_commit();
           }
+#ifdef PMV_ATTN_TRACE
+          if (fine) GTRACE(fitem, 6);
+#endif
           ++n_item;
+        } else if (has_bias && valid(nxt)) {
+          load_bias(nxt);
         }
+        if (last_chunk && warp == 2 && lane == 0) GTRACE(cur.it, 7);
         cur = nxt;
       }
-      if (lane == 0) bulk_wait_all();  // global writes complete before the CTA retires its shared memory
+      if (tc::elect_one()) bulk_wait_all();  // global writes complete before the CTA retires its shared memory
     }
   } else {
     // ------------------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4)
@@ -514,6 +571,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (first_chunk) {
         tc::mbar_wait(&acc_full[as], (uint32_t)((cu.it >> 1) & 1));
         tc::tc_fence_after();
+        if (warp == 2 && lane == 0) GTRACE(cu.it, 5);
       }
       uint32_t r[32];
       tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * Cfg::ACC_COLS + cu.c, r);
@@ -524,6 +582,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
           if (PAIR) tc::mbar_arrive_cluster(acc_empty0_cl + as * 8); else tc::mbar_arrive(&acc_empty[as]);
         }
+        if (warp == 2 && lane == 0) GTRACE(cu.it, 6);
       }
       // transpose through shared memory (XOR-swizzled 16-byte groups: conflict-free both ways) so that 8
       // consecutive lanes cover one 32-column row segment: every global access of the epilogue is a full
@@ -607,6 +666,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       __syncwarp();
+      if (last_chunk && warp == 2 && lane == 0) GTRACE(cu.it, 7);
     };
 
     Cursor cur{work0, 0, half * 32};
