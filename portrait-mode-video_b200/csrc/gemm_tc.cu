@@ -118,6 +118,7 @@ int gemm_tc_launch(int layout, const void* A, int64_t lda, const void* B, int64_
   p.trace = g_gemm_trace;
 #endif
   PMV_CHECK_ARG((int64_t)p.tiles_m * p.tiles_n * p.splits < (1ll << 31), "gemm(tc): too many tiles");
+  PMV_CHECK_ARG(MM < (1ll << 31) - 512 && NN < (1ll << 31) - 512, "gemm(tc): M and N must fit 31 bits (the epilogues index in 32 bits)");
   if (p.splits > 1) {
     PMV_CHECK_ARG(out_dtype == PMV_F32 && e.atomic, "gemm(tc): split-K needs the atomic fp32 epilogue");
   }

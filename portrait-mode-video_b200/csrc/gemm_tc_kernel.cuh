@@ -118,6 +118,9 @@ __device__ __forceinline__ void st4(float* p, float2 a, float2 b) { *reinterpret
 __device__ __forceinline__ void red_add4(float* p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+__device__ __forceinline__ void sts16(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
                "r"(tc::smem_u32(smem_src)), "r"(c0), "r"(c1)
@@ -320,11 +323,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // EK_GELU: out tiles at [0, 4 KB), aux tiles at [4 KB, 8 KB).  EK_GELU_BWD: out tiles at [0, 4 KB), aux_in at [4 KB, 8 KB)
     uint64_t* my_aux_bar = aux_bar + (warp - 2) * 2;
     const int row = lane;  // row inside the warp's 32-row slab
+    // The chunk loop below ran 237 instructions per 32 x 32 chunk for ~55 of work (ncu source page of the qkv GEMM): 64-bit
+    // bounds compares, predicated bias loads with zero fills, register copies around the optional bias add, 64-bit
+    // shared-memory addressing.  With two epilogue warps per scheduler that IS the tile time of the K <= 384 GEMMs
+    // (scripts/gemm_trace.py: the MMA warp waits for an accumulator stage), so everything here is 32-bit and branch-lean.
+    const int Mi = (int)p.M, Ni = (int)p.N;  // the host checks that both fit 31 bits
+    const uint32_t wbuf32 = tc::smem_u32(wbuf);
     auto sw16 = [&](int j) -> int {  // byte offset of 16-byte piece j of this thread's row inside a tile
       if (sizeof(TOut) == 2) return row * 64 + ((j ^ ((row >> 1) & 3)) << 4);
       return row * 128 + ((j ^ (row & 7)) << 4);
     };
     auto sw16_bf = [&](int j) -> int { return row * 64 + ((j ^ ((row >> 1) & 3)) << 4); };
+    uint32_t so[sizeof(TOut) == 2 ? 4 : 8];  // this lane's 16-byte pieces inside an output tile (constant for the kernel)
+#pragma unroll
+    for (int j = 0; j < (sizeof(TOut) == 2 ? 4 : 8); ++j) so[j] = (uint32_t)sw16(j);
 
     // the tile decode (two 32-bit divisions) runs once per tile, not once per 32-column chunk
     struct Cursor {
@@ -356,7 +368,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto load_aux = [&](const Cursor& cu) {  // EK_GELU_BWD, warp-uniform: pre-activation tile of a live chunk -> aux buffer
       int row0, col0;
       coords(cu, row0, col0);
-      if (col0 >= p.N || row0 >= p.M) return;
+      if (col0 >= Ni || row0 >= Mi) return;
       if (tc::elect_one()) {
         tc::mbar_expect_tx(&my_aux_bar[n_loaded & 1], 2048);
         tc::tma_load_2d(wbuf + 4096 + (n_loaded & 1) * 2048, &tmD, col0, row0, &my_aux_bar[n_loaded & 1]);
@@ -370,9 +382,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float4 bq[8];
     auto load_bias = [&](const Cursor& cu) {
       const int col0 = cu.colt + cu.c;
+      const float4* bp = reinterpret_cast<const float4*>(e.bias + col0);
+      if (col0 + 32 <= Ni) {  // whole slice inside the row (every GEMM of the models): eight plain loads
 #pragma unroll
-      for (int g = 0; g < 8; ++g)
-        bq[g] = (col0 + 4 * g < p.N) ? __ldg(reinterpret_cast<const float4*>(e.bias + col0 + 4 * g)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int g = 0; g < 8; ++g) bq[g] = __ldg(bp + g);
+      } else {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) bq[g] = (col0 + 4 * g < Ni) ? __ldg(bp + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     };
     if (has_bias && cur.c < BN && valid(cur)) load_bias(cur);
     if (cur.c < BN) {
@@ -384,7 +401,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         coords(cur, row0, col0);
         const int as = (int)(cur.it & 1);
         const bool first_chunk = cur.c == half * 32, last_chunk = cur.c + 64 >= BN;
-        const bool live = col0 < p.N && row0 < p.M;
+        const bool live = col0 < Ni && row0 < Mi;
         if (KIND == EK_GELU_BWD || KIND == EK_ACCUM) {
           __syncwarp();  // everyone has consumed the aux buffer the next request overwrites (two requests back)
           if (valid(nxt)) load_aux(nxt);
@@ -398,18 +415,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (warp == 2 && lane == 0) GTRACE(cur.it, 5);
         }
         uint32_t r[32];
-#ifdef PMV_ATTN_TRACE
-        const bool fine = warp == 2 && lane == 0 && cur.it == 1 && cur.c < 128;
-        const int fitem = 8 + (cur.c >> 6);
-        if (fine) GTRACE(fitem, 0);
-#endif
         if (live) {
           tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * Cfg::ACC_COLS + cur.c, r);
           tc::tmem_ld_wait();
         }
-#ifdef PMV_ATTN_TRACE
-        if (fine) GTRACE(fitem, 1);
-#endif
         if (last_chunk) {  // the accumulator stage is in registers: hand it back to the MMA warp
           tc::tc_fence_before();
           __syncwarp();
@@ -417,34 +426,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (warp == 2 && lane == 0) GTRACE(cur.it, 6);
         }
         if (live) {
-          float2 v[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-          if (use_bias) {
+          if (use_bias) {  // in place: a separate result array costs 32 register copies on the path without bias
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-              v[2 * g] = __fadd2_rn(v[2 * g], make_float2(bq[g].x, bq[g].y));
-              v[2 * g + 1] = __fadd2_rn(v[2 * g + 1], make_float2(bq[g].z, bq[g].w));
+              const float2 a = __fadd2_rn(make_float2(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1])), make_float2(bq[g].x, bq[g].y));
+              const float2 b = __fadd2_rn(make_float2(__uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3])), make_float2(bq[g].z, bq[g].w));
+              r[4 * g] = __float_as_uint(a.x); r[4 * g + 1] = __float_as_uint(a.y);
+              r[4 * g + 2] = __float_as_uint(b.x); r[4 * g + 3] = __float_as_uint(b.y);
             }
           }
           if (has_bias && valid(nxt)) load_bias(nxt);
+          float2 v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
           const int ob = n_item % OUT_BUFS;
           uint8_t* otile = wbuf + ob * OUT_TILE;
           // the bulk store that last read this buffer must be done with it
-#ifdef PMV_ATTN_TRACE
-          if (fine) GTRACE(fitem, 2);
-#endif
           if (tc::elect_one()) bulk_wait_read<OUT_BUFS - 1>();
           __syncwarp();
-#ifdef PMV_ATTN_TRACE
-          if (fine) GTRACE(fitem, 3);
-#endif
           if (KIND == EK_GELU && e.aux_out) {
-            uint8_t* atile = wbuf + 4096 + ob * 2048;
+            const uint32_t atile32 = wbuf32 + 4096u + (uint32_t)(ob * 2048);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(atile + sw16_bf(j)) =
-                  make_uint4(pack_bf2(v[4 * j]), pack_bf2(v[4 * j + 1]), pack_bf2(v[4 * j + 2]), pack_bf2(v[4 * j + 3]));
+              sts16(atile32 + (sizeof(TOut) == 2 ? so[j] : (uint32_t)sw16_bf(j)), pack_bf2(v[4 * j]), pack_bf2(v[4 * j + 1]), pack_bf2(v[4 * j + 2]),
+                    pack_bf2(v[4 * j + 3]));
           }
           if (KIND == EK_GELU) {
 #pragma unroll
@@ -474,32 +479,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               v[4 * j + 3] = __fmul2_rn(v[4 * j + 3], gelu_grad2(bf2_to_f2(u.w)));
             }
           }
+          const uint32_t otile32 = wbuf32 + (uint32_t)(ob * OUT_TILE);
           if (sizeof(TOut) == 2) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(otile + sw16(j)) =
-                  make_uint4(pack_bf2(v[4 * j]), pack_bf2(v[4 * j + 1]), pack_bf2(v[4 * j + 2]), pack_bf2(v[4 * j + 3]));
+              sts16(otile32 + so[j], pack_bf2(v[4 * j]), pack_bf2(v[4 * j + 1]), pack_bf2(v[4 * j + 2]), pack_bf2(v[4 * j + 3]));
           } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(otile + sw16(j)) = make_float4(v[2 * j].x, v[2 * j].y, v[2 * j + 1].x, v[2 * j + 1].y);
+              sts16(otile32 + so[j], __float_as_uint(v[2 * j].x), __float_as_uint(v[2 * j].y), __float_as_uint(v[2 * j + 1].x),
+                    __float_as_uint(v[2 * j + 1].y));
           }
-#ifdef PMV_ATTN_TRACE
-          if (fine) GTRACE(fitem, 4);
-#endif
           tc::fence_proxy_async();  // generic-proxy writes -> visible to the bulk store
           __syncwarp();
-#ifdef PMV_ATTN_TRACE
-          if (fine) GTRACE(fitem, 5);
-#endif
           if (tc::elect_one()) {
             tma_store_2d(&tmC, otile, col0, row0);
             if (KIND == EK_GELU && e.aux_out) tma_store_2d(&tmD, wbuf + 4096 + ob * 2048, col0, row0);
             bulk_commit();
           }
-#ifdef PMV_ATTN_TRACE
-          if (fine) GTRACE(fitem, 6);
-#endif
           ++n_item;
         } else if (has_bias && valid(nxt)) {
           load_bias(nxt);

@@ -42,15 +42,8 @@ def trace(name, fn):
             ok = v > 0
             row.append(np.median((v[ok] - t0[ok, 0]) / ghz / 1e3) if ok.any() else float("nan"))
         print(f"   {it:4d} " + " ".join(f"{x:7.2f}" for x in row))
-    fine = ["chunk start", "accumulator chunk in registers", "math done (bias / GELU)", "staging buffer free (bulk wait)", "tile written to smem",
-            "proxy fence + syncwarp", "bulk store issued"]
-    for k in range(2):
-        v = t[:, 8 + k, :7]
-        ok = (v > 0).all(1)
-        if ok.any():
-            d = (v[ok] - v[ok, 0:1]) / ghz / 1e3
-            print(f"   warp 2, work item 1, chunk {k} (TMA-store epilogues), us since chunk start: " +
-                  "; ".join(f"{fine[i]} {np.median(d[:, i]):.2f}" for i in range(1, 7)))
+    for i, n in enumerate(names):
+        print(f"      {n.split(':')[0][:3]}{i} = {n}")
 
 
 def lin(M, N, K, **kw):
