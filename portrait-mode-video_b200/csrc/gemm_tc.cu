@@ -119,6 +119,11 @@ int gemm_tc_launch(int layout, const void* A, int64_t lda, const void* B, int64_
 #endif
   PMV_CHECK_ARG((int64_t)p.tiles_m * p.tiles_n * p.splits < (1ll << 31), "gemm(tc): too many tiles");
   PMV_CHECK_ARG(MM < (1ll << 31) - 512 && NN < (1ll << 31) - 512, "gemm(tc): M and N must fit 31 bits (the epilogues index in 32 bits)");
+  {
+    int64_t ld_max = e.ldo > e.ld_residual ? e.ldo : e.ld_residual;
+    if (e.ld_aux > ld_max) ld_max = e.ld_aux;
+    PMV_CHECK_ARG((MM + 256) * ld_max < (1ll << 32), "gemm(tc): rows x leading dimension must fit 32 bits (%lld x %lld)", (long long)MM, (long long)ld_max);
+  }
   if (p.splits > 1) {
     PMV_CHECK_ARG(out_dtype == PMV_F32 && e.atomic, "gemm(tc): split-K needs the atomic fp32 epilogue");
   }

@@ -520,48 +520,63 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr bool PRE_RES = KIND == EK_RES, PRE_AUX = KIND == EK_GELU_BWD;
     const bool has_scale = (KIND == EK_RES || KIND == EK_GENERIC) && e.row_scale != nullptr;
 
+    // 32-bit indexing, and the tile decode (two divisions) once per tile: the loop below used to spend most of its ~600
+    // instructions per chunk on 64-bit row / column arithmetic, re-read constant-bank fields and per-chunk decodes
+    const int Mi = (int)p.M, Ni = (int)p.N;  // the host checks M, N < 2^31 and rows x leading dimension < 2^31 elements
+    const uint32_t ld_res = (uint32_t)e.ld_residual, ld_aux = (uint32_t)e.ld_aux, ldo = (uint32_t)e.ldo;
     struct Cursor {
       uint32_t wi, it;
       int c;
+      int row0, colt;  // first row this lane handles in the tile (q, lr included), first column of the tile
     };
     struct Pre {     // operands of one chunk fetched ahead: fp32 residual (16 B) or bf16 pre-activation (8 B) per itr
       uint4 buf[(PRE_RES || PRE_AUX) ? 8 : 1];
       float sc[KIND == EK_RES ? 8 : 1];
     };
     auto valid = [&](const Cursor& cu) { return cu.wi < num_work; };
-    auto advance = [&](Cursor& cu) {
-      cu.c += 64;
-      if (cu.c >= BN) { cu.c = half * 32; cu.wi += work_step; ++cu.it; }
-    };
-    auto coords = [&](const Cursor& cu, int64_t& row0, int64_t& col) {
+    auto decode = [&](Cursor& cu) {
       const int tn = (int)(cu.wi % tiles_n);
       const int tm = (int)((cu.wi / tiles_n) % tiles_m);
-      row0 = (int64_t)tm * BM_TILE + (int64_t)cta_rank * BM + q * 32 + lr;
-      col = (int64_t)tn * BN + cu.c + lc * 4;
+      cu.row0 = tm * BM_TILE + (int)cta_rank * BM + q * 32 + lr;
+      cu.colt = tn * BN;
+    };
+    auto advance = [&](Cursor& cu) {
+      cu.c += 64;
+      if (cu.c >= BN) { cu.c = half * 32; cu.wi += work_step; ++cu.it; decode(cu); }
+    };
+    auto coords = [&](const Cursor& cu, int& row0, int& col) {
+      row0 = cu.row0;
+      col = cu.colt + cu.c + lc * 4;
     };
     const uint32_t acc_empty0_cl = PAIR ? tc::mapa_u32(&acc_empty[0], 0) : 0u;
     auto prefetch = [&](const Cursor& cu, Pre& pre) {
       if constexpr (PRE_RES || PRE_AUX) {
         if (!valid(cu)) return;
-        int64_t row0, col;
+        int row0, col;
         coords(cu, row0, col);
-        const bool colok = col < p.N;
+        const bool colok = col < Ni;
+        if constexpr (PRE_RES) {
+          const float* rp = e.residual + (size_t)((uint32_t)row0 * ld_res + (uint32_t)col);
 #pragma unroll
-        for (int itr = 0; itr < 8; ++itr) {
-          const int64_t row = row0 + itr * 4;
-          const bool ok = colok && row < p.M;
-          if constexpr (PRE_RES) {
-            pre.buf[itr] = ok ? __ldg(reinterpret_cast<const uint4*>(e.residual + row * e.ld_residual + col)) : make_uint4(0u, 0u, 0u, 0u);
+          for (int itr = 0; itr < 8; ++itr) {
+            const int row = row0 + itr * 4;
+            const bool ok = colok && row < Mi;
+            pre.buf[itr] = ok ? __ldg(reinterpret_cast<const uint4*>(rp + (size_t)((uint32_t)(itr * 4) * ld_res))) : make_uint4(0u, 0u, 0u, 0u);
             pre.sc[itr] = (ok && has_scale) ? __ldg(e.row_scale + e.fd_scale.div((uint32_t)row)) : 1.f;
-          } else {
-            const uint2 t2 = ok ? __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(e.aux_in) + row * e.ld_aux + col)) : make_uint2(0u, 0u);
+          }
+        } else {
+          const bf16* ap = reinterpret_cast<const bf16*>(e.aux_in) + (size_t)((uint32_t)row0 * ld_aux + (uint32_t)col);
+#pragma unroll
+          for (int itr = 0; itr < 8; ++itr) {
+            const bool ok = colok && row0 + itr * 4 < Mi;
+            const uint2 t2 = ok ? __ldg(reinterpret_cast<const uint2*>(ap + (size_t)((uint32_t)(itr * 4) * ld_aux))) : make_uint2(0u, 0u);
             pre.buf[itr].x = t2.x; pre.buf[itr].y = t2.y;
           }
         }
       }
     };
     auto process = [&](const Cursor& cu, const Pre& pre) {
-      int64_t row0, col;
+      int row0, col;
       coords(cu, row0, col);
       const int as = (int)(cu.it & 1);
       const bool first_chunk = cu.c == half * 32, last_chunk = cu.c + 64 >= BN;
@@ -589,7 +604,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         *reinterpret_cast<float4*>(stage_buf + lane * 32 + ((g ^ (lane & 7)) << 2)) =
             make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
       __syncwarp();
-      const bool colok = col < p.N;
+      const bool colok = col < Ni;
+      const uint32_t off0 = (uint32_t)row0 * ldo + (uint32_t)col;  // element offset of (row0, col) in the output
       float2 b01 = make_float2(0.f, 0.f), b23 = b01;
       if (KIND != EK_GELU_BWD && KIND != EK_ATOMIC && e.bias && colok) {
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
@@ -598,30 +614,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
       for (int itr = 0; itr < 8; ++itr) {
         const int rr = itr * 4 + lr;
-        const int64_t row = row0 + itr * 4;
+        const int row = row0 + itr * 4;
         const float4 a4 = *reinterpret_cast<const float4*>(stage_buf + rr * 32 + ((lc ^ (rr & 7)) << 2));
-        if (!(colok && row < p.M)) continue;
+        if (!(colok && row < Mi)) continue;
+        const size_t off = (size_t)(off0 + (uint32_t)(itr * 4) * ldo);  // KIND != GENERIC: plain row-major output
         float2 v01 = make_float2(a4.x, a4.y), v23 = make_float2(a4.z, a4.w);
         if constexpr (KIND == EK_ATOMIC) {
-          red_add4(reinterpret_cast<float*>(e.out) + row * e.ldo + col, a4);
+          red_add4(reinterpret_cast<float*>(e.out) + off, a4);
         } else if constexpr (KIND == EK_PLAIN) {
           v01 = __fadd2_rn(v01, b01); v23 = __fadd2_rn(v23, b23);
-          st4(reinterpret_cast<TOut*>(e.out) + row * e.ldo + col, v01, v23);
+          st4(reinterpret_cast<TOut*>(e.out) + off, v01, v23);
         } else if constexpr (KIND == EK_GELU) {
           v01 = __fadd2_rn(v01, b01); v23 = __fadd2_rn(v23, b23);
-          if (e.aux_out) st4(reinterpret_cast<bf16*>(e.aux_out) + row * e.ld_aux + col, v01, v23);
-          st4(reinterpret_cast<TOut*>(e.out) + row * e.ldo + col, gelu2(v01), gelu2(v23));
+          if (e.aux_out) st4(reinterpret_cast<bf16*>(e.aux_out) + (size_t)((uint32_t)row * ld_aux + (uint32_t)col), v01, v23);
+          st4(reinterpret_cast<TOut*>(e.out) + off, gelu2(v01), gelu2(v23));
         } else if constexpr (KIND == EK_GELU_BWD) {
           v01 = __fmul2_rn(v01, gelu_grad2(bf2_to_f2(pre.buf[itr].x)));
           v23 = __fmul2_rn(v23, gelu_grad2(bf2_to_f2(pre.buf[itr].y)));
-          st4(reinterpret_cast<TOut*>(e.out) + row * e.ldo + col, v01, v23);
+          st4(reinterpret_cast<TOut*>(e.out) + off, v01, v23);
         } else if constexpr (KIND == EK_RES) {
           const float2 sc = make_float2(pre.sc[itr], pre.sc[itr]);
           const float2 r01 = make_float2(__uint_as_float(pre.buf[itr].x), __uint_as_float(pre.buf[itr].y));
           const float2 r23 = make_float2(__uint_as_float(pre.buf[itr].z), __uint_as_float(pre.buf[itr].w));
           v01 = __ffma2_rn(__fadd2_rn(v01, b01), sc, r01);
           v23 = __ffma2_rn(__fadd2_rn(v23, b23), sc, r23);
-          st4(reinterpret_cast<TOut*>(e.out) + row * e.ldo + col, v01, v23);
+          st4(reinterpret_cast<TOut*>(e.out) + off, v01, v23);
         } else {
           float v[4] = {a4.x + b01.x, a4.y + b01.y, a4.z + b23.x, a4.w + b23.y};
           if (e.atomic) {
@@ -651,7 +668,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 4; ++j) v[j] += rv[j];
           }
-          const int64_t orow = e.out_group > 0 ? row + (int64_t)(e.fd_group.div((uint32_t)row) + 1) * e.out_skip : row;
+          const int64_t orow = e.out_group > 0 ? (int64_t)row + (int64_t)(e.fd_group.div((uint32_t)row) + 1) * e.out_skip : (int64_t)row;
           TOut* o = reinterpret_cast<TOut*>(e.out) + orow * e.ldo + col;
           if (e.accumulate) {
             float pv[4];
@@ -666,7 +683,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (last_chunk && warp == 2 && lane == 0) GTRACE(cu.it, 7);
     };
 
-    Cursor cur{work0, 0, half * 32};
+    Cursor cur{work0, 0, half * 32, 0, 0};
+    decode(cur);
     if (cur.c < BN) {
       Pre pa, pb;
       prefetch(cur, pa);
