@@ -9,27 +9,28 @@ namespace {
 
 __global__ void __launch_bounds__(256) maxpool_skip_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                                uint8_t* __restrict__ win, int B, int T, int H, int W, int Ho, int Wo,
-                                                               int C) {
+                                                               int C, FastDiv fdC4, FastDiv fdN, FastDiv fdW, FastDiv fdH) {
   pdl_wait();
   const int C4 = C >> 2;
   const int Lo = T * Ho * Wo, Li = T * H * W;
   const int64_t total = (int64_t)B * (Lo + 1) * C4;
-  // 32-bit index arithmetic (the host checks total < 2^31): the two 64-bit divisions per element were most of the kernel
+  // 32-bit index arithmetic (the host checks total < 2^31) with multiply-shift divisions by the four loop-invariant
+  // divisors: the eight hardware divisions per element (~20 instructions each) were half of the kernel's issue slots
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (uint32_t)total; i += gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % (uint32_t)C4);
-    const int r = (int)(i / (uint32_t)C4);
-    const int n = r % (Lo + 1);
-    const int b = r / (Lo + 1);
+    uint32_t ru, c4u, bu, nu;
+    fdC4.divmod(i, ru, c4u);
+    fdN.divmod(ru, bu, nu);
+    const int c4 = (int)c4u, n = (int)nu, b = (int)bu;
     const float* xb = x + (int64_t)b * (Li + 1) * C + c4 * 4;
     float m[4];
     uchar4 a = make_uchar4(0, 0, 0, 0);
     if (n == 0) {
       load4(xb, m);
     } else {
-      int l = n - 1;
-      const int wo = l % Wo; l /= Wo;
-      const int ho = l % Ho;
-      const int t = l / Ho;
+      uint32_t lq, wou, tu, hou;
+      fdW.divmod((uint32_t)(n - 1), lq, wou);
+      fdH.divmod(lq, tu, hou);
+      const int wo = (int)wou, ho = (int)hou, t = (int)tu;
       bool first = true;
 #pragma unroll
       for (int dh = 0; dh < 3; ++dh) {
@@ -58,26 +59,26 @@ __global__ void __launch_bounds__(256) maxpool_skip_fwd_kernel(const float* __re
 
 __global__ void __launch_bounds__(256) maxpool_skip_bwd_kernel(const uint8_t* __restrict__ win, const float* __restrict__ dy,
                                                                float* __restrict__ dx, int B, int T, int H, int W, int Ho, int Wo,
-                                                               int C) {
+                                                               int C, FastDiv fdC4, FastDiv fdN, FastDiv fdW, FastDiv fdH) {
   pdl_wait();
   const int C4 = C >> 2;
   const int Lo = T * Ho * Wo, Li = T * H * W;
   const int64_t total = (int64_t)B * (Li + 1) * C4;
-  // 32-bit index arithmetic (the host checks total < 2^31): the two 64-bit divisions per element were most of the kernel
+  // 32-bit index arithmetic (the host checks total < 2^31), multiply-shift divisions (see the forward kernel)
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (uint32_t)total; i += gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % (uint32_t)C4);
-    const int r = (int)(i / (uint32_t)C4);
-    const int n = r % (Li + 1);
-    const int b = r / (Li + 1);
+    uint32_t ru, c4u, bu, nu;
+    fdC4.divmod(i, ru, c4u);
+    fdN.divmod(ru, bu, nu);
+    const int c4 = (int)c4u, n = (int)nu, b = (int)bu;
     const int64_t ob = (int64_t)b * (Lo + 1) * C + c4 * 4;
     float g[4] = {0.f, 0.f, 0.f, 0.f};
     if (n == 0) {
       load4(dy + ob, g);
     } else {
-      int l = n - 1;
-      const int w = l % W; l /= W;
-      const int h = l % H;
-      const int t = l / H;
+      uint32_t lq, wu, tu, hu;
+      fdW.divmod((uint32_t)(n - 1), lq, wu);
+      fdH.divmod(lq, tu, hu);
+      const int w = (int)wu, h = (int)hu, t = (int)tu;
       // windows containing row h: ho = h/2 with dh = 1 (h even), or ho = (h+1)/2 with dh = 0 and (h-1)/2 with dh = 2 (h odd).
       // All (up to four) winner words are requested before any is inspected, then the gradients of the windows this input
       // won: two dependent round trips per element instead of two per window.
@@ -130,7 +131,8 @@ extern "C" int pmv_maxpool_skip_fwd(const float* x, float* y, uint8_t* win, int 
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const int64_t total = (int64_t)B * (1 + (int64_t)T * Ho * Wo) * (C / 4);
   PMV_CHECK_ARG((int64_t)B * (1 + (int64_t)T * H * W) * (C / 4) < (1ll << 31), "maxpool: too many elements");
-  pmv_launch(maxpool_skip_fwd_kernel, grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream, x, y, win, B, T, H, W, Ho, Wo, C);
+  pmv_launch(maxpool_skip_fwd_kernel, grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream, x, y, win, B, T, H, W, Ho, Wo, C,
+             FastDiv((uint32_t)(C / 4)), FastDiv((uint32_t)(1 + T * Ho * Wo)), FastDiv((uint32_t)Wo), FastDiv((uint32_t)Ho));
   PMV_CHECK_LAUNCH();
   return PMV_OK;
 }
@@ -141,7 +143,8 @@ extern "C" int pmv_maxpool_skip_bwd(const uint8_t* win, const float* dy, float* 
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const int64_t total = (int64_t)B * (1 + (int64_t)T * H * W) * (C / 4);
   PMV_CHECK_ARG((int64_t)B * (1 + (int64_t)T * H * W) * (C / 4) < (1ll << 31), "maxpool: too many elements");
-  pmv_launch(maxpool_skip_bwd_kernel, grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream, win, dy, dx, B, T, H, W, Ho, Wo, C);
+  pmv_launch(maxpool_skip_bwd_kernel, grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream, win, dy, dx, B, T, H, W, Ho, Wo, C,
+             FastDiv((uint32_t)(C / 4)), FastDiv((uint32_t)(1 + T * H * W)), FastDiv((uint32_t)W), FastDiv((uint32_t)H));
   PMV_CHECK_LAUNCH();
   return PMV_OK;
 }
