@@ -24,17 +24,41 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ c
   const int to = r % To;
   const int b = r / To;
   // ---- stage
-  for (int rr = threadIdx.x >> 5; rr < nrows; rr += blockDim.x >> 5) {
-    const int dh = rr % kh;
-    const int dt = (rr / kh) % kt;
-    const int c = rr / (kh * kt);
-    const int ti = to * st + dt - pt, hi = ho * sh + dh - ph;
-    const bool ok = ti >= 0 && ti < Tn && hi >= 0 && hi < H;
-    const float* src = clip + (((int64_t)(b * Cin + c) * Tn + (ok ? ti : 0)) * H + (ok ? hi : 0)) * W;
-    float* dst = rows_s + rr * pitch;
-    for (int j = threadIdx.x & 31; j < span; j += 32) {
-      const int wi = j - pw;
-      dst[j] = (ok && wi >= 0 && wi < W) ? __ldg(src + wi) : 0.f;
+  if ((W & 3) == 0 && span >= W + pw) {
+    // 16-byte loads over the flattened (row, float4) index: ~14 independent loads per thread instead of ~56 scalar ones in
+    // a per-row lane loop (the staging phase, not the emit phase, was most of this kernel's 145 us); the left / right
+    // padding columns of every row are cleared separately
+    const int W4 = W >> 2;
+    for (int idx = threadIdx.x; idx < nrows * W4; idx += blockDim.x) {
+      const int rr = idx / W4, v4 = idx - rr * W4;
+      const int dh = rr % kh;
+      const int dt = (rr / kh) % kt;
+      const int c = rr / (kh * kt);
+      const int ti = to * st + dt - pt, hi = ho * sh + dh - ph;
+      const bool ok = ti >= 0 && ti < Tn && hi >= 0 && hi < H;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok) v = __ldg(reinterpret_cast<const float4*>(clip + (((int64_t)(b * Cin + c) * Tn + ti) * H + hi) * W) + v4);
+      float* dst = rows_s + rr * pitch + pw + 4 * v4;
+      dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
+    const int npad = pw + (span - W - pw);  // columns left of 0 and right of W - 1
+    for (int idx = threadIdx.x; idx < nrows * npad; idx += blockDim.x) {
+      const int rr = idx / npad, j = idx - rr * npad;
+      rows_s[rr * pitch + (j < pw ? j : W + j)] = 0.f;
+    }
+  } else {
+    for (int rr = threadIdx.x >> 5; rr < nrows; rr += blockDim.x >> 5) {
+      const int dh = rr % kh;
+      const int dt = (rr / kh) % kt;
+      const int c = rr / (kh * kt);
+      const int ti = to * st + dt - pt, hi = ho * sh + dh - ph;
+      const bool ok = ti >= 0 && ti < Tn && hi >= 0 && hi < H;
+      const float* src = clip + (((int64_t)(b * Cin + c) * Tn + (ok ? ti : 0)) * H + (ok ? hi : 0)) * W;
+      float* dst = rows_s + rr * pitch;
+      for (int j = threadIdx.x & 31; j < span; j += 32) {
+        const int wi = j - pw;
+        dst[j] = (ok && wi >= 0 && wi < W) ? __ldg(src + wi) : 0.f;
+      }
     }
   }
   __syncthreads();
